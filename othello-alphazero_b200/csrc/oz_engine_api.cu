@@ -1,0 +1,671 @@
+// Engine part of the C ABI: the MCTS facade of the reference (cpp/src/include/mcts.h,
+// cpp/src/lib/mcts.cpp) for `num_games` lockstep games whose trees live in HBM.
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "oz_common.cuh"
+#include "oz_resnet.cuh"
+#include "oz_rules.cuh"
+#include "oz_tree.cuh"
+
+using namespace oz;
+
+static_assert(sizeof(oz_ply_record) == sizeof(PlyRecordDev), "record layout");
+static_assert(OZ_MAX_CHILDREN == kStride, "stride");
+
+struct oz_resnet {
+    int device = 0;
+    ResNet net;
+    float *d_f = nullptr, *d_p = nullptr, *d_v = nullptr;
+    size_t cap = 0;
+};
+
+struct oz_engine {
+    oz_config cfg{};
+    Tree t{};
+    cudaStream_t stream = nullptr;
+    int inflight_cap = 0, planes_cap = 0;
+    float *d_features = nullptr, *d_policy = nullptr, *d_value = nullptr;
+    float *d_rate = nullptr, *d_gamma = nullptr;
+    int32_t *d_actions = nullptr, *d_unfinished = nullptr;
+    int32_t *d_stat_n = nullptr, *d_stat_counts = nullptr, *d_stat_rootn = nullptr;
+    float *d_stat_q = nullptr;
+    PlyRecordDev *d_records = nullptr;
+    int max_plies = 0;
+    float *d_spd_f = nullptr, *d_spd_p = nullptr;
+    ResNet net;
+    bool in_search = false;
+    int round = 0;
+    int active = 0;                       // games not finished
+    oz_counters ctr{};
+    bool profiling = false;
+    std::vector<cudaEvent_t> ev;          // phase boundaries of one search
+    std::vector<char> pool;               // keeps allocation list
+    std::vector<void *> allocs;
+};
+
+namespace {
+
+// ---- validation, same texts as mcts.cpp:167-241 ----
+int check_ge1(const char *name, int v) {
+    if (v < 1) return fail(OZ_ERR_INVALID_ARGUMENT, std::string("Expected ") + name + " >= 1, but got " + std::to_string(v) + ".");
+    return OZ_OK;
+}
+int check_config(const oz_config &c) {
+    OZ_TRY(check_ge1("history_size", c.history_size));
+    OZ_TRY(check_ge1("num_simulations", c.num_simulations));
+    OZ_TRY(check_ge1("num_threads", c.num_threads));
+    OZ_TRY(check_ge1("batch_size", c.batch_size));
+    if (!(c.c_puct_base > 0.0f)) return fail(OZ_ERR_INVALID_ARGUMENT, "Expected c_puct_base > 0.0, but got " + std::to_string(c.c_puct_base) + ".");
+    if (!(c.c_puct_init >= 0.0f)) return fail(OZ_ERR_INVALID_ARGUMENT, "Expected c_puct_init >= 0.0, but got " + std::to_string(c.c_puct_init) + ".");
+    if (!(0.0f <= c.dirichlet_epsilon && c.dirichlet_epsilon <= 1.0f))
+        return fail(OZ_ERR_INVALID_ARGUMENT, "Expected 0.0 <= dirichlet_epsilon <= 1.0, but got " + std::to_string(c.dirichlet_epsilon) + ".");
+    if (!(c.dirichlet_alpha >= 0.0f)) return fail(OZ_ERR_INVALID_ARGUMENT, "Expected dirichlet_alpha >= 0.0, but got " + std::to_string(c.dirichlet_alpha) + ".");
+    return OZ_OK;
+}
+int check_engine_limits(const oz_config &c) {
+    if (c.num_games < 1) return fail(OZ_ERR_INVALID_ARGUMENT, "Expected num_games >= 1, but got " + std::to_string(c.num_games) + ".");
+    if (c.history_size > kMaxHist) return fail(OZ_ERR_INVALID_ARGUMENT, "history_size above " + std::to_string(kMaxHist) + " is not supported by the device engine.");
+    return OZ_OK;
+}
+
+template <typename T>
+int dalloc(T **p, size_t n) {
+    *p = nullptr;
+    OZ_CUDA(cudaMalloc((void **)p, std::max<size_t>(1, n) * sizeof(T)));
+    return OZ_OK;
+}
+
+int rounds_of(const oz_config &c) {
+    const int inflight = c.num_threads * c.batch_size;
+    return (c.num_simulations + inflight - 1) / inflight;   // search_thread.cpp:48-50
+}
+
+int default_cap(const oz_config &c) {
+    if (c.max_nodes_per_game > 0) return c.max_nodes_per_game;
+    const long sims = (long)rounds_of(c) * c.num_threads * c.batch_size;
+    return (int)std::min<long>(40 * std::max<long>(sims, 64) + 1024, 1 << 22);
+}
+
+int alloc_pools(Tree &t, int G, int cap) {
+    const size_t n = (size_t)G * 2 * cap;
+    OZ_TRY(dalloc(&t.n_p1, n)); OZ_TRY(dalloc(&t.n_p2, n));
+    OZ_TRY(dalloc(&t.n_meta, n)); OZ_TRY(dalloc(&t.n_parent, n)); OZ_TRY(dalloc(&t.n_child, n)); OZ_TRY(dalloc(&t.n_N, n));
+    OZ_TRY(dalloc(&t.n_W, n)); OZ_TRY(dalloc(&t.n_Q, n)); OZ_TRY(dalloc(&t.n_P, n));
+    t.cap = cap;
+    return OZ_OK;
+}
+void free_pools(Tree &t) {
+    cudaFree(t.n_p1); cudaFree(t.n_p2); cudaFree(t.n_meta); cudaFree(t.n_parent); cudaFree(t.n_child); cudaFree(t.n_N);
+    cudaFree(t.n_W); cudaFree(t.n_Q); cudaFree(t.n_P);
+    t.n_p1 = t.n_p2 = nullptr; t.n_meta = t.n_parent = t.n_child = t.n_N = nullptr; t.n_W = t.n_Q = t.n_P = nullptr;
+}
+
+int alloc_slots(oz_engine *e) {
+    Tree &t = e->t;
+    const int inflight = e->cfg.num_threads * e->cfg.batch_size, planes = 1 + 2 * e->cfg.history_size;
+    if (inflight > e->inflight_cap) {
+        cudaFree(t.s_leaf); cudaFree(t.s_tf); cudaFree(t.s_len); cudaFree(t.s_path); cudaFree(e->d_policy); cudaFree(e->d_value);
+        const size_t slots = (size_t)t.G * inflight;
+        OZ_TRY(dalloc(&t.s_leaf, slots)); OZ_TRY(dalloc(&t.s_tf, slots)); OZ_TRY(dalloc(&t.s_len, slots));
+        OZ_TRY(dalloc(&t.s_path, slots * kMaxDepth));
+        OZ_TRY(dalloc(&e->d_policy, slots * 65)); OZ_TRY(dalloc(&e->d_value, slots));
+        OZ_CUDA(cudaMemset(t.s_tf, 0, slots * sizeof(int32_t)));
+        OZ_CUDA(cudaMemset(e->d_policy, 0, slots * 65 * sizeof(float)));
+        OZ_CUDA(cudaMemset(e->d_value, 0, slots * sizeof(float)));
+    }
+    if (inflight > e->inflight_cap || planes > e->planes_cap) {
+        cudaFree(e->d_features);
+        e->inflight_cap = std::max(e->inflight_cap, inflight);
+        e->planes_cap = std::max(e->planes_cap, planes);
+        // padded to 16 boards: the network evaluates whole units
+        OZ_TRY(dalloc(&e->d_features, ((size_t)t.G * e->inflight_cap + 16) * e->planes_cap * 64));
+        cudaFree(e->d_spd_f);
+        OZ_TRY(dalloc(&e->d_spd_f, (size_t)8 * e->planes_cap * 64));
+    }
+    t.inflight = inflight;
+    t.H = e->cfg.history_size;
+    return OZ_OK;
+}
+
+// Exploration rate by visit count, computed with the host libm the reference links
+// (search_thread.cpp:198-203): logf((1 + N + c_base) / c_base) + c_init.
+int build_rate_table(oz_engine *e) {
+    const long sims = (long)rounds_of(e->cfg) * e->cfg.num_threads * e->cfg.batch_size;
+    const long len = std::min<long>(std::max<long>(sims * 140 + 1024, 4096), 1L << 24);
+    std::vector<float> tab((size_t)len);
+    const float cb = e->cfg.c_puct_base, ci = e->cfg.c_puct_init;
+    for (long n = 0; n < len; ++n) tab[(size_t)n] = std::log(((float)(1 + (int)n) + cb) / cb) + ci;
+    cudaFree(e->d_rate);
+    OZ_TRY(dalloc(&e->d_rate, (size_t)len));
+    OZ_CUDA(cudaMemcpy(e->d_rate, tab.data(), (size_t)len * sizeof(float), cudaMemcpyHostToDevice));
+    e->t.rate = e->d_rate; e->t.rate_len = (int)len;
+    return OZ_OK;
+}
+
+void sync_params(oz_engine *e) {
+    Tree &t = e->t;
+    t.eps = e->cfg.dirichlet_epsilon; t.alpha = e->cfg.dirichlet_alpha;
+    t.seed_lo = (uint32_t)e->cfg.seed; t.seed_hi = (uint32_t)(e->cfg.seed >> 32);
+    t.first_game_id = e->cfg.first_game_id; t.sym_mode = e->cfg.sym_mode; t.temperature_plies = e->cfg.temperature_plies;
+}
+
+int check_device_errors(oz_engine *e) {
+    int32_t err = 0;
+    OZ_CUDA(cudaMemcpyAsync(&err, e->t.error, sizeof(err), cudaMemcpyDeviceToHost, e->stream));
+    OZ_CUDA(cudaStreamSynchronize(e->stream));
+    if (err == 0) return OZ_OK;
+    cudaMemsetAsync(e->t.error, 0, sizeof(int32_t), e->stream);
+    std::string msg = "device engine:";
+    if (err & kErrArenaFull) msg += " node arena full (raise max_nodes_per_game);";
+    if (err & kErrRateTable) msg += " visit count beyond the exploration-rate table;";
+    if (err & kErrDepth) msg += " search path deeper than " + std::to_string(kMaxDepth) + ";";
+    return fail(OZ_ERR_CAPACITY, msg);
+}
+
+int set_device(const oz_engine *e) { OZ_CUDA(cudaSetDevice(e->cfg.device)); return OZ_OK; }
+
+int grow_pools(oz_engine *e, int new_cap) {
+    Tree nt = e->t;
+    OZ_TRY(alloc_pools(nt, e->t.G, new_cap));
+    launch_copy_arenas(e->t, nt, e->stream);
+    OZ_CUDA(cudaStreamSynchronize(e->stream));
+    free_pools(e->t);
+    e->t = nt;
+    return OZ_OK;
+}
+
+int eval_round(oz_engine *e) {
+    const size_t n = (size_t)e->t.G * e->t.inflight;
+    const int planes = 1 + 2 * e->t.H;
+    switch (e->cfg.evaluator) {
+        case OZ_EVAL_SYNTH: launch_eval_synth(e->d_features, planes, n, e->d_policy, e->d_value, e->stream); break;
+        case OZ_EVAL_HASH: launch_eval_hash(e->d_features, planes, n, e->d_policy, e->d_value, e->stream); break;
+        case OZ_EVAL_RESNET:
+            if (e->net.shape().in_planes != planes)
+                return fail(OZ_ERR_STATE, "network in_planes " + std::to_string(e->net.shape().in_planes) + " != 1 + 2 * history_size");
+            OZ_TRY(e->net.forward(e->d_features, n, e->d_policy, e->d_value, e->stream));
+            break;
+        default: return fail(OZ_ERR_STATE, "oz_engine_search needs a built-in evaluator; use select/expand for OZ_EVAL_EXTERNAL");
+    }
+    e->ctr.evaluations += n;
+    return OZ_OK;
+}
+
+cudaEvent_t next_event(oz_engine *e, size_t i) {
+    while (e->ev.size() <= i) { cudaEvent_t x; cudaEventCreate(&x); e->ev.push_back(x); }
+    return e->ev[i];
+}
+
+int begin_search(oz_engine *e) {
+    if (e->in_search) return fail(OZ_ERR_STATE, "search already in progress");
+    if (e->cfg.evaluator == OZ_EVAL_RESNET && !e->net.loaded()) return fail(OZ_ERR_STATE, "no network weights loaded");
+    sync_params(e);
+    // New SearchThread per search: feature slots start from zeros (search_thread.cpp:37-39).
+    OZ_CUDA(cudaMemsetAsync(e->d_features, 0, (size_t)e->t.G * e->t.inflight * (1 + 2 * e->t.H) * 64 * sizeof(float), e->stream));
+    e->in_search = true; e->round = 0;
+    return OZ_OK;
+}
+
+int end_search(oz_engine *e) {
+    launch_end_search(e->t, e->stream);
+    e->in_search = false;
+    e->ctr.searches += 1;
+    e->ctr.simulations += (uint64_t)rounds_of(e->cfg) * e->t.inflight * (uint64_t)e->active;
+    return check_device_errors(e);
+}
+
+}  // namespace
+
+extern "C" {
+
+void oz_config_default(oz_config *c) {
+    std::memset(c, 0, sizeof(*c));
+    c->num_games = 1; c->history_size = 4; c->num_simulations = 800; c->num_threads = 2; c->batch_size = 16;
+    c->c_puct_base = 20000.0f; c->c_puct_init = 2.5f; c->dirichlet_epsilon = 0.25f; c->dirichlet_alpha = 0.5f;
+    c->seed = 0; c->first_game_id = 0; c->device = 0; c->evaluator = OZ_EVAL_EXTERNAL; c->sym_mode = OZ_SYM_RANDOM;
+    c->temperature_plies = 12; c->max_nodes_per_game = 0;
+}
+
+int oz_engine_create(const oz_config *cfg, oz_engine **out) {
+    *out = nullptr;
+    OZ_TRY(check_config(*cfg));
+    OZ_TRY(check_engine_limits(*cfg));
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+        return fail(OZ_ERR_CUDA, "no CUDA device: the engine has no CPU path");
+    if (cfg->device < 0 || cfg->device >= ndev) return fail(OZ_ERR_CUDA, "invalid CUDA device " + std::to_string(cfg->device));
+    oz_engine *e = new oz_engine();
+    e->cfg = *cfg;
+    int st = OZ_OK;
+    do {
+        if ((st = set_device(e))) break;
+        if (cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking) != cudaSuccess) { st = fail(OZ_ERR_CUDA, "stream creation failed"); break; }
+        Tree &t = e->t;
+        const int G = cfg->num_games;
+        t.G = G;
+        if ((st = alloc_pools(t, G, default_cap(*cfg)))) break;
+        if ((st = dalloc(&t.g_root, G)) || (st = dalloc(&t.g_which, G)) || (st = dalloc(&t.g_count, G)) || (st = dalloc(&t.g_status, G)) ||
+            (st = dalloc(&t.g_ply, G)) || (st = dalloc(&t.g_search, G)) || (st = dalloc(&t.h_p1, (size_t)G * kMaxHist)) ||
+            (st = dalloc(&t.h_p2, (size_t)G * kMaxHist)) || (st = dalloc(&t.h_player, (size_t)G * kMaxHist)) || (st = dalloc(&t.h_n, G)) ||
+            (st = dalloc(&t.r_p1, G)) || (st = dalloc(&t.r_p2, G)) || (st = dalloc(&t.r_player, G)) || (st = dalloc(&t.error, 1)) ||
+            (st = dalloc(&t.stats, 4)) || (st = dalloc(&e->d_actions, G)) || (st = dalloc(&e->d_unfinished, 1)) ||
+            (st = dalloc(&e->d_stat_n, G)) || (st = dalloc(&e->d_stat_counts, (size_t)G * kStride)) || (st = dalloc(&e->d_stat_q, (size_t)G * kStride)) ||
+            (st = dalloc(&e->d_stat_rootn, G)) || (st = dalloc(&e->d_spd_p, 8 * 65)))
+            break;
+        cudaMemset(t.error, 0, sizeof(int32_t)); cudaMemset(t.stats, 0, 4 * sizeof(unsigned long long));
+        e->max_plies = 128;
+        if ((st = dalloc(&e->d_records, (size_t)G * e->max_plies))) break;
+        if ((st = alloc_slots(e))) break;
+        if ((st = build_rate_table(e))) break;
+        sync_params(e);
+        launch_reset(t, e->stream);
+        e->active = G;
+        if (cudaStreamSynchronize(e->stream) != cudaSuccess) { st = fail(OZ_ERR_CUDA, std::string("engine init: ") + cudaGetErrorString(cudaGetLastError())); break; }
+    } while (0);
+    if (st) { oz_engine_destroy(e); return st; }
+    *out = e;
+    return OZ_OK;
+}
+
+void oz_engine_destroy(oz_engine *e) {
+    if (!e) return;
+    cudaSetDevice(e->cfg.device);
+    if (e->stream) cudaStreamSynchronize(e->stream);
+    Tree &t = e->t;
+    free_pools(t);
+    void *ptrs[] = {t.g_root, t.g_which, t.g_count, t.g_status, t.g_ply, t.g_search, t.h_p1, t.h_p2, t.h_player, t.h_n, t.r_p1, t.r_p2,
+                    t.r_player, t.s_leaf, t.s_tf, t.s_len, t.s_path, t.error, t.stats, e->d_features, e->d_policy, e->d_value, e->d_rate,
+                    e->d_gamma, e->d_actions, e->d_unfinished, e->d_stat_n, e->d_stat_counts, e->d_stat_q, e->d_stat_rootn, e->d_records,
+                    e->d_spd_f, e->d_spd_p};
+    for (void *p : ptrs) cudaFree(p);
+    for (cudaEvent_t x : e->ev) cudaEventDestroy(x);
+    if (e->stream) cudaStreamDestroy(e->stream);
+    delete e;
+}
+
+#define OZ_SETTER(NAME, FIELD, TYPE, AFTER)                      \
+    int oz_engine_set_##NAME(oz_engine *e, TYPE v) {             \
+        oz_config c = e->cfg;                                    \
+        c.FIELD = v;                                             \
+        OZ_TRY(check_config(c));                                 \
+        OZ_TRY(check_engine_limits(c));                          \
+        if (e->in_search) return fail(OZ_ERR_STATE, "cannot change parameters during a search"); \
+        OZ_TRY(set_device(e));                                   \
+        e->cfg = c;                                              \
+        AFTER;                                                   \
+        return OZ_OK;                                            \
+    }
+OZ_SETTER(history_size, history_size, int, OZ_TRY(alloc_slots(e)))
+OZ_SETTER(num_simulations, num_simulations, int, { OZ_TRY(build_rate_table(e)); if (default_cap(e->cfg) > e->t.cap) OZ_TRY(grow_pools(e, default_cap(e->cfg))); })
+OZ_SETTER(num_threads, num_threads, int, { OZ_TRY(alloc_slots(e)); OZ_TRY(build_rate_table(e)); })
+OZ_SETTER(batch_size, batch_size, int, { OZ_TRY(alloc_slots(e)); OZ_TRY(build_rate_table(e)); })
+OZ_SETTER(c_puct_base, c_puct_base, float, OZ_TRY(build_rate_table(e)))
+OZ_SETTER(c_puct_init, c_puct_init, float, OZ_TRY(build_rate_table(e)))
+OZ_SETTER(dirichlet_epsilon, dirichlet_epsilon, float, sync_params(e))
+OZ_SETTER(dirichlet_alpha, dirichlet_alpha, float, sync_params(e))
+
+int oz_engine_get_config(const oz_engine *e, oz_config *out) { *out = e->cfg; return OZ_OK; }
+
+int oz_engine_set_evaluator(oz_engine *e, int evaluator) {
+    if (evaluator < OZ_EVAL_EXTERNAL || evaluator > OZ_EVAL_RESNET) return fail(OZ_ERR_INVALID_ARGUMENT, "unknown evaluator");
+    if (e->in_search) return fail(OZ_ERR_STATE, "cannot change the evaluator during a search");
+    e->cfg.evaluator = evaluator;
+    return OZ_OK;
+}
+
+int oz_engine_set_gamma_table(oz_engine *e, const float *table, int len) {
+    OZ_TRY(set_device(e));
+    cudaFree(e->d_gamma); e->d_gamma = nullptr;
+    e->t.gamma_table = nullptr; e->t.gamma_len = 0;
+    if (len > 0) {
+        OZ_TRY(dalloc(&e->d_gamma, (size_t)len));
+        OZ_CUDA(cudaMemcpy(e->d_gamma, table, (size_t)len * sizeof(float), cudaMemcpyHostToDevice));
+        e->t.gamma_table = e->d_gamma; e->t.gamma_len = len;
+    }
+    return OZ_OK;
+}
+
+int oz_engine_reset(oz_engine *e) {
+    OZ_TRY(set_device(e));
+    if (e->in_search) return fail(OZ_ERR_STATE, "cannot reset during a search");
+    launch_reset(e->t, e->stream);
+    e->active = e->t.G;
+    OZ_CUDA(cudaStreamSynchronize(e->stream));
+    return OZ_OK;
+}
+
+int oz_engine_positions(oz_engine *e, oz_position *out) {
+    OZ_TRY(set_device(e));
+    const int G = e->t.G;
+    std::vector<uint64_t> p1(G), p2(G);
+    std::vector<int32_t> pl(G);
+    OZ_CUDA(cudaMemcpyAsync(p1.data(), e->t.r_p1, G * 8, cudaMemcpyDeviceToHost, e->stream));
+    OZ_CUDA(cudaMemcpyAsync(p2.data(), e->t.r_p2, G * 8, cudaMemcpyDeviceToHost, e->stream));
+    OZ_CUDA(cudaMemcpyAsync(pl.data(), e->t.r_player, G * 4, cudaMemcpyDeviceToHost, e->stream));
+    OZ_CUDA(cudaStreamSynchronize(e->stream));
+    for (int g = 0; g < G; ++g) {
+        // (player, p1, p2) determine the move masks (position.h:349-358).
+        oz_position &o = out[g];
+        o.player = pl[g]; o.p1 = p1[g]; o.p2 = p2[g]; o.legal = 0; o.next_legal = 0;
+        if (pl[g] != 0) {
+            const uint64_t me = pl[g] == 1 ? p1[g] : p2[g], opp = pl[g] == 1 ? p2[g] : p1[g];
+            o.legal = legal_moves(me, opp);
+            if (o.legal == 0) o.next_legal = legal_moves(opp, me);
+        }
+    }
+    return OZ_OK;
+}
+
+size_t oz_resnet_blob_bytes(const oz_resnet_shape *s) { return resnet_layout(*s).total; }
+
+int oz_resnet_blob_offsets(const oz_resnet_shape *s, int64_t *offsets, int capacity, int *count) {
+    ResNetLayout L = resnet_layout(*s);
+    std::vector<int64_t> v;
+    for (size_t i = 0; i < L.conv_w.size(); ++i) { v.push_back((int64_t)L.conv_w[i]); v.push_back((int64_t)L.conv_b[i]); }
+    for (size_t o : {L.pconv_w, L.pconv_b, L.pfc_w, L.pfc_b, L.vconv_w, L.vconv_b, L.vfc1_w, L.vfc1_b, L.vfc2_w, L.vfc2_b}) v.push_back((int64_t)o);
+    *count = (int)v.size();
+    if (capacity < (int)v.size()) return fail(OZ_ERR_INVALID_ARGUMENT, "offset buffer too small");
+    std::copy(v.begin(), v.end(), offsets);
+    return OZ_OK;
+}
+
+int oz_engine_load_resnet(oz_engine *e, const oz_resnet_shape *shape, const void *blob, size_t bytes) {
+    OZ_TRY(set_device(e));
+    if (e->in_search) return fail(OZ_ERR_STATE, "cannot load weights during a search");
+    OZ_CUDA(cudaStreamSynchronize(e->stream));
+    OZ_TRY(e->net.load(*shape, blob, bytes));
+    OZ_TRY(e->net.reserve((size_t)e->t.G * e->t.inflight));
+    return OZ_OK;
+}
+
+// ---- the network alone ----
+int oz_resnet_create(int device, oz_resnet **out) {
+    *out = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) return fail(OZ_ERR_CUDA, "no such CUDA device");
+    oz_resnet *n = new oz_resnet();
+    n->device = device;
+    *out = n;
+    return OZ_OK;
+}
+void oz_resnet_destroy(oz_resnet *n) {
+    if (!n) return;
+    cudaSetDevice(n->device);
+    cudaFree(n->d_f); cudaFree(n->d_p); cudaFree(n->d_v);
+    delete n;
+}
+int oz_resnet_load(oz_resnet *n, const oz_resnet_shape *shape, const void *blob, size_t bytes) {
+    OZ_CUDA(cudaSetDevice(n->device));
+    return n->net.load(*shape, blob, bytes);
+}
+int oz_resnet_forward_device(oz_resnet *n, const float *f, size_t cnt, float *p, float *v, void *stream) {
+    OZ_CUDA(cudaSetDevice(n->device));
+    return n->net.forward(f, cnt, p, v, (cudaStream_t)stream);
+}
+int oz_resnet_forward(oz_resnet *n, const float *f, size_t cnt, float *p, float *v) {
+    OZ_CUDA(cudaSetDevice(n->device));
+    if (!n->net.loaded()) return fail(OZ_ERR_STATE, "no network weights loaded");
+    if (cnt == 0) return OZ_OK;
+    const size_t planes = n->net.shape().in_planes;
+    if (cnt > n->cap) {
+        cudaFree(n->d_f); cudaFree(n->d_p); cudaFree(n->d_v);
+        OZ_TRY(dalloc(&n->d_f, cnt * planes * 64)); OZ_TRY(dalloc(&n->d_p, cnt * 65)); OZ_TRY(dalloc(&n->d_v, cnt));
+        n->cap = cnt;
+    }
+    OZ_CUDA(cudaMemcpy(n->d_f, f, cnt * planes * 64 * sizeof(float), cudaMemcpyHostToDevice));
+    OZ_TRY(n->net.forward(n->d_f, cnt, n->d_p, n->d_v, nullptr));
+    OZ_CUDA(cudaMemcpy(p, n->d_p, cnt * 65 * sizeof(float), cudaMemcpyDeviceToHost));
+    OZ_CUDA(cudaMemcpy(v, n->d_v, cnt * sizeof(float), cudaMemcpyDeviceToHost));
+    return OZ_OK;
+}
+
+int oz_debug_conv3x3(const uint16_t *in, int cin, const uint16_t *w, const float *bias, const uint16_t *skip, int relu,
+                     uint16_t *out, int cout, size_t boards, double *device_ms) {
+    const size_t pad = (boards + 15) / 16 * 16;
+    uint16_t *d_in = nullptr, *d_w = nullptr, *d_skip = nullptr, *d_out = nullptr;
+    float *d_b = nullptr;
+    int st = OZ_OK;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    do {
+        if ((st = dalloc(&d_in, pad * 64 * cin)) || (st = dalloc(&d_w, (size_t)9 * cout * cin)) || (st = dalloc(&d_b, (size_t)cout)) ||
+            (st = dalloc(&d_out, pad * 64 * cout)) || (skip && (st = dalloc(&d_skip, pad * 64 * cout)))) break;
+        cudaMemset(d_in, 0, pad * 64 * cin * 2); cudaMemset(d_out, 0, pad * 64 * cout * 2);
+        if (skip) { cudaMemset(d_skip, 0, pad * 64 * cout * 2); cudaMemcpy(d_skip, skip, boards * 64 * cout * 2, cudaMemcpyHostToDevice); }
+        cudaMemcpy(d_in, in, boards * 64 * cin * 2, cudaMemcpyHostToDevice);
+        cudaMemcpy(d_w, w, (size_t)9 * cout * cin * 2, cudaMemcpyHostToDevice);
+        cudaMemcpy(d_b, bias, cout * sizeof(float), cudaMemcpyHostToDevice);
+        cudaEventCreate(&e0); cudaEventCreate(&e1);
+        cudaEventRecord(e0);
+        if ((st = ResNet::conv3x3(d_in, cin, d_w, d_b, d_skip, relu, d_out, cout, pad, nullptr))) break;
+        cudaEventRecord(e1);
+        cudaError_t err = cudaDeviceSynchronize();
+        if (err != cudaSuccess) { st = fail(OZ_ERR_CUDA, std::string("conv3x3: ") + cudaGetErrorString(err)); break; }
+        float ms = 0.f; cudaEventElapsedTime(&ms, e0, e1);
+        if (device_ms) *device_ms = ms;
+        cudaMemcpy(out, d_out, boards * 64 * cout * 2, cudaMemcpyDeviceToHost);
+    } while (0);
+    if (e0) cudaEventDestroy(e0);
+    if (e1) cudaEventDestroy(e1);
+    cudaFree(d_in); cudaFree(d_w); cudaFree(d_skip); cudaFree(d_out); cudaFree(d_b);
+    return st;
+}
+
+// ---- search ----
+int oz_engine_rounds(const oz_engine *e) { return rounds_of(e->cfg); }
+
+int oz_engine_search_begin(oz_engine *e) { OZ_TRY(set_device(e)); return begin_search(e); }
+
+int oz_engine_select_device(oz_engine *e, float *features, void *stream) {
+    if (!e->in_search) return fail(OZ_ERR_STATE, "search_begin not called");
+    OZ_TRY(set_device(e));
+    cudaStream_t s = stream ? (cudaStream_t)stream : e->stream;
+    launch_select(e->t, e->round, s);
+    launch_encode(e->t, e->round, features ? features : e->d_features, s);
+    OZ_CUDA(cudaGetLastError());
+    return OZ_OK;
+}
+
+int oz_engine_expand_device(oz_engine *e, const float *policy, const float *value, void *stream) {
+    if (!e->in_search) return fail(OZ_ERR_STATE, "search_begin not called");
+    OZ_TRY(set_device(e));
+    cudaStream_t s = stream ? (cudaStream_t)stream : e->stream;
+    launch_expand(e->t, policy, value, s);
+    e->round += 1;
+    e->ctr.evaluations += (uint64_t)e->t.G * e->t.inflight;
+    OZ_CUDA(cudaGetLastError());
+    return OZ_OK;
+}
+
+int oz_engine_search_end(oz_engine *e) {
+    if (!e->in_search) return fail(OZ_ERR_STATE, "search_begin not called");
+    OZ_TRY(set_device(e));
+    OZ_CUDA(cudaDeviceSynchronize());   // external evaluators may have used their own streams
+    return end_search(e);
+}
+
+int oz_engine_search(oz_engine *e) {
+    OZ_TRY(set_device(e));
+    OZ_TRY(begin_search(e));
+    const int rounds = rounds_of(e->cfg);
+    size_t k = 0;
+    int st = OZ_OK;
+    for (int r = 0; r < rounds && !st; ++r) {
+        e->round = r;
+        if (e->profiling) cudaEventRecord(next_event(e, k++), e->stream);
+        launch_select(e->t, r, e->stream);
+        launch_encode(e->t, r, e->d_features, e->stream);
+        if (e->profiling) cudaEventRecord(next_event(e, k++), e->stream);
+        st = eval_round(e);
+        if (e->profiling) cudaEventRecord(next_event(e, k++), e->stream);
+        if (!st) launch_expand(e->t, e->d_policy, e->d_value, e->stream);
+        if (e->profiling) cudaEventRecord(next_event(e, k++), e->stream);
+    }
+    if (st) { e->in_search = false; return st; }
+    st = end_search(e);
+    if (!st && e->profiling) {
+        for (size_t i = 0; i + 3 < k; i += 4) {
+            float a = 0, b = 0, c = 0;
+            cudaEventElapsedTime(&a, e->ev[i], e->ev[i + 1]); cudaEventElapsedTime(&b, e->ev[i + 1], e->ev[i + 2]); cudaEventElapsedTime(&c, e->ev[i + 2], e->ev[i + 3]);
+            e->ctr.select_ms += a; e->ctr.eval_ms += b; e->ctr.expand_ms += c;
+        }
+    }
+    return st;
+}
+
+int oz_engine_root_stats(oz_engine *e, int32_t *n_children, int32_t *counts, float *q, int32_t *root_n) {
+    OZ_TRY(set_device(e));
+    const int G = e->t.G;
+    launch_root_stats(e->t, e->d_stat_n, e->d_stat_counts, e->d_stat_q, e->d_stat_rootn, e->stream);
+    if (n_children) OZ_CUDA(cudaMemcpyAsync(n_children, e->d_stat_n, G * 4, cudaMemcpyDeviceToHost, e->stream));
+    if (counts) OZ_CUDA(cudaMemcpyAsync(counts, e->d_stat_counts, (size_t)G * kStride * 4, cudaMemcpyDeviceToHost, e->stream));
+    if (q) OZ_CUDA(cudaMemcpyAsync(q, e->d_stat_q, (size_t)G * kStride * 4, cudaMemcpyDeviceToHost, e->stream));
+    if (root_n) OZ_CUDA(cudaMemcpyAsync(root_n, e->d_stat_rootn, G * 4, cudaMemcpyDeviceToHost, e->stream));
+    OZ_CUDA(cudaStreamSynchronize(e->stream));
+    return OZ_OK;
+}
+
+int oz_engine_self_play_data(oz_engine *e, int game, float *features, float *policy) {
+    OZ_TRY(set_device(e));
+    if (game < 0 || game >= e->t.G) return fail(OZ_ERR_OUT_OF_RANGE, "game index out of range");
+    std::vector<oz_position> pos(e->t.G);
+    OZ_TRY(oz_engine_positions(e, pos.data()));
+    if (pos[game].player == 0)   // mcts.cpp:64-68
+        return fail(OZ_ERR_INVALID_ARGUMENT, "Self-play data cannot be generated from a terminal position.");
+    std::vector<int32_t> nch(e->t.G);
+    OZ_TRY(oz_engine_root_stats(e, nch.data(), nullptr, nullptr, nullptr));
+    if (nch[game] == 0)          // mcts.cpp:69-71
+        return fail(OZ_ERR_INVALID_ARGUMENT, "The root node has not been expanded yet.");
+    sync_params(e);
+    launch_self_play_data(e->t, game, e->d_spd_f, e->d_spd_p, e->stream);
+    const size_t nf = (size_t)8 * (1 + 2 * e->t.H) * 64;
+    OZ_CUDA(cudaMemcpyAsync(features, e->d_spd_f, nf * sizeof(float), cudaMemcpyDeviceToHost, e->stream));
+    OZ_CUDA(cudaMemcpyAsync(policy, e->d_spd_p, 8 * 65 * sizeof(float), cudaMemcpyDeviceToHost, e->stream));
+    OZ_CUDA(cudaStreamSynchronize(e->stream));
+    return OZ_OK;
+}
+
+static int apply_device_actions(oz_engine *e) {
+    OZ_CUDA(cudaMemsetAsync(e->d_unfinished, 0, sizeof(int32_t), e->stream));
+    launch_apply(e->t, e->d_actions, e->d_unfinished, e->stream);
+    int32_t unf = 0;
+    OZ_CUDA(cudaMemcpyAsync(&unf, e->d_unfinished, sizeof(unf), cudaMemcpyDeviceToHost, e->stream));
+    OZ_CUDA(cudaStreamSynchronize(e->stream));
+    e->ctr.games_finished += (uint64_t)std::max(0, e->active - unf);
+    e->active = unf;
+    return OZ_OK;
+}
+
+int oz_engine_apply_actions(oz_engine *e, const int32_t *actions) {
+    OZ_TRY(set_device(e));
+    if (e->in_search) return fail(OZ_ERR_STATE, "cannot apply actions during a search");
+    const int G = e->t.G;
+    std::vector<oz_position> pos(G);
+    OZ_TRY(oz_engine_positions(e, pos.data()));
+    for (int g = 0; g < G; ++g) {   // validation of mcts.cpp:115-138, same texts
+        const int a = actions[g];
+        if (a < 0 && G > 1) continue;
+        if (!(0 <= a && a < 65)) return fail(OZ_ERR_OUT_OF_RANGE, "Expected 0 <= action < 65, but got " + std::to_string(a) + ".");
+        if (a == 64) {
+            if (pos[g].player == 0) return fail(OZ_ERR_INVALID_ARGUMENT, "Pass is not allowed in a terminal position.");
+            if (pos[g].legal != 0) return fail(OZ_ERR_INVALID_ARGUMENT, "Pass is not allowed when there are legal moves.");
+        } else if (((1ull << (63 - a)) & pos[g].legal) == 0) {
+            return fail(OZ_ERR_INVALID_ARGUMENT, std::to_string(a) + " is not a legal action.");
+        }
+    }
+    OZ_CUDA(cudaMemcpyAsync(e->d_actions, actions, G * sizeof(int32_t), cudaMemcpyHostToDevice, e->stream));
+    OZ_TRY(apply_device_actions(e));
+    e->ctr.plies += 1;
+    return OZ_OK;
+}
+
+int oz_engine_choose_actions(oz_engine *e, int32_t *actions) {
+    OZ_TRY(set_device(e));
+    sync_params(e);
+    launch_choose(e->t, e->d_actions, e->stream);
+    OZ_CUDA(cudaMemcpyAsync(actions, e->d_actions, e->t.G * sizeof(int32_t), cudaMemcpyDeviceToHost, e->stream));
+    OZ_CUDA(cudaStreamSynchronize(e->stream));
+    return OZ_OK;
+}
+
+int oz_engine_play_ply(oz_engine *e, int32_t *actions, int32_t *visit_counts, int32_t *unfinished) {
+    OZ_TRY(oz_engine_search(e));
+    if (visit_counts) {
+        launch_root_stats(e->t, e->d_stat_n, e->d_stat_counts, nullptr, nullptr, e->stream);
+        OZ_CUDA(cudaMemcpyAsync(visit_counts, e->d_stat_counts, (size_t)e->t.G * kStride * 4, cudaMemcpyDeviceToHost, e->stream));
+    }
+    launch_choose(e->t, e->d_actions, e->stream);
+    launch_record(e->t, e->d_actions, e->d_records, e->max_plies, e->stream);
+    if (actions) OZ_CUDA(cudaMemcpyAsync(actions, e->d_actions, e->t.G * sizeof(int32_t), cudaMemcpyDeviceToHost, e->stream));
+    OZ_TRY(apply_device_actions(e));
+    e->ctr.plies += 1;
+    if (unfinished) *unfinished = e->active;
+    return OZ_OK;
+}
+
+int oz_engine_records(oz_engine *e, int32_t *plies, oz_ply_record *records, int max_plies) {
+    OZ_TRY(set_device(e));
+    const int G = e->t.G;
+    std::vector<int32_t> p(G);
+    OZ_CUDA(cudaMemcpy(p.data(), e->t.g_ply, G * 4, cudaMemcpyDeviceToHost));
+    for (int g = 0; g < G; ++g) {
+        if (p[g] > e->max_plies) p[g] = e->max_plies;
+        if (plies) plies[g] = p[g];
+        if (records) {
+            const int n = std::min(p[g], max_plies);
+            if (n > 0) OZ_CUDA(cudaMemcpy(records + (size_t)g * max_plies, e->d_records + (size_t)g * e->max_plies, (size_t)n * sizeof(oz_ply_record), cudaMemcpyDeviceToHost));
+        }
+    }
+    return OZ_OK;
+}
+
+int oz_engine_training_samples(oz_engine *e, float *features, float *policy, float *value, size_t capacity, size_t *n_samples) {
+    OZ_TRY(set_device(e));
+    const int G = e->t.G;
+    std::vector<int32_t> plies(G), status(G);
+    OZ_CUDA(cudaMemcpy(plies.data(), e->t.g_ply, G * 4, cudaMemcpyDeviceToHost));
+    OZ_CUDA(cudaMemcpy(status.data(), e->t.g_status, G * 4, cudaMemcpyDeviceToHost));
+    std::vector<int64_t> base(G, -1);
+    size_t total = 0;
+    for (int g = 0; g < G; ++g) if (status[g] & 1) { base[g] = (int64_t)total; total += (size_t)std::min(plies[g], e->max_plies) * 8; }
+    *n_samples = total;
+    if (!features || !policy || !value || total == 0) return OZ_OK;
+    if (capacity < total) return fail(OZ_ERR_INVALID_ARGUMENT, "sample buffers too small");
+    const size_t nf = (size_t)(1 + 2 * e->t.H) * 64;
+    float *d_f = nullptr, *d_p = nullptr, *d_v = nullptr;
+    int64_t *d_base = nullptr;
+    int32_t *d_plies = nullptr;
+    int st = OZ_OK;
+    do {
+        if ((st = dalloc(&d_f, total * nf)) || (st = dalloc(&d_p, total * 65)) || (st = dalloc(&d_v, total)) || (st = dalloc(&d_base, G)) || (st = dalloc(&d_plies, G))) break;
+        for (int g = 0; g < G; ++g) plies[g] = std::min(plies[g], e->max_plies);
+        cudaMemcpy(d_base, base.data(), G * 8, cudaMemcpyHostToDevice);
+        cudaMemcpy(d_plies, plies.data(), G * 4, cudaMemcpyHostToDevice);
+        launch_training_samples(e->t, e->d_records, d_plies, d_base, e->max_plies, d_f, d_p, d_v, e->stream);
+        cudaError_t err = cudaStreamSynchronize(e->stream);
+        if (err != cudaSuccess) { st = fail(OZ_ERR_CUDA, std::string("training_samples: ") + cudaGetErrorString(err)); break; }
+        cudaMemcpy(features, d_f, total * nf * sizeof(float), cudaMemcpyDeviceToHost);
+        cudaMemcpy(policy, d_p, total * 65 * sizeof(float), cudaMemcpyDeviceToHost);
+        cudaMemcpy(value, d_v, total * sizeof(float), cudaMemcpyDeviceToHost);
+    } while (0);
+    cudaFree(d_f); cudaFree(d_p); cudaFree(d_v); cudaFree(d_base); cudaFree(d_plies);
+    return st;
+}
+
+int oz_engine_counters(oz_engine *e, oz_counters *out) {
+    OZ_TRY(set_device(e));
+    unsigned long long s[4] = {0, 0, 0, 0};
+    OZ_CUDA(cudaMemcpy(s, e->t.stats, sizeof(s), cudaMemcpyDeviceToHost));
+    e->ctr.nodes_expanded = s[0];
+    e->ctr.kernel_launches = g_kernel_launches;
+    *out = e->ctr;
+    return OZ_OK;
+}
+
+int oz_engine_set_profiling(oz_engine *e, int on) { e->profiling = on != 0; return OZ_OK; }
+void *oz_engine_stream(oz_engine *e) { return (void *)e->stream; }
+
+}  // extern "C"

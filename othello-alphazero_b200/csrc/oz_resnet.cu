@@ -1,0 +1,591 @@
+// ResNet policy/value evaluator for sm_100a (reference: neural_net.py:9-172, eval mode).
+//
+// conv3x3_kernel: implicit-GEMM 3x3 "same" convolution, bf16 in / fp32 accumulate.
+//   * D[M = 128 positions, N = 128 couts] += A[M, K=16] * B[N, K=16]^T with tcgen05.mma
+//     (cta_group::1, kind::f16), accumulators in TMEM (4 tiles x 128 columns = 512 columns).
+//   * One work item ("pass") = 16 boards x 4 board rows x 128 couts = 512 output rows.
+//   * Activations: one 4-D TMA box per 32-channel K block, dims (channel 32, board 16, x 9,
+//     y 6) read from plain NHWC with out-of-bounds zero fill (x = 8, y = -1 / 8 are the
+//     halo).  In shared memory that is row = (y*9 + x)*16 + board, 64 B per row,
+//     SWIZZLE_64B.  Sixteen boards share each (y, x) slot, so a 3x3 tap (dy, dx) is the same
+//     tile shifted by (dy*9 + dx) * 16 rows = a multiple of the 8-row swizzle atom: every
+//     tap is a plain descriptor offset into ONE copy of the tile (no im2col, one L2 read per
+//     activation, 100 % useful MMA rows: a 128-row tile is 8 x-positions x 16 boards).
+//   * Weights: [tap][cout][cin] bf16, one 2-D TMA box (32 cin x 128 cout = 8 KB) per
+//     (K block, tap), 6-deep ring.
+//   * Warp roles: 0 = activation TMA, 1 = MMA issue + TMEM alloc, 2 = weight TMA,
+//     3..6 = epilogue (tcgen05.ld -> +bias (+skip) -> ReLU -> bf16 -> global NHWC).
+// heads_kernel: 1x1 convs + FC + softmax / tanh for both heads, one CTA loop over boards.
+#include <cuda_bf16.h>
+
+#include <cmath>
+#include <cstring>
+#include <string>
+
+#include "oz_resnet.cuh"
+
+namespace oz {
+
+// ------------------------------------------------------------------ geometry
+constexpr int kBoardsPerUnit = 16;
+constexpr int kRowsPerPass = 4;                      // board rows (y) per pass
+constexpr int kKBlock = 32;                          // channels per K block (64 B rows)
+constexpr int kBoxX = 9, kBoxY = kRowsPerPass + 2;   // halo: x = 8 is the zero column
+constexpr int kRowBytes = kKBlock * 2;               // 64
+constexpr int kSlotBytes = kBoardsPerUnit * kRowBytes;            // 1024: one (y, x) slot
+constexpr int kActBoxBytes = kBoxX * kBoxY * kSlotBytes;          // 55296
+constexpr int kActStageBytes = kSlotBytes + kActBoxBytes;         // 1 guard slot in front
+constexpr int kActStages = 3;
+constexpr int kWStageBytes = 128 * kRowBytes;                     // 8192
+constexpr int kWStages = 6;
+constexpr int kTiles = kRowsPerPass;                 // accumulator tiles per pass
+constexpr int kTmemCols = 512;
+constexpr int kThreads = 7 * 32;
+constexpr int kSmemBytes = 1024 + kActStages * kActStageBytes + kWStages * kWStageBytes + 2048;
+
+// ------------------------------------------------------------------ PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t done;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+    } while (!done);
+}
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap *map, uint32_t bar, int c0, int c1, int c2, int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+        ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *map, uint32_t bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_mma(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+          "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+          "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major, SWIZZLE_64B shared-memory matrix descriptor (rows of 64 B, 8-row atoms of 512 B).
+__device__ __forceinline__ uint64_t umma_desc_sw64(uint32_t saddr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);   // start address, 16-byte units
+    d |= (uint64_t)1 << 16;                     // leading byte offset (unused for swizzled K-major)
+    d |= (uint64_t)(512 >> 4) << 32;            // stride byte offset: next 8-row group
+    d |= (uint64_t)1 << 46;                     // descriptor version (Blackwell)
+    d |= (uint64_t)4 << 61;                     // SWIZZLE_64B
+    return d;
+}
+// kind::f16 instruction descriptor: bf16 x bf16 -> f32, both operands K-major, M = 128, N = 128.
+constexpr uint32_t kIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((128u >> 3) << 17) | ((128u >> 4) << 24);
+
+struct ConvParams {
+    const __nv_bfloat16 *skip;   // NHWC, may be null
+    __nv_bfloat16 *out;          // NHWC [boards][8][8][cout_total]
+    const float *bias;           // [cout_total]
+    int units;                   // boards / 16
+    int kblocks;                 // cin / 32
+    int cout_total;              // multiple of 128
+    int relu;
+};
+
+__global__ void __launch_bounds__(kThreads, 1)
+conv3x3_kernel(const __grid_constant__ CUtensorMap map_act, const __grid_constant__ CUtensorMap map_w, const ConvParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t *gen = smem_raw + (base - smem_u32(smem_raw));       // generic pointer to the aligned base
+    const uint32_t act0 = base;
+    const uint32_t w0 = act0 + kActStages * kActStageBytes;
+    const uint32_t misc = w0 + kWStages * kWStageBytes;
+    // barriers (8 B each)
+    const uint32_t bar_act_full = misc, bar_act_empty = misc + 8 * kActStages;
+    const uint32_t bar_w_full = misc + 64, bar_w_empty = misc + 64 + 8 * kWStages;
+    const uint32_t bar_tmem_full = misc + 192, bar_tmem_empty = misc + 200;   // [kTiles]
+    uint32_t *tmem_ptr = (uint32_t *)(gen + (misc - base) + 256);
+    float *s_bias = (float *)(gen + (misc - base) + 512);                        // up to 384 floats
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int ntiles = p.cout_total >> 7;
+    const int num_pass = p.units * 2 * ntiles;
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < kActStages; ++i) { mbar_init(bar_act_full + 8 * i, 1); mbar_init(bar_act_empty + 8 * i, 1); }
+        for (int i = 0; i < kWStages; ++i) { mbar_init(bar_w_full + 8 * i, 1); mbar_init(bar_w_empty + 8 * i, 1); }
+        mbar_init(bar_tmem_full, 1);
+        for (int i = 0; i < kTiles; ++i) mbar_init(bar_tmem_empty + 8 * i, 4);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_act) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w) : "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr)), "r"(kTmemCols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    // Guard slot in front of every activation stage: the (dy,dx) = (-1,-1) tap of the first
+    // tile row starts one slot before the box and must read zeros.
+    for (int i = threadIdx.x; i < kActStages * (kSlotBytes / 16); i += kThreads) {
+        const int s = i / (kSlotBytes / 16), o = i % (kSlotBytes / 16);
+        *(uint4 *)(gen + s * kActStageBytes + o * 16) = make_uint4(0, 0, 0, 0);
+    }
+    for (int i = threadIdx.x; i < p.cout_total; i += kThreads) s_bias[i] = p.bias[i];
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr;
+
+    if (warp == 0) {
+        // ===== activation TMA producer =====
+        if (lane == 0) {
+            uint32_t it = 0;
+            for (int ps = blockIdx.x; ps < num_pass; ps += gridDim.x) {
+                const int unit = ps / (2 * ntiles), half = (ps / ntiles) & 1;
+                for (int kb = 0; kb < p.kblocks; ++kb, ++it) {
+                    const uint32_t s = it % kActStages, ph = (it / kActStages) & 1;
+                    mbar_wait(bar_act_empty + 8 * s, ph ^ 1);
+                    mbar_expect_tx(bar_act_full + 8 * s, kActBoxBytes);
+                    tma_load_4d(act0 + s * kActStageBytes + kSlotBytes, &map_act, bar_act_full + 8 * s,
+                                kb * kKBlock, unit * kBoardsPerUnit, 0, half * kRowsPerPass - 1);
+                }
+            }
+        }
+        __syncwarp();
+    } else if (warp == 2) {
+        // ===== weight TMA producer =====
+        if (lane == 0) {
+            uint32_t it = 0;
+            for (int ps = blockIdx.x; ps < num_pass; ps += gridDim.x) {
+                const int nt = ps % ntiles;
+                for (int kb = 0; kb < p.kblocks; ++kb)
+                    for (int tap = 0; tap < 9; ++tap, ++it) {
+                        const uint32_t s = it % kWStages, ph = (it / kWStages) & 1;
+                        mbar_wait(bar_w_empty + 8 * s, ph ^ 1);
+                        mbar_expect_tx(bar_w_full + 8 * s, kWStageBytes);
+                        tma_load_2d(w0 + s * kWStageBytes, &map_w, bar_w_full + 8 * s,
+                                    kb * kKBlock, tap * p.cout_total + nt * 128);
+                    }
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        // ===== MMA issuer (one thread) =====
+        if (lane == 0) {
+            uint32_t ait = 0, wit = 0, npass = 0;
+            for (int ps = blockIdx.x; ps < num_pass; ps += gridDim.x, ++npass) {
+                for (int kb = 0; kb < p.kblocks; ++kb, ++ait) {
+                    const uint32_t as = ait % kActStages;
+                    mbar_wait(bar_act_full + 8 * as, (ait / kActStages) & 1);
+                    const uint32_t abox = act0 + as * kActStageBytes + kSlotBytes;
+                    for (int tap = 0; tap < 9; ++tap, ++wit) {
+                        const uint32_t ws = wit % kWStages;
+                        mbar_wait(bar_w_full + 8 * ws, (wit / kWStages) & 1);
+                        tc_fence_after();
+                        const int dy = tap / 3 - 1, dx = tap % 3 - 1;
+                        const uint32_t wbase = w0 + ws * kWStageBytes;
+#pragma unroll
+                        for (int r = 0; r < kTiles; ++r) {
+                            if (kb == 0 && tap == 0) {   // tile r must be drained by the previous pass's epilogue
+                                mbar_wait(bar_tmem_empty + 8 * r, (npass & 1) ^ 1);
+                                tc_fence_after();
+                            }
+                            const uint32_t arow = abox + (uint32_t)(((r + 1 + dy) * kBoxX + dx) * kSlotBytes);
+#pragma unroll
+                            for (int j = 0; j < kKBlock / 16; ++j)
+                                tc_mma(tmem_base + r * 128, umma_desc_sw64(arow + j * 32), umma_desc_sw64(wbase + j * 32),
+                                       kIdesc, (kb | tap | j) != 0);
+                        }
+                        tc_commit(bar_w_empty + 8 * ws);          // weight slot free once these MMAs retire
+                    }
+                    tc_commit(bar_act_empty + 8 * as);            // activation stage free
+                }
+                tc_commit(bar_tmem_full);                         // accumulators complete
+            }
+        }
+        __syncwarp();
+    } else {
+        // ===== epilogue warps 3..6: TMEM lanes 32*(warp%4) .. +31 =====
+        const int quad = warp & 3;
+        uint32_t npass = 0;
+        for (int ps = blockIdx.x; ps < num_pass; ps += gridDim.x, ++npass) {
+            const int unit = ps / (2 * ntiles), half = (ps / ntiles) & 1, nt = ps % ntiles;
+            mbar_wait(bar_tmem_full, npass & 1);
+            tc_fence_after();
+            const int row = quad * 32 + lane;              // row in tile = x * 16 + board
+            const int x = row >> 4, bl = row & 15;
+            const size_t board = (size_t)unit * kBoardsPerUnit + bl;
+#pragma unroll 1
+            for (int r = 0; r < kTiles; ++r) {
+                const int y = half * kRowsPerPass + r;
+                const size_t off = ((board * 8 + y) * 8 + x) * (size_t)p.cout_total + nt * 128;
+#pragma unroll 1
+                for (int ch = 0; ch < 4; ++ch) {
+                    uint32_t v[32];
+                    tc_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + r * 128 + ch * 32, v);
+                    uint4 sk[4];
+                    if (p.skip) {
+                        const uint4 *sp = (const uint4 *)(p.skip + off + ch * 32);
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) sk[i] = sp[i];
+                    }
+                    tc_wait_ld();
+                    if (ch == 3) {                         // last read of tile r: hand it back to the MMA warp
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(bar_tmem_empty + 8 * r);
+                    }
+                    const float *bs = s_bias + nt * 128 + ch * 32;
+                    uint4 o[4];
+                    uint32_t *ow = (uint32_t *)o;
+                    const uint32_t *skw = (const uint32_t *)sk;
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        float a = __uint_as_float(v[2 * i]) + bs[2 * i];
+                        float b = __uint_as_float(v[2 * i + 1]) + bs[2 * i + 1];
+                        if (p.skip) {
+                            const __nv_bfloat162 s2 = *(const __nv_bfloat162 *)&skw[i];
+                            a += __bfloat162float(s2.x);
+                            b += __bfloat162float(s2.y);
+                        }
+                        if (p.relu) { a = fmaxf(a, 0.f); b = fmaxf(b, 0.f); }
+                        const __nv_bfloat162 o2 = __floats2bfloat162_rn(a, b);
+                        ow[i] = *(const uint32_t *)&o2;
+                    }
+                    uint4 *op = (uint4 *)(p.out + off + ch * 32);
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) op[i] = o[i];
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
+    }
+}
+
+// ------------------------------------------------------------------ input conversion
+// float planes [n][planes][64] -> bf16 NHWC [n_pad][64][32] (channels >= planes are zero).
+__global__ void planes_to_nhwc32_kernel(const float *__restrict__ f, int planes, size_t n, size_t n_pad, __nv_bfloat16 *__restrict__ out) {
+    const size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x;   // one thread per (board, pos, 8-channel group)
+    if (idx >= n_pad * 64 * 4) return;
+    const size_t b = idx / 256;
+    const int pos = (int)((idx / 4) % 64), g = (int)(idx % 4);
+    __align__(16) __nv_bfloat16 v[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int c = g * 8 + i;
+        v[i] = __float2bfloat16((b < n && c < planes) ? f[(b * planes + c) * 64 + pos] : 0.f);
+    }
+    *(uint4 *)(out + (b * 64 + pos) * 32 + g * 8) = *(const uint4 *)v;
+}
+
+// ------------------------------------------------------------------ heads
+struct HeadParams {
+    const __nv_bfloat16 *act;  // [n][64][C]
+    const float *pconv_w, *pconv_b, *pfc_w, *pfc_b, *vconv_w, *vconv_b, *vfc1_w, *vfc1_b, *vfc2_w, *vfc2_b;
+    float *policy, *value;
+    int C, Hv;
+    size_t n;
+};
+
+// neural_net.py:68-128.  128 threads; thread t < 64 owns board square t for the 1x1 convs.
+__global__ void __launch_bounds__(128) heads_kernel(const HeadParams p) {
+    extern __shared__ float sm[];
+    const int C = p.C, Hv = p.Hv;
+    float *s_pfc = sm;                     // [65][129] padded rows
+    float *s_vfc1 = s_pfc + 65 * 129;      // [Hv][65]
+    float *s_cw = s_vfc1 + Hv * 65;        // [3][C]: policy c0, policy c1, value
+    float *s_feat = s_cw + 3 * C;          // [128] policy features (channel-major), then [64] value features
+    float *s_v1 = s_feat + 128;
+    float *s_logit = s_v1 + 64;            // [65] + scratch
+    float *s_red = s_logit + 72;           // [8]
+    const int t = threadIdx.x;
+    for (int i = t; i < 65 * 128; i += 128) s_pfc[(i >> 7) * 129 + (i & 127)] = p.pfc_w[i];
+    for (int i = t; i < Hv * 64; i += 128) s_vfc1[(i >> 6) * 65 + (i & 63)] = p.vfc1_w[i];
+    for (int i = t; i < 2 * C; i += 128) s_cw[i] = p.pconv_w[i];
+    for (int i = t; i < C; i += 128) s_cw[2 * C + i] = p.vconv_w[i];
+    __syncthreads();
+    const float pb0 = p.pconv_b[0], pb1 = p.pconv_b[1], vb = p.vconv_b[0], v2b = p.vfc2_b[0];
+    for (size_t b = blockIdx.x; b < p.n; b += gridDim.x) {
+        if (t < 64) {
+            const uint4 *a = (const uint4 *)(p.act + (b * 64 + t) * (size_t)C);
+            float d0 = 0.f, d1 = 0.f, d2 = 0.f;
+            for (int c8 = 0; c8 < C / 8; ++c8) {
+                const uint4 q = a[c8];
+                const __nv_bfloat162 *h = (const __nv_bfloat162 *)&q;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const float x0 = __bfloat162float(h[i].x), x1 = __bfloat162float(h[i].y);
+                    const int c = c8 * 8 + 2 * i;
+                    d0 += x0 * s_cw[c] + x1 * s_cw[c + 1];
+                    d1 += x0 * s_cw[C + c] + x1 * s_cw[C + c + 1];
+                    d2 += x0 * s_cw[2 * C + c] + x1 * s_cw[2 * C + c + 1];
+                }
+            }
+            s_feat[t] = fmaxf(d0 + pb0, 0.f);
+            s_feat[64 + t] = fmaxf(d1 + pb1, 0.f);
+            s_v1[t] = fmaxf(d2 + vb, 0.f);
+        }
+        __syncthreads();
+        if (t < 65) {
+            float acc = p.pfc_b[t];
+            const float *w = s_pfc + t * 129;
+#pragma unroll 8
+            for (int i = 0; i < 128; ++i) acc += s_feat[i] * w[i];
+            s_logit[t] = acc;
+        }
+        float hv = 0.f;
+        for (int k = t; k < Hv; k += 128) {
+            float acc = p.vfc1_b[k];
+            const float *w = s_vfc1 + k * 65;
+#pragma unroll 8
+            for (int i = 0; i < 64; ++i) acc += s_v1[i] * w[i];
+            hv += fmaxf(acc, 0.f) * p.vfc2_w[k];
+        }
+#pragma unroll
+        for (int o = 16; o; o >>= 1) hv += __shfl_xor_sync(0xffffffffu, hv, o);
+        if ((t & 31) == 0) s_red[t >> 5] = hv;
+        __syncthreads();
+        if (t < 32) {
+            float l0 = s_logit[t], l1 = s_logit[t + 32], l2 = (t == 0) ? s_logit[64] : -INFINITY;
+            float m = fmaxf(fmaxf(l0, l1), l2);
+#pragma unroll
+            for (int o = 16; o; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+            const float e0 = expf(l0 - m), e1 = expf(l1 - m), e2 = (t == 0) ? expf(l2 - m) : 0.f;
+            float s = e0 + e1 + e2;
+#pragma unroll
+            for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+            const float inv = 1.f / s;
+            float *po = p.policy + b * 65;
+            po[t] = e0 * inv; po[t + 32] = e1 * inv;
+            if (t == 0) { po[64] = e2 * inv; p.value[b] = tanhf(s_red[0] + s_red[1] + s_red[2] + s_red[3] + v2b); }
+        }
+        __syncthreads();
+    }
+}
+
+// ------------------------------------------------------------------ host side
+
+static size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
+
+ResNetLayout resnet_layout(const oz_resnet_shape &s) {
+    ResNetLayout L;
+    size_t o = 0;
+    const size_t C = s.channels, Hv = s.value_hidden;
+    const int nconv = 1 + 2 * s.blocks;
+    for (int i = 0; i < nconv; ++i) {
+        const size_t cin = (i == 0) ? 32 : C;
+        L.conv_w.push_back(o); o = align256(o + 9 * C * cin * 2);
+        L.conv_b.push_back(o); o = align256(o + C * 4);
+    }
+    L.pconv_w = o; o = align256(o + 2 * C * 4);
+    L.pconv_b = o; o = align256(o + 2 * 4);
+    L.pfc_w = o; o = align256(o + 65 * 128 * 4);
+    L.pfc_b = o; o = align256(o + 65 * 4);
+    L.vconv_w = o; o = align256(o + C * 4);
+    L.vconv_b = o; o = align256(o + 4);
+    L.vfc1_w = o; o = align256(o + Hv * 64 * 4);
+    L.vfc1_b = o; o = align256(o + Hv * 4);
+    L.vfc2_w = o; o = align256(o + Hv * 4);
+    L.vfc2_b = o; o = align256(o + 4);
+    L.total = o;
+    return L;
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static int get_encode(EncodeTiledFn *fn) {
+    static EncodeTiledFn cached = nullptr;
+    if (!cached) {
+        void *ptr = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        OZ_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres));
+        if (!ptr || qres != cudaDriverEntryPointSuccess) return fail(OZ_ERR_CUDA, "cuTensorMapEncodeTiled not available");
+        cached = (EncodeTiledFn)ptr;
+    }
+    *fn = cached;
+    return OZ_OK;
+}
+
+// NHWC [boards][8][8][C] bf16 viewed as (channel, board, x, y); box = (32, 16, 9, 6).
+static int make_act_map(CUtensorMap *m, void *ptr, size_t boards, int C) {
+    EncodeTiledFn enc;
+    OZ_TRY(get_encode(&enc));
+    cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)boards, 8, 8};
+    cuuint64_t strides[3] = {(cuuint64_t)64 * C * 2, (cuuint64_t)C * 2, (cuuint64_t)8 * C * 2};
+    cuuint32_t box[4] = {kKBlock, kBoardsPerUnit, kBoxX, kBoxY};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, ptr, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(OZ_ERR_CUDA, "cuTensorMapEncodeTiled(activations) failed: " + std::to_string((int)r));
+    return OZ_OK;
+}
+
+// [tap][cout][cin] bf16 viewed as (cin, tap*cout); box = (32, 128).
+static int make_w_map(CUtensorMap *m, void *ptr, int cin, int cout) {
+    EncodeTiledFn enc;
+    OZ_TRY(get_encode(&enc));
+    cuuint64_t dims[2] = {(cuuint64_t)cin, (cuuint64_t)9 * cout};
+    cuuint64_t strides[1] = {(cuuint64_t)cin * 2};
+    cuuint32_t box[2] = {kKBlock, 128};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, ptr, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(OZ_ERR_CUDA, "cuTensorMapEncodeTiled(weights) failed: " + std::to_string((int)r));
+    return OZ_OK;
+}
+
+static int launch_conv(const CUtensorMap &ma, const CUtensorMap &mw, const ConvParams &cp, cudaStream_t stream) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        OZ_CUDA(cudaFuncSetAttribute(conv3x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+        attr_set = true;
+    }
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int num_pass = cp.units * 2 * (cp.cout_total >> 7);
+    const int grid = num_pass < sms ? num_pass : sms;
+    conv3x3_kernel<<<grid, kThreads, kSmemBytes, stream>>>(ma, mw, cp);
+    count_launch();
+    OZ_CUDA(cudaGetLastError());
+    return OZ_OK;
+}
+
+ResNet::~ResNet() {
+    cudaFree(d_blob_); cudaFree(d_x0_); cudaFree(d_a_); cudaFree(d_t_);
+}
+
+int ResNet::load(const oz_resnet_shape &shape, const void *blob, size_t bytes) {
+    if (shape.channels < 128 || shape.channels % 128 != 0 || shape.channels > 384)
+        return fail(OZ_ERR_INVALID_ARGUMENT, "conv_channels must be 128, 256 or 384 for the native evaluator");
+    if (shape.in_planes < 1 || shape.in_planes > 32)
+        return fail(OZ_ERR_INVALID_ARGUMENT, "in_planes must be in [1, 32] (history_size <= 15)");
+    if (shape.blocks < 0 || shape.value_hidden < 1 || shape.value_hidden > 512)
+        return fail(OZ_ERR_INVALID_ARGUMENT, "unsupported residual block / value head size");
+    ResNetLayout L = resnet_layout(shape);
+    if (bytes != L.total) return fail(OZ_ERR_INVALID_ARGUMENT, "weight blob has " + std::to_string(bytes) + " bytes, expected " + std::to_string(L.total));
+    const bool same = d_blob_ && shape.channels == shape_.channels && shape.blocks == shape_.blocks &&
+                      shape.value_hidden == shape_.value_hidden && shape.in_planes == shape_.in_planes;
+    if (!same) {
+        cudaFree(d_blob_); d_blob_ = nullptr;
+        OZ_CUDA(cudaMalloc(&d_blob_, L.total));
+        map_w_.assign(L.conv_w.size(), CUtensorMap{});
+        for (size_t i = 0; i < L.conv_w.size(); ++i)
+            OZ_TRY(make_w_map(&map_w_[i], d_blob_ + L.conv_w[i], i == 0 ? 32 : shape.channels, shape.channels));
+        if (shape.channels != shape_.channels) { cudaFree(d_a_); cudaFree(d_t_); cudaFree(d_x0_); d_a_ = d_t_ = d_x0_ = nullptr; cap_ = 0; }
+    }
+    shape_ = shape; layout_ = L;
+    OZ_CUDA(cudaMemcpy(d_blob_, blob, L.total, cudaMemcpyHostToDevice));
+    return OZ_OK;
+}
+
+int ResNet::reserve(size_t boards) {
+    const size_t pad = (boards + kBoardsPerUnit - 1) / kBoardsPerUnit * kBoardsPerUnit;
+    if (pad <= cap_) return OZ_OK;
+    cudaFree(d_x0_); cudaFree(d_a_); cudaFree(d_t_); d_x0_ = d_a_ = d_t_ = nullptr; cap_ = 0;
+    const size_t C = shape_.channels;
+    OZ_CUDA(cudaMalloc(&d_x0_, pad * 64 * 32 * 2));
+    OZ_CUDA(cudaMalloc(&d_a_, pad * 64 * C * 2));
+    OZ_CUDA(cudaMalloc(&d_t_, pad * 64 * C * 2));
+    OZ_CUDA(cudaMemset(d_a_, 0, pad * 64 * C * 2));
+    OZ_CUDA(cudaMemset(d_t_, 0, pad * 64 * C * 2));
+    OZ_TRY(make_act_map(&map_x0_, d_x0_, pad, 32));
+    OZ_TRY(make_act_map(&map_a_, d_a_, pad, (int)C));
+    OZ_TRY(make_act_map(&map_t_, d_t_, pad, (int)C));
+    cap_ = pad;
+    return OZ_OK;
+}
+
+int ResNet::forward(const float *d_features, size_t n, float *d_policy, float *d_value, cudaStream_t stream) {
+    if (!loaded()) return fail(OZ_ERR_STATE, "no network weights loaded");
+    if (n == 0) return OZ_OK;
+    OZ_TRY(reserve(n));
+    const size_t pad = (n + kBoardsPerUnit - 1) / kBoardsPerUnit * kBoardsPerUnit;
+    const int C = shape_.channels;
+    {
+        const size_t threads = pad * 256;
+        planes_to_nhwc32_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, stream>>>(d_features, shape_.in_planes, n, pad, (__nv_bfloat16 *)d_x0_);
+        count_launch();
+    }
+    ConvParams cp{};
+    cp.units = (int)(pad / kBoardsPerUnit); cp.cout_total = C; cp.relu = 1;
+    // conv block (neural_net.py:9-29)
+    cp.kblocks = 1; cp.skip = nullptr; cp.out = (__nv_bfloat16 *)d_a_; cp.bias = (const float *)(d_blob_ + layout_.conv_b[0]);
+    OZ_TRY(launch_conv(map_x0_, map_w_[0], cp, stream));
+    cp.kblocks = C / kKBlock;
+    for (int b = 0; b < shape_.blocks; ++b) {   // residual tower (neural_net.py:32-65)
+        cp.skip = nullptr; cp.out = (__nv_bfloat16 *)d_t_; cp.bias = (const float *)(d_blob_ + layout_.conv_b[1 + 2 * b]);
+        OZ_TRY(launch_conv(map_a_, map_w_[1 + 2 * b], cp, stream));
+        cp.skip = (const __nv_bfloat16 *)d_a_; cp.out = (__nv_bfloat16 *)d_a_; cp.bias = (const float *)(d_blob_ + layout_.conv_b[2 + 2 * b]);
+        OZ_TRY(launch_conv(map_t_, map_w_[2 + 2 * b], cp, stream));
+    }
+    HeadParams hp{};
+    hp.act = (const __nv_bfloat16 *)d_a_;
+    hp.pconv_w = (const float *)(d_blob_ + layout_.pconv_w); hp.pconv_b = (const float *)(d_blob_ + layout_.pconv_b);
+    hp.pfc_w = (const float *)(d_blob_ + layout_.pfc_w); hp.pfc_b = (const float *)(d_blob_ + layout_.pfc_b);
+    hp.vconv_w = (const float *)(d_blob_ + layout_.vconv_w); hp.vconv_b = (const float *)(d_blob_ + layout_.vconv_b);
+    hp.vfc1_w = (const float *)(d_blob_ + layout_.vfc1_w); hp.vfc1_b = (const float *)(d_blob_ + layout_.vfc1_b);
+    hp.vfc2_w = (const float *)(d_blob_ + layout_.vfc2_w); hp.vfc2_b = (const float *)(d_blob_ + layout_.vfc2_b);
+    hp.policy = d_policy; hp.value = d_value; hp.C = C; hp.Hv = shape_.value_hidden; hp.n = n;
+    const size_t hsm = (65 * 129 + (size_t)hp.Hv * 65 + 3 * C + 128 + 64 + 72 + 8) * sizeof(float);
+    static size_t hsm_set = 0;
+    if (hsm > hsm_set) { OZ_CUDA(cudaFuncSetAttribute(heads_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hsm)); hsm_set = hsm; }
+    const unsigned grid = (unsigned)(n < 148 * 2 ? n : 148 * 2);
+    heads_kernel<<<grid, 128, hsm, stream>>>(hp);
+    count_launch();
+    OZ_CUDA(cudaGetLastError());
+    return OZ_OK;
+}
+
+int ResNet::conv3x3(const void *d_in, int cin, const void *d_w, const float *d_bias, const void *d_skip, int relu,
+                    void *d_out, int cout, size_t boards_padded, cudaStream_t stream) {
+    if (cin % kKBlock || cout % 128 || boards_padded % kBoardsPerUnit)
+        return fail(OZ_ERR_INVALID_ARGUMENT, "conv3x3: cin % 32, cout % 128, boards % 16 must be 0");
+    CUtensorMap ma, mw;
+    OZ_TRY(make_act_map(&ma, const_cast<void *>(d_in), boards_padded, cin));
+    OZ_TRY(make_w_map(&mw, const_cast<void *>(d_w), cin, cout));
+    ConvParams cp{};
+    cp.skip = (const __nv_bfloat16 *)d_skip; cp.out = (__nv_bfloat16 *)d_out; cp.bias = d_bias;
+    cp.units = (int)(boards_padded / kBoardsPerUnit); cp.kblocks = cin / kKBlock; cp.cout_total = cout; cp.relu = relu;
+    return launch_conv(ma, mw, cp, stream);
+}
+
+}  // namespace oz

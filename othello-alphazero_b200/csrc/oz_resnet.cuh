@@ -1,0 +1,59 @@
+// Native ResNet evaluator (reference: python/othello_alphazero/neural_net.py:138-172):
+// folded-BN bf16 3x3 convolutions as implicit GEMM on tcgen05 / TMEM fed by TMA, fused
+// bias + residual + ReLU epilogue, and one fused kernel for both heads.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <vector>
+
+#include "oz_common.cuh"
+
+namespace oz {
+
+// Host blob layout (all offsets 256-byte aligned), produced by the Python weight folder
+// (othello_mcts/weights.py) and mirrored by oz_resnet_blob_offsets():
+//   conv[0]            bf16 [9][C][32]   tap-major, cout, cin (planes zero-padded to 32)
+//   bias[0]            f32  [C]
+//   conv[1..2*blocks]  bf16 [9][C][C]
+//   bias[1..2*blocks]  f32  [C]
+//   policy_conv  f32 [2][C]   policy_conv_bias f32 [2]
+//   policy_fc    f32 [65][128] policy_fc_bias  f32 [65]
+//   value_conv   f32 [C]      value_conv_bias  f32 [1]
+//   value_fc1    f32 [Hv][64] value_fc1_bias   f32 [Hv]
+//   value_fc2    f32 [Hv]     value_fc2_bias   f32 [1]
+struct ResNetLayout {
+    std::vector<size_t> conv_w, conv_b;  // per conv layer
+    size_t pconv_w, pconv_b, pfc_w, pfc_b, vconv_w, vconv_b, vfc1_w, vfc1_b, vfc2_w, vfc2_b;
+    size_t total;
+};
+ResNetLayout resnet_layout(const oz_resnet_shape &s);
+
+class ResNet {
+  public:
+    ~ResNet();
+    int load(const oz_resnet_shape &shape, const void *blob, size_t bytes);
+    bool loaded() const { return d_blob_ != nullptr; }
+    const oz_resnet_shape &shape() const { return shape_; }
+    // Capacity in boards (rounded up to a multiple of 16); (re)allocates activations + tensor maps.
+    int reserve(size_t boards);
+    // features: DEVICE float [n][in_planes][64] (reference plane format).  policy [n][65], value [n].
+    int forward(const float *d_features, size_t n, float *d_policy, float *d_value, cudaStream_t stream);
+    // Kernel launches one forward() issues.
+    int launches_per_forward() const { return 2 + (1 + 2 * shape_.blocks); }
+    // Debug hook: one 3x3 convolution layer on device NHWC bf16 buffers already padded to 16 boards.
+    static int conv3x3(const void *d_in, int cin, const void *d_w, const float *d_bias, const void *d_skip,
+                       int relu, void *d_out, int cout, size_t boards_padded, cudaStream_t stream);
+
+  private:
+    oz_resnet_shape shape_{};
+    ResNetLayout layout_;
+    char *d_blob_ = nullptr;
+    size_t cap_ = 0;
+    void *d_x0_ = nullptr, *d_a_ = nullptr, *d_t_ = nullptr;  // bf16 NHWC activations
+    CUtensorMap map_x0_, map_a_, map_t_;
+    std::vector<CUtensorMap> map_w_;
+};
+
+}  // namespace oz

@@ -1,0 +1,619 @@
+// Tree kernels: PUCT selection with virtual loss, feature encoding, expansion + backup,
+// action choice, re-rooting.  One warp owns one game; lanes are children / path nodes /
+// board squares.  Compiled with -fmad=false and explicit round-to-nearest intrinsics so
+// that every float decision matches the reference's scalar code (search_thread.cpp:192-260
+// compiled without FMA contraction) bit for bit.
+#include <cfloat>
+#include <climits>
+
+#include "oz_common.cuh"
+#include "oz_rules.cuh"
+#include "oz_tree.cuh"
+
+namespace oz {
+
+// ------------------------------------------------------------------ counter-based RNG
+// Philox4x32-10 keyed by the engine seed; counter = (game id, search or ply, simulation, stream).
+__device__ __forceinline__ void philox(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1, uint32_t (&out)[4]) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+        const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+        const uint32_t n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
+        c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+__device__ __forceinline__ float u01(uint32_t x) { return ((float)(x >> 8) + 0.5f) * (1.0f / 16777216.0f); }
+
+// Gamma(alpha, 1) draw for child `child` of the root at simulation `sim`
+// (reference: std::gamma_distribution, search_thread.cpp:23,233).
+__device__ float gamma_draw(const Tree &t, uint32_t game_id, uint32_t search, uint32_t sim, int child) {
+    uint32_t r[4];
+    if (t.gamma_table) {
+        philox(game_id, search, sim, 0x100u + (uint32_t)child, t.seed_lo, t.seed_hi, r);
+        return t.gamma_table[r[0] % (uint32_t)t.gamma_len];
+    }
+    if (!(t.alpha > 0.0f)) return 0.0f;
+    const float a = t.alpha < 1.0f ? t.alpha + 1.0f : t.alpha;   // Marsaglia-Tsang, boosted for alpha < 1
+    const float d = a - 1.0f / 3.0f, c = 1.0f / sqrtf(9.0f * d);
+    for (uint32_t attempt = 0;; ++attempt) {
+        philox(game_id, search, sim, 0x100u + (uint32_t)child + 64u * attempt, t.seed_lo, t.seed_hi, r);
+        const float u1 = u01(r[0]), u2 = u01(r[1]), u3 = u01(r[2]), u4 = u01(r[3]);
+        const float x = sqrtf(-2.0f * logf(u1)) * cosf(6.28318530717958647692f * u2);
+        float v = 1.0f + c * x;
+        if (v <= 0.0f) continue;
+        v = v * v * v;
+        if (logf(u3) < 0.5f * x * x + d - d * v + d * logf(v) || attempt >= 15) {
+            float g = d * v;
+            if (t.alpha < 1.0f) g *= powf(u4, 1.0f / t.alpha);
+            return g;
+        }
+    }
+}
+
+__device__ __forceinline__ int warp_sum(int v) {
+#pragma unroll
+    for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// Action index (0 = a1) of the j-th legal move in ascending action order (position.h:308-326).
+__device__ __forceinline__ int nth_action(uint64_t legal, int j) {
+    uint64_t rev = __brevll(legal);                  // bit a <-> action a
+    for (int k = 0; k < j; ++k) rev &= rev - 1;
+    return __ffsll((long long)rev) - 1;
+}
+
+__device__ __forceinline__ size_t arena_base(const Tree &t, int g) { return ((size_t)g * 2 + t.g_which[g]) * t.cap; }
+
+// ------------------------------------------------------------------ reset (mcts.cpp:40-43)
+__global__ void reset_kernel(Tree t) {
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= t.G) return;
+    t.g_which[g] = 0;
+    const size_t b = (size_t)g * 2 * t.cap;
+    t.n_p1[b] = kInitialP1; t.n_p2[b] = kInitialP2;
+    t.n_meta[b] = 1; t.n_parent[b] = -1; t.n_child[b] = -1;
+    t.n_N[b] = 0; t.n_W[b] = 0.f; t.n_Q[b] = 0.f; t.n_P[b] = 1.f;
+    t.g_root[g] = 0; t.g_count[g] = 1; t.g_status[g] = 0; t.g_ply[g] = 0; t.g_search[g] = 0; t.h_n[g] = 0;
+    t.r_p1[g] = kInitialP1; t.r_p2[g] = kInitialP2; t.r_player[g] = 1;
+}
+
+// ------------------------------------------------------------------ select (search_thread.cpp:60-79, 192-260)
+__global__ void __launch_bounds__(128) select_kernel(Tree t, int round) {
+    __shared__ int s_path[4][kMaxDepth];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int g = blockIdx.x * 4 + wib;
+    if (g >= t.G) return;
+    const int B = t.inflight;
+    int *leaf_out = t.s_leaf + (size_t)g * B;
+    if (t.g_status[g] & 1) {                         // finished game: nothing in flight
+        for (int i = lane; i < B; i += 32) leaf_out[i] = -1;
+        return;
+    }
+    const size_t base = arena_base(t, g);
+    const int root = t.g_root[g];
+    const uint32_t game_id = t.first_game_id + (uint32_t)g, search = t.g_search[g];
+    int *path = s_path[wib];
+
+    for (int i = 0; i < B; ++i) {
+        const uint32_t sim = (uint32_t)(round * B + i);
+        int node = root, depth = 0;
+        while (true) {
+            const int m = t.n_meta[base + node];
+            const int nch = m >> 8;
+            if ((m & 3) == 0 || nch == 0) break;     // terminal or childless (search_thread.cpp:65)
+            const int fc = t.n_child[base + node];
+            int next = fc;
+            if (nch > 1) {
+                int nn = t.n_N[base + node];
+                if (nn >= t.rate_len) { if (lane == 0) atomicOr(t.error, kErrRateTable); nn = t.rate_len - 1; }
+                const float rate = t.rate[nn];       // logf((1 + N + c_base) / c_base) + c_init, host libm
+                const int c0 = lane, c1 = lane + 32;
+                const bool v0 = c0 < nch, v1 = c1 < nch;
+                const size_t a0 = base + fc + c0, a1 = base + fc + c1;
+                const int n0 = v0 ? t.n_N[a0] : 0, n1 = v1 ? t.n_N[a1] : 0;
+                const float q0 = v0 ? t.n_Q[a0] : 0.f, q1 = v1 ? t.n_Q[a1] : 0.f;
+                float p0 = v0 ? t.n_P[a0] : 0.f, p1 = v1 ? t.n_P[a1] : 0.f;
+                const int total = warp_sum(n0 + n1);
+                const float mult = __fmul_rn(rate, __fsqrt_rn((float)total));
+                if (node == root && t.eps > 0.0f) {  // Dirichlet noise, re-drawn per selection (:230-249)
+                    const float g0 = v0 ? gamma_draw(t, game_id, search, sim, c0) : 0.f;
+                    const float g1 = v1 ? gamma_draw(t, game_id, search, sim, c1) : 0.f;
+                    float sum = 0.0f;                // sequential float sum in child order
+                    for (int j = 0; j < nch; ++j) {
+                        const float gj = __shfl_sync(0xffffffffu, j < 32 ? g0 : g1, j & 31);
+                        sum = __fadd_rn(sum, gj);
+                    }
+                    if (sum == 0.0f) sum = 1.0f;
+                    const float pm = __fsub_rn(1.0f, t.eps), nm = __fdiv_rn(t.eps, sum);
+                    p0 = __fadd_rn(__fmul_rn(p0, pm), __fmul_rn(g0, nm));
+                    p1 = __fadd_rn(__fmul_rn(p1, pm), __fmul_rn(g1, nm));
+                }
+                // ucb = Q + (mult * P) / (1 + N)
+                float u = -INFINITY; int idx = INT_MAX;
+                if (v0) { u = __fadd_rn(q0, __fdiv_rn(__fmul_rn(mult, p0), __fadd_rn(1.0f, (float)n0))); idx = c0; }
+                if (v1) {
+                    const float u1 = __fadd_rn(q1, __fdiv_rn(__fmul_rn(mult, p1), __fadd_rn(1.0f, (float)n1)));
+                    if (u1 > u) { u = u1; idx = c1; }
+                }
+#pragma unroll
+                for (int o = 16; o; o >>= 1) {       // first maximum wins (strict > in the reference)
+                    const float ou = __shfl_xor_sync(0xffffffffu, u, o);
+                    const int oi = __shfl_xor_sync(0xffffffffu, idx, o);
+                    if (ou > u || (ou == u && oi < idx)) { u = ou; idx = oi; }
+                }
+                next = fc + idx;
+            }
+            if (depth < kMaxDepth) { if (lane == 0) path[depth] = next; }
+            else if (lane == 0) atomicOr(t.error, kErrDepth);
+            ++depth;
+            node = next;
+        }
+        if (depth > kMaxDepth) depth = kMaxDepth;
+        __syncwarp();
+        // virtual loss on the path (root excluded), root visit count (:70-78)
+        int *gpath = t.s_path + ((size_t)g * B + i) * kMaxDepth;
+        for (int k = lane; k < depth; k += 32) {
+            const int nd = path[k];
+            gpath[k] = nd;
+            const size_t a = base + nd;
+            const int n = t.n_N[a] + 1;
+            const float w = __fsub_rn(t.n_W[a], 1.0f);
+            t.n_N[a] = n; t.n_W[a] = w; t.n_Q[a] = __fdiv_rn(w, (float)n);
+        }
+        if (lane == 0) { t.n_N[base + root] += 1; leaf_out[i] = node; t.s_len[(size_t)g * B + i] = depth; }
+        __syncwarp();
+    }
+}
+
+// ------------------------------------------------------------------ encode (search_thread.cpp:87-100, transformation.h:83-116)
+// Positions of `node` and its ancestors, newest first: the chain inside the arena, then the
+// retired ancestors of the root (position_iterator.h:49-52 crosses the root the same way).
+__device__ __forceinline__ int gather_history(const Tree &t, int g, size_t base, int node, int lane,
+                                              uint64_t *sp1, uint64_t *sp2) {
+    int n = 0;
+    if (lane == 0) {
+        int nd = node;
+        while (n < t.H && nd >= 0) { sp1[n] = t.n_p1[base + nd]; sp2[n] = t.n_p2[base + nd]; nd = t.n_parent[base + nd]; ++n; }
+        const int hn = t.h_n[g];
+        for (int r = 0; n < t.H && r < hn; ++r, ++n) { sp1[n] = t.h_p1[(size_t)g * kMaxHist + r]; sp2[n] = t.h_p2[(size_t)g * kMaxHist + r]; }
+    }
+    n = __shfl_sync(0xffffffffu, n, 0);
+    __syncwarp();
+    return n;
+}
+
+__device__ __forceinline__ void write_planes(float *f, int H, int nh, const uint64_t *sp1, const uint64_t *sp2,
+                                             float side, int tf, int lane) {
+    f[lane] = side; f[lane + 32] = side;
+    const int i0 = lane, i1 = lane + 32;
+    const int j0 = transform_action(i0, tf), j1 = transform_action(i1, tf);
+    const uint64_t m0 = 1ull << (63 - i0), m1 = 1ull << (63 - i1);
+    for (int k = 0; k < H; ++k) {
+        float *pl = f + 64 + k * 128;
+        if (k >= nh) { pl[lane] = 0.f; pl[lane + 32] = 0.f; pl[64 + lane] = 0.f; pl[96 + lane] = 0.f; continue; }
+        const uint64_t b = sp1[k], w = sp2[k];
+        pl[j0] = (b & m0) ? 1.f : 0.f; pl[j1] = (b & m1) ? 1.f : 0.f;
+        pl[64 + j0] = (w & m0) ? 1.f : 0.f; pl[64 + j1] = (w & m1) ? 1.f : 0.f;
+    }
+}
+
+__global__ void __launch_bounds__(128) encode_kernel(Tree t, int round, float *features) {
+    __shared__ uint64_t s1[4][kMaxHist], s2[4][kMaxHist];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const size_t slot = (size_t)blockIdx.x * 4 + wib;
+    if (slot >= (size_t)t.G * t.inflight) return;
+    const int g = (int)(slot / t.inflight), i = (int)(slot % t.inflight);
+    const int leaf = t.s_leaf[slot];
+    if (leaf < 0) return;
+    const size_t base = arena_base(t, g);
+    const int player = t.n_meta[base + leaf] & 3;
+    if (player == 0) return;                          // terminal leaf: slot keeps its stale planes (:88-90)
+    int tf = 0;
+    if (t.sym_mode == OZ_SYM_RANDOM) {
+        uint32_t r[4];
+        philox(t.first_game_id + (uint32_t)g, t.g_search[g], (uint32_t)(round * t.inflight + i), 0u, t.seed_lo, t.seed_hi, r);
+        tf = (int)(r[0] & 7u);
+    }
+    if (lane == 0) t.s_tf[slot] = tf;
+    const int nh = gather_history(t, g, base, leaf, lane, s1[wib], s2[wib]);
+    write_planes(features + slot * (size_t)(1 + 2 * t.H) * 64, t.H, nh, s1[wib], s2[wib], (float)player - 1.0f, tf, lane);
+}
+
+// ------------------------------------------------------------------ expand + backup (search_thread.cpp:130-190)
+__global__ void __launch_bounds__(128) expand_kernel(Tree t, const float *__restrict__ policy, const float *__restrict__ value) {
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int g = blockIdx.x * 4 + wib;
+    if (g >= t.G) return;
+    if (t.g_status[g] & 1) return;
+    const int B = t.inflight;
+    const size_t base = arena_base(t, g);
+    const int root = t.g_root[g];
+    unsigned long long expanded = 0;
+    for (int i = 0; i < B; ++i) {
+        const size_t slot = (size_t)g * B + i;
+        const int leaf = t.s_leaf[slot];
+        const int m = t.n_meta[base + leaf];
+        const int player = m & 3;
+        const uint64_t lp1 = t.n_p1[base + leaf], lp2 = t.n_p2[base + leaf];
+        if (player != 0 && (m >> 8) == 0) {           // still childless (:135)
+            const uint64_t me = player == 1 ? lp1 : lp2, opp = player == 1 ? lp2 : lp1;
+            const uint64_t legal = legal_moves(me, opp);
+            const int n = legal ? __popcll(legal) : 1;
+            const int first = t.g_count[g];
+            if (first + n > t.cap) {
+                if (lane == 0) atomicOr(t.error, kErrArenaFull);
+            } else {
+                const int tf = t.s_tf[slot];
+                const float *pol = policy + slot * 65;
+                Position s; s.player = player; s.p1 = lp1; s.p2 = lp2; s.legal = legal;
+                s.next_legal = legal ? 0 : legal_moves(opp, me);
+                for (int j = lane; j < n; j += 32) {   // one child position per lane
+                    const int a = legal ? nth_action(legal, j) : 64;
+                    const Position c = apply_action(s, a);
+                    const size_t d = base + first + j;
+                    t.n_p1[d] = c.p1; t.n_p2[d] = c.p2; t.n_meta[d] = c.player;
+                    t.n_parent[d] = leaf; t.n_child[d] = -1;
+                    t.n_N[d] = 0; t.n_W[d] = 0.f; t.n_Q[d] = 0.f;
+                    t.n_P[d] = pol[transform_action(a, tf)];   // raw softmax output, no renormalisation (:139-149)
+                }
+                if (lane == 0) { t.n_child[base + leaf] = first; t.n_meta[base + leaf] = player | (n << 8); t.g_count[g] = first + n; }
+                expanded += (unsigned)n;
+            }
+        }
+        float v;
+        if (player != 0) {
+            v = -value[slot];                          // edge value is from the parent's view (:156-157)
+        } else {                                       // terminal: disc count from the parent's side (:158-177)
+            const int par = t.n_parent[base + leaf];
+            const int pp = par >= 0 ? (t.n_meta[base + par] & 3) : t.h_player[(size_t)g * kMaxHist];
+            const int pc = __popcll(pp == 1 ? lp1 : lp2), oc = __popcll(pp == 1 ? lp2 : lp1);
+            v = pc > oc ? 1.0f : (pc < oc ? -1.0f : 0.0f);
+        }
+        // backup along the stored path (leaf last); the sign alternates towards the root
+        const int len = t.s_len[slot];
+        const int *gpath = t.s_path + slot * kMaxDepth;
+        for (int k = lane; k < len; k += 32) {
+            const size_t a = base + gpath[k];
+            const float vk = ((len - 1 - k) & 1) ? -v : v;
+            const float w = __fadd_rn(t.n_W[a], __fadd_rn(1.0f, vk));   // W += 1 + v cancels the virtual loss (:184)
+            t.n_W[a] = w; t.n_Q[a] = __fdiv_rn(w, (float)t.n_N[a]);
+        }
+        __syncwarp();
+    }
+    (void)root;
+    if (lane == 0 && expanded) atomicAdd(&t.stats[0], expanded);
+}
+
+__global__ void end_search_kernel(Tree t) {
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g < t.G) t.g_search[g] += 1;
+}
+
+// ------------------------------------------------------------------ root statistics (mcts.cpp:45-61)
+__global__ void root_stats_kernel(Tree t, int32_t *n_children, int32_t *counts, float *q, int32_t *root_n) {
+    const int lane = threadIdx.x & 31;
+    const int g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (g >= t.G) return;
+    const size_t base = arena_base(t, g);
+    const int root = t.g_root[g];
+    const int nch = t.n_meta[base + root] >> 8, fc = t.n_child[base + root];
+    if (lane == 0) { if (n_children) n_children[g] = nch; if (root_n) root_n[g] = t.n_N[base + root]; }
+    for (int j = lane; j < kStride; j += 32) {
+        if (counts) counts[(size_t)g * kStride + j] = j < nch ? t.n_N[base + fc + j] : 0;
+        if (q) q[(size_t)g * kStride + j] = j < nch ? t.n_Q[base + fc + j] : 0.f;
+    }
+}
+
+// ------------------------------------------------------------------ action choice (train.py:421-430)
+__global__ void choose_kernel(Tree t, int32_t *actions) {
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= t.G) return;
+    const int player = t.r_player[g];
+    if ((t.g_status[g] & 1) || player == 0) { actions[g] = -1; return; }
+    const size_t base = arena_base(t, g);
+    const int root = t.g_root[g];
+    const uint64_t me = player == 1 ? t.r_p1[g] : t.r_p2[g], opp = player == 1 ? t.r_p2[g] : t.r_p1[g];
+    const uint64_t legal = legal_moves(me, opp);
+    const int n = legal ? __popcll(legal) : 1;
+    const int nch = t.n_meta[base + root] >> 8, fc = t.n_child[base + root];
+    uint32_t r[4];
+    philox(t.first_game_id + (uint32_t)g, (uint32_t)t.g_ply[g], 0xFFFFFFFFu, 2u, t.seed_lo, t.seed_hi, r);
+    int pick_j = 0;
+    if (nch != 0) {
+        if (t.g_ply[g] < t.temperature_plies) {      // proportional to visit counts (tau = 1)
+            uint32_t sum = 0;
+            for (int j = 0; j < n; ++j) sum += (uint32_t)t.n_N[base + fc + j];
+            if (sum == 0) pick_j = (int)(((uint64_t)r[0] * (uint32_t)n) >> 32);
+            else {
+                const uint32_t pick = (uint32_t)(((uint64_t)r[0] * sum) >> 32);
+                uint32_t acc = 0;
+                pick_j = n - 1;
+                for (int j = 0; j < n; ++j) { acc += (uint32_t)t.n_N[base + fc + j]; if (pick < acc) { pick_j = j; break; } }
+            }
+        } else {                                      // uniformly random argmax
+            int best = -1, ties = 0;
+            for (int j = 0; j < n; ++j) { const int c = t.n_N[base + fc + j]; if (c > best) { best = c; ties = 1; } else if (c == best) ++ties; }
+            uint32_t pick = (uint32_t)(((uint64_t)r[0] * (uint32_t)ties) >> 32);
+            for (int j = 0; j < n; ++j) if (t.n_N[base + fc + j] == best && pick-- == 0) { pick_j = j; break; }
+        }
+    }
+    actions[g] = legal ? nth_action(legal, pick_j) : 64;
+}
+
+__global__ void record_kernel(Tree t, const int32_t *actions, PlyRecordDev *records, int max_plies) {
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= t.G) return;
+    const int a = actions[g], ply = t.g_ply[g];
+    if (a < 0 || (t.g_status[g] & 1) || ply >= max_plies) return;
+    const size_t base = arena_base(t, g);
+    const int root = t.g_root[g];
+    PlyRecordDev &rec = records[(size_t)g * max_plies + ply];
+    rec.p1 = t.r_p1[g]; rec.p2 = t.r_p2[g]; rec.player = t.r_player[g]; rec.action = a;
+    const int nch = t.n_meta[base + root] >> 8, fc = t.n_child[base + root];
+    rec.n_children = nch;
+    for (int j = 0; j < kStride; ++j) rec.visit_counts[j] = j < nch ? t.n_N[base + fc + j] : 0;
+}
+
+// ------------------------------------------------------------------ re-root (mcts.cpp:114-165)
+// The chosen child's subtree is copied breadth-first into the game's other arena (children stay
+// contiguous and ordered); everything else is dropped by switching arenas.  The old root joins
+// the retired-ancestor ring that feeds the history planes.
+__global__ void __launch_bounds__(128) apply_kernel(Tree t, const int32_t *__restrict__ actions, int32_t *unfinished) {
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int g = blockIdx.x * 4 + wib;
+    if (g >= t.G) return;
+    const int action = actions[g];
+    if (action < 0 || (t.g_status[g] & 1)) {
+        if (lane == 0 && !(t.g_status[g] & 1)) atomicAdd(unfinished, 1);
+        return;
+    }
+    const int which = t.g_which[g];
+    const size_t src = ((size_t)g * 2 + which) * t.cap, dst = ((size_t)g * 2 + (which ^ 1)) * t.cap;
+    const int root = t.g_root[g];
+    const int rm = t.n_meta[src + root];
+    const int player = rm & 3, nch = rm >> 8;
+    const uint64_t rp1 = t.n_p1[src + root], rp2 = t.n_p2[src + root];
+    __syncwarp();
+    if (lane == 0) {                                   // retire the old root into the history ring
+        const size_t h = (size_t)g * kMaxHist;
+        int hn = t.h_n[g];
+        for (int k = (hn < kMaxHist ? hn : kMaxHist - 1); k > 0; --k) { t.h_p1[h + k] = t.h_p1[h + k - 1]; t.h_p2[h + k] = t.h_p2[h + k - 1]; t.h_player[h + k] = t.h_player[h + k - 1]; }
+        t.h_p1[h] = rp1; t.h_p2[h] = rp2; t.h_player[h] = player;
+        t.h_n[g] = hn < kMaxHist ? hn + 1 : kMaxHist;
+    }
+    int new_count = 1;
+    int new_player;
+    uint64_t np1, np2;
+    if (nch == 0) {                                    // unexpanded root: fresh childless node (:140-148)
+        Position s; s.player = player; s.p1 = rp1; s.p2 = rp2;
+        const uint64_t me = player == 1 ? rp1 : rp2, opp = player == 1 ? rp2 : rp1;
+        s.legal = legal_moves(me, opp); s.next_legal = s.legal ? 0 : legal_moves(opp, me);
+        const Position c = apply_action(s, action);
+        np1 = c.p1; np2 = c.p2; new_player = c.player;
+        if (lane == 0) {
+            t.n_p1[dst] = np1; t.n_p2[dst] = np2; t.n_meta[dst] = new_player; t.n_parent[dst] = -1; t.n_child[dst] = -1;
+            t.n_N[dst] = 0; t.n_W[dst] = 0.f; t.n_Q[dst] = 0.f; t.n_P[dst] = 1.f;
+        }
+    } else {
+        int idx = 0;
+        if (action != 0 && nch > 1) {                  // rank of the action among the legal moves (:150-157)
+            const uint64_t me = player == 1 ? rp1 : rp2, opp = player == 1 ? rp2 : rp1;
+            idx = __popcll(legal_moves(me, opp) & (~0ull << (64 - action)));
+        }
+        const size_t c = src + t.n_child[src + root] + idx;
+        np1 = t.n_p1[c]; np2 = t.n_p2[c]; new_player = t.n_meta[c] & 3;
+        if (lane == 0) {
+            t.n_p1[dst] = np1; t.n_p2[dst] = np2; t.n_meta[dst] = t.n_meta[c]; t.n_parent[dst] = -1;
+            t.n_child[dst] = t.n_child[c];             // still an id in the OLD arena until processed below
+            t.n_N[dst] = t.n_N[c]; t.n_W[dst] = t.n_W[c]; t.n_Q[dst] = t.n_Q[c]; t.n_P[dst] = t.n_P[c];
+        }
+        __syncwarp();
+        int head = 0;
+        while (head < new_count) {
+            const int batch = min(32, new_count - head);
+            const bool valid = lane < batch;
+            const int my = head + lane;
+            const int fc_old = valid ? t.n_child[dst + my] : -1;
+            const int nc = (valid && fc_old >= 0) ? (t.n_meta[dst + my] >> 8) : 0;
+            int incl = nc;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+            const int total = __shfl_sync(0xffffffffu, incl, 31);
+            const int off = incl - nc;
+            if (nc > 0) t.n_child[dst + my] = new_count + off;
+            for (int s = 0; s < batch; ++s) {
+                const int f = __shfl_sync(0xffffffffu, fc_old, s), c2 = __shfl_sync(0xffffffffu, nc, s), o2 = __shfl_sync(0xffffffffu, off, s);
+                for (int j = lane; j < c2; j += 32) {
+                    const size_t a = src + f + j, d = dst + new_count + o2 + j;
+                    t.n_p1[d] = t.n_p1[a]; t.n_p2[d] = t.n_p2[a]; t.n_meta[d] = t.n_meta[a]; t.n_parent[d] = head + s;
+                    t.n_child[d] = t.n_child[a]; t.n_N[d] = t.n_N[a]; t.n_W[d] = t.n_W[a]; t.n_Q[d] = t.n_Q[a]; t.n_P[d] = t.n_P[a];
+                }
+            }
+            new_count += total;
+            head += batch;
+            __syncwarp();
+        }
+    }
+    if (lane == 0) {
+        t.g_which[g] = which ^ 1; t.g_root[g] = 0; t.g_count[g] = new_count; t.g_ply[g] += 1;
+        t.r_p1[g] = np1; t.r_p2[g] = np2; t.r_player[g] = new_player;
+        if (new_player == 0) t.g_status[g] |= 1; else atomicAdd(unfinished, 1);
+    }
+}
+
+// ------------------------------------------------------------------ self-play sample of one root (mcts.cpp:63-112)
+__global__ void self_play_data_kernel(Tree t, int g, float *features, float *policy) {
+    __shared__ uint64_t s1[kMaxHist], s2[kMaxHist];
+    const int lane = threadIdx.x & 31, tf = threadIdx.x >> 5;   // 8 warps = 8 symmetries
+    const size_t base = arena_base(t, g);
+    const int root = t.g_root[g];
+    const int m = t.n_meta[base + root];
+    const int player = m & 3, nch = m >> 8, fc = t.n_child[base + root];
+    if (tf == 0) gather_history(t, g, base, root, lane, s1, s2);
+    __syncthreads();
+    int nh = 0;
+    { int nd = root; while (nh < t.H && nd >= 0) { nd = t.n_parent[base + nd]; ++nh; } nh = min(t.H, nh + t.h_n[g]); }
+    write_planes(features + (size_t)tf * (1 + 2 * t.H) * 64, t.H, nh, s1, s2, (float)player - 1.0f, tf, lane);
+    float *pol = policy + tf * 65;
+    for (int i = lane; i < 65; i += 32) pol[i] = 0.f;
+    __syncwarp();
+    int sum = 0;
+    for (int j = 0; j < nch; ++j) sum += t.n_N[base + fc + j];
+    if (sum == 0) sum = 1;
+    const uint64_t me = player == 1 ? t.n_p1[base + root] : t.n_p2[base + root], opp = player == 1 ? t.n_p2[base + root] : t.n_p1[base + root];
+    const uint64_t legal = legal_moves(me, opp);
+    for (int j = lane; j < nch; j += 32) {
+        const int a = legal ? nth_action(legal, j) : 64;
+        pol[transform_action(a, tf)] = __fdiv_rn((float)t.n_N[base + fc + j], (float)sum);
+    }
+}
+
+// ------------------------------------------------------------------ built-in exact evaluators (tests, smoke)
+// One warp per board; lane l owns squares l and l + 32.  Integer weights and one correctly
+// rounded division per output, so any IEEE implementation of the same formula agrees bit for bit.
+__device__ __forceinline__ uint64_t plane_mask(const float *pl, int lane) {
+    const uint32_t b0 = __ballot_sync(0xffffffffu, pl[lane] != 0.f), b1 = __ballot_sync(0xffffffffu, pl[lane + 32] != 0.f);
+    return ((uint64_t)__brev(b0) << 32) | (uint64_t)__brev(b1);   // square i <-> bit (63 - i)
+}
+
+__device__ __forceinline__ int box_count(uint64_t occ, int sq) {
+    const uint64_t s = 1ull << (63 - sq);
+    const uint64_t h = s | ((s >> 1) & ~0x8080808080808080ull) | ((s << 1) & ~0x0101010101010101ull);
+    return __popcll((h | (h << 8) | (h >> 8)) & occ);
+}
+
+__global__ void eval_synth_kernel(const float *__restrict__ f, int planes, size_t n, float *policy, float *value) {
+    const int lane = threadIdx.x & 31;
+    const size_t b = (blockIdx.x * (size_t)blockDim.x + threadIdx.x) >> 5;
+    if (b >= n) return;
+    const float *x = f + b * (size_t)planes * 64;
+    const uint64_t bl = plane_mask(x + 64, lane), wh = plane_mask(x + 128, lane);
+    const int w0 = 1 + box_count(bl, lane) + box_count(wh, lane), w1 = 1 + box_count(bl, lane + 32) + box_count(wh, lane + 32);
+    const float sum = (float)(warp_sum(w0 + w1) + 1);
+    float *po = policy + b * 65;
+    po[lane] = __fdiv_rn((float)w0, sum); po[lane + 32] = __fdiv_rn((float)w1, sum);
+    if (lane == 0) {
+        po[64] = __fdiv_rn(1.0f, sum);
+        const float side = __fsub_rn(1.0f, __fmul_rn(2.0f, x[0]));
+        value[b] = __fdiv_rn(__fmul_rn(side, (float)(__popcll(bl) - __popcll(wh))), 64.0f);
+    }
+}
+
+__device__ __forceinline__ uint64_t mix64(uint64_t z) {
+    z ^= z >> 32; z *= 0x9E3779B97F4A7C15ull; z ^= z >> 29;
+    z *= 0xBF58476D1CE4E5B9ull; z ^= z >> 32;
+    return z;
+}
+
+__global__ void eval_hash_kernel(const float *__restrict__ f, int planes, size_t n, float *policy, float *value) {
+    const int lane = threadIdx.x & 31;
+    const size_t b = (blockIdx.x * (size_t)blockDim.x + threadIdx.x) >> 5;
+    if (b >= n) return;
+    const float *x = f + b * (size_t)planes * 64;
+    uint64_t h = 0x243F6A8885A308D3ull;
+    for (int c = 0; c < planes; ++c) h = mix64(h ^ plane_mask(x + c * 64, lane));
+    const uint32_t w0 = 1u + (uint32_t)(mix64(h + (uint64_t)(lane + 1) * 0xD1B54A32D192ED03ull) % 997u);
+    const uint32_t w1 = 1u + (uint32_t)(mix64(h + (uint64_t)(lane + 33) * 0xD1B54A32D192ED03ull) % 997u);
+    const uint32_t w64 = 1u + (uint32_t)(mix64(h + (uint64_t)65 * 0xD1B54A32D192ED03ull) % 997u);
+    const float sum = (float)((uint32_t)warp_sum((int)(w0 + w1)) + w64);
+    float *po = policy + b * 65;
+    po[lane] = __fdiv_rn((float)w0, sum); po[lane + 32] = __fdiv_rn((float)w1, sum);
+    if (lane == 0) {
+        po[64] = __fdiv_rn((float)w64, sum);
+        const int v = (int)(mix64(h ^ 0xA5A5A5A5A5A5A5A5ull) % 2001u) - 1000;
+        value[b] = __fdiv_rn((float)v, 1000.0f);
+    }
+}
+
+// ------------------------------------------------------------------ training tensors (train.py:432-450)
+__global__ void __launch_bounds__(256) training_samples_kernel(const PlyRecordDev *__restrict__ records, const int32_t *__restrict__ plies,
+                                                               const int64_t *__restrict__ sample_base, const uint64_t *fin_p1,
+                                                               const uint64_t *fin_p2, int G, int max_plies, int H,
+                                                               float *features, float *policy, float *value) {
+    __shared__ uint64_t s1[kMaxHist], s2[kMaxHist];
+    const int lane = threadIdx.x & 31, tf = threadIdx.x >> 5;    // block = one (game, ply), warps = symmetries
+    const int g = blockIdx.x / max_plies, ply = blockIdx.x % max_plies;
+    if (g >= G || ply >= plies[g] || sample_base[g] < 0) return;
+    const PlyRecordDev &rec = records[(size_t)g * max_plies + ply];
+    const int nh = min(H, ply + 1);
+    if (threadIdx.x < nh) { s1[threadIdx.x] = records[(size_t)g * max_plies + ply - threadIdx.x].p1; s2[threadIdx.x] = records[(size_t)g * max_plies + ply - threadIdx.x].p2; }
+    __syncthreads();
+    const size_t row = (size_t)sample_base[g] + (size_t)ply * 8 + tf;
+    write_planes(features + row * (size_t)(1 + 2 * H) * 64, H, nh, s1, s2, (float)rec.player - 1.0f, tf, lane);
+    float *pol = policy + row * 65;
+    for (int i = lane; i < 65; i += 32) pol[i] = 0.f;
+    __syncwarp();
+    int sum = 0;
+    for (int j = 0; j < rec.n_children; ++j) sum += rec.visit_counts[j];
+    if (sum == 0) sum = 1;
+    const uint64_t me = rec.player == 1 ? rec.p1 : rec.p2, opp = rec.player == 1 ? rec.p2 : rec.p1;
+    const uint64_t legal = legal_moves(me, opp);
+    for (int j = lane; j < rec.n_children; j += 32) {
+        const int a = legal ? nth_action(legal, j) : 64;
+        pol[transform_action(a, tf)] = __fdiv_rn((float)rec.visit_counts[j], (float)sum);
+    }
+    if (lane == 0) {
+        const int d = __popcll(fin_p1[g]) - __popcll(fin_p2[g]);
+        const float z = d > 0 ? 1.f : (d < 0 ? -1.f : 0.f);      // Black's view, sign flips every ply
+        value[row] = (ply & 1) ? -z : z;
+    }
+}
+
+// ------------------------------------------------------------------ launchers
+static inline unsigned blocks(size_t items, int per_block) { return (unsigned)((items + per_block - 1) / per_block); }
+
+void launch_reset(const Tree &t, cudaStream_t s) { reset_kernel<<<blocks(t.G, 128), 128, 0, s>>>(t); count_launch(); }
+void launch_select(const Tree &t, int round, cudaStream_t s) { select_kernel<<<blocks(t.G, 4), 128, 0, s>>>(t, round); count_launch(); }
+void launch_encode(const Tree &t, int round, float *features, cudaStream_t s) {
+    encode_kernel<<<blocks((size_t)t.G * t.inflight, 4), 128, 0, s>>>(t, round, features); count_launch();
+}
+void launch_expand(const Tree &t, const float *policy, const float *value, cudaStream_t s) {
+    expand_kernel<<<blocks(t.G, 4), 128, 0, s>>>(t, policy, value); count_launch();
+}
+void launch_end_search(const Tree &t, cudaStream_t s) { end_search_kernel<<<blocks(t.G, 128), 128, 0, s>>>(t); count_launch(); }
+void launch_root_stats(const Tree &t, int32_t *n_children, int32_t *counts, float *q, int32_t *root_n, cudaStream_t s) {
+    root_stats_kernel<<<blocks((size_t)t.G * 32, 128), 128, 0, s>>>(t, n_children, counts, q, root_n); count_launch();
+}
+void launch_choose(const Tree &t, int32_t *actions, cudaStream_t s) { choose_kernel<<<blocks(t.G, 128), 128, 0, s>>>(t, actions); count_launch(); }
+void launch_record(const Tree &t, const int32_t *actions, PlyRecordDev *records, int max_plies, cudaStream_t s) {
+    record_kernel<<<blocks(t.G, 128), 128, 0, s>>>(t, actions, records, max_plies); count_launch();
+}
+void launch_apply(const Tree &t, const int32_t *actions, int32_t *unfinished, cudaStream_t s) {
+    apply_kernel<<<blocks(t.G, 4), 128, 0, s>>>(t, actions, unfinished); count_launch();
+}
+void launch_self_play_data(const Tree &t, int game, float *features, float *policy, cudaStream_t s) {
+    self_play_data_kernel<<<1, 256, 0, s>>>(t, game, features, policy); count_launch();
+}
+void launch_eval_synth(const float *features, int planes, size_t n, float *policy, float *value, cudaStream_t s) {
+    eval_synth_kernel<<<blocks(n * 32, 128), 128, 0, s>>>(features, planes, n, policy, value); count_launch();
+}
+void launch_eval_hash(const float *features, int planes, size_t n, float *policy, float *value, cudaStream_t s) {
+    eval_hash_kernel<<<blocks(n * 32, 128), 128, 0, s>>>(features, planes, n, policy, value); count_launch();
+}
+void launch_training_samples(const Tree &t, const PlyRecordDev *records, const int32_t *plies, const int64_t *sample_base,
+                             int max_plies, float *features, float *policy, float *value, cudaStream_t s) {
+    training_samples_kernel<<<(unsigned)((size_t)t.G * max_plies), 256, 0, s>>>(records, plies, sample_base, t.r_p1, t.r_p2, t.G,
+                                                                              max_plies, t.H, features, policy, value);
+    count_launch();
+}
+
+__global__ void copy_arenas_kernel(Tree a, Tree b) {
+    const int g = blockIdx.x;
+    const int which = a.g_which[g], n = a.g_count[g];
+    const size_t src = ((size_t)g * 2 + which) * a.cap, dst = ((size_t)g * 2 + which) * b.cap;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        b.n_p1[dst + i] = a.n_p1[src + i]; b.n_p2[dst + i] = a.n_p2[src + i]; b.n_meta[dst + i] = a.n_meta[src + i];
+        b.n_parent[dst + i] = a.n_parent[src + i]; b.n_child[dst + i] = a.n_child[src + i]; b.n_N[dst + i] = a.n_N[src + i];
+        b.n_W[dst + i] = a.n_W[src + i]; b.n_Q[dst + i] = a.n_Q[src + i]; b.n_P[dst + i] = a.n_P[src + i];
+    }
+}
+void launch_copy_arenas(const Tree &from, const Tree &to, cudaStream_t s) {
+    copy_arenas_kernel<<<from.G, 256, 0, s>>>(from, to); count_launch();
+}
+
+}  // namespace oz

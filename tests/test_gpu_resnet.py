@@ -1,0 +1,127 @@
+"""GPU: the native ResNet evaluator (tcgen05 implicit-GEMM convolutions + fused heads) against a plain
+PyTorch fp32 reference of the same network.  Floating point, so a stated tolerance instead of bit
+equality:
+  * one conv layer (bf16 operands, fp32 accumulate, bf16 output): |d| <= 2^-7 * |ref| + 2e-2
+  * whole 128x10b network vs fp32 torch: policy max |dp| <= 2e-2, value max |dv| <= 5e-2
+  * the search built on it: same argmax action as the fp32 network in the large majority of roots
+"""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _bf16_bits(t: torch.Tensor) -> np.ndarray:
+    return t.to(torch.bfloat16).contiguous().view(torch.int16).numpy().view(np.uint16)
+
+
+def _from_bits(a: np.ndarray) -> torch.Tensor:
+    return torch.from_numpy(a.view(np.int16).copy()).view(torch.bfloat16).to(torch.float32)
+
+
+@pytest.mark.parametrize("cin,cout,boards,skip,relu", [
+    (32, 128, 16, False, True),      # first layer shape (planes padded to 32), one unit
+    (128, 128, 16, True, True),      # residual layer, one unit
+    (128, 128, 50, True, True),      # ragged board count (padded to 64 inside), several passes per CTA
+    (128, 128, 16 * 160, False, False),   # more passes than SMs: persistent loop + barrier phase wrap
+    (256, 256, 32, True, True),      # 256-channel tower: two cout tiles, 8 K blocks
+])
+def test_conv3x3_vs_torch(cin, cout, boards, skip, relu):
+    from othello_mcts import _lib
+    lib = _lib.load()
+    g = torch.Generator().manual_seed(cin * 1000 + boards)
+    x = torch.randn(boards, 8, 8, cin, generator=g).to(torch.bfloat16).to(torch.float32)       # NHWC
+    w = (torch.randn(cout, cin, 3, 3, generator=g) / (3.0 * cin ** 0.5)).to(torch.bfloat16).to(torch.float32)
+    bias = torch.randn(cout, generator=g) * 0.1
+    sk = torch.randn(boards, 8, 8, cout, generator=g).to(torch.bfloat16).to(torch.float32) if skip else None
+    ref = torch.nn.functional.conv2d(x.permute(0, 3, 1, 2), w, bias, padding=1).permute(0, 2, 3, 1)
+    if skip:
+        ref = ref + sk
+    if relu:
+        ref = torch.relu(ref)
+    w_taps = w.permute(2, 3, 0, 1).reshape(9, cout, cin)
+    xin, win = _bf16_bits(x), _bf16_bits(w_taps)
+    skb = _bf16_bits(sk) if skip else None
+    out = np.zeros((boards, 8, 8, cout), np.uint16)
+    b32 = bias.numpy().astype(np.float32)
+    ms = C.c_double()
+    _lib.check(lib.oz_debug_conv3x3(xin.ctypes.data_as(C.c_void_p), cin, win.ctypes.data_as(C.c_void_p),
+                                    b32.ctypes.data_as(C.c_void_p), skb.ctypes.data_as(C.c_void_p) if skip else None,
+                                    int(relu), out.ctypes.data_as(C.c_void_p), cout, boards, C.byref(ms)))
+    got = _from_bits(out)
+    err = (got - ref).abs()
+    tol = ref.abs() * 2.0 ** -7 + 2e-2
+    bad = int((err > tol).sum())
+    assert bad == 0, f"{bad} of {err.numel()} outside tolerance, max err {err.max():.4f}, kernel {ms.value:.3f} ms"
+
+
+def _net(blocks=9, channels=128, planes=17, hidden=128, seed=0):
+    from othello_mcts.neural_net import AlphaZeroNet, randomize_batchnorm
+    torch.manual_seed(seed)
+    net = AlphaZeroNet(planes, conv_channels=channels, num_residual_blocks=blocks, value_head_hidden_channels=hidden).eval()
+    randomize_batchnorm(net, seed + 1)
+    return net
+
+
+def _random_feature_planes(n, planes, seed):
+    """0/1 planes shaped like real inputs (side-to-move plane + disc planes)."""
+    g = torch.Generator().manual_seed(seed)
+    x = (torch.rand(n, planes, 8, 8, generator=g) < 0.3).to(torch.float32)
+    x[:, 0] = (torch.rand(n, 1, 1, generator=g) < 0.5).to(torch.float32)
+    return x
+
+
+@pytest.mark.parametrize("blocks,channels,planes,hidden,n", [
+    (1, 128, 9, 32, 40),
+    (9, 128, 17, 128, 300),        # 128x10b, the benchmark network
+    (2, 256, 17, 256, 48),         # 256-channel variant
+])
+def test_resnet_forward_vs_torch_fp32(blocks, channels, planes, hidden, n):
+    from othello_mcts import _lib, weights
+    lib = _lib.load()
+    net = _net(blocks, channels, planes, hidden)
+    x = _random_feature_planes(n, planes, 5)
+    with torch.no_grad():
+        ref = net(x)
+    shape, blob = weights.fold_alphazero_net(net)
+    h = C.c_void_p()
+    _lib.check(lib.oz_resnet_create(0, C.byref(h)))
+    try:
+        _lib.check(lib.oz_resnet_load(h, C.byref(shape), blob, len(blob)))
+        pol = np.zeros((n, 65), np.float32)
+        val = np.zeros(n, np.float32)
+        xs = x.numpy()
+        _lib.check(lib.oz_resnet_forward(h, xs.ctypes.data_as(C.c_void_p), n, pol.ctypes.data_as(C.c_void_p),
+                                         val.ctypes.data_as(C.c_void_p)))
+    finally:
+        lib.oz_resnet_destroy(h)
+    dp = np.abs(pol - ref["policy"].numpy()).max()
+    dv = np.abs(val - ref["value"].numpy()).max()
+    assert np.allclose(pol.sum(axis=1), 1.0, atol=1e-4)
+    assert dp <= 2e-2 and dv <= 5e-2, f"policy max abs diff {dp:.4f}, value max abs diff {dv:.4f}"
+
+
+def test_search_with_native_network():
+    """MCTS.search(AlphaZeroNet) takes the native evaluator; its root statistics track a search driven
+    by the fp32 torch module through the callable path."""
+    from othello_mcts import MCTS
+    net = _net(2, 128, 9, 64).cuda()
+    kw = dict(history_size=4, torch_device="cuda", num_simulations=128, num_threads=1, batch_size=16,
+              dirichlet_epsilon=0.0, seed=3)
+    native, viaTorch = MCTS(**kw), MCTS(**kw)
+    agree = 0
+    for ply in range(8):
+        native.search(net)
+        viaTorch.search(lambda x: net(x))          # a plain callable: fp32 torch on the same GPU
+        a, b = np.array(native.visit_counts()), np.array(viaTorch.visit_counts())
+        assert a.sum() == b.sum()
+        agree += int(a.argmax() == b.argmax())
+        act = viaTorch.position().legal_actions()[int(b.argmax())]
+        native.apply_action(act)
+        viaTorch.apply_action(act)
+    assert agree >= 6
+    c = native.counters()
+    assert c["evaluations"] > 0

@@ -1,0 +1,204 @@
+"""GPU: the device search engine against the golden traces of the unmodified reference and against the
+oracle -- visit counts, Q bit patterns, chosen actions, self-play data: all bit-exact."""
+import numpy as np
+import pytest
+
+from helpers import f32_bits
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("game", range(4))
+def test_mcts_matches_reference_golden(golden, game):
+    """The reference's own results (deterministic regime) reproduced by the CUDA engine through the
+    MCTS drop-in class with the built-in exact net."""
+    from othello_mcts import MCTS
+    g = golden["search"][game]
+    m = MCTS(history_size=g["H"], torch_device="cuda", num_simulations=g["N"], num_threads=g["T"],
+             batch_size=g["B"], dirichlet_epsilon=0.0, seed=5, game_id=game)
+    for i, ply in enumerate(g["plies"]):
+        m.search("synth")
+        assert m.visit_counts() == ply["visit_counts"], i
+        assert [f32_bits(v) for v in m.mean_action_values()] == ply["q_bits"], i
+        spd = m.self_play_data()
+        for k, t in enumerate((0, 3)):
+            assert [f32_bits(v) for v in spd["policy"][t].tolist()] == ply["policy_bits_t0_t3"][k], (i, t)
+        m.apply_action(ply["action"])
+    if len(g["plies"]) > 10:
+        p = m.position()
+        assert [p.player(), p.player1_discs(), p.player2_discs()] == g["final"]
+        assert p.is_terminal()
+
+
+def test_callable_evaluator_path_matches_golden(golden):
+    """The reference's evaluator contract: a Python callable fed device tensors (othello_mcts.cpp:36-45)."""
+    import torch
+    from othello_mcts import MCTS
+
+    def net(x):
+        assert x.is_cuda and x.dtype == torch.float32 and x.shape[1:] == (9, 8, 8)
+        occ = x[:, 1] + x[:, 2]
+        box = torch.nn.functional.conv2d(occ[:, None], torch.ones(1, 1, 3, 3, device=x.device), padding=1)[:, 0]
+        w = torch.cat([1.0 + box.flatten(1), torch.ones(x.shape[0], 1, device=x.device)], dim=1)
+        value = (1.0 - 2.0 * x[:, 0, 0, 0]) * (x[:, 1].sum(dim=(1, 2)) - x[:, 2].sum(dim=(1, 2))) / 64.0
+        return {"policy": w / w.sum(dim=1, keepdim=True), "value": value}
+
+    g = golden["search"][0]
+    m = MCTS(history_size=g["H"], torch_device="cuda", num_simulations=g["N"], num_threads=1, batch_size=g["B"],
+             dirichlet_epsilon=0.0)
+    for ply in g["plies"][:12]:
+        m.search(net)
+        assert m.visit_counts() == ply["visit_counts"]
+        assert [f32_bits(v) for v in m.mean_action_values()] == ply["q_bits"]
+        m.apply_action(ply["action"])
+
+
+@pytest.mark.parametrize("cfg", [
+    dict(H=8, N=800, T=2, B=16, eps=0.25, ev="hash"),     # the reference's default search shape
+    dict(H=4, N=96, T=1, B=8, eps=0.25, ev="hash"),
+    dict(H=1, N=130, T=3, B=7, eps=1.0, ev="synth"),      # pure-noise priors, odd batch
+    dict(H=2, N=64, T=1, B=1, eps=0.0, ev="hash"),
+])
+def test_noisy_search_vs_oracle(oracle, cfg):
+    """Dirichlet noise (injected draws), random symmetries (shared Philox streams) and a
+    non-equivariant pseudo-random net: whole games, every ply compared bit for bit."""
+    from othello_mcts import MCTS
+    table = np.random.default_rng(3).gamma(0.5, 1.0, 4099).astype(np.float32)
+    table[::97] = 0.0
+    ev = {"hash": oracle.EVAL_HASH, "synth": oracle.EVAL_SYNTH}[cfg["ev"]]
+    seed, gid = 0xC0FFEE1234, 17
+    o = oracle.OracleMCTS(history_size=cfg["H"], num_simulations=cfg["N"], num_threads=cfg["T"], batch_size=cfg["B"],
+                          dirichlet_epsilon=cfg["eps"], evaluator=ev, seed=seed, game_id=gid, gamma_table=table)
+    m = MCTS(history_size=cfg["H"], torch_device="cuda", num_simulations=cfg["N"], num_threads=cfg["T"],
+             batch_size=cfg["B"], dirichlet_epsilon=cfg["eps"], seed=seed, game_id=gid)
+    m.set_gamma_table(table)
+    max_plies = 70 if cfg["N"] < 500 else 14
+    for ply in range(max_plies):
+        if m.position().is_terminal():
+            break
+        o.search()
+        m.search(cfg["ev"])
+        assert m.visit_counts() == o.visit_counts(), ply
+        assert [f32_bits(v) for v in m.mean_action_values()] == [f32_bits(v) for v in o.mean_action_values()], ply
+        if ply % 5 == 0:
+            f, p = o.self_play_data()
+            spd = m.self_play_data()
+            assert all((spd["features"][t].numpy() == f[t]).all() for t in range(8))
+            assert all((spd["policy"][t].numpy() == p[t]).all() for t in range(8))
+        a = o.choose_action(ply, 12)
+        o.apply_action(a)
+        m.apply_action(a)
+        op = o.position()
+        mp = m.position()
+        assert (mp.player(), mp.player1_discs(), mp.player2_discs(), mp.legal_moves()) == (op.player, op.p1, op.p2, op.legal)
+
+
+def test_lockstep_games_vs_oracle(oracle):
+    """Many games in lockstep on the device, each compared with its own oracle instance, including
+    the on-device action choice, the compact records and the training tensors."""
+    from othello_mcts import SelfPlayEngine
+    G, H, N, T, B = 24, 4, 48, 2, 4
+    seed, first = 77, 1000
+    table = np.random.default_rng(9).gamma(0.5, 1.0, 1021).astype(np.float32)
+    e = SelfPlayEngine(G, history_size=H, num_simulations=N, num_threads=T, batch_size=B, dirichlet_epsilon=0.25,
+                       seed=seed, first_game_id=first, temperature_plies=6)
+    e.set_gamma_table(table)
+    e.prepare("hash")
+    os_ = [oracle.OracleMCTS(history_size=H, num_simulations=N, num_threads=T, batch_size=B, dirichlet_epsilon=0.25,
+                             evaluator=oracle.EVAL_HASH, seed=seed, game_id=first + g, gamma_table=table) for g in range(G)]
+    done = [False] * G
+    samples = [([], []) for _ in range(G)]
+    for ply in range(130):
+        want_actions = np.full(G, -1, np.int32)
+        want_counts = np.zeros((G, 36), np.int32)
+        for g, o in enumerate(os_):
+            if done[g]:
+                continue
+            o.search()
+            vc = o.visit_counts()
+            want_counts[g, : len(vc)] = vc
+            want_actions[g] = o.choose_action(ply, 6)
+            f, p = o.self_play_data()
+            samples[g][0].append(f)
+            samples[g][1].append(p)
+        actions, counts, unfinished = e.play_ply(want_counts=True)
+        live = [g for g in range(G) if not done[g]]
+        assert (counts[live] == want_counts[live]).all(), ply
+        assert (actions == want_actions).all(), ply
+        for g in live:
+            os_[g].apply_action(int(want_actions[g]))
+            done[g] = os_[g].position().player == 0
+        assert unfinished == G - sum(done)
+        if unfinished == 0:
+            break
+    assert all(done)
+    pos = e.positions()
+    for g, o in enumerate(os_):
+        op = o.position()
+        assert (pos[g].player(), pos[g].player1_discs(), pos[g].player2_discs()) == (0, op.p1, op.p2)
+    rec = e.records()
+    ts = e.training_samples()
+    row = 0
+    for g, o in enumerate(os_):
+        n = int(rec["plies"][g])
+        assert n == len(samples[g][0])
+        op = o.position()
+        d = bin(op.p1).count("1") - bin(op.p2).count("1")
+        z = 1.0 if d > 0 else (-1.0 if d < 0 else 0.0)
+        for k in range(n):
+            assert (ts["features"][row: row + 8].numpy() == samples[g][0][k]).all(), (g, k)
+            assert (ts["policies"][row: row + 8].numpy() == samples[g][1][k]).all(), (g, k)
+            assert (ts["values"][row: row + 8].numpy() == (z if k % 2 == 0 else -z)).all()
+            row += 8
+    assert row == len(ts["values"])
+    c = e.counters()
+    assert c["games_finished"] == G and c["simulations"] > 0 and c["kernel_launches"] > 0
+
+
+def test_partition_invariance():
+    """Results are keyed by game id, not by where a game runs: 16 games in one engine equal the
+    same games split over two engines (the multi-GPU partition of SURVEY.md section 8e)."""
+    from othello_mcts import SelfPlayEngine
+    kw = dict(history_size=2, num_simulations=32, num_threads=1, batch_size=8, seed=5, temperature_plies=4)
+    whole = SelfPlayEngine(16, first_game_id=0, **kw)
+    a, b = SelfPlayEngine(8, first_game_id=0, **kw), SelfPlayEngine(8, first_game_id=8, **kw)
+    for e in (whole, a, b):
+        e.prepare("hash")
+    for _ in range(10):
+        w, _, _ = whole.play_ply()
+        x, _, _ = a.play_ply()
+        y, _, _ = b.play_ply()
+        assert (w == np.concatenate([x, y])).all()
+
+
+def test_tree_reuse_setters_and_errors(oracle):
+    from othello_mcts import MCTS
+    m = MCTS(history_size=4, torch_device="cuda", num_simulations=100, num_threads=1, batch_size=16, dirichlet_epsilon=0.0)
+    o = oracle.OracleMCTS(history_size=4, num_simulations=100, num_threads=1, batch_size=16, dirichlet_epsilon=0.0)
+    assert m.visit_counts() == [] and m.mean_action_values() == []
+    with pytest.raises(ValueError, match="The root node has not been expanded yet."):
+        m.self_play_data()
+    m.apply_action(19)                 # apply on an unexpanded root (mcts.cpp:140-148)
+    o.apply_action(19)
+    m.search("synth"); o.search()
+    assert m.visit_counts() == o.visit_counts()
+    assert sum(m.visit_counts()) == 112 - 16          # Q1: the first batch only expands the root
+    with pytest.raises(ValueError, match=r"^0 is not a legal action\.$"):
+        m.apply_action(0)
+    with pytest.raises(IndexError, match=r"Expected 0 <= action < 65, but got 70\."):
+        m.apply_action(70)
+    with pytest.raises(ValueError, match="Pass is not allowed when there are legal moves."):
+        m.apply_action(64)
+    # setters between searches keep the tree (reference: plain member updates)
+    m.set_num_simulations(40); o2 = 40
+    m.set_batch_size(4)
+    assert (m.num_simulations(), m.batch_size(), m.num_threads()) == (40, 4, 1)
+    with pytest.raises(ValueError, match=r"Expected batch_size >= 1, but got 0\."):
+        m.set_batch_size(0)
+    a = m.position().legal_actions()[int(np.argmax(m.visit_counts()))]
+    before = m.visit_counts()[int(np.argmax(m.visit_counts()))]
+    m.apply_action(a)
+    m.search("synth")
+    assert sum(m.visit_counts()) >= before - 1          # Q2: the subtree and its counts survive re-rooting
+    m.reset_position()
+    assert m.position().legal_actions() == [19, 26, 37, 44] and m.visit_counts() == []
