@@ -457,12 +457,17 @@ int oz_debug_conv3x3(const uint16_t *in, int cin, const uint16_t *w, const float
 // ---- search ----
 int oz_engine_rounds(const oz_engine *e) { return rounds_of(e->cfg); }
 
-int oz_engine_search_begin(oz_engine *e) { OZ_TRY(set_device(e)); return begin_search(e); }
+int oz_engine_search_begin(oz_engine *e) {
+    OZ_TRY(set_device(e));
+    OZ_TRY(begin_search(e));
+    OZ_CUDA(cudaStreamSynchronize(e->stream));   // the caller's stream takes over from here
+    return OZ_OK;
+}
 
 int oz_engine_select_device(oz_engine *e, float *features, void *stream) {
     if (!e->in_search) return fail(OZ_ERR_STATE, "search_begin not called");
     OZ_TRY(set_device(e));
-    cudaStream_t s = stream ? (cudaStream_t)stream : e->stream;
+    cudaStream_t s = (cudaStream_t)stream;    // NULL is the legacy default stream, as in the CUDA runtime
     launch_select(e->t, e->round, s);
     launch_encode(e->t, e->round, features ? features : e->d_features, s);
     OZ_CUDA(cudaGetLastError());
@@ -472,7 +477,7 @@ int oz_engine_select_device(oz_engine *e, float *features, void *stream) {
 int oz_engine_expand_device(oz_engine *e, const float *policy, const float *value, void *stream) {
     if (!e->in_search) return fail(OZ_ERR_STATE, "search_begin not called");
     OZ_TRY(set_device(e));
-    cudaStream_t s = stream ? (cudaStream_t)stream : e->stream;
+    cudaStream_t s = (cudaStream_t)stream;
     launch_expand(e->t, policy, value, s);
     e->round += 1;
     e->ctr.evaluations += (uint64_t)e->t.G * e->t.inflight;

@@ -7,8 +7,8 @@
 // Bit 63 is square a1 (action 0); action i <-> bit (63 - i)  (position.h:275).
 //
 // The reference walks every direction with a 6-step "dumb" fill.  Here each ray is a
-// 3-step Kogge-Stone parallel-prefix fill (1+2+4 squares >= the 6-square maximum run
-// on an 8x8 board), which gives the same masks bit for bit with half the dependent ops.
+// 4-step prefix-doubling fill (runs of 1, 2, 4, 6 squares: 6 is the longest run a masked
+// ray can hold), which gives the same masks bit for bit for every input.
 #pragma once
 #include <stdint.h>
 
@@ -36,26 +36,29 @@ struct Position {
     uint64_t next_legal;  // legal moves of the other side when `legal` is empty
 };
 
-// Occluded fill of `gen` through `pro` towards higher bits (left shift by S).
+// Run of `o` squares that starts next to a `gen` square and continues towards higher bits
+// (left shift by S): the reference's 6-step fill (position.h:186-196) as a prefix doubling
+// 1, 2, 4, 6.  The generator squares themselves are never part of the result, so the two
+// agree for every input, including overlapping or otherwise unreachable disc sets.
 template <int S>
-OZ_HD uint64_t fill_up(uint64_t gen, uint64_t pro) {
-    gen |= pro & (gen << S);
-    pro &= pro << S;
-    gen |= pro & (gen << (2 * S));
-    pro &= pro << (2 * S);
-    gen |= pro & (gen << (4 * S));
-    return gen;
+OZ_HD uint64_t run_up(uint64_t gen, uint64_t o) {
+    uint64_t f = o & (gen << S);
+    f |= o & (f << S);
+    const uint64_t pairs = o & (o << S);
+    f |= pairs & (f << (2 * S));
+    f |= pairs & (f << (2 * S));
+    return f;
 }
 
 // Same towards lower bits (right shift by S).
 template <int S>
-OZ_HD uint64_t fill_down(uint64_t gen, uint64_t pro) {
-    gen |= pro & (gen >> S);
-    pro &= pro >> S;
-    gen |= pro & (gen >> (2 * S));
-    pro &= pro >> (2 * S);
-    gen |= pro & (gen >> (4 * S));
-    return gen;
+OZ_HD uint64_t run_down(uint64_t gen, uint64_t o) {
+    uint64_t f = o & (gen >> S);
+    f |= o & (f >> S);
+    const uint64_t pairs = o & (o >> S);
+    f |= pairs & (f >> (2 * S));
+    f |= pairs & (f >> (2 * S));
+    return f;
 }
 
 OZ_HD uint64_t legal_moves(uint64_t player, uint64_t opp) {
@@ -63,14 +66,14 @@ OZ_HD uint64_t legal_moves(uint64_t player, uint64_t opp) {
     const uint64_t ov = opp & kNoTopBottom;   // rays along a file
     const uint64_t od = opp & kNoEdges;       // diagonal rays
     uint64_t m = 0;
-    m |= (fill_up<1>(player, oh) & oh) << 1;
-    m |= (fill_down<1>(player, oh) & oh) >> 1;
-    m |= (fill_up<8>(player, ov) & ov) << 8;
-    m |= (fill_down<8>(player, ov) & ov) >> 8;
-    m |= (fill_up<7>(player, od) & od) << 7;
-    m |= (fill_down<7>(player, od) & od) >> 7;
-    m |= (fill_up<9>(player, od) & od) << 9;
-    m |= (fill_down<9>(player, od) & od) >> 9;
+    m |= run_up<1>(player, oh) << 1;
+    m |= run_down<1>(player, oh) >> 1;
+    m |= run_up<8>(player, ov) << 8;
+    m |= run_down<8>(player, ov) >> 8;
+    m |= run_up<7>(player, od) << 7;
+    m |= run_down<7>(player, od) >> 7;
+    m |= run_up<9>(player, od) << 9;
+    m |= run_down<9>(player, od) >> 9;
     return m & ~(player | opp);
 }
 
@@ -80,14 +83,14 @@ OZ_HD uint64_t flips(uint64_t move, uint64_t player, uint64_t opp) {
     const uint64_t od = opp & kNoEdges;
     uint64_t f = 0, r;
     // A ray counts only when the square after the run holds one of the mover's discs.
-    r = fill_up<1>(move, oh) & oh;   f |= ((r << 1) & player) ? r : 0;
-    r = fill_down<1>(move, oh) & oh; f |= ((r >> 1) & player) ? r : 0;
-    r = fill_up<8>(move, ov) & ov;   f |= ((r << 8) & player) ? r : 0;
-    r = fill_down<8>(move, ov) & ov; f |= ((r >> 8) & player) ? r : 0;
-    r = fill_up<7>(move, od) & od;   f |= ((r << 7) & player) ? r : 0;
-    r = fill_down<7>(move, od) & od; f |= ((r >> 7) & player) ? r : 0;
-    r = fill_up<9>(move, od) & od;   f |= ((r << 9) & player) ? r : 0;
-    r = fill_down<9>(move, od) & od; f |= ((r >> 9) & player) ? r : 0;
+    r = run_up<1>(move, oh);   f |= ((r << 1) & player) ? r : 0;
+    r = run_down<1>(move, oh); f |= ((r >> 1) & player) ? r : 0;
+    r = run_up<8>(move, ov);   f |= ((r << 8) & player) ? r : 0;
+    r = run_down<8>(move, ov); f |= ((r >> 8) & player) ? r : 0;
+    r = run_up<7>(move, od);   f |= ((r << 7) & player) ? r : 0;
+    r = run_down<7>(move, od); f |= ((r >> 7) & player) ? r : 0;
+    r = run_up<9>(move, od);   f |= ((r << 9) & player) ? r : 0;
+    r = run_down<9>(move, od); f |= ((r >> 9) & player) ? r : 0;
     return f;
 }
 

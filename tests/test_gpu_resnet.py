@@ -105,23 +105,40 @@ def test_resnet_forward_vs_torch_fp32(blocks, channels, planes, hidden, n):
 
 
 def test_search_with_native_network():
-    """MCTS.search(AlphaZeroNet) takes the native evaluator; its root statistics track a search driven
-    by the fp32 torch module through the callable path."""
-    from othello_mcts import MCTS
+    """MCTS.search(AlphaZeroNet) takes the fused native path (tree kernels + in-engine evaluator).  Driving
+    the same search through the callable contract, with the callable running the SAME folded network via
+    the stand-alone oz_resnet handle, must give identical trees: the two paths differ only in plumbing."""
+    from othello_mcts import MCTS, _lib, weights
+    lib = _lib.load()
     net = _net(2, 128, 9, 64).cuda()
+    shape, blob = weights.fold_alphazero_net(net)
+    h = C.c_void_p()
+    _lib.check(lib.oz_resnet_create(0, C.byref(h)))
+    _lib.check(lib.oz_resnet_load(h, C.byref(shape), blob, len(blob)))
+
+    def via_handle(x):
+        n = x.shape[0]
+        pol = torch.empty((n, 65), device="cuda", dtype=torch.float32)
+        val = torch.empty((n,), device="cuda", dtype=torch.float32)
+        stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+        _lib.check(lib.oz_resnet_forward_device(h, C.c_void_p(x.data_ptr()), n, C.c_void_p(pol.data_ptr()),
+                                                C.c_void_p(val.data_ptr()), stream))
+        return {"policy": pol, "value": val}
+
     kw = dict(history_size=4, torch_device="cuda", num_simulations=128, num_threads=1, batch_size=16,
-              dirichlet_epsilon=0.0, seed=3)
-    native, viaTorch = MCTS(**kw), MCTS(**kw)
-    agree = 0
-    for ply in range(8):
-        native.search(net)
-        viaTorch.search(lambda x: net(x))          # a plain callable: fp32 torch on the same GPU
-        a, b = np.array(native.visit_counts()), np.array(viaTorch.visit_counts())
-        assert a.sum() == b.sum()
-        agree += int(a.argmax() == b.argmax())
-        act = viaTorch.position().legal_actions()[int(b.argmax())]
-        native.apply_action(act)
-        viaTorch.apply_action(act)
-    assert agree >= 6
-    c = native.counters()
-    assert c["evaluations"] > 0
+              dirichlet_epsilon=0.25, seed=3)
+    native, callable_path = MCTS(**kw), MCTS(**kw)
+    try:
+        for ply in range(10):
+            native.search(net)
+            callable_path.search(via_handle)
+            assert native.visit_counts() == callable_path.visit_counts(), ply
+            assert native.mean_action_values() == callable_path.mean_action_values(), ply
+            if ply == 0:
+                assert sum(native.visit_counts()) == 128 - 16
+            act = native.position().legal_actions()[int(np.argmax(native.visit_counts()))]
+            native.apply_action(act)
+            callable_path.apply_action(act)
+    finally:
+        lib.oz_resnet_destroy(h)
+    assert native.counters()["evaluations"] > 0
