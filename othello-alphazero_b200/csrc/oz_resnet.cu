@@ -19,6 +19,8 @@
 #include <cuda_bf16.h>
 
 #include <cmath>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 
@@ -298,6 +300,267 @@ conv3x3_kernel(const __grid_constant__ CUtensorMap map_act, const __grid_constan
     }
 }
 
+// ------------------------------------------------------------------ CTA-pair kernel (cta_group::2)
+// conv3x3_pair_kernel: the same implicit GEMM issued for a CTA PAIR (cluster of 2, one TPC):
+//   * D[M = 256 (128 rows per CTA), N = 128 couts] += A * B^T with tcgen05.mma.cta_group::2.  Each CTA
+//     stages its own 128-row activation tiles and only HALF of the weight tile (64 couts); the pair's
+//     tensor cores read B from both shared memories, so per-SM shared-memory traffic per MMA drops from
+//     8 KB (128 B/clk, the cta_group::1 ceiling) to 6 KB.
+//   * Weights stay resident: for C = 128 a CTA's half of a layer is 9 taps x 4 K blocks x 4 KB = 144 KB,
+//     loaded once per launch.  Wider towers stream the same 4 KB tiles through the 36 slots as a ring.
+//   * A pass is 16 boards x 2 board rows (2 accumulator tiles of 128 columns); TMEM holds two passes,
+//     so the epilogue of pass p overlaps the MMAs of pass p + 1.
+//   * Eight epilogue warps (TMEM lane quarter x column half); the residual input is prefetched into
+//     registers before the accumulators are ready.
+namespace pair {
+constexpr int kYPerPass = 2;
+constexpr int kBoxYp = kYPerPass + 2;
+constexpr int kActBoxBytesP = kBoxX * kBoxYp * kSlotBytes;          // 36864
+constexpr int kActStageBytesP = kSlotBytes + kActBoxBytesP;         // guard slot in front
+constexpr int kActStagesP = 2;
+constexpr int kWTileBytes = 64 * kRowBytes;                         // 64 couts x 32 cin = 4096
+constexpr int kWSlots = 36;
+constexpr int kEpiWarps = 8;
+constexpr int kThreadsP = (3 + kEpiWarps) * 32;
+constexpr int kMiscBytes = 4096;
+constexpr int kSmemBytesP = 1024 + kActStagesP * kActStageBytesP + kWSlots * kWTileBytes + kMiscBytes;
+static_assert(kSmemBytesP <= 232448, "shared memory budget");
+// kind::f16 instruction descriptor: bf16 x bf16 -> f32, K-major operands, M = 256 (pair), N = 128.
+constexpr uint32_t kIdescP = (1u << 4) | (1u << 7) | (1u << 10) | ((128u >> 3) << 17) | ((256u >> 4) << 24);
+}  // namespace pair
+
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ uint32_t mapa_rank(uint32_t addr, uint32_t rank) {
+    uint32_t r; asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank)); return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// Bounded wait: a lost arrival traps (and fails the launch) instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait_b(uint32_t bar, uint32_t parity) {
+    uint32_t done;
+    long long t0 = 0;
+    for (uint32_t spins = 0;; ++spins) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+        if (done) return;
+        if ((spins & 1023u) == 1023u) {
+            const long long now = clock64();
+            if (t0 == 0) t0 = now;
+            else if (now - t0 > 8000000000ll) { printf("conv3x3_pair_kernel: barrier timeout (block %d thread %d bar %u)\n", (int)blockIdx.x, (int)threadIdx.x, bar); __trap(); }
+        }
+    }
+}
+__device__ __forceinline__ void tma_load_4d_pair(uint32_t dst, const CUtensorMap *map, uint32_t bar_cluster, int c0, int c1, int c2, int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+        ::"r"(dst), "l"(map), "r"(bar_cluster), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap *map, uint32_t bar_cluster, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(dst), "l"(map), "r"(bar_cluster), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tc_commit_pair(uint32_t bar) {   // arrives on the same barrier offset in both CTAs
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(bar), "h"((uint16_t)3) : "memory");
+}
+__device__ __forceinline__ void tc_mma_pair(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(pair::kThreadsP, 1)
+conv3x3_pair_kernel(const __grid_constant__ CUtensorMap map_act, const __grid_constant__ CUtensorMap map_w, const ConvParams p) {
+    using namespace pair;
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t *gen = smem_raw + (base - smem_u32(smem_raw));
+    const uint32_t act0 = base;
+    const uint32_t w0 = act0 + kActStagesP * kActStageBytesP;
+    const uint32_t misc = w0 + kWSlots * kWTileBytes;
+    const uint32_t bar_act_full = misc, bar_act_empty = misc + 16;          // [2] each
+    const uint32_t bar_tmem_full = misc + 32, bar_tmem_empty = misc + 48;    // [2] each
+    const uint32_t bar_w_full = misc + 64, bar_w_empty = misc + 64 + 8 * kWSlots;
+    uint32_t *tmem_ptr = (uint32_t *)(gen + (misc - base) + 704);
+    float *s_bias = (float *)(gen + (misc - base) + 1024);                   // up to 384 floats
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const bool leader = rank == 0;
+    const int ntiles = p.cout_total >> 7;
+    const int num_pp = p.units * 2 * ntiles;                 // pair-passes: two spatial passes x one cout tile
+    const int cluster_id = blockIdx.x >> 1, num_clusters = gridDim.x >> 1;
+    const int wtiles = p.kblocks * 9;
+    const bool resident = ntiles == 1 && wtiles <= kWSlots;
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < kActStagesP; ++i) { mbar_init(bar_act_full + 8 * i, 1); mbar_init(bar_act_empty + 8 * i, 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(bar_tmem_full + 8 * i, 1); mbar_init(bar_tmem_empty + 8 * i, 2 * kEpiWarps); }
+        for (int i = 0; i < kWSlots; ++i) { mbar_init(bar_w_full + 8 * i, 1); mbar_init(bar_w_empty + 8 * i, 1); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_act) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w) : "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr)), "r"(kTmemCols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+    for (int i = threadIdx.x; i < kActStagesP * (kSlotBytes / 16); i += kThreadsP) {   // zero guard slots
+        const int s = i / (kSlotBytes / 16), o = i % (kSlotBytes / 16);
+        *(uint4 *)(gen + s * kActStageBytesP + o * 16) = make_uint4(0, 0, 0, 0);
+    }
+    for (int i = threadIdx.x; i < p.cout_total; i += kThreadsP) s_bias[i] = p.bias[i];
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    tc_fence_before();
+    cluster_sync_all();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr;
+
+    if (warp == 0) {
+        // ===== activation TMA producer (one per CTA; bytes complete on the LEADER's barrier) =====
+        if (lane == 0) {
+            uint32_t it = 0;
+            for (int pp = cluster_id; pp < num_pp; pp += num_clusters) {
+                const int sp = 2 * (pp / ntiles) + (int)rank, unit = sp >> 2, yp = sp & 3;
+                for (int kb = 0; kb < p.kblocks; ++kb, ++it) {
+                    const uint32_t s = it % kActStagesP, ph = (it / kActStagesP) & 1;
+                    mbar_wait_b(bar_act_empty + 8 * s, ph ^ 1);
+                    if (leader) mbar_expect_tx(bar_act_full + 8 * s, 2 * kActBoxBytesP);
+                    tma_load_4d_pair(act0 + s * kActStageBytesP + kSlotBytes, &map_act, mapa_rank(bar_act_full + 8 * s, 0),
+                                     kb * kKBlock, unit * kBoardsPerUnit, 0, yp * kYPerPass - 1);
+                }
+            }
+        }
+        __syncwarp();
+    } else if (warp == 2) {
+        // ===== weight TMA producer: this CTA's 64-cout half of every (K block, tap) tile =====
+        if (lane == 0) {
+            uint32_t wit = 0;
+            for (int pp = cluster_id; pp < num_pp; pp += num_clusters) {
+                if (resident && wit >= (uint32_t)wtiles) break;
+                const int nt = pp % ntiles;
+                for (int kb = 0; kb < p.kblocks; ++kb)
+                    for (int tap = 0; tap < 9; ++tap, ++wit) {
+                        const uint32_t s = wit % kWSlots, ph = (wit / kWSlots) & 1;
+                        mbar_wait_b(bar_w_empty + 8 * s, ph ^ 1);
+                        if (leader) mbar_expect_tx(bar_w_full + 8 * s, 2 * kWTileBytes);
+                        tma_load_2d_pair(w0 + s * kWTileBytes, &map_w, mapa_rank(bar_w_full + 8 * s, 0),
+                                         kb * kKBlock, tap * p.cout_total + nt * 128 + (int)rank * 64);
+                    }
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        // ===== MMA issuer: one thread of the leader CTA drives both tensor cores =====
+        if (leader && lane == 0) {
+            uint32_t ait = 0, wit = 0, np = 0;
+            for (int pp = cluster_id; pp < num_pp; pp += num_clusters, ++np) {
+                const uint32_t acc = np & 1;
+                mbar_wait_b(bar_tmem_empty + 8 * acc, ((np >> 1) & 1) ^ 1);      // both CTAs drained this accumulator
+                tc_fence_after();
+                for (int kb = 0; kb < p.kblocks; ++kb, ++ait) {
+                    const uint32_t as = ait % kActStagesP;
+                    mbar_wait_b(bar_act_full + 8 * as, (ait / kActStagesP) & 1);
+                    tc_fence_after();
+                    const uint32_t abox = act0 + as * kActStageBytesP + kSlotBytes;
+                    for (int tap = 0; tap < 9; ++tap, ++wit) {
+                        const uint32_t ws = wit % kWSlots;
+                        if (!resident || np == 0) {
+                            mbar_wait_b(bar_w_full + 8 * ws, (wit / kWSlots) & 1);
+                            tc_fence_after();
+                        }
+                        const int dy = tap / 3 - 1, dx = tap % 3 - 1;
+                        const uint32_t wbase = w0 + ws * kWTileBytes;
+#pragma unroll
+                        for (int r = 0; r < kYPerPass; ++r) {
+                            const uint32_t arow = abox + (uint32_t)(((r + 1 + dy) * kBoxX + dx) * kSlotBytes);
+#pragma unroll
+                            for (int j = 0; j < kKBlock / 16; ++j)
+                                tc_mma_pair(tmem_base + acc * 256 + r * 128, umma_desc_sw64(arow + j * 32), umma_desc_sw64(wbase + j * 32),
+                                            kIdescP, (kb | tap | j) != 0);
+                        }
+                        if (!resident) tc_commit_pair(bar_w_empty + 8 * ws);
+                    }
+                    tc_commit_pair(bar_act_empty + 8 * as);
+                }
+                tc_commit_pair(bar_tmem_full + 8 * acc);
+            }
+        }
+        __syncwarp();
+    } else {
+        // ===== epilogue warps 3..10: TMEM lane quarter (warp % 4) x column half =====
+        const int quad = warp & 3, half = (warp - 3) >> 2;
+        const int row = quad * 32 + lane, x = row >> 4, bl = row & 15;     // row in tile = x * 16 + board
+        const uint32_t empty_remote = mapa_rank(bar_tmem_empty, 0);
+        uint32_t np = 0;
+        for (int pp = cluster_id; pp < num_pp; pp += num_clusters, ++np) {
+            const int nt = pp % ntiles, sp = 2 * (pp / ntiles) + (int)rank, unit = sp >> 2, yp = sp & 3;
+            const uint32_t acc = np & 1;
+            const size_t board = (size_t)unit * kBoardsPerUnit + bl;
+            const size_t off0 = ((board * 8 + yp * kYPerPass) * 8 + x) * (size_t)p.cout_total + nt * 128 + half * 64;
+            const size_t ystride = (size_t)8 * p.cout_total;
+            uint4 sk[kYPerPass][8];
+            if (p.skip) {
+#pragma unroll
+                for (int r = 0; r < kYPerPass; ++r) {
+                    const uint4 *sp4 = (const uint4 *)(p.skip + off0 + r * ystride);
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) sk[r][i] = sp4[i];
+                }
+            }
+            mbar_wait_b(bar_tmem_full + 8 * acc, (np >> 1) & 1);
+            tc_fence_after();
+#pragma unroll
+            for (int r = 0; r < kYPerPass; ++r) {
+#pragma unroll
+                for (int ch = 0; ch < 2; ++ch) {
+                    uint32_t v[32];
+                    tc_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + acc * 256 + r * 128 + half * 64 + ch * 32, v);
+                    tc_wait_ld();
+                    const float *bs = s_bias + nt * 128 + half * 64 + ch * 32;
+                    uint4 o[4];
+                    uint32_t *ow = (uint32_t *)o;
+                    const uint32_t *skw = (const uint32_t *)&sk[r][ch * 4];
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        float a = __uint_as_float(v[2 * i]) + bs[2 * i];
+                        float b = __uint_as_float(v[2 * i + 1]) + bs[2 * i + 1];
+                        if (p.skip) {
+                            const __nv_bfloat162 s2 = *(const __nv_bfloat162 *)&skw[i];
+                            a += __bfloat162float(s2.x);
+                            b += __bfloat162float(s2.y);
+                        }
+                        if (p.relu) { a = fmaxf(a, 0.f); b = fmaxf(b, 0.f); }
+                        const __nv_bfloat162 o2 = __floats2bfloat162_rn(a, b);
+                        ow[i] = *(const uint32_t *)&o2;
+                    }
+                    uint4 *op = (uint4 *)(p.out + off0 + r * ystride + ch * 32);
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) op[i] = o[i];
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(empty_remote + 8 * acc);   // accumulator stage back to the leader's MMA thread
+        }
+    }
+    tc_fence_before();
+    cluster_sync_all();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
+    }
+}
+
 // ------------------------------------------------------------------ input conversion
 // float planes [n][planes][64] -> bf16 NHWC [n_pad][64][32] (channels >= planes are zero).
 __global__ void planes_to_nhwc32_kernel(const float *__restrict__ f, int planes, size_t n, size_t n_pad, __nv_bfloat16 *__restrict__ out) {
@@ -445,12 +708,12 @@ static int get_encode(EncodeTiledFn *fn) {
 }
 
 // NHWC [boards][8][8][C] bf16 viewed as (channel, board, x, y); box = (32, 16, 9, 6).
-static int make_act_map(CUtensorMap *m, void *ptr, size_t boards, int C) {
+static int make_act_map(CUtensorMap *m, void *ptr, size_t boards, int C, int box_y) {
     EncodeTiledFn enc;
     OZ_TRY(get_encode(&enc));
     cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)boards, 8, 8};
     cuuint64_t strides[3] = {(cuuint64_t)64 * C * 2, (cuuint64_t)C * 2, (cuuint64_t)8 * C * 2};
-    cuuint32_t box[4] = {kKBlock, kBoardsPerUnit, kBoxX, kBoxY};
+    cuuint32_t box[4] = {kKBlock, kBoardsPerUnit, kBoxX, (cuuint32_t)box_y};
     cuuint32_t estr[4] = {1, 1, 1, 1};
     CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, ptr, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                      CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -459,12 +722,12 @@ static int make_act_map(CUtensorMap *m, void *ptr, size_t boards, int C) {
 }
 
 // [tap][cout][cin] bf16 viewed as (cin, tap*cout); box = (32, 128).
-static int make_w_map(CUtensorMap *m, void *ptr, int cin, int cout) {
+static int make_w_map(CUtensorMap *m, void *ptr, int cin, int cout, int box_rows) {
     EncodeTiledFn enc;
     OZ_TRY(get_encode(&enc));
     cuuint64_t dims[2] = {(cuuint64_t)cin, (cuuint64_t)9 * cout};
     cuuint64_t strides[1] = {(cuuint64_t)cin * 2};
-    cuuint32_t box[2] = {kKBlock, 128};
+    cuuint32_t box[2] = {kKBlock, (cuuint32_t)box_rows};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, ptr, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                      CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -472,18 +735,34 @@ static int make_w_map(CUtensorMap *m, void *ptr, int cin, int cout) {
     return OZ_OK;
 }
 
+// OZ_CONV_VARIANT=1 selects the single-CTA kernel (cta_group::1), anything else the CTA-pair kernel.
+static bool use_pair_kernel() {
+    static int v = -1;
+    if (v < 0) { const char *e = getenv("OZ_CONV_VARIANT"); v = (e && e[0] == '1') ? 0 : 1; }
+    return v == 1;
+}
+static int act_box_y() { return use_pair_kernel() ? pair::kBoxYp : kBoxY; }
+static int w_box_rows() { return use_pair_kernel() ? 64 : 128; }
+
 static int launch_conv(const CUtensorMap &ma, const CUtensorMap &mw, const ConvParams &cp, cudaStream_t stream) {
     static bool attr_set = false;
     if (!attr_set) {
         OZ_CUDA(cudaFuncSetAttribute(conv3x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+        OZ_CUDA(cudaFuncSetAttribute(conv3x3_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, pair::kSmemBytesP));
         attr_set = true;
     }
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    const int num_pass = cp.units * 2 * (cp.cout_total >> 7);
-    const int grid = num_pass < sms ? num_pass : sms;
-    conv3x3_kernel<<<grid, kThreads, kSmemBytes, stream>>>(ma, mw, cp);
+    if (use_pair_kernel()) {
+        const int num_pp = cp.units * 2 * (cp.cout_total >> 7);
+        const int clusters = num_pp < sms / 2 ? num_pp : sms / 2;
+        conv3x3_pair_kernel<<<2 * clusters, pair::kThreadsP, pair::kSmemBytesP, stream>>>(ma, mw, cp);
+    } else {
+        const int num_pass = cp.units * 2 * (cp.cout_total >> 7);
+        const int grid = num_pass < sms ? num_pass : sms;
+        conv3x3_kernel<<<grid, kThreads, kSmemBytes, stream>>>(ma, mw, cp);
+    }
     count_launch();
     OZ_CUDA(cudaGetLastError());
     return OZ_OK;
@@ -509,7 +788,7 @@ int ResNet::load(const oz_resnet_shape &shape, const void *blob, size_t bytes) {
         OZ_CUDA(cudaMalloc(&d_blob_, L.total));
         map_w_.assign(L.conv_w.size(), CUtensorMap{});
         for (size_t i = 0; i < L.conv_w.size(); ++i)
-            OZ_TRY(make_w_map(&map_w_[i], d_blob_ + L.conv_w[i], i == 0 ? 32 : shape.channels, shape.channels));
+            OZ_TRY(make_w_map(&map_w_[i], d_blob_ + L.conv_w[i], i == 0 ? 32 : shape.channels, shape.channels, w_box_rows()));
         if (shape.channels != shape_.channels) { cudaFree(d_a_); cudaFree(d_t_); cudaFree(d_x0_); d_a_ = d_t_ = d_x0_ = nullptr; cap_ = 0; }
     }
     shape_ = shape; layout_ = L;
@@ -527,9 +806,9 @@ int ResNet::reserve(size_t boards) {
     OZ_CUDA(cudaMalloc(&d_t_, pad * 64 * C * 2));
     OZ_CUDA(cudaMemset(d_a_, 0, pad * 64 * C * 2));
     OZ_CUDA(cudaMemset(d_t_, 0, pad * 64 * C * 2));
-    OZ_TRY(make_act_map(&map_x0_, d_x0_, pad, 32));
-    OZ_TRY(make_act_map(&map_a_, d_a_, pad, (int)C));
-    OZ_TRY(make_act_map(&map_t_, d_t_, pad, (int)C));
+    OZ_TRY(make_act_map(&map_x0_, d_x0_, pad, 32, act_box_y()));
+    OZ_TRY(make_act_map(&map_a_, d_a_, pad, (int)C, act_box_y()));
+    OZ_TRY(make_act_map(&map_t_, d_t_, pad, (int)C, act_box_y()));
     cap_ = pad;
     return OZ_OK;
 }
@@ -580,8 +859,8 @@ int ResNet::conv3x3(const void *d_in, int cin, const void *d_w, const float *d_b
     if (cin % kKBlock || cout % 128 || boards_padded % kBoardsPerUnit)
         return fail(OZ_ERR_INVALID_ARGUMENT, "conv3x3: cin % 32, cout % 128, boards % 16 must be 0");
     CUtensorMap ma, mw;
-    OZ_TRY(make_act_map(&ma, const_cast<void *>(d_in), boards_padded, cin));
-    OZ_TRY(make_w_map(&mw, const_cast<void *>(d_w), cin, cout));
+    OZ_TRY(make_act_map(&ma, const_cast<void *>(d_in), boards_padded, cin, act_box_y()));
+    OZ_TRY(make_w_map(&mw, const_cast<void *>(d_w), cin, cout, w_box_rows()));
     ConvParams cp{};
     cp.skip = (const __nv_bfloat16 *)d_skip; cp.out = (__nv_bfloat16 *)d_out; cp.bias = d_bias;
     cp.units = (int)(boards_padded / kBoardsPerUnit); cp.kblocks = cin / kKBlock; cp.cout_total = cout; cp.relu = relu;
