@@ -329,6 +329,11 @@ static_assert(kSmemBytesP <= 232448, "shared memory budget");
 constexpr uint32_t kIdescP = (1u << 4) | (1u << 7) | (1u << 10) | ((128u >> 3) << 17) | ((256u >> 4) << 24);
 }  // namespace pair
 
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
 __device__ __forceinline__ uint32_t mapa_rank(uint32_t addr, uint32_t rank) {
     uint32_t r; asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank)); return r;
@@ -393,7 +398,7 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap map_act, const __grid_co
     uint32_t *tmem_ptr = (uint32_t *)(gen + (misc - base) + 704);
     float *s_bias = (float *)(gen + (misc - base) + 1024);                   // up to 384 floats
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
     const uint32_t rank = cluster_ctarank();
     const bool leader = rank == 0;
     const int ntiles = p.cout_total >> 7;
@@ -423,79 +428,109 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap map_act, const __grid_co
     tc_fence_before();
     cluster_sync_all();
     tc_fence_after();
-    const uint32_t tmem_base = *tmem_ptr;
+    const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_ptr, 0);
 
+    // Roles run with warp-uniform control flow and elect one lane only around the asynchronous
+    // instruction itself, so descriptors and coordinates stay in uniform registers (a divergent
+    // `if (lane == 0)` loop makes the compiler re-broadcast every operand before every MMA).
     if (warp == 0) {
         // ===== activation TMA producer (one per CTA; bytes complete on the LEADER's barrier) =====
-        if (lane == 0) {
-            uint32_t it = 0;
-            for (int pp = cluster_id; pp < num_pp; pp += num_clusters) {
-                const int sp = 2 * (pp / ntiles) + (int)rank, unit = sp >> 2, yp = sp & 3;
-                for (int kb = 0; kb < p.kblocks; ++kb, ++it) {
-                    const uint32_t s = it % kActStagesP, ph = (it / kActStagesP) & 1;
-                    mbar_wait_b(bar_act_empty + 8 * s, ph ^ 1);
+        uint32_t it = 0;
+        const uint32_t full0 = mapa_rank(bar_act_full, 0);
+        for (int pp = cluster_id; pp < num_pp; pp += num_clusters) {
+            const int sp = 2 * (pp / ntiles) + (int)rank, unit = sp >> 2, yp = sp & 3;
+            for (int kb = 0; kb < p.kblocks; ++kb, ++it) {
+                const uint32_t s = it % kActStagesP, ph = (it / kActStagesP) & 1;
+                mbar_wait_b(bar_act_empty + 8 * s, ph ^ 1);
+                if (elect_one()) {
                     if (leader) mbar_expect_tx(bar_act_full + 8 * s, 2 * kActBoxBytesP);
-                    tma_load_4d_pair(act0 + s * kActStageBytesP + kSlotBytes, &map_act, mapa_rank(bar_act_full + 8 * s, 0),
+                    tma_load_4d_pair(act0 + s * kActStageBytesP + kSlotBytes, &map_act, full0 + 8 * s,
                                      kb * kKBlock, unit * kBoardsPerUnit, 0, yp * kYPerPass - 1);
                 }
+                __syncwarp();
             }
         }
-        __syncwarp();
     } else if (warp == 2) {
         // ===== weight TMA producer: this CTA's 64-cout half of every (K block, tap) tile =====
-        if (lane == 0) {
-            uint32_t wit = 0;
-            for (int pp = cluster_id; pp < num_pp; pp += num_clusters) {
-                if (resident && wit >= (uint32_t)wtiles) break;
-                const int nt = pp % ntiles;
-                for (int kb = 0; kb < p.kblocks; ++kb)
-                    for (int tap = 0; tap < 9; ++tap, ++wit) {
-                        const uint32_t s = wit % kWSlots, ph = (wit / kWSlots) & 1;
-                        mbar_wait_b(bar_w_empty + 8 * s, ph ^ 1);
+        uint32_t wit = 0;
+        const uint32_t full0 = mapa_rank(bar_w_full, 0);
+        for (int pp = cluster_id; pp < num_pp; pp += num_clusters) {
+            if (resident && wit >= (uint32_t)wtiles) break;
+            const int nt = pp % ntiles;
+            for (int kb = 0; kb < p.kblocks; ++kb)
+                for (int tap = 0; tap < 9; ++tap, ++wit) {
+                    const uint32_t s = wit % kWSlots, ph = (wit / kWSlots) & 1;
+                    mbar_wait_b(bar_w_empty + 8 * s, ph ^ 1);
+                    if (elect_one()) {
                         if (leader) mbar_expect_tx(bar_w_full + 8 * s, 2 * kWTileBytes);
-                        tma_load_2d_pair(w0 + s * kWTileBytes, &map_w, mapa_rank(bar_w_full + 8 * s, 0),
+                        tma_load_2d_pair(w0 + s * kWTileBytes, &map_w, full0 + 8 * s,
                                          kb * kKBlock, tap * p.cout_total + nt * 128 + (int)rank * 64);
                     }
-            }
+                    __syncwarp();
+                }
         }
-        __syncwarp();
     } else if (warp == 1) {
-        // ===== MMA issuer: one thread of the leader CTA drives both tensor cores =====
-        if (leader && lane == 0) {
+        // ===== MMA issuer: one elected thread of the leader CTA drives both tensor cores =====
+        if (leader) {
             uint32_t ait = 0, wit = 0, np = 0;
             for (int pp = cluster_id; pp < num_pp; pp += num_clusters, ++np) {
                 const uint32_t acc = np & 1;
                 mbar_wait_b(bar_tmem_empty + 8 * acc, ((np >> 1) & 1) ^ 1);      // both CTAs drained this accumulator
                 tc_fence_after();
+                const uint32_t dcol = tmem_base + acc * 256;
                 for (int kb = 0; kb < p.kblocks; ++kb, ++ait) {
                     const uint32_t as = ait % kActStagesP;
                     mbar_wait_b(bar_act_full + 8 * as, (ait / kActStagesP) & 1);
                     tc_fence_after();
                     const uint32_t abox = act0 + as * kActStageBytesP + kSlotBytes;
+                    if (resident && np != 0) {
+                        // weights already in place: the whole K block is one uninterrupted issue burst
+                        if (elect_one()) {
+#pragma unroll
+                            for (int tap = 0; tap < 9; ++tap) {
+                                const int dy = tap / 3 - 1, dx = tap % 3 - 1;
+                                const uint32_t wbase = w0 + (uint32_t)(kb * 9 + tap) * kWTileBytes;
+#pragma unroll
+                                for (int r = 0; r < kYPerPass; ++r) {
+                                    const uint32_t arow = abox + (uint32_t)(((r + 1 + dy) * kBoxX + dx) * kSlotBytes);
+#pragma unroll
+                                    for (int j = 0; j < kKBlock / 16; ++j)
+                                        tc_mma_pair(dcol + r * 128, umma_desc_sw64(arow + j * 32), umma_desc_sw64(wbase + j * 32),
+                                                    kIdescP, (kb | tap | j) != 0);
+                                }
+                            }
+                            tc_commit_pair(bar_act_empty + 8 * as);
+                        }
+                        __syncwarp();
+                        wit += 9;
+                        continue;
+                    }
                     for (int tap = 0; tap < 9; ++tap, ++wit) {
                         const uint32_t ws = wit % kWSlots;
-                        if (!resident || np == 0) {
-                            mbar_wait_b(bar_w_full + 8 * ws, (wit / kWSlots) & 1);
-                            tc_fence_after();
-                        }
+                        mbar_wait_b(bar_w_full + 8 * ws, (wit / kWSlots) & 1);
+                        tc_fence_after();
                         const int dy = tap / 3 - 1, dx = tap % 3 - 1;
                         const uint32_t wbase = w0 + ws * kWTileBytes;
+                        if (elect_one()) {
 #pragma unroll
-                        for (int r = 0; r < kYPerPass; ++r) {
-                            const uint32_t arow = abox + (uint32_t)(((r + 1 + dy) * kBoxX + dx) * kSlotBytes);
+                            for (int r = 0; r < kYPerPass; ++r) {
+                                const uint32_t arow = abox + (uint32_t)(((r + 1 + dy) * kBoxX + dx) * kSlotBytes);
 #pragma unroll
-                            for (int j = 0; j < kKBlock / 16; ++j)
-                                tc_mma_pair(tmem_base + acc * 256 + r * 128, umma_desc_sw64(arow + j * 32), umma_desc_sw64(wbase + j * 32),
-                                            kIdescP, (kb | tap | j) != 0);
+                                for (int j = 0; j < kKBlock / 16; ++j)
+                                    tc_mma_pair(dcol + r * 128, umma_desc_sw64(arow + j * 32), umma_desc_sw64(wbase + j * 32),
+                                                kIdescP, (kb | tap | j) != 0);
+                            }
+                            if (!resident) tc_commit_pair(bar_w_empty + 8 * ws);
                         }
-                        if (!resident) tc_commit_pair(bar_w_empty + 8 * ws);
+                        __syncwarp();
                     }
-                    tc_commit_pair(bar_act_empty + 8 * as);
+                    if (elect_one()) tc_commit_pair(bar_act_empty + 8 * as);
+                    __syncwarp();
                 }
-                tc_commit_pair(bar_tmem_full + 8 * acc);
+                if (elect_one()) tc_commit_pair(bar_tmem_full + 8 * acc);
+                __syncwarp();
             }
         }
-        __syncwarp();
     } else {
         // ===== epilogue warps 3..10: TMEM lane quarter (warp % 4) x column half =====
         const int quad = warp & 3, half = (warp - 3) >> 2;
