@@ -309,7 +309,7 @@ def main():
     ap.add_argument("--steps", type=int, default=4)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--games", type=int, default=1024, help="lockstep games per GPU")
+    ap.add_argument("--games", type=int, default=1000, help="lockstep games per GPU")
     ap.add_argument("--sims", type=int, default=800)
     ap.add_argument("--threads", type=int, default=2)
     ap.add_argument("--batch", type=int, default=16)

@@ -168,7 +168,7 @@ int oz_resnet_forward(oz_resnet *net, const float *features, size_t n, float *po
 int oz_resnet_forward_device(oz_resnet *net, const float *features, size_t n, float *policy, float *value, void *stream);
 /* Test hook: one 3x3 "same" convolution layer.  Host buffers: in NHWC bf16 [boards][8][8][cin],
  * w bf16 [9][cout][cin] (tap = ky*3+kx), bias f32 [cout], skip NHWC bf16 or NULL, out NHWC bf16.
- * cin % 32 == 0, cout % 128 == 0; boards is padded to 16 inside. */
+ * cin % 32 == 0, cout % 128 == 0; boards is padded to 32 inside. */
 int oz_debug_conv3x3(const uint16_t *in, int cin, const uint16_t *w, const float *bias, const uint16_t *skip,
                      int relu, uint16_t *out, int cout, size_t boards, double *device_ms);
 

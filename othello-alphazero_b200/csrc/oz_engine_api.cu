@@ -121,8 +121,8 @@ int alloc_slots(oz_engine *e) {
         cudaFree(e->d_features);
         e->inflight_cap = std::max(e->inflight_cap, inflight);
         e->planes_cap = std::max(e->planes_cap, planes);
-        // padded to 16 boards: the network evaluates whole units
-        OZ_TRY(dalloc(&e->d_features, ((size_t)t.G * e->inflight_cap + 16) * e->planes_cap * 64));
+        // padded: the network evaluates whole 32-board pairs of units
+        OZ_TRY(dalloc(&e->d_features, ((size_t)t.G * e->inflight_cap + kBoardPad) * e->planes_cap * 64));
         cudaFree(e->d_spd_f);
         OZ_TRY(dalloc(&e->d_spd_f, (size_t)8 * e->planes_cap * 64));
     }
@@ -425,7 +425,7 @@ int oz_resnet_forward(oz_resnet *n, const float *f, size_t cnt, float *p, float 
 
 int oz_debug_conv3x3(const uint16_t *in, int cin, const uint16_t *w, const float *bias, const uint16_t *skip, int relu,
                      uint16_t *out, int cout, size_t boards, double *device_ms) {
-    const size_t pad = (boards + 15) / 16 * 16;
+    const size_t pad = (boards + kBoardPad - 1) / kBoardPad * kBoardPad;
     uint16_t *d_in = nullptr, *d_w = nullptr, *d_skip = nullptr, *d_out = nullptr;
     float *d_b = nullptr;
     int st = OZ_OK;

@@ -122,6 +122,7 @@ struct ConvParams {
     int kblocks;                 // cin / 32
     int cout_total;              // multiple of 128
     int relu;
+    int flags;                   // tuning switches of the pair kernel (bit 0 TMA L2 prefetch, 1 residual L2 prefetch, 2 zero-row tap skipping)
 };
 
 __global__ void __launch_bounds__(kThreads, 1)
@@ -367,6 +368,19 @@ __device__ __forceinline__ void tma_load_4d_pair(uint32_t dst, const CUtensorMap
         "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
         ::"r"(dst), "l"(map), "r"(bar_cluster), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
 }
+// 256-bit global accesses (sm_100): one full 32-byte sector per lane per instruction.
+__device__ __forceinline__ void ldg256(const void *ptr, uint32_t *v) {
+    asm volatile("ld.global.v8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]) : "l"(ptr) : "memory");
+}
+__device__ __forceinline__ void stg256(void *ptr, const uint32_t *v) {
+    asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+                 ::"l"(ptr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]) : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_4d(const CUtensorMap *map, int c0, int c1, int c2, int c3) {
+    asm volatile("cp.async.bulk.prefetch.tensor.4d.L2.global.tile [%0, {%1, %2, %3, %4}];"
+                 ::"l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
 __device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap *map, uint32_t bar_cluster, int c0, int c1) {
     asm volatile(
         "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
@@ -438,7 +452,13 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap map_act, const __grid_co
         uint32_t it = 0;
         const uint32_t full0 = mapa_rank(bar_act_full, 0);
         for (int pp = cluster_id; pp < num_pp; pp += num_clusters) {
-            const int sp = 2 * (pp / ntiles) + (int)rank, unit = sp >> 2, yp = sp & 3;
+            const int up = pp / ntiles, unit = 2 * (up >> 2) + (int)rank, yp = up & 3;
+            if ((p.flags & 1) && pp + num_clusters < num_pp && elect_one()) {     // next pass's boxes: HBM -> L2 while this pass computes
+                const int un = (pp + num_clusters) / ntiles, unit_n = 2 * (un >> 2) + (int)rank, yp_n = un & 3;
+                for (int kb = 0; kb < p.kblocks; ++kb)
+                    tma_prefetch_4d(&map_act, kb * kKBlock, unit_n * kBoardsPerUnit, 0, yp_n * kYPerPass - 1);
+            }
+            __syncwarp();
             for (int kb = 0; kb < p.kblocks; ++kb, ++it) {
                 const uint32_t s = it % kActStagesP, ph = (it / kActStagesP) & 1;
                 mbar_wait_b(bar_act_empty + 8 * s, ph ^ 1);
@@ -478,6 +498,10 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap map_act, const __grid_co
                 mbar_wait_b(bar_tmem_empty + 8 * acc, ((np >> 1) & 1) ^ 1);      // both CTAs drained this accumulator
                 tc_fence_after();
                 const uint32_t dcol = tmem_base + acc * 256;
+                // Board rows -1 and 8 are zero padding: for the first / last row pair, three taps of one tile
+                // multiply an all-zero operand and are not issued (both CTAs of the pair work on the same rows).
+                const int yp = (pp / ntiles) & 3;
+                const bool skip_top = (p.flags & 4) && yp == 0, skip_bot = (p.flags & 4) && yp == 3;
                 for (int kb = 0; kb < p.kblocks; ++kb, ++ait) {
                     const uint32_t as = ait % kActStagesP;
                     mbar_wait_b(bar_act_full + 8 * as, (ait / kActStagesP) & 1);
@@ -492,11 +516,13 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap map_act, const __grid_co
                                 const uint32_t wbase = w0 + (uint32_t)(kb * 9 + tap) * kWTileBytes;
 #pragma unroll
                                 for (int r = 0; r < kYPerPass; ++r) {
+                                    if ((r == 0 && tap < 3 && skip_top) || (r == kYPerPass - 1 && tap >= 6 && skip_bot)) continue;
+                                    const int first_tap = (r == 0 && skip_top) ? 3 : 0;
                                     const uint32_t arow = abox + (uint32_t)(((r + 1 + dy) * kBoxX + dx) * kSlotBytes);
 #pragma unroll
                                     for (int j = 0; j < kKBlock / 16; ++j)
                                         tc_mma_pair(dcol + r * 128, umma_desc_sw64(arow + j * 32), umma_desc_sw64(wbase + j * 32),
-                                                    kIdescP, (kb | tap | j) != 0);
+                                                    kIdescP, (kb | j) != 0 || tap != first_tap);
                                 }
                             }
                             tc_commit_pair(bar_act_empty + 8 * as);
@@ -514,11 +540,13 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap map_act, const __grid_co
                         if (elect_one()) {
 #pragma unroll
                             for (int r = 0; r < kYPerPass; ++r) {
+                                if ((r == 0 && tap < 3 && skip_top) || (r == kYPerPass - 1 && tap >= 6 && skip_bot)) continue;
+                                const int first_tap = (r == 0 && skip_top) ? 3 : 0;
                                 const uint32_t arow = abox + (uint32_t)(((r + 1 + dy) * kBoxX + dx) * kSlotBytes);
 #pragma unroll
                                 for (int j = 0; j < kKBlock / 16; ++j)
                                     tc_mma_pair(dcol + r * 128, umma_desc_sw64(arow + j * 32), umma_desc_sw64(wbase + j * 32),
-                                                kIdescP, (kb | tap | j) != 0);
+                                                kIdescP, (kb | j) != 0 || tap != first_tap);
                             }
                             if (!resident) tc_commit_pair(bar_w_empty + 8 * ws);
                         }
@@ -538,18 +566,25 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap map_act, const __grid_co
         const uint32_t empty_remote = mapa_rank(bar_tmem_empty, 0);
         uint32_t np = 0;
         for (int pp = cluster_id; pp < num_pp; pp += num_clusters, ++np) {
-            const int nt = pp % ntiles, sp = 2 * (pp / ntiles) + (int)rank, unit = sp >> 2, yp = sp & 3;
+            const int nt = pp % ntiles, up = pp / ntiles, unit = 2 * (up >> 2) + (int)rank, yp = up & 3;
             const uint32_t acc = np & 1;
             const size_t board = (size_t)unit * kBoardsPerUnit + bl;
             const size_t off0 = ((board * 8 + yp * kYPerPass) * 8 + x) * (size_t)p.cout_total + nt * 128 + half * 64;
             const size_t ystride = (size_t)8 * p.cout_total;
-            uint4 sk[kYPerPass][8];
+            uint32_t sk[kYPerPass][32];                        // 64 channels of residual input per tile row
             if (p.skip) {
 #pragma unroll
                 for (int r = 0; r < kYPerPass; ++r) {
-                    const uint4 *sp4 = (const uint4 *)(p.skip + off0 + r * ystride);
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) sk[r][i] = sp4[i];
+                    for (int i = 0; i < 4; ++i) ldg256(p.skip + off0 + r * ystride + i * 16, &sk[r][i * 8]);
+                }
+                if ((p.flags & 2) && pp + num_clusters < num_pp) {               // next pass's residual rows: HBM -> L2 ahead of use
+                    const int ppn = pp + num_clusters, ntn = ppn % ntiles, un = ppn / ntiles;
+                    const size_t board_n = (size_t)(2 * (un >> 2) + (int)rank) * kBoardsPerUnit + bl;
+                    const size_t offn = ((board_n * 8 + (un & 3) * kYPerPass) * 8 + x) * (size_t)p.cout_total + ntn * 128 + half * 64;
+#pragma unroll
+                    for (int r = 0; r < kYPerPass; ++r)
+                        asm volatile("prefetch.global.L2 [%0];" ::"l"(p.skip + offn + r * ystride));
                 }
             }
             mbar_wait_b(bar_tmem_full + 8 * acc, (np >> 1) & 1);
@@ -562,9 +597,8 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap map_act, const __grid_co
                     tc_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + acc * 256 + r * 128 + half * 64 + ch * 32, v);
                     tc_wait_ld();
                     const float *bs = s_bias + nt * 128 + half * 64 + ch * 32;
-                    uint4 o[4];
-                    uint32_t *ow = (uint32_t *)o;
-                    const uint32_t *skw = (const uint32_t *)&sk[r][ch * 4];
+                    uint32_t ow[16];
+                    const uint32_t *skw = &sk[r][ch * 16];
 #pragma unroll
                     for (int i = 0; i < 16; ++i) {
                         float a = __uint_as_float(v[2 * i]) + bs[2 * i];
@@ -578,9 +612,9 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap map_act, const __grid_co
                         const __nv_bfloat162 o2 = __floats2bfloat162_rn(a, b);
                         ow[i] = *(const uint32_t *)&o2;
                     }
-                    uint4 *op = (uint4 *)(p.out + off0 + r * ystride + ch * 32);
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) op[i] = o[i];
+                    __nv_bfloat16 *op = p.out + off0 + r * ystride + ch * 32;   // full 32-byte sectors per store
+                    stg256(op, &ow[0]);
+                    stg256(op + 16, &ow[8]);
                 }
             }
             tc_fence_before();
@@ -621,79 +655,95 @@ struct HeadParams {
     size_t n;
 };
 
-// neural_net.py:68-128.  128 threads; thread t < 64 owns board square t for the 1x1 convs.
-__global__ void __launch_bounds__(128) heads_kernel(const HeadParams p) {
-    extern __shared__ float sm[];
+// neural_net.py:68-128.  One WARP per board (8 boards per CTA in flight): lane l owns board squares l and
+// l + 32 for the two 1x1 convolutions, then policy outputs l and l + 32 (output 64 is a warp reduction) and
+// every 32nd hidden unit of the value head.  FC weights live in shared memory with odd row strides (no bank
+// conflicts); only __syncwarp between the stages.
+constexpr int kHeadWarps = 8;
+__host__ __device__ inline int heads_cw_offset(int Hv) { return (65 * 129 + Hv * 65 + 3) & ~3; }       // floats
+__host__ __device__ inline int heads_smem_floats(int C, int Hv) { return heads_cw_offset(Hv) + 3 * C + 2 * Hv + kHeadWarps * 192; }
+
+__global__ void __launch_bounds__(kHeadWarps * 32, 2) heads_kernel(const HeadParams p) {
+    extern __shared__ __align__(16) float sm[];
     const int C = p.C, Hv = p.Hv;
-    float *s_pfc = sm;                     // [65][129] padded rows
-    float *s_vfc1 = s_pfc + 65 * 129;      // [Hv][65]
-    float *s_cw = s_vfc1 + Hv * 65;        // [3][C]: policy c0, policy c1, value
-    float *s_feat = s_cw + 3 * C;          // [128] policy features (channel-major), then [64] value features
+    float *s_pfc = sm;                               // [65][129]
+    float *s_vfc1 = s_pfc + 65 * 129;                // [Hv][65]
+    float *s_cw = sm + heads_cw_offset(Hv);          // [3][C]: policy c0, policy c1, value (16-byte aligned)
+    float *s_vb1 = s_cw + 3 * C;                     // [Hv] value fc1 bias
+    float *s_vw2 = s_vb1 + Hv;                       // [Hv] value fc2 weight
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    float *s_feat = s_vw2 + Hv + warp * 192;         // [128] policy features (channel-major), then [64] value features
     float *s_v1 = s_feat + 128;
-    float *s_logit = s_v1 + 64;            // [65] + scratch
-    float *s_red = s_logit + 72;           // [8]
-    const int t = threadIdx.x;
-    for (int i = t; i < 65 * 128; i += 128) s_pfc[(i >> 7) * 129 + (i & 127)] = p.pfc_w[i];
-    for (int i = t; i < Hv * 64; i += 128) s_vfc1[(i >> 6) * 65 + (i & 63)] = p.vfc1_w[i];
-    for (int i = t; i < 2 * C; i += 128) s_cw[i] = p.pconv_w[i];
-    for (int i = t; i < C; i += 128) s_cw[2 * C + i] = p.vconv_w[i];
+    for (int i = t; i < 65 * 128; i += kHeadWarps * 32) s_pfc[(i >> 7) * 129 + (i & 127)] = p.pfc_w[i];
+    for (int i = t; i < Hv * 64; i += kHeadWarps * 32) s_vfc1[(i >> 6) * 65 + (i & 63)] = p.vfc1_w[i];
+    for (int i = t; i < 2 * C; i += kHeadWarps * 32) s_cw[i] = p.pconv_w[i];
+    for (int i = t; i < C; i += kHeadWarps * 32) s_cw[2 * C + i] = p.vconv_w[i];
+    for (int i = t; i < Hv; i += kHeadWarps * 32) { s_vb1[i] = p.vfc1_b[i]; s_vw2[i] = p.vfc2_w[i]; }
     __syncthreads();
     const float pb0 = p.pconv_b[0], pb1 = p.pconv_b[1], vb = p.vconv_b[0], v2b = p.vfc2_b[0];
-    for (size_t b = blockIdx.x; b < p.n; b += gridDim.x) {
-        if (t < 64) {
-            const uint4 *a = (const uint4 *)(p.act + (b * 64 + t) * (size_t)C);
-            float d0 = 0.f, d1 = 0.f, d2 = 0.f;
-            for (int c8 = 0; c8 < C / 8; ++c8) {
-                const uint4 q = a[c8];
-                const __nv_bfloat162 *h = (const __nv_bfloat162 *)&q;
+    const float pfb0 = p.pfc_b[lane], pfb1 = p.pfc_b[lane + 32], pfb64 = p.pfc_b[64];
+    const float4 *cw0 = (const float4 *)s_cw, *cw1 = (const float4 *)(s_cw + C), *cw2 = (const float4 *)(s_cw + 2 * C);
+    for (size_t b = (size_t)blockIdx.x * kHeadWarps + warp; b < p.n; b += (size_t)gridDim.x * kHeadWarps) {
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const float x0 = __bfloat162float(h[i].x), x1 = __bfloat162float(h[i].y);
-                    const int c = c8 * 8 + 2 * i;
-                    d0 += x0 * s_cw[c] + x1 * s_cw[c + 1];
-                    d1 += x0 * s_cw[C + c] + x1 * s_cw[C + c + 1];
-                    d2 += x0 * s_cw[2 * C + c] + x1 * s_cw[2 * C + c + 1];
-                }
+        for (int h = 0; h < 2; ++h) {
+            const int sq = lane + 32 * h;
+            const uint4 *a = (const uint4 *)(p.act + (b * 64 + sq) * (size_t)C);
+            float d0 = 0.f, d1 = 0.f, d2 = 0.f;
+#pragma unroll 4
+            for (int c8 = 0; c8 < C / 8; ++c8) {
+                const uint4 q = __ldg(a + c8);
+                const __nv_bfloat162 *hh = (const __nv_bfloat162 *)&q;
+                const float x0 = __bfloat162float(hh[0].x), x1 = __bfloat162float(hh[0].y), x2 = __bfloat162float(hh[1].x), x3 = __bfloat162float(hh[1].y);
+                const float x4 = __bfloat162float(hh[2].x), x5 = __bfloat162float(hh[2].y), x6 = __bfloat162float(hh[3].x), x7 = __bfloat162float(hh[3].y);
+                float4 wa = cw0[2 * c8], wb = cw0[2 * c8 + 1];
+                d0 += x0 * wa.x + x1 * wa.y + x2 * wa.z + x3 * wa.w + x4 * wb.x + x5 * wb.y + x6 * wb.z + x7 * wb.w;
+                wa = cw1[2 * c8]; wb = cw1[2 * c8 + 1];
+                d1 += x0 * wa.x + x1 * wa.y + x2 * wa.z + x3 * wa.w + x4 * wb.x + x5 * wb.y + x6 * wb.z + x7 * wb.w;
+                wa = cw2[2 * c8]; wb = cw2[2 * c8 + 1];
+                d2 += x0 * wa.x + x1 * wa.y + x2 * wa.z + x3 * wa.w + x4 * wb.x + x5 * wb.y + x6 * wb.z + x7 * wb.w;
             }
-            s_feat[t] = fmaxf(d0 + pb0, 0.f);
-            s_feat[64 + t] = fmaxf(d1 + pb1, 0.f);
-            s_v1[t] = fmaxf(d2 + vb, 0.f);
+            s_feat[sq] = fmaxf(d0 + pb0, 0.f);
+            s_feat[64 + sq] = fmaxf(d1 + pb1, 0.f);
+            s_v1[sq] = fmaxf(d2 + vb, 0.f);
         }
-        __syncthreads();
-        if (t < 65) {
-            float acc = p.pfc_b[t];
-            const float *w = s_pfc + t * 129;
+        __syncwarp();
+        // policy FC 128 -> 65
+        float l0 = pfb0, l1 = pfb1, l2 = 0.f;
+        {
+            const float *w0 = s_pfc + lane * 129, *w1 = s_pfc + (lane + 32) * 129;
 #pragma unroll 8
-            for (int i = 0; i < 128; ++i) acc += s_feat[i] * w[i];
-            s_logit[t] = acc;
+            for (int i = 0; i < 128; ++i) { const float f = s_feat[i]; l0 += f * w0[i]; l1 += f * w1[i]; }
+            const float *w2 = s_pfc + 64 * 129 + lane * 4;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) l2 += s_feat[lane * 4 + i] * w2[i];
+#pragma unroll
+            for (int o = 16; o; o >>= 1) l2 += __shfl_xor_sync(0xffffffffu, l2, o);
+            l2 += pfb64;
         }
+        // value FC 64 -> Hv -> 1
         float hv = 0.f;
-        for (int k = t; k < Hv; k += 128) {
-            float acc = p.vfc1_b[k];
+        for (int k = lane; k < Hv; k += 32) {
+            float acc = s_vb1[k];
             const float *w = s_vfc1 + k * 65;
 #pragma unroll 8
             for (int i = 0; i < 64; ++i) acc += s_v1[i] * w[i];
-            hv += fmaxf(acc, 0.f) * p.vfc2_w[k];
+            hv += fmaxf(acc, 0.f) * s_vw2[k];
         }
 #pragma unroll
         for (int o = 16; o; o >>= 1) hv += __shfl_xor_sync(0xffffffffu, hv, o);
-        if ((t & 31) == 0) s_red[t >> 5] = hv;
-        __syncthreads();
-        if (t < 32) {
-            float l0 = s_logit[t], l1 = s_logit[t + 32], l2 = (t == 0) ? s_logit[64] : -INFINITY;
-            float m = fmaxf(fmaxf(l0, l1), l2);
+        // softmax over 65 logits
+        float m = fmaxf(fmaxf(l0, l1), l2);
 #pragma unroll
-            for (int o = 16; o; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
-            const float e0 = expf(l0 - m), e1 = expf(l1 - m), e2 = (t == 0) ? expf(l2 - m) : 0.f;
-            float s = e0 + e1 + e2;
+        for (int o = 16; o; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+        const float e0 = expf(l0 - m), e1 = expf(l1 - m), e2 = expf(l2 - m);
+        float ssum = e0 + e1;
 #pragma unroll
-            for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-            const float inv = 1.f / s;
-            float *po = p.policy + b * 65;
-            po[t] = e0 * inv; po[t + 32] = e1 * inv;
-            if (t == 0) { po[64] = e2 * inv; p.value[b] = tanhf(s_red[0] + s_red[1] + s_red[2] + s_red[3] + v2b); }
-        }
-        __syncthreads();
+        for (int o = 16; o; o >>= 1) ssum += __shfl_xor_sync(0xffffffffu, ssum, o);
+        const float inv = 1.f / (ssum + e2);
+        float *po = p.policy + b * 65;
+        po[lane] = e0 * inv; po[lane + 32] = e1 * inv;
+        if (lane == 0) { po[64] = e2 * inv; p.value[b] = tanhf(hv + v2b); }
+        __syncwarp();
     }
 }
 
@@ -776,6 +826,11 @@ static bool use_pair_kernel() {
     if (v < 0) { const char *e = getenv("OZ_CONV_VARIANT"); v = (e && e[0] == '1') ? 0 : 1; }
     return v == 1;
 }
+static int conv_flags() {
+    static int v = -1;
+    if (v < 0) { const char *e = getenv("OZ_CONV_FLAGS"); v = e ? atoi(e) : 6; }
+    return v;
+}
 static int act_box_y() { return use_pair_kernel() ? pair::kBoxYp : kBoxY; }
 static int w_box_rows() { return use_pair_kernel() ? 64 : 128; }
 
@@ -790,9 +845,11 @@ static int launch_conv(const CUtensorMap &ma, const CUtensorMap &mw, const ConvP
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     if (use_pair_kernel()) {
+        ConvParams cq = cp;
+        cq.flags = conv_flags();
         const int num_pp = cp.units * 2 * (cp.cout_total >> 7);
         const int clusters = num_pp < sms / 2 ? num_pp : sms / 2;
-        conv3x3_pair_kernel<<<2 * clusters, pair::kThreadsP, pair::kSmemBytesP, stream>>>(ma, mw, cp);
+        conv3x3_pair_kernel<<<2 * clusters, pair::kThreadsP, pair::kSmemBytesP, stream>>>(ma, mw, cq);
     } else {
         const int num_pass = cp.units * 2 * (cp.cout_total >> 7);
         const int grid = num_pass < sms ? num_pass : sms;
@@ -832,7 +889,7 @@ int ResNet::load(const oz_resnet_shape &shape, const void *blob, size_t bytes) {
 }
 
 int ResNet::reserve(size_t boards) {
-    const size_t pad = (boards + kBoardsPerUnit - 1) / kBoardsPerUnit * kBoardsPerUnit;
+    const size_t pad = (boards + kBoardPad - 1) / kBoardPad * kBoardPad;
     if (pad <= cap_) return OZ_OK;
     cudaFree(d_x0_); cudaFree(d_a_); cudaFree(d_t_); d_x0_ = d_a_ = d_t_ = nullptr; cap_ = 0;
     const size_t C = shape_.channels;
@@ -852,7 +909,7 @@ int ResNet::forward(const float *d_features, size_t n, float *d_policy, float *d
     if (!loaded()) return fail(OZ_ERR_STATE, "no network weights loaded");
     if (n == 0) return OZ_OK;
     OZ_TRY(reserve(n));
-    const size_t pad = (n + kBoardsPerUnit - 1) / kBoardsPerUnit * kBoardsPerUnit;
+    const size_t pad = (n + kBoardPad - 1) / kBoardPad * kBoardPad;
     const int C = shape_.channels;
     {
         const size_t threads = pad * 256;
@@ -879,11 +936,12 @@ int ResNet::forward(const float *d_features, size_t n, float *d_policy, float *d
     hp.vfc1_w = (const float *)(d_blob_ + layout_.vfc1_w); hp.vfc1_b = (const float *)(d_blob_ + layout_.vfc1_b);
     hp.vfc2_w = (const float *)(d_blob_ + layout_.vfc2_w); hp.vfc2_b = (const float *)(d_blob_ + layout_.vfc2_b);
     hp.policy = d_policy; hp.value = d_value; hp.C = C; hp.Hv = shape_.value_hidden; hp.n = n;
-    const size_t hsm = (65 * 129 + (size_t)hp.Hv * 65 + 3 * C + 128 + 64 + 72 + 8) * sizeof(float);
+    const size_t hsm = (size_t)heads_smem_floats(C, hp.Hv) * sizeof(float);
     static size_t hsm_set = 0;
     if (hsm > hsm_set) { OZ_CUDA(cudaFuncSetAttribute(heads_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hsm)); hsm_set = hsm; }
-    const unsigned grid = (unsigned)(n < 148 * 2 ? n : 148 * 2);
-    heads_kernel<<<grid, 128, hsm, stream>>>(hp);
+    const size_t want = (n + kHeadWarps - 1) / kHeadWarps;
+    const unsigned grid = (unsigned)(want < 148 * 2 ? want : 148 * 2);
+    heads_kernel<<<grid, kHeadWarps * 32, hsm, stream>>>(hp);
     count_launch();
     OZ_CUDA(cudaGetLastError());
     return OZ_OK;
@@ -891,8 +949,8 @@ int ResNet::forward(const float *d_features, size_t n, float *d_policy, float *d
 
 int ResNet::conv3x3(const void *d_in, int cin, const void *d_w, const float *d_bias, const void *d_skip, int relu,
                     void *d_out, int cout, size_t boards_padded, cudaStream_t stream) {
-    if (cin % kKBlock || cout % 128 || boards_padded % kBoardsPerUnit)
-        return fail(OZ_ERR_INVALID_ARGUMENT, "conv3x3: cin % 32, cout % 128, boards % 16 must be 0");
+    if (cin % kKBlock || cout % 128 || boards_padded % kBoardPad)
+        return fail(OZ_ERR_INVALID_ARGUMENT, "conv3x3: cin % 32, cout % 128, boards % 32 must be 0");
     CUtensorMap ma, mw;
     OZ_TRY(make_act_map(&ma, const_cast<void *>(d_in), boards_padded, cin, act_box_y()));
     OZ_TRY(make_w_map(&mw, const_cast<void *>(d_w), cin, cout, w_box_rows()));

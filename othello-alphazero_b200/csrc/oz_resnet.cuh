@@ -30,19 +30,22 @@ struct ResNetLayout {
 };
 ResNetLayout resnet_layout(const oz_resnet_shape &s);
 
+// Board counts are padded to this inside the evaluator: a CTA pair convolves two 16-board units at a time.
+constexpr int kBoardPad = 32;
+
 class ResNet {
   public:
     ~ResNet();
     int load(const oz_resnet_shape &shape, const void *blob, size_t bytes);
     bool loaded() const { return d_blob_ != nullptr; }
     const oz_resnet_shape &shape() const { return shape_; }
-    // Capacity in boards (rounded up to a multiple of 16); (re)allocates activations + tensor maps.
+    // Capacity in boards (rounded up to a multiple of 32); (re)allocates activations + tensor maps.
     int reserve(size_t boards);
     // features: DEVICE float [n][in_planes][64] (reference plane format).  policy [n][65], value [n].
     int forward(const float *d_features, size_t n, float *d_policy, float *d_value, cudaStream_t stream);
     // Kernel launches one forward() issues.
     int launches_per_forward() const { return 2 + (1 + 2 * shape_.blocks); }
-    // Debug hook: one 3x3 convolution layer on device NHWC bf16 buffers already padded to 16 boards.
+    // Debug hook: one 3x3 convolution layer on device NHWC bf16 buffers already padded to 32 boards.
     static int conv3x3(const void *d_in, int cin, const void *d_w, const float *d_bias, const void *d_skip,
                        int relu, void *d_out, int cout, size_t boards_padded, cudaStream_t stream);
 

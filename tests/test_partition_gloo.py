@@ -1,0 +1,80 @@
+"""CPU, world_size 2 over gloo: the multi-GPU host logic (game partition by id, final gather of records and
+training samples, counter reduction).  The hot path itself has no collective."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from othello_mcts import parallel
+
+REC = np.dtype([("p1", "<u8"), ("p2", "<u8"), ("player", "<i4"), ("action", "<i4"), ("n_children", "<i4"),
+                ("visit_counts", "<i4", (36,)), ("_pad", "<i4")])
+
+
+def test_partition_covers_every_game_once():
+    for total in (0, 1, 7, 1000, 8192):
+        for world in (1, 2, 3, 4, 8):
+            seen = []
+            for r in range(world):
+                first, n = parallel.partition_games(total, world, r)
+                seen += list(range(first, first + n))
+                for g in range(first, first + n):
+                    assert parallel.owner_of(g, total, world) == r
+            assert seen == list(range(total))
+    with pytest.raises(ValueError):
+        parallel.partition_games(10, 2, 2)
+
+
+def _fake_rank_output(first, n):
+    """Deterministic per-game stand-ins for what a rank's engine returns, keyed by GAME ID only."""
+    plies = np.array([40 + (g * 7) % 21 for g in range(first, first + n)], np.int32)
+    rec = np.zeros((n, 128), REC)
+    for i, g in enumerate(range(first, first + n)):
+        rec[i, : plies[i]]["action"] = (g + np.arange(plies[i])) % 65
+        rec[i, : plies[i]]["p1"] = np.uint64(g) << np.uint64(8)
+    rows = int(plies.sum()) * 8
+    gid = np.repeat(np.arange(first, first + n), plies * 8).astype(np.float32)
+    samples = {"features": torch.from_numpy(gid)[:, None, None, None].expand(rows, 3, 8, 8).contiguous(),
+               "policies": torch.from_numpy(gid)[:, None].expand(rows, 65).contiguous(), "values": torch.from_numpy(gid)}
+    return {"plies": plies, "records": rec}, samples
+
+
+def _worker(rank, world, port, total, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        first, n = parallel.partition_games(total, world, rank)
+        records, samples = _fake_rank_output(first, n)
+        got_r = parallel.gather_records(records)
+        got_s = parallel.gather_samples(samples)
+        ctr = parallel.reduce_counters({"simulations": 800 * n, "plies": n, "eval_ms": 1.5})
+        if rank == 0:
+            want_r, want_s = _fake_rank_output(0, total)          # what a single rank owning every game returns
+            ok = (np.array_equal(got_r["plies"], want_r["plies"]) and got_r["records"].tobytes() == want_r["records"].tobytes()
+                  and all(torch.equal(got_s[k], want_s[k]) for k in want_s)
+                  and ctr["simulations"] == 800 * total and ctr["plies"] == total)
+            q.put(bool(ok))
+        else:
+            assert got_r is None and got_s is None
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("total", [5, 16])
+def test_gather_is_invariant_to_world_size(total):
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, total, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    assert q.get(timeout=10) is True
