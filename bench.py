@@ -35,6 +35,11 @@ MCTS_KW = dict(history_size=8, num_simulations=800, num_threads=2, batch_size=16
                dirichlet_epsilon=0.25, dirichlet_alpha=0.5)
 
 
+# dram__bytes_read.sum + dram__bytes_write.sum per conv launch (32768 boards, 128 -> 128 channels), mean of the plain and the
+# residual layer of one ncu --set full capture (profiles/r01_conv_pair_kernel.json).
+NCU_TRAFFIC_BYTES_PER_LAUNCH = 1.29e9
+
+
 def flops_per_eval(cin=17, c=128, blocks=9, hv=128):
     """Dense 2*MAC convention of SURVEY.md section 8(d) (= torch.utils.flop_counter)."""
     conv = 2 * 576 * c * (cin + 2 * blocks * c)
@@ -255,6 +260,8 @@ def run_ours(args):
     evals = c1["evaluations"] - c0["evaluations"]
     launches = c1["kernel_launches"] - c0["kernel_launches"]
     eval_ms = c1["eval_ms"] - c0["eval_ms"]
+    conv_ms = c1["conv_ms"] - c0["conv_ms"]
+    conv_launches = c1["conv_launches"] - c0["conv_launches"]
     tot = torch.tensor([float(sims), float(evals), float(launches)], device="cuda", dtype=torch.float64)
     if dist is not None:
         dist.all_reduce(tot)                                      # the only collective: final counters
@@ -269,8 +276,10 @@ def run_ours(args):
         f_all, f_conv = flops_per_eval()
         pk = peaks()
         nn_share = eval_ms / ms if ms > 0 else None
-        achieved = (evals * f_all) / (eval_ms * 1e-3) / 1e12 if eval_ms > 0 else None     # this rank's network phase
-        conv_launches = 19
+        # dominant kernel: the 3x3 convolution.  Algorithmic FLOPs of this rank's conv launches in the timed region
+        # (dense 2*MAC, zero-padding taps counted: SURVEY.md 8d) / their CUDA-event time on the engine stream.
+        achieved = (evals * f_conv) / (conv_ms * 1e-3) / 1e12 if conv_ms > 0 else None
+        perft_nodes, perft_ms = om.perft(11, return_ms=True)
         line = {
             "metric": "mcts_simulations_per_second", "value": value, "unit": "sims/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
@@ -286,10 +295,17 @@ def run_ours(args):
             "gpu_launches": int(tot[2].item()),
             "nn_evals_per_second": float(tot[1].item()) / (ms * 1e-3),
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": pk["bf16_sustained"], "unit": "TFLOP/s",
-                         "frac": (achieved / pk["bf16_sustained"]) if achieved else None, "traffic": None,
-                         "kernel": "conv3x3_kernel (tcgen05 implicit GEMM), timed as the network phase of every round",
-                         "flop_per_eval": f_all, "conv_launches_per_eval_batch": conv_launches, "nn_share_of_step": nn_share,
+                         "frac": (achieved / pk["bf16_sustained"]) if achieved else None, "traffic": NCU_TRAFFIC_BYTES_PER_LAUNCH,
+                         "kernel": "conv3x3_pair_kernel (tcgen05.mma cta_group::2 implicit GEMM)",
+                         "flop_per_launch": (evals * f_conv / conv_launches) if conv_launches else None,
+                         "us_per_launch": (1e3 * conv_ms / conv_launches) if conv_launches else None,
+                         "launches_timed": int(conv_launches), "conv_share_of_step": conv_ms / ms if ms > 0 else None,
+                         "nn_share_of_step": nn_share, "frac_of_burst_peak": (achieved / pk["bf16_burst"]) if achieved else None,
+                         "traffic_note": "dram read+write bytes per launch of a 128->128 layer over 32768 boards, mean of a plain and a residual "
+                                         "layer, from profiles/ (ncu --set full); algorithmic 1.07 / 1.61 GB",
                          "peak_source": pk["source"] + ", sustained bf16 (kernel timed inside a long step)"},
+            "perft": {"depth": 11, "nodes": int(perft_nodes), "nodes_per_s": perft_nodes / (perft_ms * 1e-3) if perft_ms > 0 else None,
+                      "device_ms": perft_ms},
             "clocks": clocks,
         }
         if world == 1 and not args.no_cpu_baseline:

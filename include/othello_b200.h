@@ -221,6 +221,19 @@ int oz_engine_records(oz_engine *e, int32_t *plies, oz_ply_record *records, int 
 int oz_engine_training_samples(oz_engine *e, float *features, float *policy, float *value,
                                size_t capacity, size_t *n_samples);
 
+/* Rolling game pool (new capability; the reference replays one MCTS object game after game, train.py:394-410):
+ * the engine's num_games slots play `total_games` games with ids first_game_id .. first_game_id + total_games - 1.
+ * After every oz_engine_play_ply, finished games move to a store of completed games (completion order) and their
+ * slots restart from the initial position with the next unplayed id, so the leaf batch stays full until the pool
+ * runs dry.  RNG streams are keyed by game id: a game's record does not depend on the slot or GPU that played it.
+ * total_games = 0 switches the pool off.  Resets all games.  With a pool, oz_engine_training_samples covers the
+ * completed games of the store. */
+int oz_engine_set_game_pool(oz_engine *e, int total_games);
+int oz_engine_finished_games(oz_engine *e, int32_t *count);
+/* Rows 0 .. min(*count, capacity) - 1 of the store: global game id, plies played, records [row][max_plies]. */
+int oz_engine_finished_records(oz_engine *e, uint32_t *game_ids, int32_t *plies, oz_ply_record *records, int max_plies,
+                               int capacity, int32_t *count);
+
 typedef struct {
     uint64_t simulations;      /* reference accounting: rounds * T * B per search per game */
     uint64_t evaluations;      /* network slots actually evaluated */
@@ -230,6 +243,8 @@ typedef struct {
     uint64_t games_finished;
     uint64_t kernel_launches;  /* launches of this library's kernels */
     double   select_ms, eval_ms, expand_ms, reroot_ms; /* CUDA-event totals when profiling is on */
+    double   conv_ms;          /* part of eval_ms spent in the 3x3 convolution launches */
+    uint64_t conv_launches;    /* convolution launches timed in conv_ms */
 } oz_counters;
 int oz_engine_counters(oz_engine *e, oz_counters *out);
 int oz_engine_set_profiling(oz_engine *e, int on);

@@ -36,6 +36,8 @@ struct oz_engine {
     PlyRecordDev *d_records = nullptr;
     int max_plies = 0;
     float *d_spd_f = nullptr, *d_spd_p = nullptr;
+    DoneStore done{};                     // rolling game pool (oz_engine_set_game_pool); capacity 0 = off
+    int pool_total = 0;
     ResNet net;
     bool in_search = false;
     int round = 0;
@@ -178,7 +180,9 @@ int grow_pools(oz_engine *e, int new_cap) {
     return OZ_OK;
 }
 
-int eval_round(oz_engine *e) {
+cudaEvent_t next_event(oz_engine *e, size_t i);
+
+int eval_round(oz_engine *e, cudaEvent_t conv_begin = nullptr, cudaEvent_t conv_end = nullptr) {
     const size_t n = (size_t)e->t.G * e->t.inflight;
     const int planes = 1 + 2 * e->t.H;
     switch (e->cfg.evaluator) {
@@ -187,7 +191,7 @@ int eval_round(oz_engine *e) {
         case OZ_EVAL_RESNET:
             if (e->net.shape().in_planes != planes)
                 return fail(OZ_ERR_STATE, "network in_planes " + std::to_string(e->net.shape().in_planes) + " != 1 + 2 * history_size");
-            OZ_TRY(e->net.forward(e->d_features, n, e->d_policy, e->d_value, e->stream));
+            OZ_TRY(e->net.forward(e->d_features, n, e->d_policy, e->d_value, e->stream, conv_begin, conv_end));
             break;
         default: return fail(OZ_ERR_STATE, "oz_engine_search needs a built-in evaluator; use select/expand for OZ_EVAL_EXTERNAL");
     }
@@ -249,7 +253,7 @@ int oz_engine_create(const oz_config *cfg, oz_engine **out) {
         t.G = G;
         if ((st = alloc_pools(t, G, default_cap(*cfg)))) break;
         if ((st = dalloc(&t.g_root, G)) || (st = dalloc(&t.g_which, G)) || (st = dalloc(&t.g_count, G)) || (st = dalloc(&t.g_status, G)) ||
-            (st = dalloc(&t.g_ply, G)) || (st = dalloc(&t.g_search, G)) || (st = dalloc(&t.h_p1, (size_t)G * kMaxHist)) ||
+            (st = dalloc(&t.g_ply, G)) || (st = dalloc(&t.g_search, G)) || (st = dalloc(&t.g_gameid, G)) || (st = dalloc(&t.h_p1, (size_t)G * kMaxHist)) ||
             (st = dalloc(&t.h_p2, (size_t)G * kMaxHist)) || (st = dalloc(&t.h_player, (size_t)G * kMaxHist)) || (st = dalloc(&t.h_n, G)) ||
             (st = dalloc(&t.r_p1, G)) || (st = dalloc(&t.r_p2, G)) || (st = dalloc(&t.r_player, G)) || (st = dalloc(&t.error, 1)) ||
             (st = dalloc(&t.stats, 4)) || (st = dalloc(&e->d_actions, G)) || (st = dalloc(&e->d_unfinished, 1)) ||
@@ -277,7 +281,8 @@ void oz_engine_destroy(oz_engine *e) {
     if (e->stream) cudaStreamSynchronize(e->stream);
     Tree &t = e->t;
     free_pools(t);
-    void *ptrs[] = {t.g_root, t.g_which, t.g_count, t.g_status, t.g_ply, t.g_search, t.h_p1, t.h_p2, t.h_player, t.h_n, t.r_p1, t.r_p2,
+    void *ptrs[] = {t.g_gameid, e->done.records, e->done.plies, e->done.gameid, e->done.p1, e->done.p2, e->done.counters, e->done.slot_done,
+                    e->done.slot_new, t.g_root, t.g_which, t.g_count, t.g_status, t.g_ply, t.g_search, t.h_p1, t.h_p2, t.h_player, t.h_n, t.r_p1, t.r_p2,
                     t.r_player, t.s_leaf, t.s_tf, t.s_len, t.s_path, t.error, t.stats, e->d_features, e->d_policy, e->d_value, e->d_rate,
                     e->d_gamma, e->d_actions, e->d_unfinished, e->d_stat_n, e->d_stat_counts, e->d_stat_q, e->d_stat_rootn, e->d_records,
                     e->d_spd_f, e->d_spd_p};
@@ -332,9 +337,62 @@ int oz_engine_set_gamma_table(oz_engine *e, const float *table, int len) {
 int oz_engine_reset(oz_engine *e) {
     OZ_TRY(set_device(e));
     if (e->in_search) return fail(OZ_ERR_STATE, "cannot reset during a search");
+    sync_params(e);
     launch_reset(e->t, e->stream);
     e->active = e->t.G;
+    if (e->done.capacity > 0) {
+        const int32_t init[3] = {0, e->t.G, 0};
+        OZ_CUDA(cudaMemcpyAsync(e->done.counters, init, sizeof(init), cudaMemcpyHostToDevice, e->stream));
+    }
     OZ_CUDA(cudaStreamSynchronize(e->stream));
+    return OZ_OK;
+}
+
+int oz_engine_set_game_pool(oz_engine *e, int total_games) {
+    OZ_TRY(set_device(e));
+    if (e->in_search) return fail(OZ_ERR_STATE, "cannot change the game pool during a search");
+    DoneStore &d = e->done;
+    cudaFree(d.records); cudaFree(d.plies); cudaFree(d.gameid); cudaFree(d.p1); cudaFree(d.p2); cudaFree(d.counters);
+    cudaFree(d.slot_done); cudaFree(d.slot_new);
+    d = DoneStore{};
+    e->pool_total = 0;
+    if (total_games == 0) return oz_engine_reset(e);
+    if (total_games < e->t.G)
+        return fail(OZ_ERR_INVALID_ARGUMENT, "Expected total_games >= num_games, but got " + std::to_string(total_games) + ".");
+    OZ_TRY(dalloc(&d.records, (size_t)total_games * e->max_plies)); OZ_TRY(dalloc(&d.plies, total_games));
+    OZ_TRY(dalloc(&d.gameid, total_games)); OZ_TRY(dalloc(&d.p1, total_games)); OZ_TRY(dalloc(&d.p2, total_games));
+    OZ_TRY(dalloc(&d.counters, 4)); OZ_TRY(dalloc(&d.slot_done, e->t.G)); OZ_TRY(dalloc(&d.slot_new, e->t.G));
+    d.capacity = total_games;
+    e->pool_total = total_games;
+    return oz_engine_reset(e);
+}
+
+int oz_engine_finished_games(oz_engine *e, int32_t *count) {
+    OZ_TRY(set_device(e));
+    if (e->done.capacity == 0) return fail(OZ_ERR_STATE, "no game pool: call oz_engine_set_game_pool first");
+    OZ_CUDA(cudaMemcpy(count, e->done.counters, sizeof(int32_t), cudaMemcpyDeviceToHost));
+    return OZ_OK;
+}
+
+int oz_engine_finished_records(oz_engine *e, uint32_t *game_ids, int32_t *plies, oz_ply_record *records, int max_plies, int capacity,
+                               int32_t *count) {
+    OZ_TRY(oz_engine_finished_games(e, count));
+    const int n = std::min<int>(*count, capacity);
+    if (n <= 0) return OZ_OK;
+    if (game_ids) OZ_CUDA(cudaMemcpy(game_ids, e->done.gameid, (size_t)n * 4, cudaMemcpyDeviceToHost));
+    std::vector<int32_t> pl(n);
+    OZ_CUDA(cudaMemcpy(pl.data(), e->done.plies, (size_t)n * 4, cudaMemcpyDeviceToHost));
+    if (plies) std::copy(pl.begin(), pl.end(), plies);
+    if (records) {
+        if (max_plies == e->max_plies) {
+            OZ_CUDA(cudaMemcpy(records, e->done.records, (size_t)n * max_plies * sizeof(oz_ply_record), cudaMemcpyDeviceToHost));
+        } else {
+            for (int i = 0; i < n; ++i) {
+                const int k = std::min(pl[i], max_plies);
+                if (k > 0) OZ_CUDA(cudaMemcpy(records + (size_t)i * max_plies, e->done.records + (size_t)i * e->max_plies, (size_t)k * sizeof(oz_ply_record), cudaMemcpyDeviceToHost));
+            }
+        }
+    }
     return OZ_OK;
 }
 
@@ -498,24 +556,27 @@ int oz_engine_search(oz_engine *e) {
     const int rounds = rounds_of(e->cfg);
     size_t k = 0;
     int st = OZ_OK;
+    const bool net_prof = e->profiling && e->cfg.evaluator == OZ_EVAL_RESNET;
     for (int r = 0; r < rounds && !st; ++r) {
         e->round = r;
-        if (e->profiling) cudaEventRecord(next_event(e, k++), e->stream);
+        cudaEvent_t cb = nullptr, ce = nullptr;
+        if (e->profiling) { cudaEventRecord(next_event(e, k), e->stream); cb = next_event(e, k + 2); ce = next_event(e, k + 3); }
         launch_select(e->t, r, e->stream);
         launch_encode(e->t, r, e->d_features, e->stream);
-        if (e->profiling) cudaEventRecord(next_event(e, k++), e->stream);
-        st = eval_round(e);
-        if (e->profiling) cudaEventRecord(next_event(e, k++), e->stream);
+        if (e->profiling) cudaEventRecord(next_event(e, k + 1), e->stream);
+        st = eval_round(e, net_prof ? cb : nullptr, net_prof ? ce : nullptr);
+        if (e->profiling) cudaEventRecord(next_event(e, k + 4), e->stream);
         if (!st) launch_expand(e->t, e->d_policy, e->d_value, e->stream);
-        if (e->profiling) cudaEventRecord(next_event(e, k++), e->stream);
+        if (e->profiling) { cudaEventRecord(next_event(e, k + 5), e->stream); k += 6; }
     }
     if (st) { e->in_search = false; return st; }
     st = end_search(e);
     if (!st && e->profiling) {
-        for (size_t i = 0; i + 3 < k; i += 4) {
-            float a = 0, b = 0, c = 0;
-            cudaEventElapsedTime(&a, e->ev[i], e->ev[i + 1]); cudaEventElapsedTime(&b, e->ev[i + 1], e->ev[i + 2]); cudaEventElapsedTime(&c, e->ev[i + 2], e->ev[i + 3]);
+        for (size_t i = 0; i + 5 < k; i += 6) {
+            float a = 0, b = 0, c = 0, d = 0;
+            cudaEventElapsedTime(&a, e->ev[i], e->ev[i + 1]); cudaEventElapsedTime(&b, e->ev[i + 1], e->ev[i + 4]); cudaEventElapsedTime(&c, e->ev[i + 4], e->ev[i + 5]);
             e->ctr.select_ms += a; e->ctr.eval_ms += b; e->ctr.expand_ms += c;
+            if (net_prof) { cudaEventElapsedTime(&d, e->ev[i + 2], e->ev[i + 3]); e->ctr.conv_ms += d; e->ctr.conv_launches += (uint64_t)(1 + 2 * e->net.shape().blocks); }
         }
     }
     return st;
@@ -556,11 +617,15 @@ int oz_engine_self_play_data(oz_engine *e, int game, float *features, float *pol
 static int apply_device_actions(oz_engine *e) {
     OZ_CUDA(cudaMemsetAsync(e->d_unfinished, 0, sizeof(int32_t), e->stream));
     launch_apply(e->t, e->d_actions, e->d_unfinished, e->stream);
-    int32_t unf = 0;
+    int32_t unf = 0, assigned = 0;
     OZ_CUDA(cudaMemcpyAsync(&unf, e->d_unfinished, sizeof(unf), cudaMemcpyDeviceToHost, e->stream));
+    if (e->done.capacity > 0) {            // rolling pool: completed games leave, their slots restart with unplayed games
+        launch_harvest(e->t, e->d_records, e->max_plies, e->done, e->pool_total, e->stream);
+        OZ_CUDA(cudaMemcpyAsync(&assigned, e->done.counters + 2, sizeof(assigned), cudaMemcpyDeviceToHost, e->stream));
+    }
     OZ_CUDA(cudaStreamSynchronize(e->stream));
     e->ctr.games_finished += (uint64_t)std::max(0, e->active - unf);
-    e->active = unf;
+    e->active = unf + assigned;
     return OZ_OK;
 }
 
@@ -627,8 +692,38 @@ int oz_engine_records(oz_engine *e, int32_t *plies, oz_ply_record *records, int 
     return OZ_OK;
 }
 
+static int training_samples_from_store(oz_engine *e, float *features, float *policy, float *value, size_t capacity, size_t *n_samples) {
+    int32_t rows = 0;
+    OZ_CUDA(cudaMemcpy(&rows, e->done.counters, sizeof(rows), cudaMemcpyDeviceToHost));
+    std::vector<int32_t> plies((size_t)std::max(rows, 1));
+    if (rows > 0) OZ_CUDA(cudaMemcpy(plies.data(), e->done.plies, (size_t)rows * 4, cudaMemcpyDeviceToHost));
+    std::vector<int64_t> base((size_t)std::max(rows, 1));
+    size_t total = 0;
+    for (int i = 0; i < rows; ++i) { base[i] = (int64_t)total; total += (size_t)plies[i] * 8; }
+    *n_samples = total;
+    if (!features || !policy || !value || total == 0) return OZ_OK;
+    if (capacity < total) return fail(OZ_ERR_INVALID_ARGUMENT, "sample buffers too small");
+    const size_t nf = (size_t)(1 + 2 * e->t.H) * 64;
+    float *d_f = nullptr, *d_p = nullptr, *d_v = nullptr;
+    int64_t *d_base = nullptr;
+    int st = OZ_OK;
+    do {
+        if ((st = dalloc(&d_f, total * nf)) || (st = dalloc(&d_p, total * 65)) || (st = dalloc(&d_v, total)) || (st = dalloc(&d_base, rows))) break;
+        cudaMemcpy(d_base, base.data(), (size_t)rows * 8, cudaMemcpyHostToDevice);
+        launch_training_samples_rows(rows, e->t.H, e->done.records, e->done.plies, d_base, e->done.p1, e->done.p2, e->max_plies, d_f, d_p, d_v, e->stream);
+        cudaError_t err = cudaStreamSynchronize(e->stream);
+        if (err != cudaSuccess) { st = fail(OZ_ERR_CUDA, std::string("training_samples: ") + cudaGetErrorString(err)); break; }
+        cudaMemcpy(features, d_f, total * nf * sizeof(float), cudaMemcpyDeviceToHost);
+        cudaMemcpy(policy, d_p, total * 65 * sizeof(float), cudaMemcpyDeviceToHost);
+        cudaMemcpy(value, d_v, total * sizeof(float), cudaMemcpyDeviceToHost);
+    } while (0);
+    cudaFree(d_f); cudaFree(d_p); cudaFree(d_v); cudaFree(d_base);
+    return st;
+}
+
 int oz_engine_training_samples(oz_engine *e, float *features, float *policy, float *value, size_t capacity, size_t *n_samples) {
     OZ_TRY(set_device(e));
+    if (e->done.capacity > 0) return training_samples_from_store(e, features, policy, value, capacity, n_samples);
     const int G = e->t.G;
     std::vector<int32_t> plies(G), status(G);
     OZ_CUDA(cudaMemcpy(plies.data(), e->t.g_ply, G * 4, cudaMemcpyDeviceToHost));

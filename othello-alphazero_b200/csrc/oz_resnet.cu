@@ -122,7 +122,7 @@ struct ConvParams {
     int kblocks;                 // cin / 32
     int cout_total;              // multiple of 128
     int relu;
-    int flags;                   // tuning switches of the pair kernel (bit 0 TMA L2 prefetch, 1 residual L2 prefetch, 2 zero-row tap skipping)
+    int flags;                   // tuning switches of the pair kernel (bit 0 TMA L2 prefetch, 1 residual L2 prefetch, 2 zero-row tap skipping, 3 programmatic dependent launch)
 };
 
 __global__ void __launch_bounds__(kThreads, 1)
@@ -377,6 +377,8 @@ __device__ __forceinline__ void stg256(void *ptr, const uint32_t *v) {
     asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
                  ::"l"(ptr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]) : "memory");
 }
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void griddep_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void tma_prefetch_4d(const CUtensorMap *map, int c0, int c1, int c2, int c3) {
     asm volatile("cp.async.bulk.prefetch.tensor.4d.L2.global.tile [%0, {%1, %2, %3, %4}];"
                  ::"l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
@@ -443,6 +445,9 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap map_act, const __grid_co
     cluster_sync_all();
     tc_fence_after();
     const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_ptr, 0);
+    // Programmatic dependent launch: the next layer's CTAs may become resident as ours retire and run their own
+    // set-up (barriers, TMEM, weight tiles) under our tail; they touch activations only after griddep_wait().
+    griddep_launch_dependents();
 
     // Roles run with warp-uniform control flow and elect one lane only around the asynchronous
     // instruction itself, so descriptors and coordinates stay in uniform registers (a divergent
@@ -451,6 +456,7 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap map_act, const __grid_co
         // ===== activation TMA producer (one per CTA; bytes complete on the LEADER's barrier) =====
         uint32_t it = 0;
         const uint32_t full0 = mapa_rank(bar_act_full, 0);
+        griddep_wait();                                   // the previous layer's output is complete and visible
         for (int pp = cluster_id; pp < num_pp; pp += num_clusters) {
             const int up = pp / ntiles, unit = 2 * (up >> 2) + (int)rank, yp = up & 3;
             if ((p.flags & 1) && pp + num_clusters < num_pp && elect_one()) {     // next pass's boxes: HBM -> L2 while this pass computes
@@ -565,6 +571,7 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap map_act, const __grid_co
         const int row = quad * 32 + lane, x = row >> 4, bl = row & 15;     // row in tile = x * 16 + board
         const uint32_t empty_remote = mapa_rank(bar_tmem_empty, 0);
         uint32_t np = 0;
+        griddep_wait();
         for (int pp = cluster_id; pp < num_pp; pp += num_clusters, ++np) {
             const int nt = pp % ntiles, up = pp / ntiles, unit = 2 * (up >> 2) + (int)rank, yp = up & 3;
             const uint32_t acc = np & 1;
@@ -687,20 +694,25 @@ __global__ void __launch_bounds__(kHeadWarps * 32, 2) heads_kernel(const HeadPar
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
             const int sq = lane + 32 * h;
-            const uint4 *a = (const uint4 *)(p.act + (b * 64 + sq) * (size_t)C);
+            const __nv_bfloat16 *a = p.act + (b * 64 + sq) * (size_t)C;
             float d0 = 0.f, d1 = 0.f, d2 = 0.f;
-#pragma unroll 4
-            for (int c8 = 0; c8 < C / 8; ++c8) {
-                const uint4 q = __ldg(a + c8);
-                const __nv_bfloat162 *hh = (const __nv_bfloat162 *)&q;
-                const float x0 = __bfloat162float(hh[0].x), x1 = __bfloat162float(hh[0].y), x2 = __bfloat162float(hh[1].x), x3 = __bfloat162float(hh[1].y);
-                const float x4 = __bfloat162float(hh[2].x), x5 = __bfloat162float(hh[2].y), x6 = __bfloat162float(hh[3].x), x7 = __bfloat162float(hh[3].y);
-                float4 wa = cw0[2 * c8], wb = cw0[2 * c8 + 1];
-                d0 += x0 * wa.x + x1 * wa.y + x2 * wa.z + x3 * wa.w + x4 * wb.x + x5 * wb.y + x6 * wb.z + x7 * wb.w;
-                wa = cw1[2 * c8]; wb = cw1[2 * c8 + 1];
-                d1 += x0 * wa.x + x1 * wa.y + x2 * wa.z + x3 * wa.w + x4 * wb.x + x5 * wb.y + x6 * wb.z + x7 * wb.w;
-                wa = cw2[2 * c8]; wb = cw2[2 * c8 + 1];
-                d2 += x0 * wa.x + x1 * wa.y + x2 * wa.z + x3 * wa.w + x4 * wb.x + x5 * wb.y + x6 * wb.z + x7 * wb.w;
+#pragma unroll 2
+            for (int c16 = 0; c16 < C / 16; ++c16) {        // one full 32-byte sector (16 channels) per load
+                uint32_t q[8];
+                ldg256(a + c16 * 16, q);
+#pragma unroll
+                for (int h2 = 0; h2 < 2; ++h2) {
+                    const __nv_bfloat162 *hh = (const __nv_bfloat162 *)&q[4 * h2];
+                    const float x0 = __bfloat162float(hh[0].x), x1 = __bfloat162float(hh[0].y), x2 = __bfloat162float(hh[1].x), x3 = __bfloat162float(hh[1].y);
+                    const float x4 = __bfloat162float(hh[2].x), x5 = __bfloat162float(hh[2].y), x6 = __bfloat162float(hh[3].x), x7 = __bfloat162float(hh[3].y);
+                    const int c8 = 2 * c16 + h2;
+                    float4 wa = cw0[2 * c8], wb = cw0[2 * c8 + 1];
+                    d0 += x0 * wa.x + x1 * wa.y + x2 * wa.z + x3 * wa.w + x4 * wb.x + x5 * wb.y + x6 * wb.z + x7 * wb.w;
+                    wa = cw1[2 * c8]; wb = cw1[2 * c8 + 1];
+                    d1 += x0 * wa.x + x1 * wa.y + x2 * wa.z + x3 * wa.w + x4 * wb.x + x5 * wb.y + x6 * wb.z + x7 * wb.w;
+                    wa = cw2[2 * c8]; wb = cw2[2 * c8 + 1];
+                    d2 += x0 * wa.x + x1 * wa.y + x2 * wa.z + x3 * wa.w + x4 * wb.x + x5 * wb.y + x6 * wb.z + x7 * wb.w;
+                }
             }
             s_feat[sq] = fmaxf(d0 + pb0, 0.f);
             s_feat[64 + sq] = fmaxf(d1 + pb1, 0.f);
@@ -828,7 +840,7 @@ static bool use_pair_kernel() {
 }
 static int conv_flags() {
     static int v = -1;
-    if (v < 0) { const char *e = getenv("OZ_CONV_FLAGS"); v = e ? atoi(e) : 6; }
+    if (v < 0) { const char *e = getenv("OZ_CONV_FLAGS"); v = e ? atoi(e) : 14; }
     return v;
 }
 static int act_box_y() { return use_pair_kernel() ? pair::kBoxYp : kBoxY; }
@@ -849,7 +861,13 @@ static int launch_conv(const CUtensorMap &ma, const CUtensorMap &mw, const ConvP
         cq.flags = conv_flags();
         const int num_pp = cp.units * 2 * (cp.cout_total >> 7);
         const int clusters = num_pp < sms / 2 ? num_pp : sms / 2;
-        conv3x3_pair_kernel<<<2 * clusters, pair::kThreadsP, pair::kSmemBytesP, stream>>>(ma, mw, cq);
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(2 * clusters); cfg.blockDim = dim3(pair::kThreadsP); cfg.dynamicSmemBytes = pair::kSmemBytesP; cfg.stream = stream;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = (cq.flags & 8) ? 1 : 0;
+        cfg.attrs = attr; cfg.numAttrs = 1;
+        OZ_CUDA(cudaLaunchKernelEx(&cfg, conv3x3_pair_kernel, ma, mw, cq));
     } else {
         const int num_pass = cp.units * 2 * (cp.cout_total >> 7);
         const int grid = num_pass < sms ? num_pass : sms;
@@ -905,7 +923,8 @@ int ResNet::reserve(size_t boards) {
     return OZ_OK;
 }
 
-int ResNet::forward(const float *d_features, size_t n, float *d_policy, float *d_value, cudaStream_t stream) {
+int ResNet::forward(const float *d_features, size_t n, float *d_policy, float *d_value, cudaStream_t stream,
+                    cudaEvent_t conv_begin, cudaEvent_t conv_end) {
     if (!loaded()) return fail(OZ_ERR_STATE, "no network weights loaded");
     if (n == 0) return OZ_OK;
     OZ_TRY(reserve(n));
@@ -916,6 +935,7 @@ int ResNet::forward(const float *d_features, size_t n, float *d_policy, float *d
         planes_to_nhwc32_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, stream>>>(d_features, shape_.in_planes, n, pad, (__nv_bfloat16 *)d_x0_);
         count_launch();
     }
+    if (conv_begin) cudaEventRecord(conv_begin, stream);
     ConvParams cp{};
     cp.units = (int)(pad / kBoardsPerUnit); cp.cout_total = C; cp.relu = 1;
     // conv block (neural_net.py:9-29)
@@ -928,6 +948,7 @@ int ResNet::forward(const float *d_features, size_t n, float *d_policy, float *d
         cp.skip = (const __nv_bfloat16 *)d_a_; cp.out = (__nv_bfloat16 *)d_a_; cp.bias = (const float *)(d_blob_ + layout_.conv_b[2 + 2 * b]);
         OZ_TRY(launch_conv(map_t_, map_w_[2 + 2 * b], cp, stream));
     }
+    if (conv_end) cudaEventRecord(conv_end, stream);
     HeadParams hp{};
     hp.act = (const __nv_bfloat16 *)d_a_;
     hp.pconv_w = (const float *)(d_blob_ + layout_.pconv_w); hp.pconv_b = (const float *)(d_blob_ + layout_.pconv_b);

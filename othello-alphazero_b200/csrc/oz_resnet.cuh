@@ -42,7 +42,9 @@ class ResNet {
     // Capacity in boards (rounded up to a multiple of 32); (re)allocates activations + tensor maps.
     int reserve(size_t boards);
     // features: DEVICE float [n][in_planes][64] (reference plane format).  policy [n][65], value [n].
-    int forward(const float *d_features, size_t n, float *d_policy, float *d_value, cudaStream_t stream);
+    // conv_begin / conv_end (optional) are recorded around the convolution launches.
+    int forward(const float *d_features, size_t n, float *d_policy, float *d_value, cudaStream_t stream,
+                cudaEvent_t conv_begin = nullptr, cudaEvent_t conv_end = nullptr);
     // Kernel launches one forward() issues.
     int launches_per_forward() const { return 2 + (1 + 2 * shape_.blocks); }
     // Debug hook: one 3x3 convolution layer on device NHWC bf16 buffers already padded to 32 boards.

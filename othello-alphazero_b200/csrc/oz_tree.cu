@@ -79,6 +79,7 @@ __global__ void reset_kernel(Tree t) {
     t.n_meta[b] = 1; t.n_parent[b] = -1; t.n_child[b] = -1;
     t.n_N[b] = 0; t.n_W[b] = 0.f; t.n_Q[b] = 0.f; t.n_P[b] = 1.f;
     t.g_root[g] = 0; t.g_count[g] = 1; t.g_status[g] = 0; t.g_ply[g] = 0; t.g_search[g] = 0; t.h_n[g] = 0;
+    t.g_gameid[g] = t.first_game_id + (uint32_t)g;
     t.r_p1[g] = kInitialP1; t.r_p2[g] = kInitialP2; t.r_player[g] = 1;
 }
 
@@ -96,20 +97,21 @@ __global__ void __launch_bounds__(128) select_kernel(Tree t, int round) {
     }
     const size_t base = arena_base(t, g);
     const int root = t.g_root[g];
-    const uint32_t game_id = t.first_game_id + (uint32_t)g, search = t.g_search[g];
+    const uint32_t game_id = t.g_gameid[g], search = t.g_search[g];
     int *path = s_path[wib];
 
     for (int i = 0; i < B; ++i) {
         const uint32_t sim = (uint32_t)(round * B + i);
         int node = root, depth = 0;
+        // Header of the current node (meta, first child, visit count).  Below the root it comes from the
+        // child-statistics read of the level above (the winning lane already holds it), so a level costs
+        // one dependent memory round trip instead of two.
+        int m = t.n_meta[base + node], fc = t.n_child[base + node], nn = t.n_N[base + node];
         while (true) {
-            const int m = t.n_meta[base + node];
             const int nch = m >> 8;
             if ((m & 3) == 0 || nch == 0) break;     // terminal or childless (search_thread.cpp:65)
-            const int fc = t.n_child[base + node];
-            int next = fc;
+            int next = fc, nm, nfc, nnn;
             if (nch > 1) {
-                int nn = t.n_N[base + node];
                 if (nn >= t.rate_len) { if (lane == 0) atomicOr(t.error, kErrRateTable); nn = t.rate_len - 1; }
                 const float rate = t.rate[nn];       // logf((1 + N + c_base) / c_base) + c_init, host libm
                 const int c0 = lane, c1 = lane + 32;
@@ -118,6 +120,8 @@ __global__ void __launch_bounds__(128) select_kernel(Tree t, int round) {
                 const int n0 = v0 ? t.n_N[a0] : 0, n1 = v1 ? t.n_N[a1] : 0;
                 const float q0 = v0 ? t.n_Q[a0] : 0.f, q1 = v1 ? t.n_Q[a1] : 0.f;
                 float p0 = v0 ? t.n_P[a0] : 0.f, p1 = v1 ? t.n_P[a1] : 0.f;
+                const int cm0 = v0 ? t.n_meta[a0] : 0, cm1 = v1 ? t.n_meta[a1] : 0;
+                const int cf0 = v0 ? t.n_child[a0] : -1, cf1 = v1 ? t.n_child[a1] : -1;
                 const int total = warp_sum(n0 + n1);
                 const float mult = __fmul_rn(rate, __fsqrt_rn((float)total));
                 if (node == root && t.eps > 0.0f) {  // Dirichlet noise, re-drawn per selection (:230-249)
@@ -129,9 +133,9 @@ __global__ void __launch_bounds__(128) select_kernel(Tree t, int round) {
                         sum = __fadd_rn(sum, gj);
                     }
                     if (sum == 0.0f) sum = 1.0f;
-                    const float pm = __fsub_rn(1.0f, t.eps), nm = __fdiv_rn(t.eps, sum);
-                    p0 = __fadd_rn(__fmul_rn(p0, pm), __fmul_rn(g0, nm));
-                    p1 = __fadd_rn(__fmul_rn(p1, pm), __fmul_rn(g1, nm));
+                    const float pm = __fsub_rn(1.0f, t.eps), nm2 = __fdiv_rn(t.eps, sum);
+                    p0 = __fadd_rn(__fmul_rn(p0, pm), __fmul_rn(g0, nm2));
+                    p1 = __fadd_rn(__fmul_rn(p1, pm), __fmul_rn(g1, nm2));
                 }
                 // ucb = Q + (mult * P) / (1 + N)
                 float u = -INFINITY; int idx = INT_MAX;
@@ -147,11 +151,17 @@ __global__ void __launch_bounds__(128) select_kernel(Tree t, int round) {
                     if (ou > u || (ou == u && oi < idx)) { u = ou; idx = oi; }
                 }
                 next = fc + idx;
+                const bool hi = idx >= 32;
+                nm = __shfl_sync(0xffffffffu, hi ? cm1 : cm0, idx & 31);
+                nfc = __shfl_sync(0xffffffffu, hi ? cf1 : cf0, idx & 31);
+                nnn = __shfl_sync(0xffffffffu, hi ? n1 : n0, idx & 31);
+            } else {
+                nm = t.n_meta[base + next]; nfc = t.n_child[base + next]; nnn = t.n_N[base + next];
             }
             if (depth < kMaxDepth) { if (lane == 0) path[depth] = next; }
             else if (lane == 0) atomicOr(t.error, kErrDepth);
             ++depth;
-            node = next;
+            node = next; m = nm; fc = nfc; nn = nnn;
         }
         if (depth > kMaxDepth) depth = kMaxDepth;
         __syncwarp();
@@ -216,7 +226,7 @@ __global__ void __launch_bounds__(128) encode_kernel(Tree t, int round, float *f
     int tf = 0;
     if (t.sym_mode == OZ_SYM_RANDOM) {
         uint32_t r[4];
-        philox(t.first_game_id + (uint32_t)g, t.g_search[g], (uint32_t)(round * t.inflight + i), 0u, t.seed_lo, t.seed_hi, r);
+        philox(t.g_gameid[g], t.g_search[g], (uint32_t)(round * t.inflight + i), 0u, t.seed_lo, t.seed_hi, r);
         tf = (int)(r[0] & 7u);
     }
     if (lane == 0) t.s_tf[slot] = tf;
@@ -322,7 +332,7 @@ __global__ void choose_kernel(Tree t, int32_t *actions) {
     const int n = legal ? __popcll(legal) : 1;
     const int nch = t.n_meta[base + root] >> 8, fc = t.n_child[base + root];
     uint32_t r[4];
-    philox(t.first_game_id + (uint32_t)g, (uint32_t)t.g_ply[g], 0xFFFFFFFFu, 2u, t.seed_lo, t.seed_hi, r);
+    philox(t.g_gameid[g], (uint32_t)t.g_ply[g], 0xFFFFFFFFu, 2u, t.seed_lo, t.seed_hi, r);
     int pick_j = 0;
     if (nch != 0) {
         if (t.g_ply[g] < t.temperature_plies) {      // proportional to visit counts (tau = 1)
@@ -444,6 +454,85 @@ __global__ void __launch_bounds__(128) apply_kernel(Tree t, const int32_t *__res
         t.r_p1[g] = np1; t.r_p2[g] = np2; t.r_player[g] = new_player;
         if (new_player == 0) t.g_status[g] |= 1; else atomicAdd(unfinished, 1);
     }
+}
+
+// ------------------------------------------------------------------ rolling game pool
+// Step 1 (one block, deterministic): finished, not yet harvested slots get a row in the store of completed
+// games and -- while unplayed games remain -- the next game id, both in slot order.
+__global__ void __launch_bounds__(1024) harvest_assign_kernel(Tree t, DoneStore d, int pool_total) {
+    __shared__ int s_warp[32];
+    __shared__ int s_base;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) s_base = 0;
+    __syncthreads();
+    const int done0 = d.counters[0], next0 = d.counters[1];
+    for (int g0 = 0; g0 < t.G; g0 += 1024) {
+        const int g = g0 + threadIdx.x;
+        const int flag = (g < t.G && (t.g_status[g] & 3) == 1) ? 1 : 0;   // bit 0 finished, bit 1 harvested
+        int incl = flag;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+        if (lane == 31) s_warp[warp] = incl;
+        __syncthreads();
+        if (warp == 0) {
+            int w = s_warp[lane];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, w, o); if (lane >= o) w += v; }
+            s_warp[lane] = w;                                     // inclusive over warps
+        }
+        __syncthreads();
+        const int before = s_base + (warp ? s_warp[warp - 1] : 0) + incl - flag;   // finished slots before this one
+        if (g < t.G) {
+            int row = -1, nid = -1;
+            if (flag) {
+                if (done0 + before < d.capacity) row = done0 + before;
+                if (next0 + before < pool_total) nid = next0 + before;
+            }
+            d.slot_done[g] = row; d.slot_new[g] = nid;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) s_base += s_warp[31];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        const int fin = s_base;
+        const int assigned = max(0, min(fin, pool_total - next0));
+        d.counters[0] = min(done0 + fin, d.capacity);
+        d.counters[1] = next0 + assigned;
+        d.counters[2] = assigned;
+    }
+}
+
+// Step 2 (one block per slot): copy the finished game's records into its row, then restart the slot with the
+// new game (the body of reset_kernel) or leave it idle.
+__global__ void __launch_bounds__(128) harvest_copy_kernel(Tree t, const PlyRecordDev *__restrict__ records, int max_plies, DoneStore d) {
+    const int g = blockIdx.x;
+    const int row = d.slot_done[g], nid = d.slot_new[g];
+    if ((t.g_status[g] & 3) != 1) return;
+    if (row >= 0) {
+        const int plies = min(t.g_ply[g], max_plies);
+        const uint4 *src = (const uint4 *)(records + (size_t)g * max_plies);
+        uint4 *dst = (uint4 *)(d.records + (size_t)row * max_plies);
+        const int n16 = plies * (int)(sizeof(PlyRecordDev) / 16);
+        for (int i = threadIdx.x; i < n16; i += blockDim.x) dst[i] = src[i];
+        if (threadIdx.x == 0) { d.plies[row] = plies; d.gameid[row] = t.g_gameid[g]; d.p1[row] = t.r_p1[g]; d.p2[row] = t.r_p2[g]; }
+    }
+    __syncthreads();
+    if (threadIdx.x != 0) return;
+    if (nid < 0) { t.g_status[g] |= 2; return; }                  // pool exhausted: harvested, idle
+    t.g_which[g] = 0;
+    const size_t b = (size_t)g * 2 * t.cap;
+    t.n_p1[b] = kInitialP1; t.n_p2[b] = kInitialP2;
+    t.n_meta[b] = 1; t.n_parent[b] = -1; t.n_child[b] = -1;
+    t.n_N[b] = 0; t.n_W[b] = 0.f; t.n_Q[b] = 0.f; t.n_P[b] = 1.f;
+    t.g_root[g] = 0; t.g_count[g] = 1; t.g_status[g] = 0; t.g_ply[g] = 0; t.g_search[g] = 0; t.h_n[g] = 0;
+    t.g_gameid[g] = t.first_game_id + (uint32_t)nid;
+    t.r_p1[g] = kInitialP1; t.r_p2[g] = kInitialP2; t.r_player[g] = 1;
+}
+
+void launch_harvest(const Tree &t, const PlyRecordDev *records, int max_plies, const DoneStore &d, int pool_total, cudaStream_t s) {
+    harvest_assign_kernel<<<1, 1024, 0, s>>>(t, d, pool_total); count_launch();
+    harvest_copy_kernel<<<t.G, 128, 0, s>>>(t, records, max_plies, d); count_launch();
 }
 
 // ------------------------------------------------------------------ self-play sample of one root (mcts.cpp:63-112)
@@ -597,8 +686,14 @@ void launch_eval_hash(const float *features, int planes, size_t n, float *policy
 }
 void launch_training_samples(const Tree &t, const PlyRecordDev *records, const int32_t *plies, const int64_t *sample_base,
                              int max_plies, float *features, float *policy, float *value, cudaStream_t s) {
-    training_samples_kernel<<<(unsigned)((size_t)t.G * max_plies), 256, 0, s>>>(records, plies, sample_base, t.r_p1, t.r_p2, t.G,
-                                                                              max_plies, t.H, features, policy, value);
+    launch_training_samples_rows(t.G, t.H, records, plies, sample_base, t.r_p1, t.r_p2, max_plies, features, policy, value, s);
+}
+void launch_training_samples_rows(int rows, int H, const PlyRecordDev *records, const int32_t *plies, const int64_t *sample_base,
+                                  const uint64_t *fin_p1, const uint64_t *fin_p2, int max_plies, float *features, float *policy,
+                                  float *value, cudaStream_t s) {
+    if (rows <= 0) return;
+    training_samples_kernel<<<(unsigned)((size_t)rows * max_plies), 256, 0, s>>>(records, plies, sample_base, fin_p1, fin_p2, rows,
+                                                                               max_plies, H, features, policy, value);
     count_launch();
 }
 

@@ -34,6 +34,7 @@ struct Tree {
     // per game
     int32_t *g_root, *g_which, *g_count, *g_status, *g_ply;
     uint32_t *g_search;                  // searches since reset (RNG counter)
+    uint32_t *g_gameid;                  // global game id played in this slot (RNG streams are keyed by it)
     uint64_t *h_p1, *h_p2;               // [G][kMaxHist] retired ancestors, most recent first
     int32_t *h_player, *h_n;             // [G][kMaxHist], [G]
     uint64_t *r_p1, *r_p2; int32_t *r_player;   // root position mirror [G]
@@ -73,6 +74,22 @@ void launch_eval_hash(const float *features, int planes, size_t n, float *policy
 // Training tensors from records (train.py:432-450).  sample_base[g] = first sample row of game g.
 void launch_training_samples(const Tree &t, const PlyRecordDev *records, const int32_t *plies, const int64_t *sample_base,
                              int max_plies, float *features, float *policy, float *value, cudaStream_t s);
+// Same for `rows` record rows with explicit final positions (store of completed games).
+void launch_training_samples_rows(int rows, int H, const PlyRecordDev *records, const int32_t *plies, const int64_t *sample_base,
+                                  const uint64_t *fin_p1, const uint64_t *fin_p2, int max_plies, float *features, float *policy,
+                                  float *value, cudaStream_t s);
+// Rolling game pool: finished games are moved to a store of completed games and their slots restart with the next
+// unplayed game id.  `done_*` arrays have one row per completed game, in completion order (slot order within a ply).
+struct DoneStore {
+    PlyRecordDev *records;    // [capacity][max_plies]
+    int32_t *plies;           // [capacity]
+    uint32_t *gameid;         // [capacity]
+    uint64_t *p1, *p2;        // [capacity] final discs (train.py:438-439: the outcome)
+    int32_t *counters;        // [0] completed games, [1] next unplayed game id offset, [2] games assigned by the last harvest
+    int32_t *slot_done, *slot_new;   // [G] scratch: done row / new game id offset of a slot (-1 none)
+    int capacity;             // games in the pool (completed rows available)
+};
+void launch_harvest(const Tree &t, const PlyRecordDev *records, int max_plies, const DoneStore &d, int pool_total, cudaStream_t s);
 // Move every game's live arena into pools with a different capacity (pool growth).
 void launch_copy_arenas(const Tree &from, const Tree &to, cudaStream_t s);
 

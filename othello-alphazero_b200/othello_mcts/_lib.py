@@ -43,7 +43,8 @@ class OzPlyRecord(C.Structure):
 class OzCounters(C.Structure):
     _fields_ = [("simulations", u64), ("evaluations", u64), ("nodes_expanded", u64), ("searches", u64),
                 ("plies", u64), ("games_finished", u64), ("kernel_launches", u64), ("select_ms", C.c_double),
-                ("eval_ms", C.c_double), ("expand_ms", C.c_double), ("reroot_ms", C.c_double)]
+                ("eval_ms", C.c_double), ("expand_ms", C.c_double), ("reroot_ms", C.c_double), ("conv_ms", C.c_double),
+                ("conv_launches", u64)]
 
 
 # name -> (restype, argtypes); every symbol include/othello_b200.h declares
@@ -107,6 +108,9 @@ SIGNATURES = {
     "oz_engine_records": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]),
     "oz_engine_training_samples": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, P(C.c_size_t)]),
     "oz_engine_counters": (C.c_int, [C.c_void_p, P(OzCounters)]),
+    "oz_engine_set_game_pool": (C.c_int, [C.c_void_p, C.c_int]),
+    "oz_engine_finished_games": (C.c_int, [C.c_void_p, P(C.c_int32)]),
+    "oz_engine_finished_records": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, P(C.c_int32)]),
     "oz_engine_set_profiling": (C.c_int, [C.c_void_p, C.c_int]),
     "oz_engine_stream": (C.c_void_p, [C.c_void_p]),
 }

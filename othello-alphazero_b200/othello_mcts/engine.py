@@ -17,6 +17,8 @@ from ._lib import (EVAL_EXTERNAL, EVAL_HASH, EVAL_RESNET, EVAL_SYNTH, MAX_CHILDR
 from .position import Position
 
 _BUILTIN = {"synth": EVAL_SYNTH, "hash": EVAL_HASH}
+_RECORD_DTYPE = np.dtype([("p1", "<u8"), ("p2", "<u8"), ("player", "<i4"), ("action", "<i4"), ("n_children", "<i4"),
+                          ("visit_counts", "<i4", (MAX_CHILDREN,)), ("_pad", "<i4")])
 
 
 def _ptr(a: np.ndarray):
@@ -281,22 +283,45 @@ class SelfPlayEngine(_Engine):
                                            C.byref(unfinished)))
         return actions, counts, unfinished.value
 
-    def run(self, neural_net, max_plies: int = 128) -> dict:
-        """Play every game to the end; returns the compact records (see records())."""
+    def set_game_pool(self, total_games: int) -> None:
+        """Rolling game pool: the `num_games` slots play `total_games` games (ids first_game_id ..); a finished game
+        moves to the store of completed games and its slot restarts with the next unplayed id.  0 switches it off.
+        Resets every game."""
+        check(self._lib.oz_engine_set_game_pool(self._h, int(total_games)))
+
+    def finished_games(self) -> int:
+        n = C.c_int32()
+        check(self._lib.oz_engine_finished_games(self._h, C.byref(n)))
+        return n.value
+
+    def finished_records(self, max_plies: int = 128) -> dict:
+        """Completed games of the rolling pool, in completion order: {"game_ids", "plies", "records"}."""
+        n = self.finished_games()
+        ids = np.zeros(n, np.uint32)
+        plies = np.zeros(n, np.int32)
+        recs = (OzPlyRecord * max(1, n * max_plies))()
+        cnt = C.c_int32()
+        check(self._lib.oz_engine_finished_records(self._h, _ptr(ids), _ptr(plies), recs, max_plies, n, C.byref(cnt)))
+        arr = np.frombuffer(recs, dtype=_RECORD_DTYPE)[: n * max_plies].reshape(n, max_plies)
+        return {"game_ids": ids, "plies": plies, "records": arr}
+
+    def run(self, neural_net, total_games: int | None = None, max_plies: int = 100000) -> dict:
+        """Play to the end.  Without `total_games`: the `num_games` lockstep games, returns records().  With
+        `total_games` >= num_games: rolling pool, returns finished_records() (completion order, with game ids)."""
+        if total_games is not None:
+            self.set_game_pool(total_games)
         self.prepare(neural_net)
         for _ in range(max_plies):
             _, _, unfinished = self.play_ply()
             if unfinished == 0:
                 break
-        return self.records()
+        return self.finished_records() if total_games is not None else self.records()
 
     def records(self, max_plies: int = 128) -> dict:
         plies = np.zeros(self.num_games, np.int32)
         recs = (OzPlyRecord * (self.num_games * max_plies))()
         check(self._lib.oz_engine_records(self._h, _ptr(plies), recs, max_plies))
-        arr = np.frombuffer(recs, dtype=np.dtype([("p1", "<u8"), ("p2", "<u8"), ("player", "<i4"), ("action", "<i4"),
-                                                   ("n_children", "<i4"), ("visit_counts", "<i4", (MAX_CHILDREN,)),
-                                                   ("_pad", "<i4")])).reshape(self.num_games, max_plies)
+        arr = np.frombuffer(recs, dtype=_RECORD_DTYPE).reshape(self.num_games, max_plies)
         return {"plies": plies, "records": arr}
 
     def training_samples(self) -> dict:

@@ -202,3 +202,40 @@ def test_tree_reuse_setters_and_errors(oracle):
     assert sum(m.visit_counts()) >= before - 1          # Q2: the subtree and its counts survive re-rooting
     m.reset_position()
     assert m.position().legal_actions() == [19, 26, 37, 44] and m.visit_counts() == []
+
+
+def test_rolling_pool_is_invariant_to_slot_count():
+    """Rolling game pool: 10 games through 3 slots (finished games leave, slots restart with the next unplayed id)
+    give, game id by game id, the records of 10 games played side by side -- RNG streams are keyed by game id, not
+    by slot -- and the training tensors of the store match the side-by-side ones."""
+    import torch
+    from othello_mcts import SelfPlayEngine
+    kw = dict(history_size=4, num_simulations=48, num_threads=1, batch_size=8, dirichlet_epsilon=0.25, seed=77,
+              first_game_id=100, temperature_plies=6)
+    wide = SelfPlayEngine(10, **kw)
+    wide.run("hash")
+    ref = wide.records()
+    ref_samples = wide.training_samples()
+    roll = SelfPlayEngine(3, **kw)
+    got = roll.run("hash", total_games=10)
+    assert roll.finished_games() == 10
+    assert sorted(got["game_ids"].tolist()) == list(range(100, 110))
+    offsets, rows = {}, 0
+    for g in range(10):
+        offsets[100 + g] = rows
+        rows += int(ref["plies"][g]) * 8
+    roll_samples = roll.training_samples()
+    assert roll_samples["features"].shape[0] == rows
+    r0 = 0
+    for row, gid in enumerate(got["game_ids"].tolist()):
+        g = gid - 100
+        n = int(ref["plies"][g])
+        assert int(got["plies"][row]) == n
+        for name in ("p1", "p2", "player", "action", "n_children", "visit_counts"):      # every field but the padding
+            assert np.array_equal(got["records"][row, :n][name], ref["records"][g, :n][name]), (gid, name)
+        a, b = offsets[gid], offsets[gid] + n * 8
+        for k in ("features", "policies", "values"):
+            assert torch.equal(roll_samples[k][r0:r0 + n * 8], ref_samples[k][a:b]), (gid, k)
+        r0 += n * 8
+    c = roll.counters()
+    assert c["games_finished"] == 10

@@ -22,7 +22,7 @@ def test_library_exports_every_declared_symbol():
     assert not missing, f"declared in include/othello_b200.h but not exported: {missing}"
     unbound = sorted(declared - set(_lib.SIGNATURES))
     assert not unbound, f"no ctypes signature for: {unbound}"
-    assert _lib.load().oz_abi_version() == 1
+    assert _lib.load().oz_abi_version() == 2
 
 
 def test_struct_sizes_match_abi():
