@@ -187,6 +187,8 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dist = None
     if world > 1:
+        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":      # keeps NCCL's banner off stdout: one JSON line only
+            os.environ["NCCL_DEBUG"] = "WARN"
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
@@ -230,22 +232,27 @@ def run_ours(args):
     rng = np.random.default_rng(args.seed + rank)
     h2d = d2h = 0
 
+    sq = np.arange(64, dtype=np.uint64)
+
     def e2e_step():
+        """search -> visit counts to the host -> action choice on the host (train.py:421-430, tau = 1: proportional to
+        the visit counts) -> apply_action from a host array.  The choice is vectorised over games with NumPy."""
         nonlocal h2d, d2h
         eng.search(net)
         n, counts, _, _ = eng._root_stats()                       # D2H: visit counts, child counts, Q, root N
-        positions = eng.positions()                               # D2H: root positions
-        acts = np.full(G, -1, np.int32)
-        for g in range(G):                                        # host-side action choice, as train.py:421-430
-            k = int(n[g])
-            if k == 0:
-                continue
-            c = counts[g, :k].astype(np.float64)
-            legal = positions[g].legal_actions()
-            acts[g] = legal[int(rng.choice(k, p=c / c.sum()))] if c.sum() > 0 else legal[0]
+        pos = eng.positions_array()                               # D2H: root positions
+        c = counts.astype(np.float64)
+        tot_c = c.sum(axis=1)
+        pick = (rng.random(G) * tot_c)[:, None]
+        j = np.minimum((np.cumsum(c, axis=1) <= pick).sum(axis=1), np.maximum(n - 1, 0))     # sampled child index
+        bits = ((pos["legal"][:, None] >> (np.uint64(63) - sq)[None, :]) & np.uint64(1)).astype(np.int32)   # [G,64] by action
+        rank = np.cumsum(bits, axis=1) * bits                     # 1-based rank of every legal action
+        acts = np.argmax(rank == (j + 1)[:, None], axis=1).astype(np.int32)
+        acts[pos["legal"] == 0] = 64                              # pass
+        acts[(n == 0) | (pos["player"] == 0)] = -1                # finished games
         eng.apply_actions(acts)                                   # H2D: actions (+ D2H of positions for validation)
         h2d = G * 4
-        d2h = G * (4 + 36 * 4 + 36 * 4 + 4) + 2 * G * 24
+        d2h = G * (4 + 36 * 4 + 36 * 4 + 4) + 2 * G * 40
 
     for _ in range(max(args.warmup, 3)):
         dev_step()
@@ -266,6 +273,30 @@ def run_ours(args):
     if dist is not None:
         dist.all_reduce(tot)                                      # the only collective: final counters
     value = float(tot[0].item()) / (ms * 1e-3)
+
+    # Same device-resident step measured in the middle game: every game is fast-forwarded to ply `--midgame-ply` with
+    # full-width searches on the built-in hash evaluator (tree kernels only), then the network is switched back.
+    mid = None
+    if args.midgame_ply > 0:
+        eng.reset()
+        eng.prepare("hash")
+        for _ in range(args.midgame_ply):
+            eng.play_ply(want_counts=False)
+        eng.prepare(net)
+        dev_step()
+        m0 = eng.counters()
+        ms_mid = timed(dev_step, 2)
+        m1 = eng.counters()
+        mid_sims = torch.tensor([float(m1["simulations"] - m0["simulations"])], device="cuda", dtype=torch.float64)
+        if dist is not None:
+            dist.all_reduce(mid_sims)
+        mid = {"ply": args.midgame_ply + 1, "steps": 2, "value": float(mid_sims.item()) / (ms_mid * 1e-3), "unit": "sims/s",
+               "ms_per_step": ms_mid / 2, "select_ms_per_step": (m1["select_ms"] - m0["select_ms"]) / 2,
+               "expand_ms_per_step": (m1["expand_ms"] - m0["expand_ms"]) / 2}
+        eng.reset()
+        eng.prepare(net)
+        for _ in range(2):
+            dev_step()
 
     ms_e2e = timed(e2e_step, max(1, min(args.steps, 3)))
     e2e_steps = max(1, min(args.steps, 3))
@@ -306,6 +337,7 @@ def run_ours(args):
                          "peak_source": pk["source"] + ", sustained bf16 (kernel timed inside a long step)"},
             "perft": {"depth": 11, "nodes": int(perft_nodes), "nodes_per_s": perft_nodes / (perft_ms * 1e-3) if perft_ms > 0 else None,
                       "device_ms": perft_ms},
+            "midgame": mid,
             "clocks": clocks,
         }
         if world == 1 and not args.no_cpu_baseline:
@@ -332,6 +364,7 @@ def main():
     ap.add_argument("--seed", type=int, default=2026)
     ap.add_argument("--cpu-steps", type=int, default=12)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--midgame-ply", type=int, default=24, help="also time 2 plies after fast-forwarding every game this far (0 = skip)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

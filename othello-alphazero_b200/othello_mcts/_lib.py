@@ -83,7 +83,7 @@ SIGNATURES = {
     "oz_engine_get_config": (C.c_int, [C.c_void_p, P(OzConfig)]),
     "oz_engine_set_gamma_table": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),
     "oz_engine_reset": (C.c_int, [C.c_void_p]),
-    "oz_engine_positions": (C.c_int, [C.c_void_p, P(OzPosition)]),
+    "oz_engine_positions": (C.c_int, [C.c_void_p, C.c_void_p]),
     "oz_resnet_blob_bytes": (C.c_size_t, [P(OzResnetShape)]),
     "oz_resnet_blob_offsets": (C.c_int, [P(OzResnetShape), P(i64), C.c_int, P(C.c_int)]),
     "oz_engine_load_resnet": (C.c_int, [C.c_void_p, P(OzResnetShape), C.c_void_p, C.c_size_t]),

@@ -249,6 +249,13 @@ class SelfPlayEngine(_Engine):
     def positions(self) -> list[Position]:
         return self._positions()
 
+    def positions_array(self) -> np.ndarray:
+        """Root positions of all games as one structured array (batch.POSITION_DTYPE: player, p1, p2, legal, next_legal)."""
+        from .batch import POSITION_DTYPE
+        out = np.zeros(self.num_games, POSITION_DTYPE)
+        check(self._lib.oz_engine_positions(self._h, _ptr(out)))
+        return out
+
     def search(self, neural_net) -> None:
         self._search(neural_net)
 
