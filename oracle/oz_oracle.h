@@ -4,7 +4,7 @@
  * and bench.py's cpu_baseline / --impl reference legs may load this library, and only
  * as the checker (or the reported CPU baseline), never as the thing shipped.
  *
- * Parity status: PINNED.  tests/test_oracle_vs_reference.py checks every function here
+ * Parity status: PINNED.  tests/test_oracle.py checks every function here
  * against the unmodified reference compiled from /root/reference (oracle/_ref, built by
  * oracle/build_oracle.py) and against the golden vectors committed in tests/golden/
  * (generated from the reference by tests/golden/generate_golden.py).  The Dirichlet /

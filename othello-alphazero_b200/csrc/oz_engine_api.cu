@@ -42,6 +42,7 @@ struct oz_engine {
     bool in_search = false;
     int round = 0;
     int active = 0;                       // games not finished
+    long tree_bound = 1;                  // upper bound on the nodes of the largest live tree
     oz_counters ctr{};
     bool profiling = false;
     std::vector<cudaEvent_t> ev;          // phase boundaries of one search
@@ -86,10 +87,19 @@ int rounds_of(const oz_config &c) {
     return (c.num_simulations + inflight - 1) / inflight;   // search_thread.cpp:48-50
 }
 
+constexpr int kMaxChildrenPerNode = 33;   // most legal moves an Othello position can have
+
+// Nodes one search can add to a tree: every simulation expands at most one leaf.
+long search_growth(const oz_config &c) {
+    return (long)rounds_of(c) * c.num_threads * c.batch_size * kMaxChildrenPerNode;
+}
+
+// Initial arena size: room for a typical carried-over tree plus one worst-case search.  Arenas grow on demand
+// (ensure_capacity), so this is a starting point, not a limit.
 int default_cap(const oz_config &c) {
     if (c.max_nodes_per_game > 0) return c.max_nodes_per_game;
     const long sims = (long)rounds_of(c) * c.num_threads * c.batch_size;
-    return (int)std::min<long>(40 * std::max<long>(sims, 64) + 1024, 1 << 22);
+    return (int)std::min<long>(48 * std::max<long>(sims, 64) + search_growth(c) + 1024, 1 << 22);
 }
 
 int alloc_pools(Tree &t, int G, int cap) {
@@ -182,6 +192,28 @@ int grow_pools(oz_engine *e, int new_cap) {
 
 cudaEvent_t next_event(oz_engine *e, size_t i);
 
+// The reference's trees are heap-allocated and unbounded (search_node.h:29); ours live in fixed arenas, so before
+// a search every game must have room for the worst case.  tree_bound is exact after a re-root (apply_kernel reports
+// the largest tree) and grows by the worst case per search in between.
+int ensure_capacity(oz_engine *e) {
+    const long growth = search_growth(e->cfg);
+    if (e->tree_bound + growth > e->t.cap) {           // tighten the bound before paying for a reallocation
+        int32_t mx = 0;
+        OZ_CUDA(cudaMemsetAsync(e->d_unfinished + 1, 0, sizeof(int32_t), e->stream));
+        launch_max_count(e->t, e->d_unfinished + 1, e->stream);
+        OZ_CUDA(cudaMemcpyAsync(&mx, e->d_unfinished + 1, sizeof(mx), cudaMemcpyDeviceToHost, e->stream));
+        OZ_CUDA(cudaStreamSynchronize(e->stream));
+        e->tree_bound = mx;
+    }
+    if (e->tree_bound + growth > e->t.cap) {
+        const long want = std::max<long>(2L * e->t.cap, (e->tree_bound + growth) * 5 / 4);
+        if (want > (1L << 24)) return fail(OZ_ERR_CAPACITY, "search tree beyond 16 M nodes per game");
+        OZ_TRY(grow_pools(e, (int)want));
+    }
+    e->tree_bound += growth;
+    return OZ_OK;
+}
+
 int eval_round(oz_engine *e, cudaEvent_t conv_begin = nullptr, cudaEvent_t conv_end = nullptr) {
     const size_t n = (size_t)e->t.G * e->t.inflight;
     const int planes = 1 + 2 * e->t.H;
@@ -208,6 +240,7 @@ int begin_search(oz_engine *e) {
     if (e->in_search) return fail(OZ_ERR_STATE, "search already in progress");
     if (e->cfg.evaluator == OZ_EVAL_RESNET && !e->net.loaded()) return fail(OZ_ERR_STATE, "no network weights loaded");
     sync_params(e);
+    OZ_TRY(ensure_capacity(e));
     // New SearchThread per search: feature slots start from zeros (search_thread.cpp:37-39).
     OZ_CUDA(cudaMemsetAsync(e->d_features, 0, (size_t)e->t.G * e->t.inflight * (1 + 2 * e->t.H) * 64 * sizeof(float), e->stream));
     e->in_search = true; e->round = 0;
@@ -256,7 +289,7 @@ int oz_engine_create(const oz_config *cfg, oz_engine **out) {
             (st = dalloc(&t.g_ply, G)) || (st = dalloc(&t.g_search, G)) || (st = dalloc(&t.g_gameid, G)) || (st = dalloc(&t.h_p1, (size_t)G * kMaxHist)) ||
             (st = dalloc(&t.h_p2, (size_t)G * kMaxHist)) || (st = dalloc(&t.h_player, (size_t)G * kMaxHist)) || (st = dalloc(&t.h_n, G)) ||
             (st = dalloc(&t.r_p1, G)) || (st = dalloc(&t.r_p2, G)) || (st = dalloc(&t.r_player, G)) || (st = dalloc(&t.error, 1)) ||
-            (st = dalloc(&t.stats, 4)) || (st = dalloc(&e->d_actions, G)) || (st = dalloc(&e->d_unfinished, 1)) ||
+            (st = dalloc(&t.stats, 4)) || (st = dalloc(&e->d_actions, G)) || (st = dalloc(&e->d_unfinished, 2)) ||
             (st = dalloc(&e->d_stat_n, G)) || (st = dalloc(&e->d_stat_counts, (size_t)G * kStride)) || (st = dalloc(&e->d_stat_q, (size_t)G * kStride)) ||
             (st = dalloc(&e->d_stat_rootn, G)) || (st = dalloc(&e->d_spd_p, 8 * 65)))
             break;
@@ -340,6 +373,7 @@ int oz_engine_reset(oz_engine *e) {
     sync_params(e);
     launch_reset(e->t, e->stream);
     e->active = e->t.G;
+    e->tree_bound = 1;
     if (e->done.capacity > 0) {
         const int32_t init[3] = {0, e->t.G, 0};
         OZ_CUDA(cudaMemcpyAsync(e->done.counters, init, sizeof(init), cudaMemcpyHostToDevice, e->stream));
@@ -615,15 +649,17 @@ int oz_engine_self_play_data(oz_engine *e, int game, float *features, float *pol
 }
 
 static int apply_device_actions(oz_engine *e) {
-    OZ_CUDA(cudaMemsetAsync(e->d_unfinished, 0, sizeof(int32_t), e->stream));
+    OZ_CUDA(cudaMemsetAsync(e->d_unfinished, 0, 2 * sizeof(int32_t), e->stream));
     launch_apply(e->t, e->d_actions, e->d_unfinished, e->stream);
-    int32_t unf = 0, assigned = 0;
-    OZ_CUDA(cudaMemcpyAsync(&unf, e->d_unfinished, sizeof(unf), cudaMemcpyDeviceToHost, e->stream));
+    int32_t unf2[2] = {0, 0}, assigned = 0;
+    OZ_CUDA(cudaMemcpyAsync(unf2, e->d_unfinished, sizeof(unf2), cudaMemcpyDeviceToHost, e->stream));
     if (e->done.capacity > 0) {            // rolling pool: completed games leave, their slots restart with unplayed games
         launch_harvest(e->t, e->d_records, e->max_plies, e->done, e->pool_total, e->stream);
         OZ_CUDA(cudaMemcpyAsync(&assigned, e->done.counters + 2, sizeof(assigned), cudaMemcpyDeviceToHost, e->stream));
     }
     OZ_CUDA(cudaStreamSynchronize(e->stream));
+    const int32_t unf = unf2[0];
+    e->tree_bound = std::max<long>(1, unf2[1]);       // exact: the largest live tree after the re-root
     e->ctr.games_finished += (uint64_t)std::max(0, e->active - unf);
     e->active = unf + assigned;
     return OZ_OK;

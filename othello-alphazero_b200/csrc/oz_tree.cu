@@ -379,7 +379,7 @@ __global__ void __launch_bounds__(128) apply_kernel(Tree t, const int32_t *__res
     if (g >= t.G) return;
     const int action = actions[g];
     if (action < 0 || (t.g_status[g] & 1)) {
-        if (lane == 0 && !(t.g_status[g] & 1)) atomicAdd(unfinished, 1);
+        if (lane == 0 && !(t.g_status[g] & 1)) { atomicAdd(unfinished, 1); atomicMax(unfinished + 1, t.g_count[g]); }
         return;
     }
     const int which = t.g_which[g];
@@ -453,6 +453,7 @@ __global__ void __launch_bounds__(128) apply_kernel(Tree t, const int32_t *__res
         t.g_which[g] = which ^ 1; t.g_root[g] = 0; t.g_count[g] = new_count; t.g_ply[g] += 1;
         t.r_p1[g] = np1; t.r_p2[g] = np2; t.r_player[g] = new_player;
         if (new_player == 0) t.g_status[g] |= 1; else atomicAdd(unfinished, 1);
+        atomicMax(unfinished + 1, new_count);         // largest tree after the re-root (arena sizing on the host)
     }
 }
 
@@ -672,6 +673,14 @@ void launch_choose(const Tree &t, int32_t *actions, cudaStream_t s) { choose_ker
 void launch_record(const Tree &t, const int32_t *actions, PlyRecordDev *records, int max_plies, cudaStream_t s) {
     record_kernel<<<blocks(t.G, 128), 128, 0, s>>>(t, actions, records, max_plies); count_launch();
 }
+__global__ void max_count_kernel(Tree t, int32_t *out) {
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    int c = g < t.G ? t.g_count[g] : 0;
+#pragma unroll
+    for (int o = 16; o; o >>= 1) c = max(c, __shfl_xor_sync(0xffffffffu, c, o));
+    if ((threadIdx.x & 31) == 0) atomicMax(out, c);
+}
+void launch_max_count(const Tree &t, int32_t *out, cudaStream_t s) { max_count_kernel<<<blocks(t.G, 128), 128, 0, s>>>(t, out); count_launch(); }
 void launch_apply(const Tree &t, const int32_t *actions, int32_t *unfinished, cudaStream_t s) {
     apply_kernel<<<blocks(t.G, 4), 128, 0, s>>>(t, actions, unfinished); count_launch();
 }

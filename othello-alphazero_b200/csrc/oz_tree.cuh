@@ -67,7 +67,10 @@ void launch_end_search(const Tree &t, cudaStream_t s);
 void launch_root_stats(const Tree &t, int32_t *n_children, int32_t *counts, float *q, int32_t *root_n, cudaStream_t s);
 void launch_choose(const Tree &t, int32_t *actions, cudaStream_t s);
 void launch_record(const Tree &t, const int32_t *actions, PlyRecordDev *records, int max_plies, cudaStream_t s);
+// unfinished[0] += games still running, unfinished[1] = max(unfinished[1], nodes in the largest re-rooted tree).
 void launch_apply(const Tree &t, const int32_t *actions, int32_t *unfinished, cudaStream_t s);
+// *out = max(*out, largest g_count).
+void launch_max_count(const Tree &t, int32_t *out, cudaStream_t s);
 void launch_self_play_data(const Tree &t, int game, float *features, float *policy, cudaStream_t s);
 void launch_eval_synth(const float *features, int planes, size_t n, float *policy, float *value, cudaStream_t s);
 void launch_eval_hash(const float *features, int planes, size_t n, float *policy, float *value, cudaStream_t s);

@@ -239,3 +239,18 @@ def test_rolling_pool_is_invariant_to_slot_count():
         r0 += n * 8
     c = roll.counters()
     assert c["games_finished"] == 10
+
+
+def test_arena_growth_is_transparent():
+    """Trees live in fixed arenas (the reference's are heap-allocated, search_node.h:29).  Before every search the
+    engine checks the worst case (one new node with 33 children per simulation) and reallocates bigger arenas when
+    needed; a run that starts with absurdly small arenas must give exactly the records of a run that never grows."""
+    from othello_mcts import SelfPlayEngine
+    kw = dict(history_size=4, num_simulations=64, num_threads=2, batch_size=8, dirichlet_epsilon=0.25, seed=9, temperature_plies=8)
+    small = SelfPlayEngine(6, max_nodes_per_game=64, **kw)
+    big = SelfPlayEngine(6, **kw)
+    a = small.run("hash")
+    b = big.run("hash")
+    assert (a["plies"] == b["plies"]).all() and a["plies"].min() > 8
+    for name in ("p1", "p2", "player", "action", "n_children", "visit_counts"):
+        assert np.array_equal(a["records"][name], b["records"][name]), name
