@@ -452,7 +452,7 @@ int oz_engine_positions(oz_engine *e, oz_position *out) {
     return OZ_OK;
 }
 
-size_t oz_resnet_blob_bytes(const oz_resnet_shape *s) { return resnet_layout(*s).total; }
+size_t oz_resnet_blob_bytes(const oz_resnet_shape *s) { return resnet_layout(*s).head_w; }
 
 int oz_resnet_blob_offsets(const oz_resnet_shape *s, int64_t *offsets, int capacity, int *count) {
     ResNetLayout L = resnet_layout(*s);

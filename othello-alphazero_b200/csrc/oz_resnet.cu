@@ -122,6 +122,8 @@ struct ConvParams {
     int kblocks;                 // cin / 32
     int cout_total;              // multiple of 128
     int relu;
+    const float *head_w;         // pair kernel, last layer of a 128-channel tower: [3][128] 1x1 head-conv weights (policy 0, policy 1, value)
+    float *head_out;             // ... and their pre-activations [boards][64][4] (zeroed by the caller; two column halves add up)
     int flags;                   // tuning switches of the pair kernel (bit 0 TMA L2 prefetch, 1 residual L2 prefetch, 2 zero-row tap skipping, 3 programmatic dependent launch)
 };
 
@@ -413,6 +415,7 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap map_act, const __grid_co
     const uint32_t bar_w_full = misc + 64, bar_w_empty = misc + 64 + 8 * kWSlots;
     uint32_t *tmem_ptr = (uint32_t *)(gen + (misc - base) + 704);
     float *s_bias = (float *)(gen + (misc - base) + 1024);                   // up to 384 floats
+    float *s_head = (float *)(gen + (misc - base) + 2560);                   // [3][128] head-conv weights (fused heads)
 
     const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
     const uint32_t rank = cluster_ctarank();
@@ -440,6 +443,7 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap map_act, const __grid_co
         *(uint4 *)(gen + s * kActStageBytesP + o * 16) = make_uint4(0, 0, 0, 0);
     }
     for (int i = threadIdx.x; i < p.cout_total; i += kThreadsP) s_bias[i] = p.bias[i];
+    if (p.head_out) for (int i = threadIdx.x; i < 3 * 128; i += kThreadsP) s_head[i] = p.head_w[i];
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     tc_fence_before();
     cluster_sync_all();
@@ -598,6 +602,7 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap map_act, const __grid_co
             tc_fence_after();
 #pragma unroll
             for (int r = 0; r < kYPerPass; ++r) {
+                float h0 = 0.f, h1 = 0.f, h2 = 0.f;          // fused 1x1 head convolutions over this thread's 64 channels
 #pragma unroll
                 for (int ch = 0; ch < 2; ++ch) {
                     uint32_t v[32];
@@ -616,12 +621,23 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap map_act, const __grid_co
                             b += __bfloat162float(s2.y);
                         }
                         if (p.relu) { a = fmaxf(a, 0.f); b = fmaxf(b, 0.f); }
+                        if (p.head_out) {
+                            const int c = half * 64 + ch * 32 + 2 * i;
+                            const float2 w0 = *(const float2 *)(s_head + c), w1 = *(const float2 *)(s_head + 128 + c), w2 = *(const float2 *)(s_head + 256 + c);
+                            h0 += a * w0.x + b * w0.y; h1 += a * w1.x + b * w1.y; h2 += a * w2.x + b * w2.y;
+                        }
                         const __nv_bfloat162 o2 = __floats2bfloat162_rn(a, b);
                         ow[i] = *(const uint32_t *)&o2;
                     }
-                    __nv_bfloat16 *op = p.out + off0 + r * ystride + ch * 32;   // full 32-byte sectors per store
-                    stg256(op, &ow[0]);
-                    stg256(op + 16, &ow[8]);
+                    if (p.out) {
+                        __nv_bfloat16 *op = p.out + off0 + r * ystride + ch * 32;   // full 32-byte sectors per store
+                        stg256(op, &ow[0]);
+                        stg256(op + 16, &ow[8]);
+                    }
+                }
+                if (p.head_out) {                            // the two column halves of a row add into zeroed memory: order-free
+                    float *hp = p.head_out + ((board * 8 + yp * kYPerPass + r) * 8 + x) * 4;
+                    atomicAdd(hp, h0); atomicAdd(hp + 1, h1); atomicAdd(hp + 2, h2);
                 }
             }
             tc_fence_before();
@@ -657,6 +673,7 @@ __global__ void planes_to_nhwc32_kernel(const float *__restrict__ f, int planes,
 struct HeadParams {
     const __nv_bfloat16 *act;  // [n][64][C]
     const float *pconv_w, *pconv_b, *pfc_w, *pfc_b, *vconv_w, *vconv_b, *vfc1_w, *vfc1_b, *vfc2_w, *vfc2_b;
+    const float *pre;          // optional [n][64][4]: 1x1 head-conv pre-activations written by the last conv layer
     float *policy, *value;
     int C, Hv;
     size_t n;
@@ -691,6 +708,16 @@ __global__ void __launch_bounds__(kHeadWarps * 32, 2) heads_kernel(const HeadPar
     const float pfb0 = p.pfc_b[lane], pfb1 = p.pfc_b[lane + 32], pfb64 = p.pfc_b[64];
     const float4 *cw0 = (const float4 *)s_cw, *cw1 = (const float4 *)(s_cw + C), *cw2 = (const float4 *)(s_cw + 2 * C);
     for (size_t b = (size_t)blockIdx.x * kHeadWarps + warp; b < p.n; b += (size_t)gridDim.x * kHeadWarps) {
+        if (p.pre) {
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int sq = lane + 32 * h;
+                const float4 d = __ldg((const float4 *)(p.pre + (b * 64 + sq) * 4));
+                s_feat[sq] = fmaxf(d.x + pb0, 0.f);
+                s_feat[64 + sq] = fmaxf(d.y + pb1, 0.f);
+                s_v1[sq] = fmaxf(d.z + vb, 0.f);
+            }
+        } else
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
             const int sq = lane + 32 * h;
@@ -783,6 +810,7 @@ ResNetLayout resnet_layout(const oz_resnet_shape &s) {
     L.vfc1_b = o; o = align256(o + Hv * 4);
     L.vfc2_w = o; o = align256(o + Hv * 4);
     L.vfc2_b = o; o = align256(o + 4);
+    L.head_w = o; o = align256(o + 3 * C * 4);     // device-side scratch: [policy c0 | policy c1 | value] rows, filled by load()
     L.total = o;
     return L;
 }
@@ -879,7 +907,7 @@ static int launch_conv(const CUtensorMap &ma, const CUtensorMap &mw, const ConvP
 }
 
 ResNet::~ResNet() {
-    cudaFree(d_blob_); cudaFree(d_x0_); cudaFree(d_a_); cudaFree(d_t_);
+    cudaFree(d_blob_); cudaFree(d_x0_); cudaFree(d_a_); cudaFree(d_t_); cudaFree(d_head_pre_);
 }
 
 int ResNet::load(const oz_resnet_shape &shape, const void *blob, size_t bytes) {
@@ -890,7 +918,7 @@ int ResNet::load(const oz_resnet_shape &shape, const void *blob, size_t bytes) {
     if (shape.blocks < 0 || shape.value_hidden < 1 || shape.value_hidden > 512)
         return fail(OZ_ERR_INVALID_ARGUMENT, "unsupported residual block / value head size");
     ResNetLayout L = resnet_layout(shape);
-    if (bytes != L.total) return fail(OZ_ERR_INVALID_ARGUMENT, "weight blob has " + std::to_string(bytes) + " bytes, expected " + std::to_string(L.total));
+    if (bytes != L.head_w) return fail(OZ_ERR_INVALID_ARGUMENT, "weight blob has " + std::to_string(bytes) + " bytes, expected " + std::to_string(L.head_w));
     const bool same = d_blob_ && shape.channels == shape_.channels && shape.blocks == shape_.blocks &&
                       shape.value_hidden == shape_.value_hidden && shape.in_planes == shape_.in_planes;
     if (!same) {
@@ -899,21 +927,24 @@ int ResNet::load(const oz_resnet_shape &shape, const void *blob, size_t bytes) {
         map_w_.assign(L.conv_w.size(), CUtensorMap{});
         for (size_t i = 0; i < L.conv_w.size(); ++i)
             OZ_TRY(make_w_map(&map_w_[i], d_blob_ + L.conv_w[i], i == 0 ? 32 : shape.channels, shape.channels, w_box_rows()));
-        if (shape.channels != shape_.channels) { cudaFree(d_a_); cudaFree(d_t_); cudaFree(d_x0_); d_a_ = d_t_ = d_x0_ = nullptr; cap_ = 0; }
+        if (shape.channels != shape_.channels) { cudaFree(d_a_); cudaFree(d_t_); cudaFree(d_x0_); cudaFree(d_head_pre_); d_a_ = d_t_ = d_x0_ = nullptr; d_head_pre_ = nullptr; cap_ = 0; }
     }
     shape_ = shape; layout_ = L;
-    OZ_CUDA(cudaMemcpy(d_blob_, blob, L.total, cudaMemcpyHostToDevice));
+    OZ_CUDA(cudaMemcpy(d_blob_, blob, L.head_w, cudaMemcpyHostToDevice));
+    OZ_CUDA(cudaMemcpy(d_blob_ + L.head_w, (const char *)blob + L.pconv_w, 2 * (size_t)shape.channels * 4, cudaMemcpyHostToDevice));
+    OZ_CUDA(cudaMemcpy(d_blob_ + L.head_w + 2 * (size_t)shape.channels * 4, (const char *)blob + L.vconv_w, (size_t)shape.channels * 4, cudaMemcpyHostToDevice));
     return OZ_OK;
 }
 
 int ResNet::reserve(size_t boards) {
     const size_t pad = (boards + kBoardPad - 1) / kBoardPad * kBoardPad;
     if (pad <= cap_) return OZ_OK;
-    cudaFree(d_x0_); cudaFree(d_a_); cudaFree(d_t_); d_x0_ = d_a_ = d_t_ = nullptr; cap_ = 0;
+    cudaFree(d_x0_); cudaFree(d_a_); cudaFree(d_t_); cudaFree(d_head_pre_); d_x0_ = d_a_ = d_t_ = nullptr; d_head_pre_ = nullptr; cap_ = 0;
     const size_t C = shape_.channels;
     OZ_CUDA(cudaMalloc(&d_x0_, pad * 64 * 32 * 2));
     OZ_CUDA(cudaMalloc(&d_a_, pad * 64 * C * 2));
     OZ_CUDA(cudaMalloc(&d_t_, pad * 64 * C * 2));
+    OZ_CUDA(cudaMalloc(&d_head_pre_, pad * 64 * 4 * sizeof(float)));
     OZ_CUDA(cudaMemset(d_a_, 0, pad * 64 * C * 2));
     OZ_CUDA(cudaMemset(d_t_, 0, pad * 64 * C * 2));
     OZ_TRY(make_act_map(&map_x0_, d_x0_, pad, 32, act_box_y()));
@@ -942,11 +973,19 @@ int ResNet::forward(const float *d_features, size_t n, float *d_policy, float *d
     cp.kblocks = 1; cp.skip = nullptr; cp.out = (__nv_bfloat16 *)d_a_; cp.bias = (const float *)(d_blob_ + layout_.conv_b[0]);
     OZ_TRY(launch_conv(map_x0_, map_w_[0], cp, stream));
     cp.kblocks = C / kKBlock;
+    // Last layer of a 128-channel tower (pair kernel): the epilogue also applies the three 1x1 head convolutions to its
+    // fp32 values, so the final activation tensor is never written and the head kernel reads 1 KB instead of 16 KB per board.
+    const bool fuse_heads = use_pair_kernel() && C == 128 && shape_.blocks > 0 && d_head_pre_ != nullptr;
     for (int b = 0; b < shape_.blocks; ++b) {   // residual tower (neural_net.py:32-65)
         cp.skip = nullptr; cp.out = (__nv_bfloat16 *)d_t_; cp.bias = (const float *)(d_blob_ + layout_.conv_b[1 + 2 * b]);
         OZ_TRY(launch_conv(map_a_, map_w_[1 + 2 * b], cp, stream));
         cp.skip = (const __nv_bfloat16 *)d_a_; cp.out = (__nv_bfloat16 *)d_a_; cp.bias = (const float *)(d_blob_ + layout_.conv_b[2 + 2 * b]);
+        if (fuse_heads && b == shape_.blocks - 1) {
+            OZ_CUDA(cudaMemsetAsync(d_head_pre_, 0, pad * 64 * 4 * sizeof(float), stream));
+            cp.out = nullptr; cp.head_w = (const float *)(d_blob_ + layout_.head_w); cp.head_out = d_head_pre_;
+        }
         OZ_TRY(launch_conv(map_t_, map_w_[2 + 2 * b], cp, stream));
+        cp.head_w = nullptr; cp.head_out = nullptr;
     }
     if (conv_end) cudaEventRecord(conv_end, stream);
     HeadParams hp{};
@@ -956,6 +995,7 @@ int ResNet::forward(const float *d_features, size_t n, float *d_policy, float *d
     hp.vconv_w = (const float *)(d_blob_ + layout_.vconv_w); hp.vconv_b = (const float *)(d_blob_ + layout_.vconv_b);
     hp.vfc1_w = (const float *)(d_blob_ + layout_.vfc1_w); hp.vfc1_b = (const float *)(d_blob_ + layout_.vfc1_b);
     hp.vfc2_w = (const float *)(d_blob_ + layout_.vfc2_w); hp.vfc2_b = (const float *)(d_blob_ + layout_.vfc2_b);
+    hp.pre = fuse_heads ? d_head_pre_ : nullptr;
     hp.policy = d_policy; hp.value = d_value; hp.C = C; hp.Hv = shape_.value_hidden; hp.n = n;
     const size_t hsm = (size_t)heads_smem_floats(C, hp.Hv) * sizeof(float);
     static size_t hsm_set = 0;

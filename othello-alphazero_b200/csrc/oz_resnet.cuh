@@ -26,7 +26,8 @@ namespace oz {
 struct ResNetLayout {
     std::vector<size_t> conv_w, conv_b;  // per conv layer
     size_t pconv_w, pconv_b, pfc_w, pfc_b, vconv_w, vconv_b, vfc1_w, vfc1_b, vfc2_w, vfc2_b;
-    size_t total;
+    size_t head_w;   // end of the host blob; device-only [3][C] copy of the 1x1 head-conv weights behind it
+    size_t total;    // device allocation
 };
 ResNetLayout resnet_layout(const oz_resnet_shape &s);
 
@@ -57,6 +58,7 @@ class ResNet {
     char *d_blob_ = nullptr;
     size_t cap_ = 0;
     void *d_x0_ = nullptr, *d_a_ = nullptr, *d_t_ = nullptr;  // bf16 NHWC activations
+    float *d_head_pre_ = nullptr;                             // [boards][64][4] fused head-conv pre-activations
     CUtensorMap map_x0_, map_a_, map_t_;
     std::vector<CUtensorMap> map_w_;
 };
