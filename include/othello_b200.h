@@ -248,6 +248,9 @@ typedef struct {
 } oz_counters;
 int oz_engine_counters(oz_engine *e, oz_counters *out);
 int oz_engine_set_profiling(oz_engine *e, int on);
+/* CUDA-graph replay of the search rounds: 0 never, 1 (default) when the leaf batch is launch-bound (<= 8192 boards,
+ * e.g. the single-game MCTS of the reference's play CLI), 2 always.  Results are identical either way. */
+int oz_engine_set_graphs(oz_engine *e, int mode);
 /* Stream the engine launches on (a cudaStream_t), for callers that time with CUDA events. */
 void *oz_engine_stream(oz_engine *e);
 

@@ -41,6 +41,10 @@ struct oz_engine {
     ResNet net;
     bool in_search = false;
     int round = 0;
+    cudaGraphExec_t round_graph = nullptr;   // one search round (select, encode, network, expand) for launch-bound batches
+    unsigned long long graph_launches = 0;   // kernels inside round_graph
+    bool warmed = false;
+    int graph_mode = 1;                      // 0 never, 1 when the leaf batch is launch-bound, 2 always                     // an eager search has run with the current allocations
     int active = 0;                       // games not finished
     long tree_bound = 1;                  // upper bound on the nodes of the largest live tree
     oz_counters ctr{};
@@ -116,7 +120,10 @@ void free_pools(Tree &t) {
     t.n_p1 = t.n_p2 = nullptr; t.n_meta = t.n_parent = t.n_child = t.n_N = nullptr; t.n_W = t.n_Q = t.n_P = nullptr;
 }
 
+void drop_graph(oz_engine *e);
+
 int alloc_slots(oz_engine *e) {
+    drop_graph(e);
     Tree &t = e->t;
     const int inflight = e->cfg.num_threads * e->cfg.batch_size, planes = 1 + 2 * e->cfg.history_size;
     if (inflight > e->inflight_cap) {
@@ -180,7 +187,14 @@ int check_device_errors(oz_engine *e) {
 
 int set_device(const oz_engine *e) { OZ_CUDA(cudaSetDevice(e->cfg.device)); return OZ_OK; }
 
+// Anything the captured round depends on (pointers, by-value parameters, evaluator) changed.
+void drop_graph(oz_engine *e) {
+    if (e->round_graph) { cudaGraphExecDestroy(e->round_graph); e->round_graph = nullptr; }
+    e->warmed = false;
+}
+
 int grow_pools(oz_engine *e, int new_cap) {
+    drop_graph(e);
     Tree nt = e->t;
     OZ_TRY(alloc_pools(nt, e->t.G, new_cap));
     launch_copy_arenas(e->t, nt, e->stream);
@@ -243,6 +257,7 @@ int begin_search(oz_engine *e) {
     OZ_TRY(ensure_capacity(e));
     // New SearchThread per search: feature slots start from zeros (search_thread.cpp:37-39).
     OZ_CUDA(cudaMemsetAsync(e->d_features, 0, (size_t)e->t.G * e->t.inflight * (1 + 2 * e->t.H) * 64 * sizeof(float), e->stream));
+    OZ_CUDA(cudaMemsetAsync(e->t.round, 0, sizeof(int32_t), e->stream));
     e->in_search = true; e->round = 0;
     return OZ_OK;
 }
@@ -289,7 +304,7 @@ int oz_engine_create(const oz_config *cfg, oz_engine **out) {
             (st = dalloc(&t.g_ply, G)) || (st = dalloc(&t.g_search, G)) || (st = dalloc(&t.g_gameid, G)) || (st = dalloc(&t.h_p1, (size_t)G * kMaxHist)) ||
             (st = dalloc(&t.h_p2, (size_t)G * kMaxHist)) || (st = dalloc(&t.h_player, (size_t)G * kMaxHist)) || (st = dalloc(&t.h_n, G)) ||
             (st = dalloc(&t.r_p1, G)) || (st = dalloc(&t.r_p2, G)) || (st = dalloc(&t.r_player, G)) || (st = dalloc(&t.error, 1)) ||
-            (st = dalloc(&t.stats, 4)) || (st = dalloc(&e->d_actions, G)) || (st = dalloc(&e->d_unfinished, 2)) ||
+            (st = dalloc(&t.stats, 4)) || (st = dalloc(&t.round, 1)) || (st = dalloc(&e->d_actions, G)) || (st = dalloc(&e->d_unfinished, 2)) ||
             (st = dalloc(&e->d_stat_n, G)) || (st = dalloc(&e->d_stat_counts, (size_t)G * kStride)) || (st = dalloc(&e->d_stat_q, (size_t)G * kStride)) ||
             (st = dalloc(&e->d_stat_rootn, G)) || (st = dalloc(&e->d_spd_p, 8 * 65)))
             break;
@@ -314,7 +329,8 @@ void oz_engine_destroy(oz_engine *e) {
     if (e->stream) cudaStreamSynchronize(e->stream);
     Tree &t = e->t;
     free_pools(t);
-    void *ptrs[] = {t.g_gameid, e->done.records, e->done.plies, e->done.gameid, e->done.p1, e->done.p2, e->done.counters, e->done.slot_done,
+    drop_graph(e);
+    void *ptrs[] = {t.round, t.g_gameid, e->done.records, e->done.plies, e->done.gameid, e->done.p1, e->done.p2, e->done.counters, e->done.slot_done,
                     e->done.slot_new, t.g_root, t.g_which, t.g_count, t.g_status, t.g_ply, t.g_search, t.h_p1, t.h_p2, t.h_player, t.h_n, t.r_p1, t.r_p2,
                     t.r_player, t.s_leaf, t.s_tf, t.s_len, t.s_path, t.error, t.stats, e->d_features, e->d_policy, e->d_value, e->d_rate,
                     e->d_gamma, e->d_actions, e->d_unfinished, e->d_stat_n, e->d_stat_counts, e->d_stat_q, e->d_stat_rootn, e->d_records,
@@ -333,6 +349,7 @@ void oz_engine_destroy(oz_engine *e) {
         OZ_TRY(check_engine_limits(c));                          \
         if (e->in_search) return fail(OZ_ERR_STATE, "cannot change parameters during a search"); \
         OZ_TRY(set_device(e));                                   \
+        drop_graph(e);                                           \
         e->cfg = c;                                              \
         AFTER;                                                   \
         return OZ_OK;                                            \
@@ -351,12 +368,14 @@ int oz_engine_get_config(const oz_engine *e, oz_config *out) { *out = e->cfg; re
 int oz_engine_set_evaluator(oz_engine *e, int evaluator) {
     if (evaluator < OZ_EVAL_EXTERNAL || evaluator > OZ_EVAL_RESNET) return fail(OZ_ERR_INVALID_ARGUMENT, "unknown evaluator");
     if (e->in_search) return fail(OZ_ERR_STATE, "cannot change the evaluator during a search");
+    if (e->cfg.evaluator != evaluator) drop_graph(e);
     e->cfg.evaluator = evaluator;
     return OZ_OK;
 }
 
 int oz_engine_set_gamma_table(oz_engine *e, const float *table, int len) {
     OZ_TRY(set_device(e));
+    drop_graph(e);
     cudaFree(e->d_gamma); e->d_gamma = nullptr;
     e->t.gamma_table = nullptr; e->t.gamma_len = 0;
     if (len > 0) {
@@ -469,6 +488,7 @@ int oz_engine_load_resnet(oz_engine *e, const oz_resnet_shape *shape, const void
     OZ_TRY(set_device(e));
     if (e->in_search) return fail(OZ_ERR_STATE, "cannot load weights during a search");
     OZ_CUDA(cudaStreamSynchronize(e->stream));
+    drop_graph(e);
     OZ_TRY(e->net.load(*shape, blob, bytes));
     OZ_TRY(e->net.reserve((size_t)e->t.G * e->t.inflight));
     return OZ_OK;
@@ -560,8 +580,8 @@ int oz_engine_select_device(oz_engine *e, float *features, void *stream) {
     if (!e->in_search) return fail(OZ_ERR_STATE, "search_begin not called");
     OZ_TRY(set_device(e));
     cudaStream_t s = (cudaStream_t)stream;    // NULL is the legacy default stream, as in the CUDA runtime
-    launch_select(e->t, e->round, s);
-    launch_encode(e->t, e->round, features ? features : e->d_features, s);
+    launch_select(e->t, s);
+    launch_encode(e->t, features ? features : e->d_features, s);
     OZ_CUDA(cudaGetLastError());
     return OZ_OK;
 }
@@ -591,12 +611,48 @@ int oz_engine_search(oz_engine *e) {
     size_t k = 0;
     int st = OZ_OK;
     const bool net_prof = e->profiling && e->cfg.evaluator == OZ_EVAL_RESNET;
+    // Launch-bound batches (a single game is 26 launches of a few microseconds per round) replay one captured round;
+    // the round index lives on the device, so the same graph serves every round of every search.
+    const size_t boards = (size_t)e->t.G * e->t.inflight;
+    const bool want_graph = !e->profiling && e->warmed && (e->graph_mode == 2 || (e->graph_mode == 1 && boards <= 8192));
+    if (want_graph && !e->round_graph) {
+        cudaGraph_t g = nullptr;
+        const unsigned long long before = g_kernel_launches;
+        const uint64_t evals_before = e->ctr.evaluations;
+        OZ_CUDA(cudaStreamBeginCapture(e->stream, cudaStreamCaptureModeThreadLocal));
+        launch_select(e->t, e->stream);
+        launch_encode(e->t, e->d_features, e->stream);
+        st = eval_round(e);
+        if (!st) launch_expand(e->t, e->d_policy, e->d_value, e->stream);
+        cudaError_t ce = cudaStreamEndCapture(e->stream, &g);
+        e->graph_launches = g_kernel_launches - before;
+        g_kernel_launches = before;                    // capturing launched nothing
+        e->ctr.evaluations = evals_before;
+        if (st || ce != cudaSuccess || !g) {
+            if (g) cudaGraphDestroy(g);
+            cudaGetLastError();
+            e->in_search = false;
+            return st ? st : fail(OZ_ERR_CUDA, std::string("graph capture of a search round failed: ") + cudaGetErrorString(ce));
+        }
+        ce = cudaGraphInstantiate(&e->round_graph, g, 0);
+        cudaGraphDestroy(g);
+        if (ce != cudaSuccess) { e->round_graph = nullptr; e->in_search = false; return fail(OZ_ERR_CUDA, std::string("cudaGraphInstantiate: ") + cudaGetErrorString(ce)); }
+    }
+    if (want_graph) {
+        for (int r = 0; r < rounds; ++r) {
+            OZ_CUDA(cudaGraphLaunch(e->round_graph, e->stream));
+            count_launch((int)e->graph_launches);
+            e->ctr.evaluations += boards;
+        }
+        e->round = rounds;
+        return end_search(e);
+    }
     for (int r = 0; r < rounds && !st; ++r) {
         e->round = r;
         cudaEvent_t cb = nullptr, ce = nullptr;
         if (e->profiling) { cudaEventRecord(next_event(e, k), e->stream); cb = next_event(e, k + 2); ce = next_event(e, k + 3); }
-        launch_select(e->t, r, e->stream);
-        launch_encode(e->t, r, e->d_features, e->stream);
+        launch_select(e->t, e->stream);
+        launch_encode(e->t, e->d_features, e->stream);
         if (e->profiling) cudaEventRecord(next_event(e, k + 1), e->stream);
         st = eval_round(e, net_prof ? cb : nullptr, net_prof ? ce : nullptr);
         if (e->profiling) cudaEventRecord(next_event(e, k + 4), e->stream);
@@ -604,6 +660,7 @@ int oz_engine_search(oz_engine *e) {
         if (e->profiling) { cudaEventRecord(next_event(e, k + 5), e->stream); k += 6; }
     }
     if (st) { e->in_search = false; return st; }
+    e->warmed = true;
     st = end_search(e);
     if (!st && e->profiling) {
         for (size_t i = 0; i + 5 < k; i += 6) {
@@ -802,6 +859,7 @@ int oz_engine_counters(oz_engine *e, oz_counters *out) {
 }
 
 int oz_engine_set_profiling(oz_engine *e, int on) { e->profiling = on != 0; return OZ_OK; }
+int oz_engine_set_graphs(oz_engine *e, int mode) { e->graph_mode = mode; if (mode == 0) drop_graph(e); return OZ_OK; }
 void *oz_engine_stream(oz_engine *e) { return (void *)e->stream; }
 
 }  // extern "C"

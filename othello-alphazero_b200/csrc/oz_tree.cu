@@ -84,12 +84,12 @@ __global__ void reset_kernel(Tree t) {
 }
 
 // ------------------------------------------------------------------ select (search_thread.cpp:60-79, 192-260)
-__global__ void __launch_bounds__(128) select_kernel(Tree t, int round) {
+__global__ void __launch_bounds__(128) select_kernel(Tree t) {
     __shared__ int s_path[4][kMaxDepth];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int g = blockIdx.x * 4 + wib;
     if (g >= t.G) return;
-    const int B = t.inflight;
+    const int B = t.inflight, round = *t.round;
     int *leaf_out = t.s_leaf + (size_t)g * B;
     if (t.g_status[g] & 1) {                         // finished game: nothing in flight
         for (int i = lane; i < B; i += 32) leaf_out[i] = -1;
@@ -212,7 +212,7 @@ __device__ __forceinline__ void write_planes(float *f, int H, int nh, const uint
     }
 }
 
-__global__ void __launch_bounds__(128) encode_kernel(Tree t, int round, float *features) {
+__global__ void __launch_bounds__(128) encode_kernel(Tree t, float *features) {
     __shared__ uint64_t s1[4][kMaxHist], s2[4][kMaxHist];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const size_t slot = (size_t)blockIdx.x * 4 + wib;
@@ -226,7 +226,7 @@ __global__ void __launch_bounds__(128) encode_kernel(Tree t, int round, float *f
     int tf = 0;
     if (t.sym_mode == OZ_SYM_RANDOM) {
         uint32_t r[4];
-        philox(t.g_gameid[g], t.g_search[g], (uint32_t)(round * t.inflight + i), 0u, t.seed_lo, t.seed_hi, r);
+        philox(t.g_gameid[g], t.g_search[g], (uint32_t)(*t.round * t.inflight + i), 0u, t.seed_lo, t.seed_hi, r);
         tf = (int)(r[0] & 7u);
     }
     if (lane == 0) t.s_tf[slot] = tf;
@@ -238,6 +238,7 @@ __global__ void __launch_bounds__(128) encode_kernel(Tree t, int round, float *f
 __global__ void __launch_bounds__(128) expand_kernel(Tree t, const float *__restrict__ policy, const float *__restrict__ value) {
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int g = blockIdx.x * 4 + wib;
+    if (blockIdx.x == 0 && threadIdx.x == 0) *t.round += 1;     // select / encode of this round are done
     if (g >= t.G) return;
     if (t.g_status[g] & 1) return;
     const int B = t.inflight;
@@ -658,9 +659,9 @@ __global__ void __launch_bounds__(256) training_samples_kernel(const PlyRecordDe
 static inline unsigned blocks(size_t items, int per_block) { return (unsigned)((items + per_block - 1) / per_block); }
 
 void launch_reset(const Tree &t, cudaStream_t s) { reset_kernel<<<blocks(t.G, 128), 128, 0, s>>>(t); count_launch(); }
-void launch_select(const Tree &t, int round, cudaStream_t s) { select_kernel<<<blocks(t.G, 4), 128, 0, s>>>(t, round); count_launch(); }
-void launch_encode(const Tree &t, int round, float *features, cudaStream_t s) {
-    encode_kernel<<<blocks((size_t)t.G * t.inflight, 4), 128, 0, s>>>(t, round, features); count_launch();
+void launch_select(const Tree &t, cudaStream_t s) { select_kernel<<<blocks(t.G, 4), 128, 0, s>>>(t); count_launch(); }
+void launch_encode(const Tree &t, float *features, cudaStream_t s) {
+    encode_kernel<<<blocks((size_t)t.G * t.inflight, 4), 128, 0, s>>>(t, features); count_launch();
 }
 void launch_expand(const Tree &t, const float *policy, const float *value, cudaStream_t s) {
     expand_kernel<<<blocks(t.G, 4), 128, 0, s>>>(t, policy, value); count_launch();

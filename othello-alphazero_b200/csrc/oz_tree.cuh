@@ -44,6 +44,7 @@ struct Tree {
     const float *rate;                   // exploration rate by node visit count
     int rate_len;
     const float *gamma_table; int gamma_len;    // injected Dirichlet draws (tests)
+    int32_t *round;                      // round of the current search (device-side, so one CUDA graph serves every round)
     int32_t *error;                      // TreeError bits
     unsigned long long *stats;           // [0] nodes expanded
     // configuration
@@ -60,8 +61,9 @@ struct PlyRecordDev {     // matches oz_ply_record
 };
 
 void launch_reset(const Tree &t, cudaStream_t s);
-void launch_select(const Tree &t, int round, cudaStream_t s);
-void launch_encode(const Tree &t, int round, float *features, cudaStream_t s);
+// select / encode read the round from *t.round; expand increments it.
+void launch_select(const Tree &t, cudaStream_t s);
+void launch_encode(const Tree &t, float *features, cudaStream_t s);
 void launch_expand(const Tree &t, const float *policy, const float *value, cudaStream_t s);
 void launch_end_search(const Tree &t, cudaStream_t s);
 void launch_root_stats(const Tree &t, int32_t *n_children, int32_t *counts, float *q, int32_t *root_n, cudaStream_t s);

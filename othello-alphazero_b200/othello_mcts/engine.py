@@ -160,6 +160,10 @@ class _Engine:
     def set_profiling(self, on: bool) -> None:
         check(self._lib.oz_engine_set_profiling(self._h, int(on)))
 
+    def set_graphs(self, mode: int) -> None:
+        """CUDA-graph replay of search rounds: 0 never, 1 (default) for launch-bound leaf batches, 2 always."""
+        check(self._lib.oz_engine_set_graphs(self._h, int(mode)))
+
 
 class MCTS(_Engine):
     """Drop-in for the reference's `othello_mcts.MCTS` (othello_mcts.cpp:89-150): one game, same

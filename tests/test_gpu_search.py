@@ -254,3 +254,33 @@ def test_arena_growth_is_transparent():
     assert (a["plies"] == b["plies"]).all() and a["plies"].min() > 8
     for name in ("p1", "p2", "player", "action", "n_children", "visit_counts"):
         assert np.array_equal(a["records"][name], b["records"][name]), name
+
+
+@pytest.mark.parametrize("evaluator", ["hash", "resnet"])
+def test_graph_replay_equals_eager_launches(evaluator):
+    """Launch-bound batches replay one captured search round (the round index lives on the device).  Same trees as
+    launching every kernel eagerly, search after search, across re-roots and an arena growth."""
+    import torch
+    from othello_mcts import MCTS
+    from othello_mcts.neural_net import AlphaZeroNet
+    net = "hash"
+    if evaluator == "resnet":
+        torch.manual_seed(1)
+        net = AlphaZeroNet(9, conv_channels=128, num_residual_blocks=2, value_head_hidden_channels=32).eval().cuda()
+    kw = dict(history_size=4, torch_device="cuda", num_simulations=96, num_threads=2, batch_size=8, dirichlet_epsilon=0.25, seed=4)
+    eager, graph = MCTS(**kw), MCTS(**kw)
+    eager.set_graphs(0)
+    graph.set_graphs(2)
+    launches0 = graph.counters()["kernel_launches"]
+    for ply in range(14):
+        eager.search(net)
+        graph.search(net)
+        assert eager.visit_counts() == graph.visit_counts(), ply
+        assert eager.mean_action_values() == graph.mean_action_values(), ply
+        if ply == 6:
+            graph.set_num_simulations(128)             # parameter change: the graph is rebuilt
+            eager.set_num_simulations(128)
+        a = graph.position().legal_actions()[int(np.argmax(graph.visit_counts()))]
+        eager.apply_action(a)
+        graph.apply_action(a)
+    assert graph.counters()["kernel_launches"] > launches0
