@@ -35,9 +35,9 @@ MCTS_KW = dict(history_size=8, num_simulations=800, num_threads=2, batch_size=16
                dirichlet_epsilon=0.25, dirichlet_alpha=0.5)
 
 
-# dram__bytes_read.sum + dram__bytes_write.sum per conv launch (32768 boards, 128 -> 128 channels), mean of the plain and the
-# residual layer of one ncu --set full capture (profiles/r01_conv_pair_kernel.json).
-NCU_TRAFFIC_BYTES_PER_LAUNCH = 1.29e9
+# dram__bytes_read.sum + dram__bytes_write.sum of a conv launch per board, from one ncu --set full capture of a 128 -> 128
+# layer over 32768 boards (profiles/r01_conv_pair_kernel.json): plain layer 0.537 + 0.497 GB, residual layer 1.074 + 0.496 GB.
+NCU_TRAFFIC_BYTES_PER_BOARD = (0.537230e9 + 0.498725e9 + 1.074230e9 + 0.494879e9) / 2 / 32768
 
 
 def flops_per_eval(cin=17, c=128, blocks=9, hv=128):
@@ -93,11 +93,11 @@ class ClockSampler:
 
 
 # ----------------------------------------------------------------------------------------------
-def make_net():
+def make_net(net_kw=None):
     import torch
     from othello_mcts.neural_net import AlphaZeroNet
     torch.manual_seed(0)
-    return AlphaZeroNet(**NET).eval()
+    return AlphaZeroNet(**(net_kw or NET)).eval()
 
 
 def reference_search_rate(steps: int, warmup: int, threads: int):
@@ -197,7 +197,9 @@ def run_ours(args):
     kw.update(num_simulations=args.sims, num_threads=args.threads, batch_size=args.batch)
     inflight = args.threads * args.batch
     sims_per_search = -(-args.sims // inflight) * inflight
-    net = make_net()
+    net_kw = dict(NET, conv_channels=args.channels, num_residual_blocks=args.blocks, value_head_hidden_channels=args.hidden)
+    net_name = f"{args.channels}x{args.blocks + 1}b"
+    net = make_net(net_kw)
     # games are partitioned contiguously by id: rank r owns [r*G, (r+1)*G); no collective on the hot path
     eng = om.SelfPlayEngine(G, seed=args.seed, first_game_id=rank * G, cuda_device=local, **kw)
     eng.prepare(net)
@@ -304,7 +306,7 @@ def run_ours(args):
     e2e_value = active_sims / (ms_e2e * 1e-3)
 
     if rank == 0:
-        f_all, f_conv = flops_per_eval()
+        f_all, f_conv = flops_per_eval(c=args.channels, blocks=args.blocks, hv=args.hidden)
         pk = peaks()
         nn_share = eval_ms / ms if ms > 0 else None
         # dominant kernel: the 3x3 convolution.  Algorithmic FLOPs of this rank's conv launches in the timed region
@@ -315,7 +317,7 @@ def run_ours(args):
             "metric": "mcts_simulations_per_second", "value": value, "unit": "sims/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": f"128x10b random-init ResNet self-play, {G} lockstep games per GPU, {args.sims} sims/move "
+            "config": {"workload": f"{net_name} random-init ResNet self-play, {G} lockstep games per GPU, {args.sims} sims/move "
                                    f"(T={args.threads} x B={args.batch} leaves in flight per game, leaf batch {G * inflight} per network call), "
                                    "random-symmetry eval, Dirichlet eps 0.25 alpha 0.5",
                        "games_per_gpu": G, "sims_per_move": sims_per_search, "leaf_batch": G * inflight,
@@ -326,17 +328,22 @@ def run_ours(args):
             "gpu_launches": int(tot[2].item()),
             "nn_evals_per_second": float(tot[1].item()) / (ms * 1e-3),
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": pk["bf16_sustained"], "unit": "TFLOP/s",
-                         "frac": (achieved / pk["bf16_sustained"]) if achieved else None, "traffic": NCU_TRAFFIC_BYTES_PER_LAUNCH,
+                         "frac": (achieved / pk["bf16_sustained"]) if achieved else None, "traffic": NCU_TRAFFIC_BYTES_PER_BOARD * G * inflight if args.channels == 128 else None,
                          "kernel": "conv3x3_pair_kernel (tcgen05.mma cta_group::2 implicit GEMM)",
                          "flop_per_launch": (evals * f_conv / conv_launches) if conv_launches else None,
                          "us_per_launch": (1e3 * conv_ms / conv_launches) if conv_launches else None,
                          "launches_timed": int(conv_launches), "conv_share_of_step": conv_ms / ms if ms > 0 else None,
                          "nn_share_of_step": nn_share, "frac_of_burst_peak": (achieved / pk["bf16_burst"]) if achieved else None,
-                         "traffic_note": "dram read+write bytes per launch of a 128->128 layer over 32768 boards, mean of a plain and a residual "
-                                         "layer, from profiles/ (ncu --set full); algorithmic 1.07 / 1.61 GB",
+                         "traffic_note": "dram read+write bytes per launch (mean of a plain and a residual 128->128 layer, ncu --set full capture in "
+                                         "profiles/ scaled to this leaf batch); algorithmic: 32 KB / 48 KB per board",
                          "peak_source": pk["source"] + ", sustained bf16 (kernel timed inside a long step)"},
             "perft": {"depth": 11, "nodes": int(perft_nodes), "nodes_per_s": perft_nodes / (perft_ms * 1e-3) if perft_ms > 0 else None,
                       "device_ms": perft_ms},
+            "phases_ms_per_step": {"select_encode": (c1["select_ms"] - c0["select_ms"]) / args.steps,
+                                   "network": eval_ms / args.steps, "of_which_conv": conv_ms / args.steps,
+                                   "expand_backup": (c1["expand_ms"] - c0["expand_ms"]) / args.steps,
+                                   "rest_of_ply (choose, record, re-root, syncs)": (ms - (c1["select_ms"] - c0["select_ms"]) - eval_ms
+                                                                                   - (c1["expand_ms"] - c0["expand_ms"])) / args.steps},
             "midgame": mid,
             "clocks": clocks,
         }
@@ -362,6 +369,9 @@ def main():
     ap.add_argument("--threads", type=int, default=2)
     ap.add_argument("--batch", type=int, default=16)
     ap.add_argument("--seed", type=int, default=2026)
+    ap.add_argument("--channels", type=int, default=128, help="conv_channels (BASELINE config 5: 256)")
+    ap.add_argument("--blocks", type=int, default=9, help="residual blocks (config 5: 19)")
+    ap.add_argument("--hidden", type=int, default=128, help="value head hidden units (config 5: 256)")
     ap.add_argument("--cpu-steps", type=int, default=12)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--midgame-ply", type=int, default=24, help="also time 2 plies after fast-forwarding every game this far (0 = skip)")

@@ -1,21 +1,8 @@
 // ResNet policy/value evaluator for sm_100a (reference: neural_net.py:9-172, eval mode).
 //
-// conv3x3_kernel: implicit-GEMM 3x3 "same" convolution, bf16 in / fp32 accumulate.
-//   * D[M = 128 positions, N = 128 couts] += A[M, K=16] * B[N, K=16]^T with tcgen05.mma
-//     (cta_group::1, kind::f16), accumulators in TMEM (4 tiles x 128 columns = 512 columns).
-//   * One work item ("pass") = 16 boards x 4 board rows x 128 couts = 512 output rows.
-//   * Activations: one 4-D TMA box per 32-channel K block, dims (channel 32, board 16, x 9,
-//     y 6) read from plain NHWC with out-of-bounds zero fill (x = 8, y = -1 / 8 are the
-//     halo).  In shared memory that is row = (y*9 + x)*16 + board, 64 B per row,
-//     SWIZZLE_64B.  Sixteen boards share each (y, x) slot, so a 3x3 tap (dy, dx) is the same
-//     tile shifted by (dy*9 + dx) * 16 rows = a multiple of the 8-row swizzle atom: every
-//     tap is a plain descriptor offset into ONE copy of the tile (no im2col, one L2 read per
-//     activation, 100 % useful MMA rows: a 128-row tile is 8 x-positions x 16 boards).
-//   * Weights: [tap][cout][cin] bf16, one 2-D TMA box (32 cin x 128 cout = 8 KB) per
-//     (K block, tap), 6-deep ring.
-//   * Warp roles: 0 = activation TMA, 1 = MMA issue + TMEM alloc, 2 = weight TMA,
-//     3..6 = epilogue (tcgen05.ld -> +bias (+skip) -> ReLU -> bf16 -> global NHWC).
-// heads_kernel: 1x1 convs + FC + softmax / tanh for both heads, one CTA loop over boards.
+// conv3x3_pair_kernel: implicit-GEMM 3x3 "same" convolution, bf16 in / fp32 accumulate, issued for a CTA PAIR
+// (tcgen05.mma cta_group::2, M = 256, N = 128, K = 16; accumulators in TMEM, operands staged by TMA); see the
+// comment above the kernel.  heads_kernel: 1x1 convs + FC + softmax / tanh for both heads, one warp per board.
 #include <cuda_bf16.h>
 
 #include <cmath>
@@ -30,20 +17,11 @@ namespace oz {
 
 // ------------------------------------------------------------------ geometry
 constexpr int kBoardsPerUnit = 16;
-constexpr int kRowsPerPass = 4;                      // board rows (y) per pass
 constexpr int kKBlock = 32;                          // channels per K block (64 B rows)
-constexpr int kBoxX = 9, kBoxY = kRowsPerPass + 2;   // halo: x = 8 is the zero column
+constexpr int kBoxX = 9;                             // halo: x = 8 is the zero column
 constexpr int kRowBytes = kKBlock * 2;               // 64
 constexpr int kSlotBytes = kBoardsPerUnit * kRowBytes;            // 1024: one (y, x) slot
-constexpr int kActBoxBytes = kBoxX * kBoxY * kSlotBytes;          // 55296
-constexpr int kActStageBytes = kSlotBytes + kActBoxBytes;         // 1 guard slot in front
-constexpr int kActStages = 3;
-constexpr int kWStageBytes = 128 * kRowBytes;                     // 8192
-constexpr int kWStages = 6;
-constexpr int kTiles = kRowsPerPass;                 // accumulator tiles per pass
 constexpr int kTmemCols = 512;
-constexpr int kThreads = 7 * 32;
-constexpr int kSmemBytes = 1024 + kActStages * kActStageBytes + kWStages * kWStageBytes + 2048;
 
 // ------------------------------------------------------------------ PTX wrappers
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -54,40 +32,8 @@ __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-    uint32_t done;
-    do {
-        asm volatile(
-            "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-            "selp.u32 %0, 1, 0, p;\n\t}"
-            : "=r"(done) : "r"(bar), "r"(parity) : "memory");
-    } while (!done);
-}
-__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap *map, uint32_t bar, int c0, int c1, int c2, int c3) {
-    asm volatile(
-        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
-        ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
-}
-__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *map, uint32_t bar, int c0, int c1) {
-    asm volatile(
-        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-        ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1) : "memory");
-}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_commit(uint32_t bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void tc_mma(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-        ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
-}
 __device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&v)[32]) {
     asm volatile(
         "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
@@ -111,9 +57,6 @@ __device__ __forceinline__ uint64_t umma_desc_sw64(uint32_t saddr) {
     d |= (uint64_t)4 << 61;                     // SWIZZLE_64B
     return d;
 }
-// kind::f16 instruction descriptor: bf16 x bf16 -> f32, both operands K-major, M = 128, N = 128.
-constexpr uint32_t kIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((128u >> 3) << 17) | ((128u >> 4) << 24);
-
 struct ConvParams {
     const __nv_bfloat16 *skip;   // NHWC, may be null
     __nv_bfloat16 *out;          // NHWC [boards][8][8][cout_total]
@@ -124,184 +67,7 @@ struct ConvParams {
     int relu;
     const float *head_w;         // pair kernel, last layer of a 128-channel tower: [3][128] 1x1 head-conv weights (policy 0, policy 1, value)
     float *head_out;             // ... and their pre-activations [boards][64][4] (zeroed by the caller; two column halves add up)
-    int flags;                   // tuning switches of the pair kernel (bit 0 TMA L2 prefetch, 1 residual L2 prefetch, 2 zero-row tap skipping, 3 programmatic dependent launch)
 };
-
-__global__ void __launch_bounds__(kThreads, 1)
-conv3x3_kernel(const __grid_constant__ CUtensorMap map_act, const __grid_constant__ CUtensorMap map_w, const ConvParams p) {
-    extern __shared__ uint8_t smem_raw[];
-    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-    uint8_t *gen = smem_raw + (base - smem_u32(smem_raw));       // generic pointer to the aligned base
-    const uint32_t act0 = base;
-    const uint32_t w0 = act0 + kActStages * kActStageBytes;
-    const uint32_t misc = w0 + kWStages * kWStageBytes;
-    // barriers (8 B each)
-    const uint32_t bar_act_full = misc, bar_act_empty = misc + 8 * kActStages;
-    const uint32_t bar_w_full = misc + 64, bar_w_empty = misc + 64 + 8 * kWStages;
-    const uint32_t bar_tmem_full = misc + 192, bar_tmem_empty = misc + 200;   // [kTiles]
-    uint32_t *tmem_ptr = (uint32_t *)(gen + (misc - base) + 256);
-    float *s_bias = (float *)(gen + (misc - base) + 512);                        // up to 384 floats
-
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int ntiles = p.cout_total >> 7;
-    const int num_pass = p.units * 2 * ntiles;
-
-    if (threadIdx.x == 0) {
-        for (int i = 0; i < kActStages; ++i) { mbar_init(bar_act_full + 8 * i, 1); mbar_init(bar_act_empty + 8 * i, 1); }
-        for (int i = 0; i < kWStages; ++i) { mbar_init(bar_w_full + 8 * i, 1); mbar_init(bar_w_empty + 8 * i, 1); }
-        mbar_init(bar_tmem_full, 1);
-        for (int i = 0; i < kTiles; ++i) mbar_init(bar_tmem_empty + 8 * i, 4);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_act) : "memory");
-        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w) : "memory");
-    }
-    if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr)), "r"(kTmemCols) : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-    }
-    // Guard slot in front of every activation stage: the (dy,dx) = (-1,-1) tap of the first
-    // tile row starts one slot before the box and must read zeros.
-    for (int i = threadIdx.x; i < kActStages * (kSlotBytes / 16); i += kThreads) {
-        const int s = i / (kSlotBytes / 16), o = i % (kSlotBytes / 16);
-        *(uint4 *)(gen + s * kActStageBytes + o * 16) = make_uint4(0, 0, 0, 0);
-    }
-    for (int i = threadIdx.x; i < p.cout_total; i += kThreads) s_bias[i] = p.bias[i];
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    const uint32_t tmem_base = *tmem_ptr;
-
-    if (warp == 0) {
-        // ===== activation TMA producer =====
-        if (lane == 0) {
-            uint32_t it = 0;
-            for (int ps = blockIdx.x; ps < num_pass; ps += gridDim.x) {
-                const int unit = ps / (2 * ntiles), half = (ps / ntiles) & 1;
-                for (int kb = 0; kb < p.kblocks; ++kb, ++it) {
-                    const uint32_t s = it % kActStages, ph = (it / kActStages) & 1;
-                    mbar_wait(bar_act_empty + 8 * s, ph ^ 1);
-                    mbar_expect_tx(bar_act_full + 8 * s, kActBoxBytes);
-                    tma_load_4d(act0 + s * kActStageBytes + kSlotBytes, &map_act, bar_act_full + 8 * s,
-                                kb * kKBlock, unit * kBoardsPerUnit, 0, half * kRowsPerPass - 1);
-                }
-            }
-        }
-        __syncwarp();
-    } else if (warp == 2) {
-        // ===== weight TMA producer =====
-        if (lane == 0) {
-            uint32_t it = 0;
-            for (int ps = blockIdx.x; ps < num_pass; ps += gridDim.x) {
-                const int nt = ps % ntiles;
-                for (int kb = 0; kb < p.kblocks; ++kb)
-                    for (int tap = 0; tap < 9; ++tap, ++it) {
-                        const uint32_t s = it % kWStages, ph = (it / kWStages) & 1;
-                        mbar_wait(bar_w_empty + 8 * s, ph ^ 1);
-                        mbar_expect_tx(bar_w_full + 8 * s, kWStageBytes);
-                        tma_load_2d(w0 + s * kWStageBytes, &map_w, bar_w_full + 8 * s,
-                                    kb * kKBlock, tap * p.cout_total + nt * 128);
-                    }
-            }
-        }
-        __syncwarp();
-    } else if (warp == 1) {
-        // ===== MMA issuer (one thread) =====
-        if (lane == 0) {
-            uint32_t ait = 0, wit = 0, npass = 0;
-            for (int ps = blockIdx.x; ps < num_pass; ps += gridDim.x, ++npass) {
-                for (int kb = 0; kb < p.kblocks; ++kb, ++ait) {
-                    const uint32_t as = ait % kActStages;
-                    mbar_wait(bar_act_full + 8 * as, (ait / kActStages) & 1);
-                    const uint32_t abox = act0 + as * kActStageBytes + kSlotBytes;
-                    for (int tap = 0; tap < 9; ++tap, ++wit) {
-                        const uint32_t ws = wit % kWStages;
-                        mbar_wait(bar_w_full + 8 * ws, (wit / kWStages) & 1);
-                        tc_fence_after();
-                        const int dy = tap / 3 - 1, dx = tap % 3 - 1;
-                        const uint32_t wbase = w0 + ws * kWStageBytes;
-#pragma unroll
-                        for (int r = 0; r < kTiles; ++r) {
-                            if (kb == 0 && tap == 0) {   // tile r must be drained by the previous pass's epilogue
-                                mbar_wait(bar_tmem_empty + 8 * r, (npass & 1) ^ 1);
-                                tc_fence_after();
-                            }
-                            const uint32_t arow = abox + (uint32_t)(((r + 1 + dy) * kBoxX + dx) * kSlotBytes);
-#pragma unroll
-                            for (int j = 0; j < kKBlock / 16; ++j)
-                                tc_mma(tmem_base + r * 128, umma_desc_sw64(arow + j * 32), umma_desc_sw64(wbase + j * 32),
-                                       kIdesc, (kb | tap | j) != 0);
-                        }
-                        tc_commit(bar_w_empty + 8 * ws);          // weight slot free once these MMAs retire
-                    }
-                    tc_commit(bar_act_empty + 8 * as);            // activation stage free
-                }
-                tc_commit(bar_tmem_full);                         // accumulators complete
-            }
-        }
-        __syncwarp();
-    } else {
-        // ===== epilogue warps 3..6: TMEM lanes 32*(warp%4) .. +31 =====
-        const int quad = warp & 3;
-        uint32_t npass = 0;
-        for (int ps = blockIdx.x; ps < num_pass; ps += gridDim.x, ++npass) {
-            const int unit = ps / (2 * ntiles), half = (ps / ntiles) & 1, nt = ps % ntiles;
-            mbar_wait(bar_tmem_full, npass & 1);
-            tc_fence_after();
-            const int row = quad * 32 + lane;              // row in tile = x * 16 + board
-            const int x = row >> 4, bl = row & 15;
-            const size_t board = (size_t)unit * kBoardsPerUnit + bl;
-#pragma unroll 1
-            for (int r = 0; r < kTiles; ++r) {
-                const int y = half * kRowsPerPass + r;
-                const size_t off = ((board * 8 + y) * 8 + x) * (size_t)p.cout_total + nt * 128;
-#pragma unroll 1
-                for (int ch = 0; ch < 4; ++ch) {
-                    uint32_t v[32];
-                    tc_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + r * 128 + ch * 32, v);
-                    uint4 sk[4];
-                    if (p.skip) {
-                        const uint4 *sp = (const uint4 *)(p.skip + off + ch * 32);
-#pragma unroll
-                        for (int i = 0; i < 4; ++i) sk[i] = sp[i];
-                    }
-                    tc_wait_ld();
-                    if (ch == 3) {                         // last read of tile r: hand it back to the MMA warp
-                        tc_fence_before();
-                        __syncwarp();
-                        if (lane == 0) mbar_arrive(bar_tmem_empty + 8 * r);
-                    }
-                    const float *bs = s_bias + nt * 128 + ch * 32;
-                    uint4 o[4];
-                    uint32_t *ow = (uint32_t *)o;
-                    const uint32_t *skw = (const uint32_t *)sk;
-#pragma unroll
-                    for (int i = 0; i < 16; ++i) {
-                        float a = __uint_as_float(v[2 * i]) + bs[2 * i];
-                        float b = __uint_as_float(v[2 * i + 1]) + bs[2 * i + 1];
-                        if (p.skip) {
-                            const __nv_bfloat162 s2 = *(const __nv_bfloat162 *)&skw[i];
-                            a += __bfloat162float(s2.x);
-                            b += __bfloat162float(s2.y);
-                        }
-                        if (p.relu) { a = fmaxf(a, 0.f); b = fmaxf(b, 0.f); }
-                        const __nv_bfloat162 o2 = __floats2bfloat162_rn(a, b);
-                        ow[i] = *(const uint32_t *)&o2;
-                    }
-                    uint4 *op = (uint4 *)(p.out + off + ch * 32);
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) op[i] = o[i];
-                }
-            }
-        }
-    }
-    tc_fence_before();
-    __syncthreads();
-    if (warp == 1) {
-        tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
-    }
-}
 
 // ------------------------------------------------------------------ CTA-pair kernel (cta_group::2)
 // conv3x3_pair_kernel: the same implicit GEMM issued for a CTA PAIR (cluster of 2, one TPC):
@@ -381,10 +147,6 @@ __device__ __forceinline__ void stg256(void *ptr, const uint32_t *v) {
 }
 __device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void griddep_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
-__device__ __forceinline__ void tma_prefetch_4d(const CUtensorMap *map, int c0, int c1, int c2, int c3) {
-    asm volatile("cp.async.bulk.prefetch.tensor.4d.L2.global.tile [%0, {%1, %2, %3, %4}];"
-                 ::"l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
-}
 __device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap *map, uint32_t bar_cluster, int c0, int c1) {
     asm volatile(
         "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
@@ -463,12 +225,6 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap map_act, const __grid_co
         griddep_wait();                                   // the previous layer's output is complete and visible
         for (int pp = cluster_id; pp < num_pp; pp += num_clusters) {
             const int up = pp / ntiles, unit = 2 * (up >> 2) + (int)rank, yp = up & 3;
-            if ((p.flags & 1) && pp + num_clusters < num_pp && elect_one()) {     // next pass's boxes: HBM -> L2 while this pass computes
-                const int un = (pp + num_clusters) / ntiles, unit_n = 2 * (un >> 2) + (int)rank, yp_n = un & 3;
-                for (int kb = 0; kb < p.kblocks; ++kb)
-                    tma_prefetch_4d(&map_act, kb * kKBlock, unit_n * kBoardsPerUnit, 0, yp_n * kYPerPass - 1);
-            }
-            __syncwarp();
             for (int kb = 0; kb < p.kblocks; ++kb, ++it) {
                 const uint32_t s = it % kActStagesP, ph = (it / kActStagesP) & 1;
                 mbar_wait_b(bar_act_empty + 8 * s, ph ^ 1);
@@ -511,7 +267,7 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap map_act, const __grid_co
                 // Board rows -1 and 8 are zero padding: for the first / last row pair, three taps of one tile
                 // multiply an all-zero operand and are not issued (both CTAs of the pair work on the same rows).
                 const int yp = (pp / ntiles) & 3;
-                const bool skip_top = (p.flags & 4) && yp == 0, skip_bot = (p.flags & 4) && yp == 3;
+                const bool skip_top = yp == 0, skip_bot = yp == 3;
                 for (int kb = 0; kb < p.kblocks; ++kb, ++ait) {
                     const uint32_t as = ait % kActStagesP;
                     mbar_wait_b(bar_act_full + 8 * as, (ait / kActStagesP) & 1);
@@ -589,7 +345,7 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap map_act, const __grid_co
 #pragma unroll
                     for (int i = 0; i < 4; ++i) ldg256(p.skip + off0 + r * ystride + i * 16, &sk[r][i * 8]);
                 }
-                if ((p.flags & 2) && pp + num_clusters < num_pp) {               // next pass's residual rows: HBM -> L2 ahead of use
+                if (pp + num_clusters < num_pp) {               // next pass's residual rows: HBM -> L2 ahead of use
                     const int ppn = pp + num_clusters, ntn = ppn % ntiles, un = ppn / ntiles;
                     const size_t board_n = (size_t)(2 * (un >> 2) + (int)rank) * kBoardsPerUnit + bl;
                     const size_t offn = ((board_n * 8 + (un & 3) * kYPerPass) * 8 + x) * (size_t)p.cout_total + ntn * 128 + half * 64;
@@ -860,47 +616,24 @@ static int make_w_map(CUtensorMap *m, void *ptr, int cin, int cout, int box_rows
     return OZ_OK;
 }
 
-// OZ_CONV_VARIANT=1 selects the single-CTA kernel (cta_group::1), anything else the CTA-pair kernel.
-static bool use_pair_kernel() {
-    static int v = -1;
-    if (v < 0) { const char *e = getenv("OZ_CONV_VARIANT"); v = (e && e[0] == '1') ? 0 : 1; }
-    return v == 1;
-}
-static int conv_flags() {
-    static int v = -1;
-    if (v < 0) { const char *e = getenv("OZ_CONV_FLAGS"); v = e ? atoi(e) : 14; }
-    return v;
-}
-static int act_box_y() { return use_pair_kernel() ? pair::kBoxYp : kBoxY; }
-static int w_box_rows() { return use_pair_kernel() ? 64 : 128; }
-
 static int launch_conv(const CUtensorMap &ma, const CUtensorMap &mw, const ConvParams &cp, cudaStream_t stream) {
     static bool attr_set = false;
     if (!attr_set) {
-        OZ_CUDA(cudaFuncSetAttribute(conv3x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
         OZ_CUDA(cudaFuncSetAttribute(conv3x3_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, pair::kSmemBytesP));
         attr_set = true;
     }
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    if (use_pair_kernel()) {
-        ConvParams cq = cp;
-        cq.flags = conv_flags();
-        const int num_pp = cp.units * 2 * (cp.cout_total >> 7);
-        const int clusters = num_pp < sms / 2 ? num_pp : sms / 2;
-        cudaLaunchConfig_t cfg = {};
-        cfg.gridDim = dim3(2 * clusters); cfg.blockDim = dim3(pair::kThreadsP); cfg.dynamicSmemBytes = pair::kSmemBytesP; cfg.stream = stream;
-        cudaLaunchAttribute attr[1];
-        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-        attr[0].val.programmaticStreamSerializationAllowed = (cq.flags & 8) ? 1 : 0;
-        cfg.attrs = attr; cfg.numAttrs = 1;
-        OZ_CUDA(cudaLaunchKernelEx(&cfg, conv3x3_pair_kernel, ma, mw, cq));
-    } else {
-        const int num_pass = cp.units * 2 * (cp.cout_total >> 7);
-        const int grid = num_pass < sms ? num_pass : sms;
-        conv3x3_kernel<<<grid, kThreads, kSmemBytes, stream>>>(ma, mw, cp);
-    }
+    const int num_pp = cp.units * 2 * (cp.cout_total >> 7);
+    const int clusters = num_pp < sms / 2 ? num_pp : sms / 2;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(2 * clusters); cfg.blockDim = dim3(pair::kThreadsP); cfg.dynamicSmemBytes = pair::kSmemBytesP; cfg.stream = stream;
+    cudaLaunchAttribute attr[1];                       // programmatic dependent launch: see griddep_wait() in the kernel
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    OZ_CUDA(cudaLaunchKernelEx(&cfg, conv3x3_pair_kernel, ma, mw, cp));
     count_launch();
     OZ_CUDA(cudaGetLastError());
     return OZ_OK;
@@ -926,7 +659,7 @@ int ResNet::load(const oz_resnet_shape &shape, const void *blob, size_t bytes) {
         OZ_CUDA(cudaMalloc(&d_blob_, L.total));
         map_w_.assign(L.conv_w.size(), CUtensorMap{});
         for (size_t i = 0; i < L.conv_w.size(); ++i)
-            OZ_TRY(make_w_map(&map_w_[i], d_blob_ + L.conv_w[i], i == 0 ? 32 : shape.channels, shape.channels, w_box_rows()));
+            OZ_TRY(make_w_map(&map_w_[i], d_blob_ + L.conv_w[i], i == 0 ? 32 : shape.channels, shape.channels, 64));
         if (shape.channels != shape_.channels) { cudaFree(d_a_); cudaFree(d_t_); cudaFree(d_x0_); cudaFree(d_head_pre_); d_a_ = d_t_ = d_x0_ = nullptr; d_head_pre_ = nullptr; cap_ = 0; }
     }
     shape_ = shape; layout_ = L;
@@ -947,9 +680,9 @@ int ResNet::reserve(size_t boards) {
     OZ_CUDA(cudaMalloc(&d_head_pre_, pad * 64 * 4 * sizeof(float)));
     OZ_CUDA(cudaMemset(d_a_, 0, pad * 64 * C * 2));
     OZ_CUDA(cudaMemset(d_t_, 0, pad * 64 * C * 2));
-    OZ_TRY(make_act_map(&map_x0_, d_x0_, pad, 32, act_box_y()));
-    OZ_TRY(make_act_map(&map_a_, d_a_, pad, (int)C, act_box_y()));
-    OZ_TRY(make_act_map(&map_t_, d_t_, pad, (int)C, act_box_y()));
+    OZ_TRY(make_act_map(&map_x0_, d_x0_, pad, 32, pair::kBoxYp));
+    OZ_TRY(make_act_map(&map_a_, d_a_, pad, (int)C, pair::kBoxYp));
+    OZ_TRY(make_act_map(&map_t_, d_t_, pad, (int)C, pair::kBoxYp));
     cap_ = pad;
     return OZ_OK;
 }
@@ -975,7 +708,7 @@ int ResNet::forward(const float *d_features, size_t n, float *d_policy, float *d
     cp.kblocks = C / kKBlock;
     // Last layer of a 128-channel tower (pair kernel): the epilogue also applies the three 1x1 head convolutions to its
     // fp32 values, so the final activation tensor is never written and the head kernel reads 1 KB instead of 16 KB per board.
-    const bool fuse_heads = use_pair_kernel() && C == 128 && shape_.blocks > 0 && d_head_pre_ != nullptr;
+    const bool fuse_heads = C == 128 && shape_.blocks > 0 && d_head_pre_ != nullptr;
     for (int b = 0; b < shape_.blocks; ++b) {   // residual tower (neural_net.py:32-65)
         cp.skip = nullptr; cp.out = (__nv_bfloat16 *)d_t_; cp.bias = (const float *)(d_blob_ + layout_.conv_b[1 + 2 * b]);
         OZ_TRY(launch_conv(map_a_, map_w_[1 + 2 * b], cp, stream));
@@ -1013,8 +746,8 @@ int ResNet::conv3x3(const void *d_in, int cin, const void *d_w, const float *d_b
     if (cin % kKBlock || cout % 128 || boards_padded % kBoardPad)
         return fail(OZ_ERR_INVALID_ARGUMENT, "conv3x3: cin % 32, cout % 128, boards % 32 must be 0");
     CUtensorMap ma, mw;
-    OZ_TRY(make_act_map(&ma, const_cast<void *>(d_in), boards_padded, cin, act_box_y()));
-    OZ_TRY(make_w_map(&mw, const_cast<void *>(d_w), cin, cout, w_box_rows()));
+    OZ_TRY(make_act_map(&ma, const_cast<void *>(d_in), boards_padded, cin, pair::kBoxYp));
+    OZ_TRY(make_w_map(&mw, const_cast<void *>(d_w), cin, cout, 64));
     ConvParams cp{};
     cp.skip = (const __nv_bfloat16 *)d_skip; cp.out = (__nv_bfloat16 *)d_out; cp.bias = d_bias;
     cp.units = (int)(boards_padded / kBoardsPerUnit); cp.kblocks = cin / kKBlock; cp.cout_total = cout; cp.relu = relu;
