@@ -204,6 +204,7 @@ def run_ours(args):
     eng = om.SelfPlayEngine(G, seed=args.seed, first_game_id=rank * G, cuda_device=local, **kw)
     eng.prepare(net)
     eng.set_profiling(True)
+    eng.set_pipeline(args.pipeline, bool(args.pipeline_pdl))
     lib = _lib.load()
     stream = torch.cuda.ExternalStream(lib.oz_engine_stream(eng._h), device=torch.device("cuda", local))
 
@@ -305,6 +306,17 @@ def run_ours(args):
     active_sims = e2e_steps * G * sims_per_search * world
     e2e_value = active_sims / (ms_e2e * 1e-3)
 
+    groups = max(1, args.pipeline)
+    sel_ms, exp_ms = (c1["select_ms"] - c0["select_ms"]) / args.steps, (c1["expand_ms"] - c0["expand_ms"]) / args.steps
+    if groups > 1:     # phases of different game groups overlap: network / conv = time at least one group spent there
+        phases = {"pipeline_groups": groups, "network (union over groups)": eval_ms / args.steps, "of_which_conv": conv_ms / args.steps,
+                  "select_encode (sum over groups, runs under the other group's network)": sel_ms,
+                  "expand_backup (sum over groups, runs under the other group's network)": exp_ms,
+                  "step time with no network running": (ms - eval_ms) / args.steps}
+    else:
+        phases = {"pipeline_groups": 1, "select_encode": sel_ms, "network": eval_ms / args.steps, "of_which_conv": conv_ms / args.steps,
+                  "expand_backup": exp_ms,
+                  "rest_of_ply (choose, record, re-root, syncs)": (ms - eval_ms) / args.steps - sel_ms - exp_ms}
     if rank == 0:
         f_all, f_conv = flops_per_eval(c=args.channels, blocks=args.blocks, hv=args.hidden)
         pk = peaks()
@@ -339,11 +351,7 @@ def run_ours(args):
                          "peak_source": pk["source"] + ", sustained bf16 (kernel timed inside a long step)"},
             "perft": {"depth": 11, "nodes": int(perft_nodes), "nodes_per_s": perft_nodes / (perft_ms * 1e-3) if perft_ms > 0 else None,
                       "device_ms": perft_ms},
-            "phases_ms_per_step": {"select_encode": (c1["select_ms"] - c0["select_ms"]) / args.steps,
-                                   "network": eval_ms / args.steps, "of_which_conv": conv_ms / args.steps,
-                                   "expand_backup": (c1["expand_ms"] - c0["expand_ms"]) / args.steps,
-                                   "rest_of_ply (choose, record, re-root, syncs)": (ms - (c1["select_ms"] - c0["select_ms"]) - eval_ms
-                                                                                   - (c1["expand_ms"] - c0["expand_ms"])) / args.steps},
+            "phases_ms_per_step": phases,
             "midgame": mid,
             "clocks": clocks,
         }
@@ -372,6 +380,8 @@ def main():
     ap.add_argument("--channels", type=int, default=128, help="conv_channels (BASELINE config 5: 256)")
     ap.add_argument("--blocks", type=int, default=9, help="residual blocks (config 5: 19)")
     ap.add_argument("--hidden", type=int, default=128, help="value head hidden units (config 5: 256)")
+    ap.add_argument("--pipeline", type=int, default=0, help="game groups of the pipelined search: 0 auto, 1 off, 2..4")
+    ap.add_argument("--pipeline-pdl", type=int, default=1, help="keep programmatic dependent launch while pipelined")
     ap.add_argument("--cpu-steps", type=int, default=12)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--midgame-ply", type=int, default=24, help="also time 2 plies after fast-forwarding every game this far (0 = skip)")

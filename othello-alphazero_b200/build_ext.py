@@ -37,7 +37,7 @@ def _deps() -> float:
 
 def _compile(name: str, flags: list[str], verbose: bool) -> Path:
     obj = OBJ / (name + ".o")
-    cmd = [NVCC, *ARCH, *COMMON, *flags, "-c", str(CSRC / name), "-o", str(obj)]
+    cmd = [NVCC, *ARCH, *COMMON, *flags, *os.environ.get("OZ_NVCC_FLAGS", "").split(), "-c", str(CSRC / name), "-o", str(obj)]
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
     proc = subprocess.run(cmd, capture_output=True, text=True)

@@ -4,6 +4,7 @@
 #include <cmath>
 #include <cstring>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "oz_common.cuh"
@@ -22,6 +23,8 @@ struct oz_resnet {
     float *d_f = nullptr, *d_p = nullptr, *d_v = nullptr;
     size_t cap = 0;
 };
+
+constexpr int kMaxGroups = 4;             // game groups of the pipelined search
 
 struct oz_engine {
     oz_config cfg{};
@@ -45,6 +48,13 @@ struct oz_engine {
     unsigned long long graph_launches = 0;   // kernels inside round_graph
     bool warmed = false;
     int graph_mode = 1;                      // 0 never, 1 when the leaf batch is launch-bound, 2 always                     // an eager search has run with the current allocations
+    // Pipelined search: the games are split into groups that run select -> network -> expand on their own streams, so
+    // one group's tree kernels run underneath another group's convolutions (results do not depend on the grouping).
+    int pipeline = 0;                     // 0 auto, 1 off, 2..kMaxGroups groups
+    bool pipeline_pdl = true;             // keep programmatic dependent launch between conv layers while pipelined
+    cudaStream_t gstream[kMaxGroups] = {};     // tree streams (low priority), one per group
+    cudaStream_t nstream = nullptr;            // network stream (high priority), shared: the conv layers of all groups stay one chain
+    cudaEvent_t ev_fork = nullptr, ev_join[kMaxGroups] = {}, ev_sel[kMaxGroups] = {}, ev_net[kMaxGroups] = {};
     int active = 0;                       // games not finished
     long tree_bound = 1;                  // upper bound on the nodes of the largest live tree
     oz_counters ctr{};
@@ -228,21 +238,27 @@ int ensure_capacity(oz_engine *e) {
     return OZ_OK;
 }
 
-int eval_round(oz_engine *e, cudaEvent_t conv_begin = nullptr, cudaEvent_t conv_end = nullptr) {
-    const size_t n = (size_t)e->t.G * e->t.inflight;
+// One evaluator call over `n` leaf slots starting at slot `first` (ws = network workspace = pipeline group).
+int eval_slots(oz_engine *e, size_t first, size_t n, cudaStream_t stream, int ws, cudaEvent_t conv_begin = nullptr, cudaEvent_t conv_end = nullptr) {
     const int planes = 1 + 2 * e->t.H;
+    const float *f = e->d_features + first * planes * 64;
+    float *p = e->d_policy + first * 65, *v = e->d_value + first;
     switch (e->cfg.evaluator) {
-        case OZ_EVAL_SYNTH: launch_eval_synth(e->d_features, planes, n, e->d_policy, e->d_value, e->stream); break;
-        case OZ_EVAL_HASH: launch_eval_hash(e->d_features, planes, n, e->d_policy, e->d_value, e->stream); break;
+        case OZ_EVAL_SYNTH: launch_eval_synth(f, planes, n, p, v, stream); break;
+        case OZ_EVAL_HASH: launch_eval_hash(f, planes, n, p, v, stream); break;
         case OZ_EVAL_RESNET:
             if (e->net.shape().in_planes != planes)
                 return fail(OZ_ERR_STATE, "network in_planes " + std::to_string(e->net.shape().in_planes) + " != 1 + 2 * history_size");
-            OZ_TRY(e->net.forward(e->d_features, n, e->d_policy, e->d_value, e->stream, conv_begin, conv_end));
+            OZ_TRY(e->net.forward(f, n, p, v, stream, conv_begin, conv_end, ws));
             break;
         default: return fail(OZ_ERR_STATE, "oz_engine_search needs a built-in evaluator; use select/expand for OZ_EVAL_EXTERNAL");
     }
     e->ctr.evaluations += n;
     return OZ_OK;
+}
+
+int eval_round(oz_engine *e, cudaEvent_t conv_begin = nullptr, cudaEvent_t conv_end = nullptr) {
+    return eval_slots(e, 0, (size_t)e->t.G * e->t.inflight, e->stream, 0, conv_begin, conv_end);
 }
 
 cudaEvent_t next_event(oz_engine *e, size_t i) {
@@ -257,7 +273,7 @@ int begin_search(oz_engine *e) {
     OZ_TRY(ensure_capacity(e));
     // New SearchThread per search: feature slots start from zeros (search_thread.cpp:37-39).
     OZ_CUDA(cudaMemsetAsync(e->d_features, 0, (size_t)e->t.G * e->t.inflight * (1 + 2 * e->t.H) * 64 * sizeof(float), e->stream));
-    OZ_CUDA(cudaMemsetAsync(e->t.round, 0, sizeof(int32_t), e->stream));
+    OZ_CUDA(cudaMemsetAsync(e->t.round, 0, (1 + kMaxGroups) * sizeof(int32_t), e->stream));
     e->in_search = true; e->round = 0;
     return OZ_OK;
 }
@@ -268,6 +284,106 @@ int end_search(oz_engine *e) {
     e->ctr.searches += 1;
     e->ctr.simulations += (uint64_t)rounds_of(e->cfg) * e->t.inflight * (uint64_t)e->active;
     return check_device_errors(e);
+}
+
+// ---- pipelined search ----
+int pipeline_groups(const oz_engine *e) {
+    if (e->cfg.evaluator == OZ_EVAL_EXTERNAL) return 1;
+    int want = e->pipeline;
+    // Automatic = off: measured on B200 (profiles/r01_pipeline_experiment.md) the convolutions lose more to the
+    // co-running tree kernels (1 354 -> 1 160-1 210 TFLOP/s) than the hidden select / expand time gives back.
+    if (want == 0) want = 1;
+    return std::max(1, std::min({want, kMaxGroups, e->t.G}));
+}
+
+// The games [g0, g1) as a Tree of their own: every per-game, per-slot and per-node array is indexed by the local game.
+Tree group_view(const oz_engine *e, int g0, int g1, int k) {
+    Tree v = e->t;
+    const size_t nb = (size_t)g0 * 2 * v.cap, sb = (size_t)g0 * v.inflight;
+    v.n_p1 += nb; v.n_p2 += nb; v.n_meta += nb; v.n_parent += nb; v.n_child += nb; v.n_N += nb; v.n_W += nb; v.n_Q += nb; v.n_P += nb;
+    v.g_root += g0; v.g_which += g0; v.g_count += g0; v.g_status += g0; v.g_ply += g0; v.g_search += g0; v.g_gameid += g0;
+    v.h_p1 += (size_t)g0 * kMaxHist; v.h_p2 += (size_t)g0 * kMaxHist; v.h_player += (size_t)g0 * kMaxHist; v.h_n += g0;
+    v.r_p1 += g0; v.r_p2 += g0; v.r_player += g0;
+    v.s_leaf += sb; v.s_tf += sb; v.s_len += sb; v.s_path += sb * kMaxDepth;
+    v.round = e->t.round + 1 + k;
+    v.G = g1 - g0;
+    return v;
+}
+
+// Length of the union of [a, b) intervals.
+double union_ms(std::vector<std::pair<float, float>> iv) {
+    std::sort(iv.begin(), iv.end());
+    double total = 0.0; float hi = -1e30f;
+    for (const auto &x : iv) {
+        if (x.second <= hi) continue;
+        total += (double)x.second - (double)std::max(x.first, hi);
+        hi = x.second;
+    }
+    return total;
+}
+
+int search_pipelined(oz_engine *e, int groups) {
+    const int rounds = rounds_of(e->cfg), G = e->t.G, B = e->t.inflight;
+    // Tree kernels go to low-priority streams, the network to one high-priority stream: a pending convolution CTA is
+    // always placed before pending tree blocks, which then take the registers the convolution leaves free.
+    int prio_lo = 0, prio_hi = 0;
+    cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+    for (int k = 0; k < groups; ++k) {
+        if (!e->gstream[k] && cudaStreamCreateWithPriority(&e->gstream[k], cudaStreamNonBlocking, prio_lo) != cudaSuccess) { e->in_search = false; return fail(OZ_ERR_CUDA, "stream creation failed"); }
+        if (!e->ev_join[k]) { cudaEventCreateWithFlags(&e->ev_join[k], cudaEventDisableTiming); cudaEventCreateWithFlags(&e->ev_sel[k], cudaEventDisableTiming); cudaEventCreateWithFlags(&e->ev_net[k], cudaEventDisableTiming); }
+    }
+    if (!e->nstream && cudaStreamCreateWithPriority(&e->nstream, cudaStreamNonBlocking, prio_hi) != cudaSuccess) { e->in_search = false; return fail(OZ_ERR_CUDA, "stream creation failed"); }
+    if (!e->ev_fork) cudaEventCreate(&e->ev_fork);
+    const bool net_prof = e->profiling && e->cfg.evaluator == OZ_EVAL_RESNET;
+    cudaEventRecord(e->ev_fork, e->stream);
+    for (int k = 0; k < groups; ++k) cudaStreamWaitEvent(e->gstream[k], e->ev_fork, 0);
+    cudaStreamWaitEvent(e->nstream, e->ev_fork, 0);
+    e->net.set_pdl(e->pipeline_pdl);
+    size_t n_ev = 0;
+    int st = OZ_OK;
+    for (int r = 0; r < rounds && !st; ++r) {
+        e->round = r;
+        for (int k = 0; k < groups && !st; ++k) {
+            const int g0 = (int)((long)G * k / groups), g1 = (int)((long)G * (k + 1) / groups);
+            const Tree v = group_view(e, g0, g1, k);
+            cudaStream_t ts = e->gstream[k], ns = e->nstream;
+            const size_t first = (size_t)g0 * B, n = (size_t)(g1 - g0) * B;
+            cudaEvent_t cb = nullptr, ce = nullptr;
+            if (e->profiling) { cudaEventRecord(next_event(e, n_ev), ts); cb = next_event(e, n_ev + 2); ce = next_event(e, n_ev + 3); }
+            launch_select(v, ts, true);
+            launch_encode(v, e->d_features + first * (1 + 2 * e->t.H) * 64, ts, true);
+            cudaEventRecord(e->ev_sel[k], ts);
+            cudaStreamWaitEvent(ns, e->ev_sel[k], 0);
+            if (e->profiling) cudaEventRecord(next_event(e, n_ev + 1), ns);
+            st = eval_slots(e, first, n, ns, k, net_prof ? cb : nullptr, net_prof ? ce : nullptr);
+            if (e->profiling) cudaEventRecord(next_event(e, n_ev + 4), ns);
+            cudaEventRecord(e->ev_net[k], ns);
+            cudaStreamWaitEvent(ts, e->ev_net[k], 0);
+            if (!st) launch_expand(v, e->d_policy + first * 65, e->d_value + first, ts, true);
+            if (e->profiling) { cudaEventRecord(next_event(e, n_ev + 5), ts); n_ev += 6; }
+        }
+    }
+    e->net.set_pdl(true);
+    for (int k = 0; k < groups; ++k) { cudaEventRecord(e->ev_join[k], e->gstream[k]); cudaStreamWaitEvent(e->stream, e->ev_join[k], 0); }
+    if (st) { cudaStreamSynchronize(e->stream); e->in_search = false; return st; }
+    e->round = rounds;
+    e->warmed = true;
+    st = end_search(e);
+    if (!st && e->profiling) {
+        // Phases of different groups overlap: the network and the convolutions are charged the time at least one group
+        // spent in them (union of intervals on the fork event's clock); select / expand are the per-group sums.
+        std::vector<std::pair<float, float>> net_iv, conv_iv;
+        auto at = [&](size_t i) { float ms = 0.f; cudaEventElapsedTime(&ms, e->ev_fork, e->ev[i]); return ms; };
+        for (size_t i = 0; i + 5 < n_ev; i += 6) {
+            const float t0 = at(i), t1 = at(i + 1), t4 = at(i + 4), t5 = at(i + 5);
+            e->ctr.select_ms += std::max(0.f, t1 - t0); e->ctr.expand_ms += std::max(0.f, t5 - t4);
+            net_iv.emplace_back(t1, t4);
+            if (net_prof) { conv_iv.emplace_back(at(i + 2), at(i + 3)); e->ctr.conv_launches += (uint64_t)(1 + 2 * e->net.shape().blocks); }
+        }
+        e->ctr.eval_ms += union_ms(net_iv);
+        e->ctr.conv_ms += union_ms(conv_iv);
+    }
+    return st;
 }
 
 }  // namespace
@@ -304,7 +420,7 @@ int oz_engine_create(const oz_config *cfg, oz_engine **out) {
             (st = dalloc(&t.g_ply, G)) || (st = dalloc(&t.g_search, G)) || (st = dalloc(&t.g_gameid, G)) || (st = dalloc(&t.h_p1, (size_t)G * kMaxHist)) ||
             (st = dalloc(&t.h_p2, (size_t)G * kMaxHist)) || (st = dalloc(&t.h_player, (size_t)G * kMaxHist)) || (st = dalloc(&t.h_n, G)) ||
             (st = dalloc(&t.r_p1, G)) || (st = dalloc(&t.r_p2, G)) || (st = dalloc(&t.r_player, G)) || (st = dalloc(&t.error, 1)) ||
-            (st = dalloc(&t.stats, 4)) || (st = dalloc(&t.round, 1)) || (st = dalloc(&e->d_actions, G)) || (st = dalloc(&e->d_unfinished, 2)) ||
+            (st = dalloc(&t.stats, 4)) || (st = dalloc(&t.round, 1 + kMaxGroups)) || (st = dalloc(&e->d_actions, G)) || (st = dalloc(&e->d_unfinished, 2)) ||
             (st = dalloc(&e->d_stat_n, G)) || (st = dalloc(&e->d_stat_counts, (size_t)G * kStride)) || (st = dalloc(&e->d_stat_q, (size_t)G * kStride)) ||
             (st = dalloc(&e->d_stat_rootn, G)) || (st = dalloc(&e->d_spd_p, 8 * 65)))
             break;
@@ -337,6 +453,12 @@ void oz_engine_destroy(oz_engine *e) {
                     e->d_spd_f, e->d_spd_p};
     for (void *p : ptrs) cudaFree(p);
     for (cudaEvent_t x : e->ev) cudaEventDestroy(x);
+    for (int k = 0; k < kMaxGroups; ++k) {
+        if (e->gstream[k]) cudaStreamDestroy(e->gstream[k]);
+        if (e->ev_join[k]) { cudaEventDestroy(e->ev_join[k]); cudaEventDestroy(e->ev_sel[k]); cudaEventDestroy(e->ev_net[k]); }
+    }
+    if (e->nstream) cudaStreamDestroy(e->nstream);
+    if (e->ev_fork) cudaEventDestroy(e->ev_fork);
     if (e->stream) cudaStreamDestroy(e->stream);
     delete e;
 }
@@ -615,6 +737,8 @@ int oz_engine_search(oz_engine *e) {
     // the round index lives on the device, so the same graph serves every round of every search.
     const size_t boards = (size_t)e->t.G * e->t.inflight;
     const bool want_graph = !e->profiling && e->warmed && (e->graph_mode == 2 || (e->graph_mode == 1 && boards <= 8192));
+    const int groups = pipeline_groups(e);
+    if (groups > 1 && !(want_graph && e->pipeline == 0)) return search_pipelined(e, groups);
     if (want_graph && !e->round_graph) {
         cudaGraph_t g = nullptr;
         const unsigned long long before = g_kernel_launches;
@@ -859,6 +983,12 @@ int oz_engine_counters(oz_engine *e, oz_counters *out) {
 }
 
 int oz_engine_set_profiling(oz_engine *e, int on) { e->profiling = on != 0; return OZ_OK; }
+int oz_engine_set_pipeline(oz_engine *e, int groups, int pdl) {
+    if (groups < 0 || groups > kMaxGroups) return fail(OZ_ERR_INVALID_ARGUMENT, "Expected 0 <= groups <= " + std::to_string(kMaxGroups) + ", but got " + std::to_string(groups) + ".");
+    if (e->in_search) return fail(OZ_ERR_STATE, "cannot change the pipeline during a search");
+    e->pipeline = groups; e->pipeline_pdl = pdl != 0;
+    return OZ_OK;
+}
 int oz_engine_set_graphs(oz_engine *e, int mode) { e->graph_mode = mode; if (mode == 0) drop_graph(e); return OZ_OK; }
 void *oz_engine_stream(oz_engine *e) { return (void *)e->stream; }
 

@@ -616,7 +616,7 @@ static int make_w_map(CUtensorMap *m, void *ptr, int cin, int cout, int box_rows
     return OZ_OK;
 }
 
-static int launch_conv(const CUtensorMap &ma, const CUtensorMap &mw, const ConvParams &cp, cudaStream_t stream) {
+static int launch_conv(const CUtensorMap &ma, const CUtensorMap &mw, const ConvParams &cp, cudaStream_t stream, bool pdl = true) {
     static bool attr_set = false;
     if (!attr_set) {
         OZ_CUDA(cudaFuncSetAttribute(conv3x3_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, pair::kSmemBytesP));
@@ -632,15 +632,21 @@ static int launch_conv(const CUtensorMap &ma, const CUtensorMap &mw, const ConvP
     cudaLaunchAttribute attr[1];                       // programmatic dependent launch: see griddep_wait() in the kernel
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = attr; cfg.numAttrs = 1;
+    cfg.attrs = attr; cfg.numAttrs = pdl ? 1 : 0;
     OZ_CUDA(cudaLaunchKernelEx(&cfg, conv3x3_pair_kernel, ma, mw, cp));
     count_launch();
     OZ_CUDA(cudaGetLastError());
     return OZ_OK;
 }
 
+void ResNet::free_workspaces() {
+    for (Workspace &w : ws_) { cudaFree(w.x0); cudaFree(w.a); cudaFree(w.t); cudaFree(w.head_pre); }
+    ws_.clear();
+}
+
 ResNet::~ResNet() {
-    cudaFree(d_blob_); cudaFree(d_x0_); cudaFree(d_a_); cudaFree(d_t_); cudaFree(d_head_pre_);
+    cudaFree(d_blob_);
+    free_workspaces();
 }
 
 int ResNet::load(const oz_resnet_shape &shape, const void *blob, size_t bytes) {
@@ -660,7 +666,7 @@ int ResNet::load(const oz_resnet_shape &shape, const void *blob, size_t bytes) {
         map_w_.assign(L.conv_w.size(), CUtensorMap{});
         for (size_t i = 0; i < L.conv_w.size(); ++i)
             OZ_TRY(make_w_map(&map_w_[i], d_blob_ + L.conv_w[i], i == 0 ? 32 : shape.channels, shape.channels, 64));
-        if (shape.channels != shape_.channels) { cudaFree(d_a_); cudaFree(d_t_); cudaFree(d_x0_); cudaFree(d_head_pre_); d_a_ = d_t_ = d_x0_ = nullptr; d_head_pre_ = nullptr; cap_ = 0; }
+        if (shape.channels != shape_.channels) free_workspaces();
     }
     shape_ = shape; layout_ = L;
     OZ_CUDA(cudaMemcpy(d_blob_, blob, L.head_w, cudaMemcpyHostToDevice));
@@ -669,29 +675,37 @@ int ResNet::load(const oz_resnet_shape &shape, const void *blob, size_t bytes) {
     return OZ_OK;
 }
 
-int ResNet::reserve(size_t boards) {
+int ResNet::reserve(size_t boards, int ws) {
+    if (ws < 0 || ws >= 16) return fail(OZ_ERR_INVALID_ARGUMENT, "workspace index out of range");
+    if ((size_t)ws >= ws_.size()) ws_.resize((size_t)ws + 1);
+    Workspace &w = ws_[(size_t)ws];
     const size_t pad = (boards + kBoardPad - 1) / kBoardPad * kBoardPad;
-    if (pad <= cap_) return OZ_OK;
-    cudaFree(d_x0_); cudaFree(d_a_); cudaFree(d_t_); cudaFree(d_head_pre_); d_x0_ = d_a_ = d_t_ = nullptr; d_head_pre_ = nullptr; cap_ = 0;
+    if (pad <= w.cap) return OZ_OK;
+    cudaFree(w.x0); cudaFree(w.a); cudaFree(w.t); cudaFree(w.head_pre);
+    w = Workspace{};
     const size_t C = shape_.channels;
-    OZ_CUDA(cudaMalloc(&d_x0_, pad * 64 * 32 * 2));
-    OZ_CUDA(cudaMalloc(&d_a_, pad * 64 * C * 2));
-    OZ_CUDA(cudaMalloc(&d_t_, pad * 64 * C * 2));
-    OZ_CUDA(cudaMalloc(&d_head_pre_, pad * 64 * 4 * sizeof(float)));
-    OZ_CUDA(cudaMemset(d_a_, 0, pad * 64 * C * 2));
-    OZ_CUDA(cudaMemset(d_t_, 0, pad * 64 * C * 2));
-    OZ_TRY(make_act_map(&map_x0_, d_x0_, pad, 32, pair::kBoxYp));
-    OZ_TRY(make_act_map(&map_a_, d_a_, pad, (int)C, pair::kBoxYp));
-    OZ_TRY(make_act_map(&map_t_, d_t_, pad, (int)C, pair::kBoxYp));
-    cap_ = pad;
+    OZ_CUDA(cudaMalloc(&w.x0, pad * 64 * 32 * 2));
+    OZ_CUDA(cudaMalloc(&w.a, pad * 64 * C * 2));
+    OZ_CUDA(cudaMalloc(&w.t, pad * 64 * C * 2));
+    OZ_CUDA(cudaMalloc(&w.head_pre, pad * 64 * 4 * sizeof(float)));
+    OZ_CUDA(cudaMemset(w.a, 0, pad * 64 * C * 2));
+    OZ_CUDA(cudaMemset(w.t, 0, pad * 64 * C * 2));
+    OZ_TRY(make_act_map(&w.map_x0, w.x0, pad, 32, pair::kBoxYp));
+    OZ_TRY(make_act_map(&w.map_a, w.a, pad, (int)C, pair::kBoxYp));
+    OZ_TRY(make_act_map(&w.map_t, w.t, pad, (int)C, pair::kBoxYp));
+    w.cap = pad;
     return OZ_OK;
 }
 
 int ResNet::forward(const float *d_features, size_t n, float *d_policy, float *d_value, cudaStream_t stream,
-                    cudaEvent_t conv_begin, cudaEvent_t conv_end) {
+                    cudaEvent_t conv_begin, cudaEvent_t conv_end, int ws) {
     if (!loaded()) return fail(OZ_ERR_STATE, "no network weights loaded");
     if (n == 0) return OZ_OK;
-    OZ_TRY(reserve(n));
+    OZ_TRY(reserve(n, ws));
+    const Workspace &w = ws_[(size_t)ws];
+    void *const d_x0_ = w.x0, *const d_a_ = w.a, *const d_t_ = w.t;
+    float *const d_head_pre_ = w.head_pre;
+    const CUtensorMap &map_x0_ = w.map_x0, &map_a_ = w.map_a, &map_t_ = w.map_t;
     const size_t pad = (n + kBoardPad - 1) / kBoardPad * kBoardPad;
     const int C = shape_.channels;
     {
@@ -704,20 +718,20 @@ int ResNet::forward(const float *d_features, size_t n, float *d_policy, float *d
     cp.units = (int)(pad / kBoardsPerUnit); cp.cout_total = C; cp.relu = 1;
     // conv block (neural_net.py:9-29)
     cp.kblocks = 1; cp.skip = nullptr; cp.out = (__nv_bfloat16 *)d_a_; cp.bias = (const float *)(d_blob_ + layout_.conv_b[0]);
-    OZ_TRY(launch_conv(map_x0_, map_w_[0], cp, stream));
+    OZ_TRY(launch_conv(map_x0_, map_w_[0], cp, stream, pdl_));
     cp.kblocks = C / kKBlock;
     // Last layer of a 128-channel tower (pair kernel): the epilogue also applies the three 1x1 head convolutions to its
     // fp32 values, so the final activation tensor is never written and the head kernel reads 1 KB instead of 16 KB per board.
     const bool fuse_heads = C == 128 && shape_.blocks > 0 && d_head_pre_ != nullptr;
     for (int b = 0; b < shape_.blocks; ++b) {   // residual tower (neural_net.py:32-65)
         cp.skip = nullptr; cp.out = (__nv_bfloat16 *)d_t_; cp.bias = (const float *)(d_blob_ + layout_.conv_b[1 + 2 * b]);
-        OZ_TRY(launch_conv(map_a_, map_w_[1 + 2 * b], cp, stream));
+        OZ_TRY(launch_conv(map_a_, map_w_[1 + 2 * b], cp, stream, pdl_));
         cp.skip = (const __nv_bfloat16 *)d_a_; cp.out = (__nv_bfloat16 *)d_a_; cp.bias = (const float *)(d_blob_ + layout_.conv_b[2 + 2 * b]);
         if (fuse_heads && b == shape_.blocks - 1) {
             OZ_CUDA(cudaMemsetAsync(d_head_pre_, 0, pad * 64 * 4 * sizeof(float), stream));
             cp.out = nullptr; cp.head_w = (const float *)(d_blob_ + layout_.head_w); cp.head_out = d_head_pre_;
         }
-        OZ_TRY(launch_conv(map_t_, map_w_[2 + 2 * b], cp, stream));
+        OZ_TRY(launch_conv(map_t_, map_w_[2 + 2 * b], cp, stream, pdl_));
         cp.head_w = nullptr; cp.head_out = nullptr;
     }
     if (conv_end) cudaEventRecord(conv_end, stream);

@@ -40,12 +40,17 @@ class ResNet {
     int load(const oz_resnet_shape &shape, const void *blob, size_t bytes);
     bool loaded() const { return d_blob_ != nullptr; }
     const oz_resnet_shape &shape() const { return shape_; }
-    // Capacity in boards (rounded up to a multiple of 32); (re)allocates activations + tensor maps.
-    int reserve(size_t boards);
+    // Capacity in boards (rounded up to a multiple of 32) of workspace `ws`; (re)allocates activations + tensor maps.
+    // Workspaces are independent activation sets, so forward() calls on different workspaces may run concurrently on
+    // different streams (the engine's pipelined search: one workspace per game group).
+    int reserve(size_t boards, int ws = 0);
     // features: DEVICE float [n][in_planes][64] (reference plane format).  policy [n][65], value [n].
     // conv_begin / conv_end (optional) are recorded around the convolution launches.
     int forward(const float *d_features, size_t n, float *d_policy, float *d_value, cudaStream_t stream,
-                cudaEvent_t conv_begin = nullptr, cudaEvent_t conv_end = nullptr);
+                cudaEvent_t conv_begin = nullptr, cudaEvent_t conv_end = nullptr, int ws = 0);
+    // Chain the convolution layers with programmatic dependent launch (default on).  Off for concurrent forwards: a
+    // layer that is resident early and waits for its predecessor would keep the other stream's CTAs off the SM.
+    void set_pdl(bool on) { pdl_ = on; }
     // Kernel launches one forward() issues.
     int launches_per_forward() const { return 2 + (1 + 2 * shape_.blocks); }
     // Debug hook: one 3x3 convolution layer on device NHWC bf16 buffers already padded to 32 boards.
@@ -56,10 +61,15 @@ class ResNet {
     oz_resnet_shape shape_{};
     ResNetLayout layout_;
     char *d_blob_ = nullptr;
-    size_t cap_ = 0;
-    void *d_x0_ = nullptr, *d_a_ = nullptr, *d_t_ = nullptr;  // bf16 NHWC activations
-    float *d_head_pre_ = nullptr;                             // [boards][64][4] fused head-conv pre-activations
-    CUtensorMap map_x0_, map_a_, map_t_;
+    struct Workspace {
+        size_t cap = 0;
+        void *x0 = nullptr, *a = nullptr, *t = nullptr;       // bf16 NHWC activations
+        float *head_pre = nullptr;                            // [boards][64][4] fused head-conv pre-activations
+        CUtensorMap map_x0, map_a, map_t;
+    };
+    void free_workspaces();
+    std::vector<Workspace> ws_;
+    bool pdl_ = true;
     std::vector<CUtensorMap> map_w_;
 };
 

@@ -3,6 +3,8 @@
 // board squares.  Compiled with -fmad=false and explicit round-to-nearest intrinsics so
 // that every float decision matches the reference's scalar code (search_thread.cpp:192-260
 // compiled without FMA contraction) bit for bit.
+#include <algorithm>
+#include <cstdlib>
 #include <cfloat>
 #include <climits>
 
@@ -84,25 +86,28 @@ __global__ void reset_kernel(Tree t) {
 }
 
 // ------------------------------------------------------------------ select (search_thread.cpp:60-79, 192-260)
-__global__ void __launch_bounds__(128) select_kernel(Tree t) {
-    __shared__ int s_path[4][kMaxDepth];
+// WARPS = warps (games) per block; a warp walks games g, g + stride, ...  The pipelined search launches a bounded grid
+// of single-warp blocks without shared memory: they fit into the registers a resident convolution CTA leaves free on
+// its SM (6 400 of 65 536), so one game group's tree work runs underneath the other group's network and never keeps a
+// convolution CTA off an SM.  The path of a selection lives in registers (lane k holds nodes k, k + 32, ...).
+template <int WARPS>
+__global__ void __launch_bounds__(WARPS * 32) select_kernel(Tree t) {
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    const int g = blockIdx.x * 4 + wib;
-    if (g >= t.G) return;
     const int B = t.inflight, round = *t.round;
+    for (int g = blockIdx.x * WARPS + wib; g < t.G; g += gridDim.x * WARPS) {
     int *leaf_out = t.s_leaf + (size_t)g * B;
     if (t.g_status[g] & 1) {                         // finished game: nothing in flight
         for (int i = lane; i < B; i += 32) leaf_out[i] = -1;
-        return;
+        continue;
     }
     const size_t base = arena_base(t, g);
     const int root = t.g_root[g];
     const uint32_t game_id = t.g_gameid[g], search = t.g_search[g];
-    int *path = s_path[wib];
 
     for (int i = 0; i < B; ++i) {
         const uint32_t sim = (uint32_t)(round * B + i);
         int node = root, depth = 0;
+        int pr0 = 0, pr1 = 0, pr2 = 0, pr3 = 0;      // path nodes lane, lane + 32, lane + 64, lane + 96
         // Header of the current node (meta, first child, visit count).  Below the root it comes from the
         // child-statistics read of the level above (the winning lane already holds it), so a level costs
         // one dependent memory round trip instead of two.
@@ -158,25 +163,33 @@ __global__ void __launch_bounds__(128) select_kernel(Tree t) {
             } else {
                 nm = t.n_meta[base + next]; nfc = t.n_child[base + next]; nnn = t.n_N[base + next];
             }
-            if (depth < kMaxDepth) { if (lane == 0) path[depth] = next; }
-            else if (lane == 0) atomicOr(t.error, kErrDepth);
+            if (depth < kMaxDepth) {
+                if (lane == (depth & 31)) {
+                    const int q = depth >> 5;
+                    if (q == 0) pr0 = next; else if (q == 1) pr1 = next; else if (q == 2) pr2 = next; else pr3 = next;
+                }
+            } else if (lane == 0) atomicOr(t.error, kErrDepth);
             ++depth;
             node = next; m = nm; fc = nfc; nn = nnn;
         }
         if (depth > kMaxDepth) depth = kMaxDepth;
-        __syncwarp();
         // virtual loss on the path (root excluded), root visit count (:70-78)
         int *gpath = t.s_path + ((size_t)g * B + i) * kMaxDepth;
-        for (int k = lane; k < depth; k += 32) {
-            const int nd = path[k];
-            gpath[k] = nd;
-            const size_t a = base + nd;
-            const int n = t.n_N[a] + 1;
-            const float w = __fsub_rn(t.n_W[a], 1.0f);
-            t.n_N[a] = n; t.n_W[a] = w; t.n_Q[a] = __fdiv_rn(w, (float)n);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int k = lane + 32 * q;
+            if (k < depth) {
+                const int nd = q == 0 ? pr0 : (q == 1 ? pr1 : (q == 2 ? pr2 : pr3));
+                gpath[k] = nd;
+                const size_t a = base + nd;
+                const int n = t.n_N[a] + 1;
+                const float w = __fsub_rn(t.n_W[a], 1.0f);
+                t.n_N[a] = n; t.n_W[a] = w; t.n_Q[a] = __fdiv_rn(w, (float)n);
+            }
         }
         if (lane == 0) { t.n_N[base + root] += 1; leaf_out[i] = node; t.s_len[(size_t)g * B + i] = depth; }
         __syncwarp();
+    }
     }
 }
 
@@ -212,39 +225,41 @@ __device__ __forceinline__ void write_planes(float *f, int H, int nh, const uint
     }
 }
 
-__global__ void __launch_bounds__(128) encode_kernel(Tree t, float *features) {
-    __shared__ uint64_t s1[4][kMaxHist], s2[4][kMaxHist];
+template <int WARPS>
+__global__ void __launch_bounds__(WARPS * 32) encode_kernel(Tree t, float *features) {
+    __shared__ uint64_t s1[WARPS][kMaxHist], s2[WARPS][kMaxHist];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    const size_t slot = (size_t)blockIdx.x * 4 + wib;
-    if (slot >= (size_t)t.G * t.inflight) return;
-    const int g = (int)(slot / t.inflight), i = (int)(slot % t.inflight);
-    const int leaf = t.s_leaf[slot];
-    if (leaf < 0) return;
-    const size_t base = arena_base(t, g);
-    const int player = t.n_meta[base + leaf] & 3;
-    if (player == 0) return;                          // terminal leaf: slot keeps its stale planes (:88-90)
-    int tf = 0;
-    if (t.sym_mode == OZ_SYM_RANDOM) {
-        uint32_t r[4];
-        philox(t.g_gameid[g], t.g_search[g], (uint32_t)(*t.round * t.inflight + i), 0u, t.seed_lo, t.seed_hi, r);
-        tf = (int)(r[0] & 7u);
+    const size_t slots = (size_t)t.G * t.inflight;
+    for (size_t slot = (size_t)blockIdx.x * WARPS + wib; slot < slots; slot += (size_t)gridDim.x * WARPS) {
+        const int g = (int)(slot / t.inflight), i = (int)(slot % t.inflight);
+        const int leaf = t.s_leaf[slot];
+        if (leaf < 0) continue;
+        const size_t base = arena_base(t, g);
+        const int player = t.n_meta[base + leaf] & 3;
+        if (player == 0) continue;                        // terminal leaf: slot keeps its stale planes (:88-90)
+        int tf = 0;
+        if (t.sym_mode == OZ_SYM_RANDOM) {
+            uint32_t r[4];
+            philox(t.g_gameid[g], t.g_search[g], (uint32_t)(*t.round * t.inflight + i), 0u, t.seed_lo, t.seed_hi, r);
+            tf = (int)(r[0] & 7u);
+        }
+        if (lane == 0) t.s_tf[slot] = tf;
+        const int nh = gather_history(t, g, base, leaf, lane, s1[wib], s2[wib]);
+        write_planes(features + slot * (size_t)(1 + 2 * t.H) * 64, t.H, nh, s1[wib], s2[wib], (float)player - 1.0f, tf, lane);
+        __syncwarp();                                     // the history buffer is reused by the next slot
     }
-    if (lane == 0) t.s_tf[slot] = tf;
-    const int nh = gather_history(t, g, base, leaf, lane, s1[wib], s2[wib]);
-    write_planes(features + slot * (size_t)(1 + 2 * t.H) * 64, t.H, nh, s1[wib], s2[wib], (float)player - 1.0f, tf, lane);
 }
 
 // ------------------------------------------------------------------ expand + backup (search_thread.cpp:130-190)
-__global__ void __launch_bounds__(128) expand_kernel(Tree t, const float *__restrict__ policy, const float *__restrict__ value) {
+template <int WARPS>
+__global__ void __launch_bounds__(WARPS * 32) expand_kernel(Tree t, const float *__restrict__ policy, const float *__restrict__ value) {
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    const int g = blockIdx.x * 4 + wib;
     if (blockIdx.x == 0 && threadIdx.x == 0) *t.round += 1;     // select / encode of this round are done
-    if (g >= t.G) return;
-    if (t.g_status[g] & 1) return;
     const int B = t.inflight;
-    const size_t base = arena_base(t, g);
-    const int root = t.g_root[g];
     unsigned long long expanded = 0;
+    for (int g = blockIdx.x * WARPS + wib; g < t.G; g += gridDim.x * WARPS) {
+    if (t.g_status[g] & 1) continue;
+    const size_t base = arena_base(t, g);
     for (int i = 0; i < B; ++i) {
         const size_t slot = (size_t)g * B + i;
         const int leaf = t.s_leaf[slot];
@@ -296,7 +311,7 @@ __global__ void __launch_bounds__(128) expand_kernel(Tree t, const float *__rest
         }
         __syncwarp();
     }
-    (void)root;
+    }
     if (lane == 0 && expanded) atomicAdd(&t.stats[0], expanded);
 }
 
@@ -657,14 +672,37 @@ __global__ void __launch_bounds__(256) training_samples_kernel(const PlyRecordDe
 
 // ------------------------------------------------------------------ launchers
 static inline unsigned blocks(size_t items, int per_block) { return (unsigned)((items + per_block - 1) / per_block); }
+// Narrow launches are bounded to two blocks per SM: spread round-robin they never fill the registers a convolution
+// CTA needs on any SM (see select_kernel).
+constexpr unsigned kNarrowGrid = 2 * 148;
+// An SM runs one shared-memory / L1 split at a time.  The convolution needs the largest shared-memory carve-out; a
+// kernel that prefers another split cannot share the SM with it (the SM drains first), so the narrow kernels ask for
+// the same carve-out although they use next to no shared memory.
+static void narrow_attributes() {
+    static bool done = false;
+    if (done) return;
+    cudaFuncSetAttribute(select_kernel<1>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    cudaFuncSetAttribute(encode_kernel<2>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    cudaFuncSetAttribute(expand_kernel<1>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    done = true;
+}
 
 void launch_reset(const Tree &t, cudaStream_t s) { reset_kernel<<<blocks(t.G, 128), 128, 0, s>>>(t); count_launch(); }
-void launch_select(const Tree &t, cudaStream_t s) { select_kernel<<<blocks(t.G, 4), 128, 0, s>>>(t); count_launch(); }
-void launch_encode(const Tree &t, float *features, cudaStream_t s) {
-    encode_kernel<<<blocks((size_t)t.G * t.inflight, 4), 128, 0, s>>>(t, features); count_launch();
+void launch_select(const Tree &t, cudaStream_t s, bool narrow) {
+    if (narrow) narrow_attributes();
+    if (narrow) select_kernel<1><<<std::min(blocks(t.G, 1), kNarrowGrid), 32, 0, s>>>(t);
+    else select_kernel<4><<<blocks(t.G, 4), 128, 0, s>>>(t);
+    count_launch();
 }
-void launch_expand(const Tree &t, const float *policy, const float *value, cudaStream_t s) {
-    expand_kernel<<<blocks(t.G, 4), 128, 0, s>>>(t, policy, value); count_launch();
+void launch_encode(const Tree &t, float *features, cudaStream_t s, bool narrow) {
+    if (narrow) encode_kernel<2><<<std::min(blocks((size_t)t.G * t.inflight, 2), kNarrowGrid), 64, 0, s>>>(t, features);
+    else encode_kernel<4><<<blocks((size_t)t.G * t.inflight, 4), 128, 0, s>>>(t, features);
+    count_launch();
+}
+void launch_expand(const Tree &t, const float *policy, const float *value, cudaStream_t s, bool narrow) {
+    if (narrow) expand_kernel<1><<<std::min(blocks(t.G, 1), kNarrowGrid), 32, 0, s>>>(t, policy, value);
+    else expand_kernel<4><<<blocks(t.G, 4), 128, 0, s>>>(t, policy, value);
+    count_launch();
 }
 void launch_end_search(const Tree &t, cudaStream_t s) { end_search_kernel<<<blocks(t.G, 128), 128, 0, s>>>(t); count_launch(); }
 void launch_root_stats(const Tree &t, int32_t *n_children, int32_t *counts, float *q, int32_t *root_n, cudaStream_t s) {

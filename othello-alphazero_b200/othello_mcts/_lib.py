@@ -109,6 +109,7 @@ SIGNATURES = {
     "oz_engine_training_samples": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, P(C.c_size_t)]),
     "oz_engine_counters": (C.c_int, [C.c_void_p, P(OzCounters)]),
     "oz_engine_set_graphs": (C.c_int, [C.c_void_p, C.c_int]),
+    "oz_engine_set_pipeline": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
     "oz_engine_set_game_pool": (C.c_int, [C.c_void_p, C.c_int]),
     "oz_engine_finished_games": (C.c_int, [C.c_void_p, P(C.c_int32)]),
     "oz_engine_finished_records": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, P(C.c_int32)]),

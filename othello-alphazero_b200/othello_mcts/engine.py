@@ -164,6 +164,11 @@ class _Engine:
         """CUDA-graph replay of search rounds: 0 never, 1 (default) for launch-bound leaf batches, 2 always."""
         check(self._lib.oz_engine_set_graphs(self._h, int(mode)))
 
+    def set_pipeline(self, groups: int, pdl: bool = True) -> None:
+        """Pipelined search: split the games into `groups` groups on their own streams so one group's tree kernels run
+        underneath another group's convolutions.  0 = automatic, 1 = off, 2..4.  Results do not depend on it."""
+        check(self._lib.oz_engine_set_pipeline(self._h, int(groups), int(pdl)))
+
 
 class MCTS(_Engine):
     """Drop-in for the reference's `othello_mcts.MCTS` (othello_mcts.cpp:89-150): one game, same

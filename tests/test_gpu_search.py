@@ -284,3 +284,32 @@ def test_graph_replay_equals_eager_launches(evaluator):
         eager.apply_action(a)
         graph.apply_action(a)
     assert graph.counters()["kernel_launches"] > launches0
+
+
+@pytest.mark.parametrize("evaluator,groups", [("hash", 2), ("hash", 3), ("resnet", 2), ("resnet", 4)])
+def test_pipelined_search_equals_single_stream(evaluator, groups):
+    """The pipelined search splits the games into groups on their own streams (one group's tree kernels run underneath
+    another group's convolutions).  Every game's search is independent of the others, so whole games must come out
+    identical to the single-stream engine: same records, bit for bit, also with profiling events on."""
+    import torch
+    from othello_mcts import SelfPlayEngine
+    from othello_mcts.neural_net import AlphaZeroNet
+    net = "hash"
+    if evaluator == "resnet":
+        torch.manual_seed(2)
+        net = AlphaZeroNet(9, conv_channels=128, num_residual_blocks=2, value_head_hidden_channels=32).eval().cuda()
+    kw = dict(history_size=4, num_simulations=64, num_threads=2, batch_size=8, dirichlet_epsilon=0.25, seed=11, temperature_plies=8)
+    one, piped = SelfPlayEngine(11, **kw), SelfPlayEngine(11, **kw)
+    one.set_pipeline(1)
+    piped.set_pipeline(groups, pdl=(groups == 4))
+    piped.set_profiling(groups == 2)
+    a = one.run(net)
+    b = piped.run(net)
+    assert (a["plies"] == b["plies"]).all() and a["plies"].min() > 8
+    for name in ("p1", "p2", "player", "action", "n_children", "visit_counts"):
+        assert np.array_equal(a["records"][name], b["records"][name]), name
+    ca, cb = one.counters(), piped.counters()
+    for name in ("simulations", "evaluations", "nodes_expanded", "searches", "plies"):
+        assert ca[name] == cb[name], name
+    if groups == 2:
+        assert cb["eval_ms"] > 0 and cb["select_ms"] > 0
