@@ -175,6 +175,11 @@ int oz_debug_conv3x3(const uint16_t *in, int cin, const uint16_t *w, const float
 /* MCTS::search (mcts.h:220-256) for every game, with a built-in evaluator
  * (synth / hash / resnet).  Blocking. */
 int oz_engine_search(oz_engine *e);
+/* The same search for the games [first_game, first_game + num_games) only; the others keep their trees untouched and
+ * cost nothing (the network batch is num_games * T * B).  New capability for lockstep match play, where each of two
+ * engines (one per network) searches the games in which its player is to move (reference: evaluation.py:15-90 plays
+ * such games one at a time through play_game, player.py:33-96). */
+int oz_engine_search_range(oz_engine *e, int first_game, int num_games);
 /* The same search split at the evaluator, for OZ_EVAL_EXTERNAL (reference: the Python
  * callable of othello_mcts.cpp:36-45).  rounds() = ceil(N / (T*B)).  Each round:
  * select_device writes features [num_games*T*B, 1+2H, 8, 8] float32 to the DEVICE buffer,

@@ -278,13 +278,15 @@ int begin_search(oz_engine *e) {
     return OZ_OK;
 }
 
-int end_search(oz_engine *e) {
-    launch_end_search(e->t, e->stream);
+// `searched` = the games of this search (the whole tree or a range view), `active` = how many of them are unfinished.
+int end_search(oz_engine *e, const Tree &searched, int active) {
+    launch_end_search(searched, e->stream);
     e->in_search = false;
     e->ctr.searches += 1;
-    e->ctr.simulations += (uint64_t)rounds_of(e->cfg) * e->t.inflight * (uint64_t)e->active;
+    e->ctr.simulations += (uint64_t)rounds_of(e->cfg) * e->t.inflight * (uint64_t)active;
     return check_device_errors(e);
 }
+int end_search(oz_engine *e) { return end_search(e, e->t, e->active); }
 
 // ---- pipelined search ----
 int pipeline_groups(const oz_engine *e) {
@@ -726,8 +728,22 @@ int oz_engine_search_end(oz_engine *e) {
     return end_search(e);
 }
 
-int oz_engine_search(oz_engine *e) {
+// Unfinished games among [g0, g1) (one small read-back; only range searches need it).
+static int count_unfinished(oz_engine *e, int g0, int g1, int *out) {
+    std::vector<int32_t> st((size_t)(g1 - g0));
+    OZ_CUDA(cudaMemcpyAsync(st.data(), e->t.g_status + g0, st.size() * sizeof(int32_t), cudaMemcpyDeviceToHost, e->stream));
+    OZ_CUDA(cudaStreamSynchronize(e->stream));
+    int n = 0;
+    for (int32_t x : st) n += (x & 1) ? 0 : 1;
+    *out = n;
+    return OZ_OK;
+}
+
+static int search_games(oz_engine *e, int g0, int g1) {
     OZ_TRY(set_device(e));
+    const bool whole = g0 == 0 && g1 == e->t.G;
+    int active = e->active;
+    if (!whole) OZ_TRY(count_unfinished(e, g0, g1, &active));
     OZ_TRY(begin_search(e));
     const int rounds = rounds_of(e->cfg);
     size_t k = 0;
@@ -736,8 +752,8 @@ int oz_engine_search(oz_engine *e) {
     // Launch-bound batches (a single game is 26 launches of a few microseconds per round) replay one captured round;
     // the round index lives on the device, so the same graph serves every round of every search.
     const size_t boards = (size_t)e->t.G * e->t.inflight;
-    const bool want_graph = !e->profiling && e->warmed && (e->graph_mode == 2 || (e->graph_mode == 1 && boards <= 8192));
-    const int groups = pipeline_groups(e);
+    const bool want_graph = whole && !e->profiling && e->warmed && (e->graph_mode == 2 || (e->graph_mode == 1 && boards <= 8192));
+    const int groups = whole ? pipeline_groups(e) : 1;
     if (groups > 1 && !(want_graph && e->pipeline == 0)) return search_pipelined(e, groups);
     if (want_graph && !e->round_graph) {
         cudaGraph_t g = nullptr;
@@ -771,21 +787,25 @@ int oz_engine_search(oz_engine *e) {
         e->round = rounds;
         return end_search(e);
     }
+    // A range search walks a view of the games [g0, g1): its own round counter, slots and network batch.
+    const Tree v = whole ? e->t : group_view(e, g0, g1, 0);
+    const size_t first = (size_t)g0 * e->t.inflight, n = (size_t)(g1 - g0) * e->t.inflight;
+    float *feat = e->d_features + first * (1 + 2 * e->t.H) * 64;
     for (int r = 0; r < rounds && !st; ++r) {
         e->round = r;
         cudaEvent_t cb = nullptr, ce = nullptr;
         if (e->profiling) { cudaEventRecord(next_event(e, k), e->stream); cb = next_event(e, k + 2); ce = next_event(e, k + 3); }
-        launch_select(e->t, e->stream);
-        launch_encode(e->t, e->d_features, e->stream);
+        launch_select(v, e->stream);
+        launch_encode(v, feat, e->stream);
         if (e->profiling) cudaEventRecord(next_event(e, k + 1), e->stream);
-        st = eval_round(e, net_prof ? cb : nullptr, net_prof ? ce : nullptr);
+        st = eval_slots(e, first, n, e->stream, 0, net_prof ? cb : nullptr, net_prof ? ce : nullptr);
         if (e->profiling) cudaEventRecord(next_event(e, k + 4), e->stream);
-        if (!st) launch_expand(e->t, e->d_policy, e->d_value, e->stream);
+        if (!st) launch_expand(v, e->d_policy + first * 65, e->d_value + first, e->stream);
         if (e->profiling) { cudaEventRecord(next_event(e, k + 5), e->stream); k += 6; }
     }
     if (st) { e->in_search = false; return st; }
-    e->warmed = true;
-    st = end_search(e);
+    if (whole) e->warmed = true;
+    st = end_search(e, v, active);
     if (!st && e->profiling) {
         for (size_t i = 0; i + 5 < k; i += 6) {
             float a = 0, b = 0, c = 0, d = 0;
@@ -795,6 +815,16 @@ int oz_engine_search(oz_engine *e) {
         }
     }
     return st;
+}
+
+int oz_engine_search(oz_engine *e) { return search_games(e, 0, e->t.G); }
+
+int oz_engine_search_range(oz_engine *e, int first_game, int num_games) {
+    if (first_game < 0 || num_games < 1 || first_game + num_games > e->t.G)
+        return fail(OZ_ERR_OUT_OF_RANGE, "Expected 0 <= first_game and first_game + num_games <= " + std::to_string(e->t.G) + ", but got " +
+                                             std::to_string(first_game) + " + " + std::to_string(num_games) + ".");
+    if (e->cfg.evaluator == OZ_EVAL_EXTERNAL) return fail(OZ_ERR_STATE, "oz_engine_search_range needs a built-in evaluator");
+    return search_games(e, first_game, first_game + num_games);
 }
 
 int oz_engine_root_stats(oz_engine *e, int32_t *n_children, int32_t *counts, float *q, int32_t *root_n) {

@@ -313,3 +313,39 @@ def test_pipelined_search_equals_single_stream(evaluator, groups):
         assert ca[name] == cb[name], name
     if groups == 2:
         assert cb["eval_ms"] > 0 and cb["select_ms"] > 0
+
+
+def test_match_engine_equals_game_by_game_play():
+    """Lockstep match play (two engines, each searching the games where its network is to move) must give exactly the
+    games the reference's loop gives when it plays them one at a time: play_game (player.py:33-96) with two
+    AlphaZeroPlayer-shaped players (own tree each, epsilon = 0, most visited action, both apply every action)."""
+    import torch
+    from othello_mcts import MatchEngine, SelfPlayEngine
+    from othello_mcts.neural_net import AlphaZeroNet
+    torch.manual_seed(5)
+    net_a = AlphaZeroNet(9, conv_channels=128, num_residual_blocks=1, value_head_hidden_channels=32).eval().cuda()
+    net_b = AlphaZeroNet(9, conv_channels=128, num_residual_blocks=1, value_head_hidden_channels=32).eval().cuda()
+    P = 3
+    kw = dict(history_size=4, num_simulations=48, num_threads=1, batch_size=8, seed=21)
+    match = MatchEngine(P, **kw)
+    out = match.play(net_a, net_b)
+    assert out["plies"] >= 50 and set(out["result"]) <= {0, 1, 2}
+    assert (out["black_discs"] + out["white_discs"] <= 64).all()
+    rows = MatchEngine.game_results(out, "a", "b")
+    assert len(rows) == 2 * P and rows[0]["player1"] == "a" and rows[1]["player1"] == "b"
+    final = match.engines()[0].positions_array()
+
+    for g in range(2 * P):
+        black_net, white_net = (net_a, net_b) if g < P else (net_b, net_a)
+        pk = dict(kw, dirichlet_epsilon=0.0, temperature_plies=0, first_game_id=g)
+        players = [SelfPlayEngine(1, **pk), SelfPlayEngine(1, **pk)]          # index 0 = Black's player, 1 = White's
+        while True:
+            pos = players[0].positions_array()[0]
+            if pos["player"] == 0:
+                break
+            mover = int(pos["player"]) - 1
+            players[mover].search(black_net if mover == 0 else white_net)
+            a = players[mover].choose_actions()
+            players[0].apply_actions(a)
+            players[1].apply_actions(a)
+        assert pos["p1"] == final["p1"][g] and pos["p2"] == final["p2"][g], g
