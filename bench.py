@@ -100,6 +100,18 @@ def make_net(net_kw=None):
     return AlphaZeroNet(**(net_kw or NET)).eval()
 
 
+def workload_config(args, world: int) -> dict:
+    """The workload both arms are quoted on (BASELINE.json configs[2], per GPU)."""
+    G, inflight = args.games, args.threads * args.batch
+    sims_per_search = -(-args.sims // inflight) * inflight
+    return {"workload": f"{args.channels}x{args.blocks + 1}b random-init ResNet self-play, {G} lockstep games per GPU, {args.sims} sims/move "
+                        f"(T={args.threads} x B={args.batch} leaves in flight per game, leaf batch {G * inflight} per network call), "
+                        "random-symmetry eval, Dirichlet eps 0.25 alpha 0.5",
+            "games_per_gpu": G, "sims_per_move": sims_per_search, "leaf_batch": G * inflight,
+            "l2": "per-step working set (activations 16 KB/board/layer x leaf batch) far exceeds the 126 MB L2",
+            "parallelism": f"games partitioned by id over {world} GPU(s), no collective on the hot path"}
+
+
 def reference_search_rate(steps: int, warmup: int, threads: int):
     """BASELINE.json config 1: the reference's C++ MCTS (or the oracle port) + LibTorch CPU evaluation of
     the random-init 128x10b net, 800 sims/move, T=2 x B=16, on the host cores.  Each step = one search."""
@@ -166,8 +178,9 @@ def run_reference(args):
     line = {"metric": "mcts_simulations_per_second", "value": rate, "unit": "sims/s", "n_gpus": args.gpus, "steps": steps,
             "warmup": warmup, "ms_per_step": 1e3 * t / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic", "impl": "reference",
-            "config": {"workload": "128x10b random-init ResNet self-play, 800 sims/move, reference C++ MCTS (T=2 x B=16) + LibTorch on CPU; "
-                                   "each step = one 800-simulation search of one game"},
+            "config": dict(workload_config(args, max(1, args.gpus)),
+                           reference_sample="the reference plays the games one at a time (train.py:394-398): each step = one 800-simulation "
+                                            "search of one game, C++ MCTS (T=2 x B=16) + LibTorch CPU on all host cores"),
             "cpu_baseline": {"value": rate, "unit": "sims/s", "cores": cores, "kind": kind,
                              "sample": f"{steps} searches x 800 sims, one game, after {warmup} warm-up searches"},
             "e2e": {"value": rate, "unit": "sims/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
@@ -317,6 +330,16 @@ def run_ours(args):
         phases = {"pipeline_groups": 1, "select_encode": sel_ms, "network": eval_ms / args.steps, "of_which_conv": conv_ms / args.steps,
                   "expand_backup": exp_ms,
                   "rest_of_ply (choose, record, re-root, syncs)": (ms - eval_ms) / args.steps - sel_ms - exp_ms}
+    # Tree traffic: algorithmic bytes of select / encode / expand from the engine's counters, per simulation:
+    # select reads a (N, Q, P, meta, child) row = 20 B per child per level and 12 B of node header, then writes the virtual
+    # loss along the path (read N, W; write N, W, Q; path entry = 24 B per node); expand reads the leaf (20 B), writes 44 B
+    # per new node (+ 4 B prior gathered from the 260 B policy row), and backs up along the path (read N, W; write W, Q;
+    # path entry = 20 B per node); encode gathers 16 B per history position and writes the 4 352 B float32 planes.
+    d_sims = max(1, c1["simulations"] - c0["simulations"])
+    d_path, d_child, d_nodes = c1["path_nodes"] - c0["path_nodes"], c1["children_read"] - c0["children_read"], c1["nodes_expanded"] - c0["nodes_expanded"]
+    planes_bytes = (1 + 2 * MCTS_KW["history_size"]) * 64 * 4
+    tree_bytes = 20 * d_child + 12 * (d_path + d_sims) + 24 * d_path + 20 * d_path + 48 * d_nodes + d_sims * (20 + 4 + 16 * MCTS_KW["history_size"] + planes_bytes)
+    tree_ms = (c1["select_ms"] - c0["select_ms"]) + (c1["expand_ms"] - c0["expand_ms"])
     if rank == 0:
         f_all, f_conv = flops_per_eval(c=args.channels, blocks=args.blocks, hv=args.hidden)
         pk = peaks()
@@ -329,12 +352,7 @@ def run_ours(args):
             "metric": "mcts_simulations_per_second", "value": value, "unit": "sims/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": f"{net_name} random-init ResNet self-play, {G} lockstep games per GPU, {args.sims} sims/move "
-                                   f"(T={args.threads} x B={args.batch} leaves in flight per game, leaf batch {G * inflight} per network call), "
-                                   "random-symmetry eval, Dirichlet eps 0.25 alpha 0.5",
-                       "games_per_gpu": G, "sims_per_move": sims_per_search, "leaf_batch": G * inflight,
-                       "l2": "per-step working set (activations 16 KB/board/layer x leaf batch) far exceeds the 126 MB L2",
-                       "parallelism": f"games partitioned by id over {world} GPU(s), no collective on the hot path"},
+            "config": workload_config(args, world),
             "e2e": {"value": e2e_value, "unit": "sims/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "steps": e2e_steps, "path": "SelfPlayEngine.search(net) -> root_stats (host) -> numpy action choice -> apply_actions (host buffers)"},
             "gpu_launches": int(tot[2].item()),
@@ -352,6 +370,11 @@ def run_ours(args):
             "perft": {"depth": 11, "nodes": int(perft_nodes), "nodes_per_s": perft_nodes / (perft_ms * 1e-3) if perft_ms > 0 else None,
                       "device_ms": perft_ms},
             "phases_ms_per_step": phases,
+            "tree": {"bound": "latency (HBM pointer chasing, sequential within a game)", "bytes_per_sim": tree_bytes / d_sims,
+                     "mean_path_nodes": d_path / d_sims, "mean_children_per_level": d_child / max(1, d_path),
+                     "nodes_expanded_per_sim": d_nodes / d_sims, "achieved": (tree_bytes / (tree_ms * 1e-3) / 1e9) if tree_ms > 0 else None,
+                     "peak": pk["hbm"], "unit": "GB/s", "frac": (tree_bytes / (tree_ms * 1e-3) / 1e9 / pk["hbm"]) if tree_ms > 0 else None,
+                     "kernels": "select_kernel + encode_kernel + expand_kernel, CUDA-event time on the engine stream (rank 0)"},
             "midgame": mid,
             "clocks": clocks,
         }

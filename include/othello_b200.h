@@ -250,6 +250,8 @@ typedef struct {
     double   select_ms, eval_ms, expand_ms, reroot_ms; /* CUDA-event totals when profiling is on */
     double   conv_ms;          /* part of eval_ms spent in the 3x3 convolution launches */
     uint64_t conv_launches;    /* convolution launches timed in conv_ms */
+    uint64_t path_nodes;       /* tree levels descended by the selections (sum of path lengths, root excluded) */
+    uint64_t children_read;    /* child (N, Q, P, header) rows read by PUCT selection */
 } oz_counters;
 int oz_engine_counters(oz_engine *e, oz_counters *out);
 int oz_engine_set_profiling(oz_engine *e, int on);

@@ -1006,7 +1006,7 @@ int oz_engine_counters(oz_engine *e, oz_counters *out) {
     OZ_TRY(set_device(e));
     unsigned long long s[4] = {0, 0, 0, 0};
     OZ_CUDA(cudaMemcpy(s, e->t.stats, sizeof(s), cudaMemcpyDeviceToHost));
-    e->ctr.nodes_expanded = s[0];
+    e->ctr.nodes_expanded = s[0]; e->ctr.path_nodes = s[1]; e->ctr.children_read = s[2];
     e->ctr.kernel_launches = g_kernel_launches;
     *out = e->ctr;
     return OZ_OK;

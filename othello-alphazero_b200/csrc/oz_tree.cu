@@ -94,6 +94,7 @@ template <int WARPS>
 __global__ void __launch_bounds__(WARPS * 32) select_kernel(Tree t) {
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int B = t.inflight, round = *t.round;
+    unsigned long long path_nodes = 0, children_read = 0;      // traffic counters (oz_counters)
     for (int g = blockIdx.x * WARPS + wib; g < t.G; g += gridDim.x * WARPS) {
     int *leaf_out = t.s_leaf + (size_t)g * B;
     if (t.g_status[g] & 1) {                         // finished game: nothing in flight
@@ -128,6 +129,7 @@ __global__ void __launch_bounds__(WARPS * 32) select_kernel(Tree t) {
                 const int cm0 = v0 ? t.n_meta[a0] : 0, cm1 = v1 ? t.n_meta[a1] : 0;
                 const int cf0 = v0 ? t.n_child[a0] : -1, cf1 = v1 ? t.n_child[a1] : -1;
                 const int total = warp_sum(n0 + n1);
+                children_read += (unsigned)nch;
                 const float mult = __fmul_rn(rate, __fsqrt_rn((float)total));
                 if (node == root && t.eps > 0.0f) {  // Dirichlet noise, re-drawn per selection (:230-249)
                     const float g0 = v0 ? gamma_draw(t, game_id, search, sim, c0) : 0.f;
@@ -173,6 +175,7 @@ __global__ void __launch_bounds__(WARPS * 32) select_kernel(Tree t) {
             node = next; m = nm; fc = nfc; nn = nnn;
         }
         if (depth > kMaxDepth) depth = kMaxDepth;
+        path_nodes += (unsigned)depth;
         // virtual loss on the path (root excluded), root visit count (:70-78)
         int *gpath = t.s_path + ((size_t)g * B + i) * kMaxDepth;
 #pragma unroll
@@ -191,6 +194,7 @@ __global__ void __launch_bounds__(WARPS * 32) select_kernel(Tree t) {
         __syncwarp();
     }
     }
+    if (lane == 0 && path_nodes) { atomicAdd(&t.stats[1], path_nodes); atomicAdd(&t.stats[2], children_read); }
 }
 
 // ------------------------------------------------------------------ encode (search_thread.cpp:87-100, transformation.h:83-116)

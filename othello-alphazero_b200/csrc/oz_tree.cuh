@@ -46,7 +46,7 @@ struct Tree {
     const float *gamma_table; int gamma_len;    // injected Dirichlet draws (tests)
     int32_t *round;                      // round of the current search (device-side, so one CUDA graph serves every round)
     int32_t *error;                      // TreeError bits
-    unsigned long long *stats;           // [0] nodes expanded
+    unsigned long long *stats;           // [0] nodes expanded, [1] path nodes walked by select, [2] child statistics read by select
     // configuration
     int G, cap, H, inflight;
     float eps, alpha;

@@ -44,7 +44,7 @@ class OzCounters(C.Structure):
     _fields_ = [("simulations", u64), ("evaluations", u64), ("nodes_expanded", u64), ("searches", u64),
                 ("plies", u64), ("games_finished", u64), ("kernel_launches", u64), ("select_ms", C.c_double),
                 ("eval_ms", C.c_double), ("expand_ms", C.c_double), ("reroot_ms", C.c_double), ("conv_ms", C.c_double),
-                ("conv_launches", u64)]
+                ("conv_launches", u64), ("path_nodes", u64), ("children_read", u64)]
 
 
 # name -> (restype, argtypes); every symbol include/othello_b200.h declares

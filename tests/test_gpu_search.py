@@ -349,3 +349,46 @@ def test_match_engine_equals_game_by_game_play():
             players[0].apply_actions(a)
             players[1].apply_actions(a)
         assert pos["p1"] == final["p1"][g] and pos["p2"] == final["p2"][g], g
+
+
+def test_full_size_search_invariants():
+    """BASELINE.json config 3 at full size (128x10b random-init, 1 000 lockstep games, 800 sims/move, T x B = 2 x 16, random
+    symmetries, Dirichlet noise on), checked through properties that do not depend on the size: the reference's visit
+    accounting, value bounds, counters, and invariance of every game to how the games are partitioned."""
+    import torch
+    from othello_mcts import SelfPlayEngine
+    from othello_mcts.neural_net import AlphaZeroNet
+    torch.manual_seed(0)
+    net = AlphaZeroNet(17, conv_channels=128, num_residual_blocks=9, value_head_hidden_channels=128).eval()
+    kw = dict(history_size=8, num_simulations=800, num_threads=2, batch_size=16, c_puct_base=20000.0, c_puct_init=2.5,
+              dirichlet_epsilon=0.25, dirichlet_alpha=0.5, seed=2026)
+    G = 1000
+    eng = SelfPlayEngine(G, **kw)
+    eng.prepare(net)
+    eng.search(net)
+    n, counts, q, root_n = eng.root_stats()
+    assert (n == 4).all()                                              # four legal moves at the start
+    assert (root_n == 800).all()                                       # root.N += 1 per simulation (search_thread.cpp:78)
+    assert (counts.sum(axis=1) == 800 - 32).all()                      # Q1: the first T*B selections hit the childless root
+    assert (counts[:, 4:] == 0).all() and (counts[:, :4] >= 0).all()
+    assert np.isfinite(q).all() and (np.abs(q) <= 1.0).all()           # Q is a mean of values in [-1, 1]
+    c = eng.counters()
+    assert c["simulations"] == G * 800 and c["evaluations"] == G * 800
+    assert 0 < c["nodes_expanded"] <= G * 800 * 33 and c["path_nodes"] > 0 and c["children_read"] > 0
+    assert len({tuple(r) for r in counts[:, :4]}) > G // 2             # noise + random symmetries: games differ
+
+    # the same games 500..999 in an engine of their own (as another GPU would own them): identical, bit for bit
+    part = SelfPlayEngine(G // 2, first_game_id=G // 2, **kw)
+    part.search(net)
+    n2, counts2, q2, root_n2 = part.root_stats()
+    assert np.array_equal(counts[G // 2:], counts2) and np.array_equal(q[G // 2:].view(np.uint32), q2.view(np.uint32))
+
+    # Q2: the chosen child's visits carry over into the next search's root count
+    actions, _, unfinished = eng.play_ply(want_counts=False)          # searches again (tree reuse is off at ply 0: same root), then moves
+    assert unfinished == G
+    _, counts_b, _, _ = eng.root_stats()                                # the new roots' children after the re-root
+    eng.search(net)
+    _, counts_c, _, root_n_c = eng.root_stats()
+    assert (root_n_c >= 800).all() and (counts_c.sum(axis=1) >= counts_b.sum(axis=1) + 800 - 32 - 1).all()
+    pos = eng.positions_array()
+    assert (pos["player"] == 2).all() and (np.bitwise_count(pos["p1"]) + np.bitwise_count(pos["p2"]) == 5).all()

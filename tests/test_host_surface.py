@@ -22,7 +22,7 @@ def test_library_exports_every_declared_symbol():
     assert not missing, f"declared in include/othello_b200.h but not exported: {missing}"
     unbound = sorted(declared - set(_lib.SIGNATURES))
     assert not unbound, f"no ctypes signature for: {unbound}"
-    assert _lib.load().oz_abi_version() == 2
+    assert _lib.load().oz_abi_version() == 3
 
 
 def test_struct_sizes_match_abi():
@@ -30,6 +30,7 @@ def test_struct_sizes_match_abi():
     assert C.sizeof(_lib.OzPosition) == 40
     assert C.sizeof(_lib.OzPlyRecord) == 176
     assert C.sizeof(_lib.OzConfig) == 72
+    assert C.sizeof(_lib.OzCounters) == 120
 
 
 def test_position_matches_golden(golden):
