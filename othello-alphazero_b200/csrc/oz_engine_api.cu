@@ -239,9 +239,11 @@ int ensure_capacity(oz_engine *e) {
 }
 
 // One evaluator call over `n` leaf slots starting at slot `first` (ws = network workspace = pipeline group).
-int eval_slots(oz_engine *e, size_t first, size_t n, cudaStream_t stream, int ws, cudaEvent_t conv_begin = nullptr, cudaEvent_t conv_end = nullptr) {
+// staged = the encode kernel already wrote the network's own input tensor (encode_target).
+int eval_slots(oz_engine *e, size_t first, size_t n, cudaStream_t stream, int ws, cudaEvent_t conv_begin = nullptr, cudaEvent_t conv_end = nullptr,
+               bool staged = false) {
     const int planes = 1 + 2 * e->t.H;
-    const float *f = e->d_features + first * planes * 64;
+    const float *f = staged ? nullptr : e->d_features + first * planes * 64;
     float *p = e->d_policy + first * 65, *v = e->d_value + first;
     switch (e->cfg.evaluator) {
         case OZ_EVAL_SYNTH: launch_eval_synth(f, planes, n, p, v, stream); break;
@@ -257,8 +259,14 @@ int eval_slots(oz_engine *e, size_t first, size_t n, cudaStream_t stream, int ws
     return OZ_OK;
 }
 
-int eval_round(oz_engine *e, cudaEvent_t conv_begin = nullptr, cudaEvent_t conv_end = nullptr) {
-    return eval_slots(e, 0, (size_t)e->t.G * e->t.inflight, e->stream, 0, conv_begin, conv_end);
+// With the native network the encode kernel writes bf16 NHWC planes straight into the network's input tensor (the
+// float32 planes of the reference's evaluator contract are only materialised for the other evaluators).
+int encode_target(oz_engine *e, size_t n, int ws, void **x0) {
+    *x0 = nullptr;
+    if (e->cfg.evaluator != OZ_EVAL_RESNET) return OZ_OK;
+    if (e->net.shape().in_planes != 1 + 2 * e->t.H)
+        return fail(OZ_ERR_STATE, "network in_planes " + std::to_string(e->net.shape().in_planes) + " != 1 + 2 * history_size");
+    return e->net.input_buffer(n, ws, x0);
 }
 
 cudaEvent_t next_event(oz_engine *e, size_t i) {
@@ -271,8 +279,10 @@ int begin_search(oz_engine *e) {
     if (e->cfg.evaluator == OZ_EVAL_RESNET && !e->net.loaded()) return fail(OZ_ERR_STATE, "no network weights loaded");
     sync_params(e);
     OZ_TRY(ensure_capacity(e));
-    // New SearchThread per search: feature slots start from zeros (search_thread.cpp:37-39).
-    OZ_CUDA(cudaMemsetAsync(e->d_features, 0, (size_t)e->t.G * e->t.inflight * (1 + 2 * e->t.H) * 64 * sizeof(float), e->stream));
+    // New SearchThread per search: feature slots start from zeros (search_thread.cpp:37-39).  Only slots of terminal
+    // leaves keep them, and their network outputs are never read, so the native network's own input tensor is not re-zeroed.
+    if (e->cfg.evaluator != OZ_EVAL_RESNET)
+        OZ_CUDA(cudaMemsetAsync(e->d_features, 0, (size_t)e->t.G * e->t.inflight * (1 + 2 * e->t.H) * 64 * sizeof(float), e->stream));
     OZ_CUDA(cudaMemsetAsync(e->t.round, 0, (1 + kMaxGroups) * sizeof(int32_t), e->stream));
     e->in_search = true; e->round = 0;
     return OZ_OK;
@@ -352,12 +362,14 @@ int search_pipelined(oz_engine *e, int groups) {
             const size_t first = (size_t)g0 * B, n = (size_t)(g1 - g0) * B;
             cudaEvent_t cb = nullptr, ce = nullptr;
             if (e->profiling) { cudaEventRecord(next_event(e, n_ev), ts); cb = next_event(e, n_ev + 2); ce = next_event(e, n_ev + 3); }
+            void *x0 = nullptr;
+            if ((st = encode_target(e, n, k, &x0))) break;
             launch_select(v, ts, true);
-            launch_encode(v, e->d_features + first * (1 + 2 * e->t.H) * 64, ts, true);
+            launch_encode(v, e->d_features + first * (1 + 2 * e->t.H) * 64, ts, true, x0);
             cudaEventRecord(e->ev_sel[k], ts);
             cudaStreamWaitEvent(ns, e->ev_sel[k], 0);
             if (e->profiling) cudaEventRecord(next_event(e, n_ev + 1), ns);
-            st = eval_slots(e, first, n, ns, k, net_prof ? cb : nullptr, net_prof ? ce : nullptr);
+            st = eval_slots(e, first, n, ns, k, net_prof ? cb : nullptr, net_prof ? ce : nullptr, x0 != nullptr);
             if (e->profiling) cudaEventRecord(next_event(e, n_ev + 4), ns);
             cudaEventRecord(e->ev_net[k], ns);
             cudaStreamWaitEvent(ts, e->ev_net[k], 0);
@@ -759,10 +771,12 @@ static int search_games(oz_engine *e, int g0, int g1) {
         cudaGraph_t g = nullptr;
         const unsigned long long before = g_kernel_launches;
         const uint64_t evals_before = e->ctr.evaluations;
+        void *gx0 = nullptr;
+        if ((st = encode_target(e, boards, 0, &gx0))) { e->in_search = false; return st; }
         OZ_CUDA(cudaStreamBeginCapture(e->stream, cudaStreamCaptureModeThreadLocal));
         launch_select(e->t, e->stream);
-        launch_encode(e->t, e->d_features, e->stream);
-        st = eval_round(e);
+        launch_encode(e->t, e->d_features, e->stream, false, gx0);
+        st = eval_slots(e, 0, boards, e->stream, 0, nullptr, nullptr, gx0 != nullptr);
         if (!st) launch_expand(e->t, e->d_policy, e->d_value, e->stream);
         cudaError_t ce = cudaStreamEndCapture(e->stream, &g);
         e->graph_launches = g_kernel_launches - before;
@@ -791,14 +805,16 @@ static int search_games(oz_engine *e, int g0, int g1) {
     const Tree v = whole ? e->t : group_view(e, g0, g1, 0);
     const size_t first = (size_t)g0 * e->t.inflight, n = (size_t)(g1 - g0) * e->t.inflight;
     float *feat = e->d_features + first * (1 + 2 * e->t.H) * 64;
+    void *x0 = nullptr;
+    if ((st = encode_target(e, n, 0, &x0))) { e->in_search = false; return st; }
     for (int r = 0; r < rounds && !st; ++r) {
         e->round = r;
         cudaEvent_t cb = nullptr, ce = nullptr;
         if (e->profiling) { cudaEventRecord(next_event(e, k), e->stream); cb = next_event(e, k + 2); ce = next_event(e, k + 3); }
         launch_select(v, e->stream);
-        launch_encode(v, feat, e->stream);
+        launch_encode(v, feat, e->stream, false, x0);
         if (e->profiling) cudaEventRecord(next_event(e, k + 1), e->stream);
-        st = eval_slots(e, first, n, e->stream, 0, net_prof ? cb : nullptr, net_prof ? ce : nullptr);
+        st = eval_slots(e, first, n, e->stream, 0, net_prof ? cb : nullptr, net_prof ? ce : nullptr, x0 != nullptr);
         if (e->profiling) cudaEventRecord(next_event(e, k + 4), e->stream);
         if (!st) launch_expand(v, e->d_policy + first * 65, e->d_value + first, e->stream);
         if (e->profiling) { cudaEventRecord(next_event(e, k + 5), e->stream); k += 6; }

@@ -435,27 +435,33 @@ struct HeadParams {
     size_t n;
 };
 
-// neural_net.py:68-128.  One WARP per board (8 boards per CTA in flight): lane l owns board squares l and
-// l + 32 for the two 1x1 convolutions, then policy outputs l and l + 32 (output 64 is a warp reduction) and
-// every 32nd hidden unit of the value head.  FC weights live in shared memory with odd row strides (no bank
-// conflicts); only __syncwarp between the stages.
+// neural_net.py:68-128.  One WARP works on kHeadBoards boards at a time (8 warps per CTA): lane l owns board squares l
+// and l + 32 for the two 1x1 convolutions, then policy outputs l and l + 32 (output 64 is a warp reduction) and every
+// 32nd hidden unit of the value head.  FC weights live in shared memory (row strides = 4 mod 32 floats: conflict-free
+// 128-bit loads) and every weight vector read is used for all kHeadBoards boards, so the kernel is no longer bound by
+// shared-memory bandwidth (the one-board-per-warp version did 3 LDS per 2 FMA).  Summation order per output is the plain
+// i = 0, 1, 2, ... order.
 constexpr int kHeadWarps = 8;
-__host__ __device__ inline int heads_cw_offset(int Hv) { return (65 * 129 + Hv * 65 + 3) & ~3; }       // floats
-__host__ __device__ inline int heads_smem_floats(int C, int Hv) { return heads_cw_offset(Hv) + 3 * C + 2 * Hv + kHeadWarps * 192; }
+constexpr int kHeadBoards = 4;
+constexpr int kPfcStride = 132, kVfcStride = 68, kFeatStride = 192;   // floats
+__host__ __device__ inline int heads_cw_offset(int Hv) { return (65 * kPfcStride + Hv * kVfcStride + 3) & ~3; }       // floats
+__host__ __device__ inline int heads_smem_floats(int C, int Hv) {
+    return ((heads_cw_offset(Hv) + 3 * C + 2 * Hv + 3) & ~3) + kHeadWarps * kHeadBoards * kFeatStride;
+}
 
 __global__ void __launch_bounds__(kHeadWarps * 32, 2) heads_kernel(const HeadParams p) {
     extern __shared__ __align__(16) float sm[];
     const int C = p.C, Hv = p.Hv;
-    float *s_pfc = sm;                               // [65][129]
-    float *s_vfc1 = s_pfc + 65 * 129;                // [Hv][65]
+    float *s_pfc = sm;                               // [65][132]
+    float *s_vfc1 = s_pfc + 65 * kPfcStride;         // [Hv][68]
     float *s_cw = sm + heads_cw_offset(Hv);          // [3][C]: policy c0, policy c1, value (16-byte aligned)
     float *s_vb1 = s_cw + 3 * C;                     // [Hv] value fc1 bias
     float *s_vw2 = s_vb1 + Hv;                       // [Hv] value fc2 weight
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
-    float *s_feat = s_vw2 + Hv + warp * 192;         // [128] policy features (channel-major), then [64] value features
-    float *s_v1 = s_feat + 128;
-    for (int i = t; i < 65 * 128; i += kHeadWarps * 32) s_pfc[(i >> 7) * 129 + (i & 127)] = p.pfc_w[i];
-    for (int i = t; i < Hv * 64; i += kHeadWarps * 32) s_vfc1[(i >> 6) * 65 + (i & 63)] = p.vfc1_w[i];
+    // per warp and board: [128] policy features (channel-major), then [64] value features
+    float *s_feat = sm + ((heads_cw_offset(Hv) + 3 * C + 2 * Hv + 3) & ~3) + warp * kHeadBoards * kFeatStride;
+    for (int i = t; i < 65 * 128; i += kHeadWarps * 32) s_pfc[(i >> 7) * kPfcStride + (i & 127)] = p.pfc_w[i];
+    for (int i = t; i < Hv * 64; i += kHeadWarps * 32) s_vfc1[(i >> 6) * kVfcStride + (i & 63)] = p.vfc1_w[i];
     for (int i = t; i < 2 * C; i += kHeadWarps * 32) s_cw[i] = p.pconv_w[i];
     for (int i = t; i < C; i += kHeadWarps * 32) s_cw[2 * C + i] = p.vconv_w[i];
     for (int i = t; i < Hv; i += kHeadWarps * 32) { s_vb1[i] = p.vfc1_b[i]; s_vw2[i] = p.vfc2_w[i]; }
@@ -463,81 +469,137 @@ __global__ void __launch_bounds__(kHeadWarps * 32, 2) heads_kernel(const HeadPar
     const float pb0 = p.pconv_b[0], pb1 = p.pconv_b[1], vb = p.vconv_b[0], v2b = p.vfc2_b[0];
     const float pfb0 = p.pfc_b[lane], pfb1 = p.pfc_b[lane + 32], pfb64 = p.pfc_b[64];
     const float4 *cw0 = (const float4 *)s_cw, *cw1 = (const float4 *)(s_cw + C), *cw2 = (const float4 *)(s_cw + 2 * C);
-    for (size_t b = (size_t)blockIdx.x * kHeadWarps + warp; b < p.n; b += (size_t)gridDim.x * kHeadWarps) {
-        if (p.pre) {
+    for (size_t b0 = ((size_t)blockIdx.x * kHeadWarps + warp) * kHeadBoards; b0 < p.n; b0 += (size_t)gridDim.x * kHeadWarps * kHeadBoards) {
+        // ---- 1x1 convolutions + BN + ReLU (or their fused pre-activations) -> features in shared memory
 #pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                const int sq = lane + 32 * h;
-                const float4 d = __ldg((const float4 *)(p.pre + (b * 64 + sq) * 4));
-                s_feat[sq] = fmaxf(d.x + pb0, 0.f);
-                s_feat[64 + sq] = fmaxf(d.y + pb1, 0.f);
-                s_v1[sq] = fmaxf(d.z + vb, 0.f);
-            }
-        } else
+        for (int bi = 0; bi < kHeadBoards; ++bi) {
+            const size_t b = b0 + bi < p.n ? b0 + bi : p.n - 1;      // tail: recompute the last board, never stored
+            float *feat = s_feat + bi * kFeatStride, *v1 = feat + 128;
+            if (p.pre) {
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
-            const int sq = lane + 32 * h;
-            const __nv_bfloat16 *a = p.act + (b * 64 + sq) * (size_t)C;
-            float d0 = 0.f, d1 = 0.f, d2 = 0.f;
+                for (int h = 0; h < 2; ++h) {
+                    const int sq = lane + 32 * h;
+                    const float4 d = __ldg((const float4 *)(p.pre + (b * 64 + sq) * 4));
+                    feat[sq] = fmaxf(d.x + pb0, 0.f);
+                    feat[64 + sq] = fmaxf(d.y + pb1, 0.f);
+                    v1[sq] = fmaxf(d.z + vb, 0.f);
+                }
+            } else {
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const int sq = lane + 32 * h;
+                    const __nv_bfloat16 *a = p.act + (b * 64 + sq) * (size_t)C;
+                    float d0 = 0.f, d1 = 0.f, d2 = 0.f;
 #pragma unroll 2
-            for (int c16 = 0; c16 < C / 16; ++c16) {        // one full 32-byte sector (16 channels) per load
-                uint32_t q[8];
-                ldg256(a + c16 * 16, q);
+                    for (int c16 = 0; c16 < C / 16; ++c16) {        // one full 32-byte sector (16 channels) per load
+                        uint32_t q[8];
+                        ldg256(a + c16 * 16, q);
 #pragma unroll
-                for (int h2 = 0; h2 < 2; ++h2) {
-                    const __nv_bfloat162 *hh = (const __nv_bfloat162 *)&q[4 * h2];
-                    const float x0 = __bfloat162float(hh[0].x), x1 = __bfloat162float(hh[0].y), x2 = __bfloat162float(hh[1].x), x3 = __bfloat162float(hh[1].y);
-                    const float x4 = __bfloat162float(hh[2].x), x5 = __bfloat162float(hh[2].y), x6 = __bfloat162float(hh[3].x), x7 = __bfloat162float(hh[3].y);
-                    const int c8 = 2 * c16 + h2;
-                    float4 wa = cw0[2 * c8], wb = cw0[2 * c8 + 1];
-                    d0 += x0 * wa.x + x1 * wa.y + x2 * wa.z + x3 * wa.w + x4 * wb.x + x5 * wb.y + x6 * wb.z + x7 * wb.w;
-                    wa = cw1[2 * c8]; wb = cw1[2 * c8 + 1];
-                    d1 += x0 * wa.x + x1 * wa.y + x2 * wa.z + x3 * wa.w + x4 * wb.x + x5 * wb.y + x6 * wb.z + x7 * wb.w;
-                    wa = cw2[2 * c8]; wb = cw2[2 * c8 + 1];
-                    d2 += x0 * wa.x + x1 * wa.y + x2 * wa.z + x3 * wa.w + x4 * wb.x + x5 * wb.y + x6 * wb.z + x7 * wb.w;
+                        for (int h2 = 0; h2 < 2; ++h2) {
+                            const __nv_bfloat162 *hh = (const __nv_bfloat162 *)&q[4 * h2];
+                            const float x0 = __bfloat162float(hh[0].x), x1 = __bfloat162float(hh[0].y), x2 = __bfloat162float(hh[1].x), x3 = __bfloat162float(hh[1].y);
+                            const float x4 = __bfloat162float(hh[2].x), x5 = __bfloat162float(hh[2].y), x6 = __bfloat162float(hh[3].x), x7 = __bfloat162float(hh[3].y);
+                            const int c8 = 2 * c16 + h2;
+                            float4 wa = cw0[2 * c8], wb = cw0[2 * c8 + 1];
+                            d0 += x0 * wa.x + x1 * wa.y + x2 * wa.z + x3 * wa.w + x4 * wb.x + x5 * wb.y + x6 * wb.z + x7 * wb.w;
+                            wa = cw1[2 * c8]; wb = cw1[2 * c8 + 1];
+                            d1 += x0 * wa.x + x1 * wa.y + x2 * wa.z + x3 * wa.w + x4 * wb.x + x5 * wb.y + x6 * wb.z + x7 * wb.w;
+                            wa = cw2[2 * c8]; wb = cw2[2 * c8 + 1];
+                            d2 += x0 * wa.x + x1 * wa.y + x2 * wa.z + x3 * wa.w + x4 * wb.x + x5 * wb.y + x6 * wb.z + x7 * wb.w;
+                        }
+                    }
+                    feat[sq] = fmaxf(d0 + pb0, 0.f);
+                    feat[64 + sq] = fmaxf(d1 + pb1, 0.f);
+                    v1[sq] = fmaxf(d2 + vb, 0.f);
                 }
             }
-            s_feat[sq] = fmaxf(d0 + pb0, 0.f);
-            s_feat[64 + sq] = fmaxf(d1 + pb1, 0.f);
-            s_v1[sq] = fmaxf(d2 + vb, 0.f);
         }
         __syncwarp();
-        // policy FC 128 -> 65
-        float l0 = pfb0, l1 = pfb1, l2 = 0.f;
+        // ---- policy FC 128 -> 65: outputs lane, lane + 32 per board; output 64 by warp reduction
+        float l0[kHeadBoards], l1[kHeadBoards], l2[kHeadBoards];
+#pragma unroll
+        for (int bi = 0; bi < kHeadBoards; ++bi) { l0[bi] = pfb0; l1[bi] = pfb1; l2[bi] = 0.f; }
         {
-            const float *w0 = s_pfc + lane * 129, *w1 = s_pfc + (lane + 32) * 129;
-#pragma unroll 8
-            for (int i = 0; i < 128; ++i) { const float f = s_feat[i]; l0 += f * w0[i]; l1 += f * w1[i]; }
-            const float *w2 = s_pfc + 64 * 129 + lane * 4;
+            const float4 *w0 = (const float4 *)(s_pfc + lane * kPfcStride), *w1 = (const float4 *)(s_pfc + (lane + 32) * kPfcStride);
+#pragma unroll 4
+            for (int i4 = 0; i4 < 32; ++i4) {
+                const float4 a = w0[i4], c = w1[i4];
 #pragma unroll
-            for (int i = 0; i < 4; ++i) l2 += s_feat[lane * 4 + i] * w2[i];
+                for (int bi = 0; bi < kHeadBoards; ++bi) {
+                    const float4 f = *(const float4 *)(s_feat + bi * kFeatStride + 4 * i4);
+                    l0[bi] += f.x * a.x; l0[bi] += f.y * a.y; l0[bi] += f.z * a.z; l0[bi] += f.w * a.w;
+                    l1[bi] += f.x * c.x; l1[bi] += f.y * c.y; l1[bi] += f.z * c.z; l1[bi] += f.w * c.w;
+                }
+            }
+            const float4 w2 = *(const float4 *)(s_pfc + 64 * kPfcStride + lane * 4);
 #pragma unroll
-            for (int o = 16; o; o >>= 1) l2 += __shfl_xor_sync(0xffffffffu, l2, o);
-            l2 += pfb64;
+            for (int bi = 0; bi < kHeadBoards; ++bi) {
+                const float4 f = *(const float4 *)(s_feat + bi * kFeatStride + 4 * lane);
+                float x = 0.f;
+                x += f.x * w2.x; x += f.y * w2.y; x += f.z * w2.z; x += f.w * w2.w;
+#pragma unroll
+                for (int o = 16; o; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+                l2[bi] = x + pfb64;
+            }
         }
-        // value FC 64 -> Hv -> 1
-        float hv = 0.f;
-        for (int k = lane; k < Hv; k += 32) {
-            float acc = s_vb1[k];
-            const float *w = s_vfc1 + k * 65;
-#pragma unroll 8
-            for (int i = 0; i < 64; ++i) acc += s_v1[i] * w[i];
-            hv += fmaxf(acc, 0.f) * s_vw2[k];
+        // ---- value FC 64 -> Hv -> 1: hidden units lane + 32 j, four j at a time
+        float hv[kHeadBoards];
+#pragma unroll
+        for (int bi = 0; bi < kHeadBoards; ++bi) hv[bi] = 0.f;
+        for (int k0 = 0; k0 < Hv; k0 += 128) {
+            float acc[kHeadBoards][4];
+            const float4 *wr[4];
+            bool live[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int k = k0 + lane + 32 * j;
+                live[j] = k < Hv;
+                wr[j] = (const float4 *)(s_vfc1 + (live[j] ? k : 0) * kVfcStride);
+#pragma unroll
+                for (int bi = 0; bi < kHeadBoards; ++bi) acc[bi][j] = live[j] ? s_vb1[k] : 0.f;
+            }
+#pragma unroll 2
+            for (int i4 = 0; i4 < 16; ++i4) {
+                float4 f[kHeadBoards];
+#pragma unroll
+                for (int bi = 0; bi < kHeadBoards; ++bi) f[bi] = *(const float4 *)(s_feat + bi * kFeatStride + 128 + 4 * i4);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const float4 w = wr[j][i4];
+#pragma unroll
+                    for (int bi = 0; bi < kHeadBoards; ++bi) {
+                        acc[bi][j] += f[bi].x * w.x; acc[bi][j] += f[bi].y * w.y; acc[bi][j] += f[bi].z * w.z; acc[bi][j] += f[bi].w * w.w;
+                    }
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float w2v = live[j] ? s_vw2[k0 + lane + 32 * j] : 0.f;
+#pragma unroll
+                for (int bi = 0; bi < kHeadBoards; ++bi) hv[bi] += fmaxf(acc[bi][j], 0.f) * w2v;
+            }
         }
+        // ---- softmax over 65 logits, tanh
 #pragma unroll
-        for (int o = 16; o; o >>= 1) hv += __shfl_xor_sync(0xffffffffu, hv, o);
-        // softmax over 65 logits
-        float m = fmaxf(fmaxf(l0, l1), l2);
+        for (int bi = 0; bi < kHeadBoards; ++bi) {
+            float h = hv[bi];
 #pragma unroll
-        for (int o = 16; o; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
-        const float e0 = expf(l0 - m), e1 = expf(l1 - m), e2 = expf(l2 - m);
-        float ssum = e0 + e1;
+            for (int o = 16; o; o >>= 1) h += __shfl_xor_sync(0xffffffffu, h, o);
+            float m = fmaxf(fmaxf(l0[bi], l1[bi]), l2[bi]);
 #pragma unroll
-        for (int o = 16; o; o >>= 1) ssum += __shfl_xor_sync(0xffffffffu, ssum, o);
-        const float inv = 1.f / (ssum + e2);
-        float *po = p.policy + b * 65;
-        po[lane] = e0 * inv; po[lane + 32] = e1 * inv;
-        if (lane == 0) { po[64] = e2 * inv; p.value[b] = tanhf(hv + v2b); }
+            for (int o = 16; o; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+            const float e0 = expf(l0[bi] - m), e1 = expf(l1[bi] - m), e2 = expf(l2[bi] - m);
+            float ssum = e0 + e1;
+#pragma unroll
+            for (int o = 16; o; o >>= 1) ssum += __shfl_xor_sync(0xffffffffu, ssum, o);
+            const float inv = 1.f / (ssum + e2);
+            const size_t b = b0 + bi;
+            if (b < p.n) {
+                float *po = p.policy + b * 65;
+                po[lane] = e0 * inv; po[lane + 32] = e1 * inv;
+                if (lane == 0) { po[64] = e2 * inv; p.value[b] = tanhf(h + v2b); }
+            }
+        }
         __syncwarp();
     }
 }
@@ -688,12 +750,20 @@ int ResNet::reserve(size_t boards, int ws) {
     OZ_CUDA(cudaMalloc(&w.a, pad * 64 * C * 2));
     OZ_CUDA(cudaMalloc(&w.t, pad * 64 * C * 2));
     OZ_CUDA(cudaMalloc(&w.head_pre, pad * 64 * 4 * sizeof(float)));
+    OZ_CUDA(cudaMemset(w.x0, 0, pad * 64 * 32 * 2));
     OZ_CUDA(cudaMemset(w.a, 0, pad * 64 * C * 2));
     OZ_CUDA(cudaMemset(w.t, 0, pad * 64 * C * 2));
     OZ_TRY(make_act_map(&w.map_x0, w.x0, pad, 32, pair::kBoxYp));
     OZ_TRY(make_act_map(&w.map_a, w.a, pad, (int)C, pair::kBoxYp));
     OZ_TRY(make_act_map(&w.map_t, w.t, pad, (int)C, pair::kBoxYp));
     w.cap = pad;
+    return OZ_OK;
+}
+
+int ResNet::input_buffer(size_t boards, int ws, void **x0) {
+    if (!loaded()) return fail(OZ_ERR_STATE, "no network weights loaded");
+    OZ_TRY(reserve(boards, ws));
+    *x0 = ws_[(size_t)ws].x0;
     return OZ_OK;
 }
 
@@ -708,7 +778,7 @@ int ResNet::forward(const float *d_features, size_t n, float *d_policy, float *d
     const CUtensorMap &map_x0_ = w.map_x0, &map_a_ = w.map_a, &map_t_ = w.map_t;
     const size_t pad = (n + kBoardPad - 1) / kBoardPad * kBoardPad;
     const int C = shape_.channels;
-    {
+    if (d_features) {                                   // nullptr: the caller staged the input in input_buffer()
         const size_t threads = pad * 256;
         planes_to_nhwc32_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, stream>>>(d_features, shape_.in_planes, n, pad, (__nv_bfloat16 *)d_x0_);
         count_launch();
@@ -747,7 +817,7 @@ int ResNet::forward(const float *d_features, size_t n, float *d_policy, float *d
     const size_t hsm = (size_t)heads_smem_floats(C, hp.Hv) * sizeof(float);
     static size_t hsm_set = 0;
     if (hsm > hsm_set) { OZ_CUDA(cudaFuncSetAttribute(heads_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hsm)); hsm_set = hsm; }
-    const size_t want = (n + kHeadWarps - 1) / kHeadWarps;
+    const size_t want = (n + kHeadWarps * kHeadBoards - 1) / (kHeadWarps * kHeadBoards);
     const unsigned grid = (unsigned)(want < 148 * 2 ? want : 148 * 2);
     heads_kernel<<<grid, kHeadWarps * 32, hsm, stream>>>(hp);
     count_launch();

@@ -44,7 +44,10 @@ class ResNet {
     // Workspaces are independent activation sets, so forward() calls on different workspaces may run concurrently on
     // different streams (the engine's pipelined search: one workspace per game group).
     int reserve(size_t boards, int ws = 0);
-    // features: DEVICE float [n][in_planes][64] (reference plane format).  policy [n][65], value [n].
+    // The network's own input tensor of workspace `ws`: bf16 NHWC [boards padded to 32][64][32] (channel c = plane c,
+    // channels >= in_planes zero).  A caller that writes it directly passes d_features = nullptr to forward().
+    int input_buffer(size_t boards, int ws, void **x0);
+    // features: DEVICE float [n][in_planes][64] (reference plane format), or nullptr (see input_buffer).  policy [n][65], value [n].
     // conv_begin / conv_end (optional) are recorded around the convolution launches.
     int forward(const float *d_features, size_t n, float *d_policy, float *d_value, cudaStream_t stream,
                 cudaEvent_t conv_begin = nullptr, cudaEvent_t conv_end = nullptr, int ws = 0);

@@ -229,8 +229,35 @@ __device__ __forceinline__ void write_planes(float *f, int H, int nh, const uint
     }
 }
 
+// The same planes written straight into the native network's input tensor: bf16 NHWC [slot][64][32], channel = plane
+// (planes >= 1 + 2H stay zero).  Square i of the board lands on position transform_action(i, tf) (transformation.h:104-112).  To keep the stores coalesced a lane owns the TARGET positions lane and lane + 32
+// and looks its source squares up through the inverse symmetry (a mirrored symmetry is its own inverse, a pure rotation
+// by r quarter turns is undone by 4 - r).
+__device__ __forceinline__ void write_planes_nhwc(uint16_t *x, int nh, const uint64_t *sp1, const uint64_t *sp2, int player, int tf, int lane) {
+    const int inv = (tf & 1) ? tf : (((4 - (tf >> 1)) & 3) << 1);
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        const int j = lane + 32 * h, i = transform_action(j, inv);
+        const uint64_t m = 1ull << (63 - i);
+        uint32_t w[16];
+#pragma unroll
+        for (int q = 0; q < 16; ++q) w[q] = 0u;
+        if (player == 2) w[0] = 0x3F80u;                                   // plane 0 = player - 1 (transformation.h:91)
+#pragma unroll
+        for (int k = 0; k < 15; ++k) {
+            if (k < nh) {
+                if (sp1[k] & m) w[(1 + 2 * k) >> 1] |= 0x3F800000u;       // odd channel 1 + 2k: high half
+                if (sp2[k] & m) w[(2 + 2 * k) >> 1] |= 0x00003F80u;       // even channel 2 + 2k: low half
+            }
+        }
+        uint4 *dst = (uint4 *)(x + (size_t)j * 32);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) dst[q] = make_uint4(w[4 * q], w[4 * q + 1], w[4 * q + 2], w[4 * q + 3]);
+    }
+}
+
 template <int WARPS>
-__global__ void __launch_bounds__(WARPS * 32) encode_kernel(Tree t, float *features) {
+__global__ void __launch_bounds__(WARPS * 32) encode_kernel(Tree t, float *features, uint16_t *nhwc) {
     __shared__ uint64_t s1[WARPS][kMaxHist], s2[WARPS][kMaxHist];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const size_t slots = (size_t)t.G * t.inflight;
@@ -249,7 +276,8 @@ __global__ void __launch_bounds__(WARPS * 32) encode_kernel(Tree t, float *featu
         }
         if (lane == 0) t.s_tf[slot] = tf;
         const int nh = gather_history(t, g, base, leaf, lane, s1[wib], s2[wib]);
-        write_planes(features + slot * (size_t)(1 + 2 * t.H) * 64, t.H, nh, s1[wib], s2[wib], (float)player - 1.0f, tf, lane);
+        if (nhwc) write_planes_nhwc(nhwc + slot * 64 * 32, nh, s1[wib], s2[wib], player, tf, lane);
+        else write_planes(features + slot * (size_t)(1 + 2 * t.H) * 64, t.H, nh, s1[wib], s2[wib], (float)player - 1.0f, tf, lane);
         __syncwarp();                                     // the history buffer is reused by the next slot
     }
 }
@@ -698,9 +726,9 @@ void launch_select(const Tree &t, cudaStream_t s, bool narrow) {
     else select_kernel<4><<<blocks(t.G, 4), 128, 0, s>>>(t);
     count_launch();
 }
-void launch_encode(const Tree &t, float *features, cudaStream_t s, bool narrow) {
-    if (narrow) encode_kernel<2><<<std::min(blocks((size_t)t.G * t.inflight, 2), kNarrowGrid), 64, 0, s>>>(t, features);
-    else encode_kernel<4><<<blocks((size_t)t.G * t.inflight, 4), 128, 0, s>>>(t, features);
+void launch_encode(const Tree &t, float *features, cudaStream_t s, bool narrow, void *nhwc) {
+    if (narrow) encode_kernel<2><<<std::min(blocks((size_t)t.G * t.inflight, 2), kNarrowGrid), 64, 0, s>>>(t, features, (uint16_t *)nhwc);
+    else encode_kernel<4><<<blocks((size_t)t.G * t.inflight, 4), 128, 0, s>>>(t, features, (uint16_t *)nhwc);
     count_launch();
 }
 void launch_expand(const Tree &t, const float *policy, const float *value, cudaStream_t s, bool narrow) {

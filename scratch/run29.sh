@@ -1,0 +1,5 @@
+set -x
+O=gpurun_out/r01n2; mkdir -p $O
+timeout 900 python -m pytest tests -m gpu -x -q > $O/pytest_gpu.log 2>&1; echo "pytest rc=$?" >> $O/summary.txt
+timeout 600 python bench.py --no-cpu-baseline > $O/bench.log 2> $O/bench.err; echo "bench rc=$?" >> $O/summary.txt
+timeout 600 python tools/nn_forward.py --boards 32000 > $O/nn.log 2>&1
