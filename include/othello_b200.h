@@ -267,6 +267,43 @@ int oz_engine_set_pipeline(oz_engine *e, int groups, int pdl);
 /* Stream the engine launches on (a cudaStream_t), for callers that time with CUDA events. */
 void *oz_engine_stream(oz_engine *e);
 
+/* ------------------------------------------------------------ training step (train.py:486-502) */
+
+/* One optimisation step of the reference's _train loop on the GPU: forward in train mode (BatchNorm batch statistics,
+ * running statistics updated), policy cross-entropy + value MSE + explicit L2 over all parameters (train.py:494-499),
+ * backward, torch.optim.SGD with momentum (train.py:261).  The 3x3 convolutions (forward and input gradients) run on the
+ * engine's tcgen05 kernel in bf16 with fp32 accumulation; BatchNorm, heads, losses and the optimizer are fp32; master
+ * weights are fp32.  Parameters travel as ONE flat float vector in the order of AlphaZeroNet.parameters()
+ * (= torch.nn.utils.parameters_to_vector); buffers as the running_mean, running_var of every BatchNorm in module order. */
+typedef struct oz_trainer oz_trainer;
+typedef struct {
+    float lr;          /* SGD learning rate (train.py:103-106) */
+    float momentum;    /* SGD momentum (train.py:109-112) */
+    float l2_weight;   /* --l2-weight-regulation (train.py:202-206) */
+    float bn_momentum; /* nn.BatchNorm2d momentum (0.1) */
+    float bn_eps;      /* nn.BatchNorm2d eps (1e-5) */
+} oz_train_config;
+void oz_train_config_default(oz_train_config *cfg);
+/* max_batch: largest batch size (a multiple of 32; batches must be multiples of 32 as well). */
+int oz_trainer_create(int device, const oz_resnet_shape *shape, int max_batch, oz_trainer **out);
+void oz_trainer_destroy(oz_trainer *t);
+size_t oz_trainer_num_params(const oz_trainer *t);
+size_t oz_trainer_num_buffers(const oz_trainer *t);
+/* Host vectors; any pointer may be NULL (left as it is / not read back).  momentum = the SGD momentum buffers. */
+int oz_trainer_set_state(oz_trainer *t, const float *params, const float *buffers, const float *momentum);
+int oz_trainer_get_state(oz_trainer *t, float *params, float *buffers, float *momentum, float *grads);
+/* features [n][in_planes][8][8], policy targets [n][65], value targets [n] (HOST float32, what the DataLoader of
+ * train.py:472-489 yields).  apply_update = 0 computes losses and gradients only.  losses (optional, host):
+ * total, policy, value, l2 -- the four numbers train.py:504-507 logs. */
+int oz_trainer_step(oz_trainer *t, const float *features, const float *policy, const float *value, int n,
+                    const oz_train_config *cfg, int apply_update, float *losses);
+/* The same on DEVICE pointers (asynchronous on the trainer's stream unless losses != NULL). */
+int oz_trainer_step_device(oz_trainer *t, const float *features, const float *policy, const float *value, int n,
+                           const oz_train_config *cfg, int apply_update, float *losses);
+/* Network outputs of the last step's forward pass (train mode): policy [n][65], value [n]. */
+int oz_trainer_outputs(oz_trainer *t, int n, float *policy, float *value);
+void *oz_trainer_stream(oz_trainer *t);
+
 #ifdef __cplusplus
 }
 #endif

@@ -28,6 +28,7 @@ SOURCES = {
     "oz_tree.cu": ["-fmad=false"],
     "oz_resnet.cu": [],
     "oz_engine_api.cu": ["-fmad=false"],
+    "oz_train.cu": [],
 }
 
 
@@ -55,7 +56,7 @@ def build(force: bool = False, verbose: bool = False) -> Path:
     OBJ.mkdir(exist_ok=True)
     with ThreadPoolExecutor(max_workers=4) as pool:
         objs = list(pool.map(lambda kv: _compile(kv[0], kv[1], verbose), srcs.items()))
-    cmd = [NVCC, *ARCH, "-shared", "-o", str(OUT), *map(str, objs), "-lcudart"]
+    cmd = [NVCC, *ARCH, "-shared", "-o", str(OUT), *map(str, objs), "-lcudart", "-ldl"]
     proc = subprocess.run(cmd, capture_output=True, text=True)
     if proc.returncode != 0:
         raise RuntimeError(f"link failed:\n{proc.stdout}\n{proc.stderr}")

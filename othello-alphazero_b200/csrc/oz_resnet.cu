@@ -706,6 +706,12 @@ void ResNet::free_workspaces() {
     ws_.clear();
 }
 
+void launch_planes_to_nhwc32(const float *d_features, int planes, size_t n, size_t n_pad, void *d_out, cudaStream_t stream) {
+    const size_t threads = n_pad * 256;
+    planes_to_nhwc32_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, stream>>>(d_features, planes, n, n_pad, (__nv_bfloat16 *)d_out);
+    count_launch();
+}
+
 ResNet::~ResNet() {
     cudaFree(d_blob_);
     free_workspaces();

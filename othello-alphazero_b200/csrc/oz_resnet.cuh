@@ -76,4 +76,7 @@ class ResNet {
     std::vector<CUtensorMap> map_w_;
 };
 
+// float planes [n][planes][64] -> bf16 NHWC [n_pad][64][32] (channels >= planes and boards >= n are zero).
+void launch_planes_to_nhwc32(const float *d_features, int planes, size_t n, size_t n_pad, void *d_out, cudaStream_t stream);
+
 }  // namespace oz

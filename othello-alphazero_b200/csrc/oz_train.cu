@@ -1,0 +1,704 @@
+// Native training step of the AlphaZero ResNet.
+// reference: python/othello_alphazero/train.py:486-502 (the body of the batch loop of _train: forward in train mode,
+// policy cross-entropy + value MSE + explicit L2 over all parameters, backward, SGD with momentum) on the network of
+// python/othello_alphazero/neural_net.py:9-172.
+//
+// The 3x3 convolutions -- forward and input gradients -- run on the tcgen05 implicit-GEMM kernel of oz_resnet.cu in
+// bf16 with fp32 accumulation (the input gradient of a convolution is the same convolution with the taps rotated by 180
+// degrees and the channel roles swapped, so only the weight packing differs).  Weight gradients are a plain GEMM over an
+// im2col view, [C x positions] x [positions x 9 cin], handed to cuBLAS (loaded with dlopen: the library does not link
+// it).  BatchNorm uses batch statistics (train mode) in fp32; the heads, the losses and the optimizer are fp32.  Master
+// weights, gradients and momentum are fp32 vectors in the order of AlphaZeroNet.parameters().
+#include <cublas_v2.h>
+#include <cuda_bf16.h>
+#include <dlfcn.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "oz_common.cuh"
+#include "oz_resnet.cuh"
+
+namespace oz {
+namespace {
+
+typedef __nv_bfloat16 bf16;
+
+// ------------------------------------------------------------------ cuBLAS through dlopen
+struct Cublas {
+    void *lib = nullptr;
+    cublasStatus_t (*create)(cublasHandle_t *) = nullptr;
+    cublasStatus_t (*destroy)(cublasHandle_t) = nullptr;
+    cublasStatus_t (*set_stream)(cublasHandle_t, cudaStream_t) = nullptr;
+    cublasStatus_t (*gemm_ex)(cublasHandle_t, cublasOperation_t, cublasOperation_t, int, int, int, const void *, const void *, cudaDataType,
+                              int, const void *, cudaDataType, int, const void *, void *, cudaDataType, int, cublasComputeType_t,
+                              cublasGemmAlgo_t) = nullptr;
+};
+
+int load_cublas(Cublas **out) {
+    static Cublas cb;
+    if (!cb.lib) {
+        const char *names[] = {"libcublas.so.12", "/usr/local/cuda/lib64/libcublas.so.12", "libcublas.so"};
+        for (const char *n : names) { cb.lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL); if (cb.lib) break; }
+        if (!cb.lib) return fail(OZ_ERR_CUDA, std::string("the trainer needs cuBLAS for the weight-gradient GEMMs: ") + dlerror());
+        cb.create = (decltype(cb.create))dlsym(cb.lib, "cublasCreate_v2");
+        cb.destroy = (decltype(cb.destroy))dlsym(cb.lib, "cublasDestroy_v2");
+        cb.set_stream = (decltype(cb.set_stream))dlsym(cb.lib, "cublasSetStream_v2");
+        cb.gemm_ex = (decltype(cb.gemm_ex))dlsym(cb.lib, "cublasGemmEx");
+        if (!cb.create || !cb.destroy || !cb.set_stream || !cb.gemm_ex) { cb.lib = nullptr; return fail(OZ_ERR_CUDA, "cuBLAS symbols missing"); }
+    }
+    *out = &cb;
+    return OZ_OK;
+}
+
+// ------------------------------------------------------------------ small helpers
+__device__ __forceinline__ float warp_sum_f(float v) {
+#pragma unroll
+    for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// Block-wide sum of `v` (blockDim.x <= 1024); result valid in thread 0.
+__device__ float block_sum(float v, float *scratch /* >= 32 floats */) {
+    v = warp_sum_f(v);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) scratch[threadIdx.x >> 5] = v;
+    __syncthreads();
+    float r = 0.f;
+    if (threadIdx.x < 32) {
+        r = threadIdx.x < (blockDim.x + 31) / 32 ? scratch[threadIdx.x] : 0.f;
+        r = warp_sum_f(r);
+    }
+    return r;
+}
+
+// ------------------------------------------------------------------ weight packing
+// master fp32 W [C][cin][9] (PyTorch OIHW, tap = ky*3+kx) ->
+//   wf bf16 [9][C][cinp]          forward operand of conv3x3_pair_kernel ([tap][cout][cin], cin zero-padded to cinp)
+//   wd bf16 [9][cin][C] (cin==C)  input-gradient operand: Wd[8 - tap][ci][co] = W[co][ci][tap]
+__global__ void pack_weights_kernel(const float *__restrict__ w, int C, int cin, int cinp, bf16 *__restrict__ wf, bf16 *__restrict__ wd) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= 9 * C * cinp) return;
+    const int ci = idx % cinp, co = (idx / cinp) % C, tap = idx / (cinp * C);
+    const float v = ci < cin ? w[((size_t)co * cin + ci) * 9 + tap] : 0.f;
+    wf[idx] = __float2bfloat16(v);
+    if (wd && ci < cin) wd[((size_t)(8 - tap) * cin + ci) * C + co] = __float2bfloat16(v);
+}
+
+// ------------------------------------------------------------------ BatchNorm (train mode), tensors bf16 [P][C]
+// sums[c] += sum z, sums[C + c] += sum z^2.  A thread owns a channel pair; threads with the same pair walk different rows.
+__global__ void bn_stats_kernel(const bf16 *__restrict__ z, size_t P, int C, float *__restrict__ sums) {
+    const int tpr = C / 2, rows = blockDim.x / tpr;
+    const int cp = threadIdx.x % tpr, r0 = threadIdx.x / tpr;
+    if (r0 >= rows) return;
+    float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
+    for (size_t p = (size_t)blockIdx.x * rows + r0; p < P; p += (size_t)gridDim.x * rows) {
+        const float2 v = __bfloat1622float2(*(const __nv_bfloat162 *)(z + p * C + 2 * cp));
+        s0 += v.x; s1 += v.y; q0 += v.x * v.x; q1 += v.y * v.y;
+    }
+    atomicAdd(&sums[2 * cp], s0); atomicAdd(&sums[2 * cp + 1], s1);
+    atomicAdd(&sums[C + 2 * cp], q0); atomicAdd(&sums[C + 2 * cp + 1], q1);
+}
+
+// mean / invstd from the sums; running statistics as nn.BatchNorm2d updates them (momentum, unbiased variance).  The
+// convolution bias only shifts the mean: the normalised output does not depend on it, the running mean does.
+__global__ void bn_finalize_kernel(const float *__restrict__ sums, float count, int C, const float *__restrict__ conv_bias, float eps, float momentum,
+                                   float *__restrict__ mean, float *__restrict__ invstd, float *__restrict__ run_mean, float *__restrict__ run_var) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    const float m = sums[c] / count;
+    const float var = fmaxf(sums[C + c] / count - m * m, 0.f);
+    mean[c] = m; invstd[c] = rsqrtf(var + eps);
+    run_mean[c] = (1.f - momentum) * run_mean[c] + momentum * (m + (conv_bias ? conv_bias[c] : 0.f));
+    run_var[c] = (1.f - momentum) * run_var[c] + momentum * var * (count / fmaxf(count - 1.f, 1.f));
+}
+
+// a = relu(gamma * (z - mean) * invstd + beta [+ skip])
+__global__ void bn_apply_kernel(const bf16 *__restrict__ z, const bf16 *__restrict__ skip, size_t P, int C, const float *__restrict__ mean,
+                                const float *__restrict__ invstd, const float *__restrict__ gamma, const float *__restrict__ beta, bf16 *__restrict__ a) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;     // one channel pair
+    if (i >= P * (size_t)(C / 2)) return;
+    const int c = 2 * (int)(i % (C / 2));
+    const float2 v = __bfloat1622float2(((const __nv_bfloat162 *)z)[i]);
+    float y0 = gamma[c] * (v.x - mean[c]) * invstd[c] + beta[c], y1 = gamma[c + 1] * (v.y - mean[c + 1]) * invstd[c + 1] + beta[c + 1];
+    if (skip) { const float2 s = __bfloat1622float2(((const __nv_bfloat162 *)skip)[i]); y0 += s.x; y1 += s.y; }
+    ((__nv_bfloat162 *)a)[i] = __floats2bfloat162_rn(fmaxf(y0, 0.f), fmaxf(y1, 0.f));
+}
+
+// Backward through ReLU and BatchNorm.  dy = da * [a > 0]; s[c] += sum dy, s[C + c] += sum dy * zhat.
+__global__ void bn_bwd_reduce_kernel(const bf16 *__restrict__ da, const bf16 *__restrict__ a, const bf16 *__restrict__ z, size_t P, int C,
+                                     const float *__restrict__ mean, const float *__restrict__ invstd, float *__restrict__ s) {
+    const int tpr = C / 2, rows = blockDim.x / tpr;
+    const int cp = threadIdx.x % tpr, r0 = threadIdx.x / tpr;
+    if (r0 >= rows) return;
+    const float m0 = mean[2 * cp], m1 = mean[2 * cp + 1], i0 = invstd[2 * cp], i1 = invstd[2 * cp + 1];
+    float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
+    for (size_t p = (size_t)blockIdx.x * rows + r0; p < P; p += (size_t)gridDim.x * rows) {
+        const size_t o = p * C + 2 * cp;
+        const float2 g = __bfloat1622float2(*(const __nv_bfloat162 *)(da + o)), av = __bfloat1622float2(*(const __nv_bfloat162 *)(a + o));
+        const float2 zv = __bfloat1622float2(*(const __nv_bfloat162 *)(z + o));
+        const float d0 = av.x > 0.f ? g.x : 0.f, d1 = av.y > 0.f ? g.y : 0.f;
+        s0 += d0; s1 += d1; q0 += d0 * (zv.x - m0) * i0; q1 += d1 * (zv.y - m1) * i1;
+    }
+    atomicAdd(&s[2 * cp], s0); atomicAdd(&s[2 * cp + 1], s1);
+    atomicAdd(&s[C + 2 * cp], q0); atomicAdd(&s[C + 2 * cp + 1], q1);
+}
+
+// dz = gamma * invstd * (dy - s1 / M - zhat * s2 / M); optionally keeps dy (the gradient that also flows into the skip
+// connection).  Block 0 writes dgamma = s2, dbeta = s1.
+__global__ void bn_bwd_apply_kernel(const bf16 *__restrict__ da, const bf16 *__restrict__ a, const bf16 *__restrict__ z, size_t P, int C,
+                                    const float *__restrict__ mean, const float *__restrict__ invstd, const float *__restrict__ gamma,
+                                    const float *__restrict__ s, bf16 *__restrict__ dz, bf16 *__restrict__ dy_out, float *__restrict__ dgamma,
+                                    float *__restrict__ dbeta) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (blockIdx.x == 0) for (int c = threadIdx.x; c < C; c += blockDim.x) { dgamma[c] = s[C + c]; dbeta[c] = s[c]; }
+    if (i >= P * (size_t)(C / 2)) return;
+    const int c = 2 * (int)(i % (C / 2));
+    const float invM = 1.f / (float)P;
+    const float2 g = __bfloat1622float2(((const __nv_bfloat162 *)da)[i]), av = __bfloat1622float2(((const __nv_bfloat162 *)a)[i]);
+    const float2 zv = __bfloat1622float2(((const __nv_bfloat162 *)z)[i]);
+    const float d0 = av.x > 0.f ? g.x : 0.f, d1 = av.y > 0.f ? g.y : 0.f;
+    const float zh0 = (zv.x - mean[c]) * invstd[c], zh1 = (zv.y - mean[c + 1]) * invstd[c + 1];
+    const float r0 = gamma[c] * invstd[c] * (d0 - s[c] * invM - zh0 * s[C + c] * invM);
+    const float r1 = gamma[c + 1] * invstd[c + 1] * (d1 - s[c + 1] * invM - zh1 * s[C + c + 1] * invM);
+    ((__nv_bfloat162 *)dz)[i] = __floats2bfloat162_rn(r0, r1);
+    if (dy_out) ((__nv_bfloat162 *)dy_out)[i] = __floats2bfloat162_rn(d0, d1);
+}
+
+// ------------------------------------------------------------------ weight gradient: im2col + (cuBLAS) + scatter
+// x bf16 [N][8][8][cinp] -> cols bf16 [P][9][cinp], zero outside the board; one thread per 16-byte channel group.
+__global__ void im2col_kernel(const bf16 *__restrict__ x, size_t P, int cinp, bf16 *__restrict__ cols) {
+    const int gpt = cinp / 8;
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= P * 9 * gpt) return;
+    const int g = (int)(i % gpt), tap = (int)((i / gpt) % 9);
+    const size_t p = i / ((size_t)gpt * 9);
+    const int y = (int)((p >> 3) & 7) + tap / 3 - 1, xx = (int)(p & 7) + tap % 3 - 1;
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (y >= 0 && y < 8 && xx >= 0 && xx < 8) v = *(const uint4 *)(x + ((p & ~(size_t)63) + y * 8 + xx) * cinp + g * 8);
+    *(uint4 *)(cols + (p * 9 + tap) * cinp + g * 8) = v;
+}
+
+// G fp32 [C][9][cinp] (GEMM output) -> dW fp32 [C][cin][9] (OIHW)
+__global__ void wgrad_scatter_kernel(const float *__restrict__ G, int C, int cin, int cinp, float *__restrict__ dw) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= C * cin * 9) return;
+    const int tap = idx % 9, ci = (idx / 9) % cin, co = idx / (9 * cin);
+    dw[idx] = G[((size_t)co * 9 + tap) * cinp + ci];
+}
+
+// ------------------------------------------------------------------ heads (fp32)
+// h[k][p] = sum_c a[p][c] * w[k][c] + b[k], k = 0, 1 (policy), 2 (value); one warp per position.
+__global__ void head_conv_fwd_kernel(const bf16 *__restrict__ a, size_t P, int C, const float *__restrict__ pw, const float *__restrict__ pb,
+                                     const float *__restrict__ vw, const float *__restrict__ vb, float *__restrict__ h) {
+    const size_t p = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (p >= P) return;
+    float d0 = 0.f, d1 = 0.f, d2 = 0.f;
+    for (int c = lane; c < C; c += 32) {
+        const float v = __bfloat162float(a[p * C + c]);
+        d0 += v * pw[c]; d1 += v * pw[C + c]; d2 += v * vw[c];
+    }
+    d0 = warp_sum_f(d0); d1 = warp_sum_f(d1); d2 = warp_sum_f(d2);
+    if (lane == 0) { h[p] = d0 + pb[0]; h[P + p] = d1 + pb[1]; h[2 * P + p] = d2 + vb[0]; }
+}
+
+// BatchNorm + ReLU of the three head channels (block k = channel k): hn[k][p] = relu(bn(h[k][p])); also scattered into the
+// flattened FC inputs hp [N][128] (index k*64 + pos) and hv [N][64].  stat[k] = mean, stat[3 + k] = invstd.
+__global__ void head_bn_fwd_kernel(const float *__restrict__ h, size_t P, const float *__restrict__ gamma_p, const float *__restrict__ beta_p,
+                                   const float *__restrict__ gamma_v, const float *__restrict__ beta_v, float eps, float momentum,
+                                   float *__restrict__ run_p /* mean[2], var[2] */, float *__restrict__ run_v /* mean[1], var[1] */,
+                                   float *__restrict__ stat, float *__restrict__ hn, float *__restrict__ hp, float *__restrict__ hv) {
+    __shared__ float scratch[32];
+    __shared__ float sh_mean, sh_inv;
+    const int k = blockIdx.x;
+    const float *hk = h + (size_t)k * P;
+    float s = 0.f, q = 0.f;
+    for (size_t p = threadIdx.x; p < P; p += blockDim.x) { const float v = hk[p]; s += v; q += v * v; }
+    s = block_sum(s, scratch); q = block_sum(q, scratch);
+    if (threadIdx.x == 0) {
+        const float cnt = (float)P, m = s / cnt, var = fmaxf(q / cnt - m * m, 0.f);
+        sh_mean = m; sh_inv = rsqrtf(var + eps);
+        stat[k] = m; stat[3 + k] = sh_inv;
+        float *rm = k < 2 ? run_p + k : run_v, *rv = k < 2 ? run_p + 2 + k : run_v + 1;
+        *rm = (1.f - momentum) * *rm + momentum * m;
+        *rv = (1.f - momentum) * *rv + momentum * var * (cnt / fmaxf(cnt - 1.f, 1.f));
+    }
+    __syncthreads();
+    const float g = k < 2 ? gamma_p[k] : gamma_v[0], b = k < 2 ? beta_p[k] : beta_v[0];
+    for (size_t p = threadIdx.x; p < P; p += blockDim.x) {
+        const float y = fmaxf(g * (hk[p] - sh_mean) * sh_inv + b, 0.f);
+        hn[(size_t)k * P + p] = y;
+        const size_t n = p >> 6; const int pos = (int)(p & 63);
+        if (k < 2) hp[n * 128 + k * 64 + pos] = y; else hv[n * 64 + pos] = y;
+    }
+}
+
+// One warp per board: policy logits -> softmax -> loss and dlogits; value MLP -> tanh -> loss and its gradients.
+// loss[0] += -sum_j t_j log p_j / N, loss[1] += (v - t)^2 / N.
+__global__ void head_fc_fwd_kernel(const float *__restrict__ hp, const float *__restrict__ hv, int N, int Hv, const float *__restrict__ lw,
+                                   const float *__restrict__ lb, const float *__restrict__ w1, const float *__restrict__ b1,
+                                   const float *__restrict__ w2, const float *__restrict__ b2, const float *__restrict__ tp,
+                                   const float *__restrict__ tv, float *__restrict__ policy, float *__restrict__ value, float *__restrict__ dlogits,
+                                   float *__restrict__ u, float *__restrict__ dvpre, float *__restrict__ loss) {
+    const int n = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (n >= N) return;
+    const float *x = hp + (size_t)n * 128;
+    float lg[3] = {-INFINITY, -INFINITY, -INFINITY};
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+        const int j = lane + 32 * r;
+        if (j < 65) {
+            float acc = lb[j];
+            for (int i = 0; i < 128; ++i) acc += x[i] * lw[j * 128 + i];
+            lg[r] = acc;
+        }
+    }
+    float m = fmaxf(fmaxf(lg[0], lg[1]), lg[2]);
+#pragma unroll
+    for (int o = 16; o; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    float e[3], se = 0.f, st = 0.f, ce = 0.f;
+#pragma unroll
+    for (int r = 0; r < 3; ++r) { const int j = lane + 32 * r; e[r] = j < 65 ? expf(lg[r] - m) : 0.f; se += e[r]; if (j < 65) st += tp[(size_t)n * 65 + j]; }
+    se = warp_sum_f(se); st = warp_sum_f(st);
+    const float lse = logf(se);
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+        const int j = lane + 32 * r;
+        if (j < 65) {
+            const float p = e[r] / se, t = tp[(size_t)n * 65 + j];
+            policy[(size_t)n * 65 + j] = p;
+            ce -= t * (lg[r] - m - lse);                        // -t log p
+            dlogits[(size_t)n * 65 + j] = (p * st - t) / (float)N;
+        }
+    }
+    ce = warp_sum_f(ce);
+    // value head
+    const float *xv = hv + (size_t)n * 64;
+    float acc2 = 0.f;
+    for (int k = lane; k < Hv; k += 32) {
+        float a = b1[k];
+        for (int i = 0; i < 64; ++i) a += xv[i] * w1[k * 64 + i];
+        a = fmaxf(a, 0.f);
+        u[(size_t)n * Hv + k] = a;
+        acc2 += a * w2[k];
+    }
+    acc2 = warp_sum_f(acc2);
+    if (lane == 0) {
+        const float v = tanhf(acc2 + b2[0]), d = v - tv[n];
+        value[n] = v;
+        dvpre[n] = 2.f * d / (float)N * (1.f - v * v);
+        atomicAdd(&loss[0], ce / (float)N);
+        atomicAdd(&loss[1], d * d / (float)N);
+    }
+}
+
+// Gradients of the FC parameters: one thread per output element, loops over the batch.
+__global__ void head_fc_bwd_params_kernel(const float *__restrict__ hp, const float *__restrict__ hv, const float *__restrict__ dlogits,
+                                          const float *__restrict__ u, const float *__restrict__ dvpre, const float *__restrict__ w2, int N, int Hv,
+                                          float *__restrict__ dlw, float *__restrict__ dlb, float *__restrict__ dw1, float *__restrict__ db1,
+                                          float *__restrict__ dw2, float *__restrict__ db2) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    const int n_lw = 65 * 128, n_w1 = Hv * 64;
+    if (idx < n_lw) {
+        const int j = idx / 128, i = idx % 128;
+        float acc = 0.f;
+        for (int n = 0; n < N; ++n) acc += dlogits[(size_t)n * 65 + j] * hp[(size_t)n * 128 + i];
+        dlw[idx] = acc;
+    } else if (idx < n_lw + 65) {
+        const int j = idx - n_lw;
+        float acc = 0.f;
+        for (int n = 0; n < N; ++n) acc += dlogits[(size_t)n * 65 + j];
+        dlb[j] = acc;
+    } else if (idx < n_lw + 65 + n_w1) {
+        const int r = idx - n_lw - 65, k = r / 64, i = r % 64;
+        const float wk = w2[k];
+        float acc = 0.f;
+        for (int n = 0; n < N; ++n) acc += (u[(size_t)n * Hv + k] > 0.f ? dvpre[n] * wk : 0.f) * hv[(size_t)n * 64 + i];
+        dw1[r] = acc;
+    } else if (idx < n_lw + 65 + n_w1 + Hv) {
+        const int k = idx - n_lw - 65 - n_w1;
+        const float wk = w2[k];
+        float a1 = 0.f, a2 = 0.f;
+        for (int n = 0; n < N; ++n) { const float uu = u[(size_t)n * Hv + k]; a1 += uu > 0.f ? dvpre[n] * wk : 0.f; a2 += dvpre[n] * uu; }
+        db1[k] = a1; dw2[k] = a2;
+    } else if (idx == n_lw + 65 + n_w1 + Hv) {
+        float acc = 0.f;
+        for (int n = 0; n < N; ++n) acc += dvpre[n];
+        db2[0] = acc;
+    }
+}
+
+// Gradients wrt the normalised head features, masked by their ReLU: dhn[k][p].
+__global__ void head_fc_bwd_input_kernel(const float *__restrict__ dlogits, const float *__restrict__ lw, const float *__restrict__ u,
+                                         const float *__restrict__ dvpre, const float *__restrict__ w1, const float *__restrict__ w2,
+                                         const float *__restrict__ hn, size_t P, int Hv, float *__restrict__ dhn) {
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= 3 * P) return;
+    const int k = (int)(idx / P);
+    const size_t p = idx % P, n = p >> 6;
+    const int pos = (int)(p & 63);
+    float acc = 0.f;
+    if (k < 2) {
+        const int i = k * 64 + pos;
+        for (int j = 0; j < 65; ++j) acc += dlogits[n * 65 + j] * lw[j * 128 + i];
+    } else {
+        const float dv = dvpre[n];
+        for (int q = 0; q < Hv; ++q) acc += (u[n * Hv + q] > 0.f ? dv * w2[q] : 0.f) * w1[q * 64 + pos];
+    }
+    dhn[idx] = hn[idx] > 0.f ? acc : 0.f;
+}
+
+// BatchNorm backward of the three head channels (block k): dh[k][p] (gradient wrt the 1x1 conv output), dgamma, dbeta.
+__global__ void head_bn_bwd_kernel(const float *__restrict__ h, const float *__restrict__ dhn, size_t P, const float *__restrict__ stat,
+                                   const float *__restrict__ gamma_p, const float *__restrict__ gamma_v, float *__restrict__ dh,
+                                   float *__restrict__ dgamma_p, float *__restrict__ dbeta_p, float *__restrict__ dgamma_v, float *__restrict__ dbeta_v) {
+    __shared__ float scratch[32];
+    __shared__ float sh1, sh2;
+    const int k = blockIdx.x;
+    const float mean = stat[k], inv = stat[3 + k];
+    const float *hk = h + (size_t)k * P, *dk = dhn + (size_t)k * P;
+    float s1 = 0.f, s2 = 0.f;
+    for (size_t p = threadIdx.x; p < P; p += blockDim.x) { const float d = dk[p]; s1 += d; s2 += d * (hk[p] - mean) * inv; }
+    s1 = block_sum(s1, scratch); s2 = block_sum(s2, scratch);
+    if (threadIdx.x == 0) {
+        sh1 = s1; sh2 = s2;
+        if (k < 2) { dgamma_p[k] = s2; dbeta_p[k] = s1; } else { dgamma_v[0] = s2; dbeta_v[0] = s1; }
+    }
+    __syncthreads();
+    const float g = k < 2 ? gamma_p[k] : gamma_v[0], invM = 1.f / (float)P;
+    for (size_t p = threadIdx.x; p < P; p += blockDim.x)
+        dh[(size_t)k * P + p] = g * inv * (dk[p] - sh1 * invM - (hk[p] - mean) * inv * sh2 * invM);
+}
+
+// 1x1 head convolutions backward.  da[p][c] = sum_k dh[k][p] * w[k][c] (bf16, the gradient entering the tower);
+// dw[k][c] += sum_p dh[k][p] * a[p][c]; db[k] += sum_p dh[k][p].  One block per 64 positions, one thread per channel.
+__global__ void head_conv_bwd_kernel(const bf16 *__restrict__ a, const float *__restrict__ dh, size_t P, int C, const float *__restrict__ pw,
+                                     const float *__restrict__ vw, bf16 *__restrict__ da, float *__restrict__ dpw, float *__restrict__ dpb,
+                                     float *__restrict__ dvw, float *__restrict__ dvb) {
+    __shared__ float sd[3][64];
+    const size_t p0 = (size_t)blockIdx.x * 64;
+    for (int i = threadIdx.x; i < 3 * 64; i += blockDim.x) sd[i / 64][i % 64] = p0 + (i % 64) < P ? dh[(size_t)(i / 64) * P + p0 + (i % 64)] : 0.f;
+    __syncthreads();
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        const float w0 = pw[c], w1 = pw[C + c], w2 = vw[c];
+        float g0 = 0.f, g1 = 0.f, g2 = 0.f;
+        for (int r = 0; r < 64 && p0 + r < P; ++r) {
+            const float av = __bfloat162float(a[(p0 + r) * C + c]);
+            g0 += sd[0][r] * av; g1 += sd[1][r] * av; g2 += sd[2][r] * av;
+            da[(p0 + r) * C + c] = __float2bfloat16(sd[0][r] * w0 + sd[1][r] * w1 + sd[2][r] * w2);
+        }
+        atomicAdd(&dpw[c], g0); atomicAdd(&dpw[C + c], g1); atomicAdd(&dvw[c], g2);
+    }
+    if (threadIdx.x < 3) {
+        float s = 0.f;
+        for (int r = 0; r < 64; ++r) s += sd[threadIdx.x][r];
+        atomicAdd(threadIdx.x < 2 ? &dpb[threadIdx.x] : &dvb[0], s);
+    }
+}
+
+// ------------------------------------------------------------------ L2 term + SGD with momentum (torch.optim.SGD, dampening 0)
+// g += 2 * l2 * p; loss[2] += l2 * sum p^2; if (apply) { buf = momentum * buf + g; p -= lr * buf; }
+__global__ void l2_sgd_kernel(float *__restrict__ p, float *__restrict__ g, float *__restrict__ buf, size_t n, float l2, float lr, float momentum,
+                              int apply, float *__restrict__ loss) {
+    __shared__ float scratch[32];
+    float sq = 0.f;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const float pv = p[i];
+        sq += pv * pv;
+        const float gv = g[i] + 2.f * l2 * pv;
+        g[i] = gv;
+        if (apply) { const float b = momentum * buf[i] + gv; buf[i] = b; p[i] = pv - lr * b; }
+    }
+    sq = block_sum(sq, scratch);
+    if (threadIdx.x == 0) atomicAdd(&loss[2], l2 * sq);
+}
+
+unsigned grid_for(size_t items, int block) { return (unsigned)((items + block - 1) / block); }
+
+}  // namespace
+}  // namespace oz
+
+using namespace oz;
+
+// ------------------------------------------------------------------ trainer object
+struct ConvLayerT {
+    size_t w, b, gamma, beta;     // offsets (floats) into the parameter vector
+    size_t rm, rv;                // offsets into the buffer vector
+    int cin, cinp;
+    bf16 *wf = nullptr, *wd = nullptr;
+};
+
+struct oz_trainer {
+    int device = 0;
+    oz_resnet_shape shape{};
+    int max_batch = 0;
+    size_t n_params = 0, n_buffers = 0;
+    std::vector<ConvLayerT> conv;
+    // head offsets (params): policy conv w,b, bn gamma,beta, linear w,b; value conv w,b, bn g,b, linear1 w,b, linear2 w,b
+    size_t pcw, pcb, pg, pb, plw, plb, vcw, vcb, vg, vb, v1w, v1b, v2w, v2b;
+    size_t prm, vrm;              // buffers: policy running mean[2] var[2]; value running mean[1] var[1]
+    float *d_params = nullptr, *d_grads = nullptr, *d_mom = nullptr, *d_buffers = nullptr;
+    float *d_features = nullptr, *d_tpolicy = nullptr, *d_tvalue = nullptr;
+    bf16 *d_x0 = nullptr;
+    std::vector<bf16 *> A, Z;     // per conv layer: post-activation, pre-BN
+    float *d_mean = nullptr, *d_invstd = nullptr;   // [layers][C]
+    float *d_sums = nullptr;      // [2C] scratch
+    float *d_zero_bias = nullptr;
+    bf16 *d_dA = nullptr, *d_dA2 = nullptr, *d_dY = nullptr, *d_dZ = nullptr, *d_cols = nullptr;
+    float *d_G = nullptr;
+    float *d_h = nullptr, *d_hn = nullptr, *d_dhn = nullptr, *d_dh = nullptr, *d_stat = nullptr, *d_hp = nullptr, *d_hv = nullptr;
+    float *d_policy = nullptr, *d_value = nullptr, *d_dlogits = nullptr, *d_u = nullptr, *d_dvpre = nullptr, *d_loss = nullptr;
+    cublasHandle_t blas = nullptr;
+    Cublas *cb = nullptr;
+    cudaStream_t stream = nullptr;
+    std::vector<void *> allocs;
+};
+
+namespace {
+
+template <typename T>
+int talloc(oz_trainer *t, T **p, size_t n) {
+    *p = nullptr;
+    OZ_CUDA(cudaMalloc((void **)p, std::max<size_t>(1, n) * sizeof(T)));
+    OZ_CUDA(cudaMemset(*p, 0, std::max<size_t>(1, n) * sizeof(T)));
+    t->allocs.push_back((void *)*p);
+    return OZ_OK;
+}
+
+void layout_params(oz_trainer *t) {
+    const size_t C = t->shape.channels, Hv = t->shape.value_hidden;
+    const int L = 1 + 2 * t->shape.blocks;
+    size_t o = 0, bo = 0;
+    t->conv.resize(L);
+    for (int l = 0; l < L; ++l) {
+        ConvLayerT &c = t->conv[l];
+        c.cin = l == 0 ? t->shape.in_planes : (int)C;
+        c.cinp = l == 0 ? 32 : (int)C;
+        c.w = o; o += C * c.cin * 9;
+        c.b = o; o += C;
+        c.gamma = o; o += C;
+        c.beta = o; o += C;
+        c.rm = bo; bo += C;
+        c.rv = bo; bo += C;
+    }
+    t->pcw = o; o += 2 * C; t->pcb = o; o += 2; t->pg = o; o += 2; t->pb = o; o += 2; t->plw = o; o += 65 * 128; t->plb = o; o += 65;
+    t->vcw = o; o += C; t->vcb = o; o += 1; t->vg = o; o += 1; t->vb = o; o += 1; t->v1w = o; o += Hv * 64; t->v1b = o; o += Hv;
+    t->v2w = o; o += Hv; t->v2b = o; o += 1;
+    t->prm = bo; bo += 4; t->vrm = bo; bo += 2;
+    t->n_params = o; t->n_buffers = bo;
+}
+
+int pack_all_weights(oz_trainer *t) {
+    const int C = t->shape.channels;
+    for (ConvLayerT &c : t->conv) {
+        const int n = 9 * C * c.cinp;
+        pack_weights_kernel<<<grid_for(n, 256), 256, 0, t->stream>>>(t->d_params + c.w, C, c.cin, c.cinp, c.wf, c.wd);
+        count_launch();
+    }
+    OZ_CUDA(cudaGetLastError());
+    return OZ_OK;
+}
+
+// One training step on device-resident inputs.  features: float [n][in_planes][64]; policy targets [n][65]; value [n].
+int step_device(oz_trainer *t, const float *d_features, const float *d_tp, const float *d_tv, int n, const oz_train_config *cfg, int apply,
+                float *losses_host) {
+    if (n < 1 || n > t->max_batch || n % kBoardPad != 0)
+        return fail(OZ_ERR_INVALID_ARGUMENT, "Expected a batch size in [32, " + std::to_string(t->max_batch) + "] that is a multiple of 32, but got " + std::to_string(n) + ".");
+    const int C = t->shape.channels, Hv = t->shape.value_hidden, L = (int)t->conv.size();
+    const size_t P = (size_t)n * 64, half = P * (size_t)(C / 2);
+    cudaStream_t s = t->stream;
+    float *par = t->d_params, *grd = t->d_grads, *buf = t->d_buffers;
+    OZ_CUDA(cudaMemsetAsync(grd, 0, t->n_params * sizeof(float), s));
+    OZ_CUDA(cudaMemsetAsync(t->d_loss, 0, 4 * sizeof(float), s));
+    OZ_TRY(pack_all_weights(t));
+    launch_planes_to_nhwc32(d_features, t->shape.in_planes, (size_t)n, (size_t)n, t->d_x0, s);
+    const int bn_block = 256, bn_grid = 296;
+
+    // ---- forward through the tower (neural_net.py:9-65, train mode)
+    for (int l = 0; l < L; ++l) {
+        ConvLayerT &c = t->conv[l];
+        const bf16 *in = l == 0 ? t->d_x0 : t->A[l - 1];
+        OZ_TRY(ResNet::conv3x3(in, c.cinp, c.wf, t->d_zero_bias, nullptr, 0, t->Z[l], C, (size_t)n, s));
+        OZ_CUDA(cudaMemsetAsync(t->d_sums, 0, 2 * C * sizeof(float), s));
+        bn_stats_kernel<<<bn_grid, bn_block, 0, s>>>(t->Z[l], P, C, t->d_sums); count_launch();
+        bn_finalize_kernel<<<grid_for(C, 128), 128, 0, s>>>(t->d_sums, (float)P, C, par + c.b, cfg->bn_eps, cfg->bn_momentum, t->d_mean + (size_t)l * C,
+                                                            t->d_invstd + (size_t)l * C, buf + c.rm, buf + c.rv); count_launch();
+        const bf16 *skip = (l >= 2 && l % 2 == 0) ? t->A[l - 2] : nullptr;     // second conv of a residual block
+        bn_apply_kernel<<<grid_for(half, 256), 256, 0, s>>>(t->Z[l], skip, P, C, t->d_mean + (size_t)l * C, t->d_invstd + (size_t)l * C, par + c.gamma,
+                                                            par + c.beta, t->A[l]); count_launch();
+    }
+    // ---- heads forward + losses (neural_net.py:68-128, train.py:494-495)
+    const bf16 *a_last = t->A[L - 1];
+    head_conv_fwd_kernel<<<grid_for(P * 32, 256), 256, 0, s>>>(a_last, P, C, par + t->pcw, par + t->pcb, par + t->vcw, par + t->vcb, t->d_h); count_launch();
+    head_bn_fwd_kernel<<<3, 1024, 0, s>>>(t->d_h, P, par + t->pg, par + t->pb, par + t->vg, par + t->vb, cfg->bn_eps, cfg->bn_momentum, buf + t->prm,
+                                          buf + t->vrm, t->d_stat, t->d_hn, t->d_hp, t->d_hv); count_launch();
+    head_fc_fwd_kernel<<<grid_for((size_t)n * 32, 128), 128, 0, s>>>(t->d_hp, t->d_hv, n, Hv, par + t->plw, par + t->plb, par + t->v1w, par + t->v1b,
+                                                                     par + t->v2w, par + t->v2b, d_tp, d_tv, t->d_policy, t->d_value, t->d_dlogits,
+                                                                     t->d_u, t->d_dvpre, t->d_loss); count_launch();
+    // ---- heads backward
+    const int n_head_params = 65 * 128 + 65 + Hv * 64 + Hv + 1;
+    head_fc_bwd_params_kernel<<<grid_for(n_head_params, 128), 128, 0, s>>>(t->d_hp, t->d_hv, t->d_dlogits, t->d_u, t->d_dvpre, par + t->v2w, n, Hv,
+                                                                           grd + t->plw, grd + t->plb, grd + t->v1w, grd + t->v1b, grd + t->v2w,
+                                                                           grd + t->v2b); count_launch();
+    head_fc_bwd_input_kernel<<<grid_for(3 * P, 256), 256, 0, s>>>(t->d_dlogits, par + t->plw, t->d_u, t->d_dvpre, par + t->v1w, par + t->v2w, t->d_hn, P,
+                                                                  Hv, t->d_dhn); count_launch();
+    head_bn_bwd_kernel<<<3, 1024, 0, s>>>(t->d_h, t->d_dhn, P, t->d_stat, par + t->pg, par + t->vg, t->d_dh, grd + t->pg, grd + t->pb, grd + t->vg,
+                                          grd + t->vb); count_launch();
+    bf16 *dA = t->d_dA, *dA_other = t->d_dA2;
+    head_conv_bwd_kernel<<<grid_for(P, 64), 128, 0, s>>>(a_last, t->d_dh, P, C, par + t->pcw, par + t->vcw, dA, grd + t->pcw, grd + t->pcb, grd + t->vcw,
+                                                         grd + t->vcb); count_launch();
+    // ---- tower backward
+    const float one = 1.f, zero = 0.f;
+    for (int l = L - 1; l >= 0; --l) {
+        ConvLayerT &c = t->conv[l];
+        const float *mean = t->d_mean + (size_t)l * C, *inv = t->d_invstd + (size_t)l * C;
+        const bool block_out = l >= 2 && l % 2 == 0;            // output of a residual block: dy also flows into the skip connection
+        OZ_CUDA(cudaMemsetAsync(t->d_sums, 0, 2 * C * sizeof(float), s));
+        bn_bwd_reduce_kernel<<<bn_grid, bn_block, 0, s>>>(dA, t->A[l], t->Z[l], P, C, mean, inv, t->d_sums); count_launch();
+        bn_bwd_apply_kernel<<<grid_for(half, 256), 256, 0, s>>>(dA, t->A[l], t->Z[l], P, C, mean, inv, par + c.gamma, t->d_sums, t->d_dZ,
+                                                                block_out ? t->d_dY : nullptr, grd + c.gamma, grd + c.beta); count_launch();
+        // weight gradient: dW[co][tap][ci] = sum_p dZ[p][co] * cols[p][tap][ci]
+        const bf16 *in = l == 0 ? t->d_x0 : t->A[l - 1];
+        const int K9 = 9 * c.cinp;
+        im2col_kernel<<<grid_for(P * 9 * (c.cinp / 8), 256), 256, 0, s>>>(in, P, c.cinp, t->d_cols); count_launch();
+        cublasStatus_t bs = t->cb->gemm_ex(t->blas, CUBLAS_OP_N, CUBLAS_OP_T, K9, C, (int)P, &one, t->d_cols, CUDA_R_16BF, K9, t->d_dZ, CUDA_R_16BF, C,
+                                           &zero, t->d_G, CUDA_R_32F, K9, CUBLAS_COMPUTE_32F, CUBLAS_GEMM_DEFAULT);
+        if (bs != CUBLAS_STATUS_SUCCESS) return fail(OZ_ERR_CUDA, "cublasGemmEx (weight gradient) failed: " + std::to_string((int)bs));
+        wgrad_scatter_kernel<<<grid_for((size_t)C * c.cin * 9, 256), 256, 0, s>>>(t->d_G, C, c.cin, c.cinp, grd + c.w); count_launch();
+        // (the conv bias has no gradient besides the L2 term: BatchNorm removes it)
+        if (l == 0) break;
+        // input gradient: the same convolution with rotated taps; the second-to-last layer of a block adds the skip gradient
+        const bool block_in = l % 2 == 1;                       // first conv of a residual block: its input is the block input
+        OZ_TRY(ResNet::conv3x3(t->d_dZ, C, c.wd, t->d_zero_bias, block_in ? t->d_dY : nullptr, 0, dA_other, C, (size_t)n, s));
+        std::swap(dA, dA_other);
+    }
+    // ---- L2 term, optimizer
+    l2_sgd_kernel<<<296, 256, 0, s>>>(par, grd, t->d_mom, t->n_params, cfg->l2_weight, cfg->lr, cfg->momentum, apply, t->d_loss); count_launch();
+    OZ_CUDA(cudaGetLastError());
+    if (losses_host) {
+        float h[4];
+        OZ_CUDA(cudaMemcpyAsync(h, t->d_loss, sizeof(h), cudaMemcpyDeviceToHost, s));
+        OZ_CUDA(cudaStreamSynchronize(s));
+        losses_host[0] = h[0] + h[1] + h[2]; losses_host[1] = h[0]; losses_host[2] = h[1]; losses_host[3] = h[2];   // total, policy, value, l2
+    }
+    return OZ_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+void oz_train_config_default(oz_train_config *c) {
+    c->lr = 0.001f; c->momentum = 0.9f; c->l2_weight = 1e-4f;          // train.py:103-112, 202-206
+    c->bn_momentum = 0.1f; c->bn_eps = 1e-5f;                          // nn.BatchNorm2d defaults
+}
+
+int oz_trainer_create(int device, const oz_resnet_shape *shape, int max_batch, oz_trainer **out) {
+    *out = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) return fail(OZ_ERR_CUDA, "no such CUDA device: the trainer has no CPU path");
+    if (shape->channels < 128 || shape->channels % 128 != 0 || shape->channels > 384)
+        return fail(OZ_ERR_INVALID_ARGUMENT, "conv_channels must be 128, 256 or 384 for the native trainer");
+    if (shape->in_planes < 1 || shape->in_planes > 32 || shape->blocks < 0 || shape->value_hidden < 1)
+        return fail(OZ_ERR_INVALID_ARGUMENT, "unsupported network shape");
+    if (max_batch < kBoardPad || max_batch % kBoardPad != 0) return fail(OZ_ERR_INVALID_ARGUMENT, "Expected max_batch to be a positive multiple of 32.");
+    OZ_CUDA(cudaSetDevice(device));
+    oz_trainer *t = new oz_trainer();
+    t->device = device; t->shape = *shape; t->max_batch = max_batch;
+    layout_params(t);
+    int st = OZ_OK;
+    do {
+        if ((st = load_cublas(&t->cb))) break;
+        if (cudaStreamCreateWithFlags(&t->stream, cudaStreamNonBlocking) != cudaSuccess) { st = fail(OZ_ERR_CUDA, "stream creation failed"); break; }
+        if (t->cb->create(&t->blas) != CUBLAS_STATUS_SUCCESS) { st = fail(OZ_ERR_CUDA, "cublasCreate failed"); break; }
+        t->cb->set_stream(t->blas, t->stream);
+        const size_t C = shape->channels, Hv = shape->value_hidden, N = max_batch, P = N * 64;
+        const int L = (int)t->conv.size();
+        if ((st = talloc(t, &t->d_params, t->n_params)) || (st = talloc(t, &t->d_grads, t->n_params)) || (st = talloc(t, &t->d_mom, t->n_params)) ||
+            (st = talloc(t, &t->d_buffers, t->n_buffers)) || (st = talloc(t, &t->d_features, N * shape->in_planes * 64)) ||
+            (st = talloc(t, &t->d_tpolicy, N * 65)) || (st = talloc(t, &t->d_tvalue, N)) || (st = talloc(t, &t->d_x0, P * 32)) ||
+            (st = talloc(t, &t->d_mean, L * C)) || (st = talloc(t, &t->d_invstd, L * C)) || (st = talloc(t, &t->d_sums, 2 * C)) ||
+            (st = talloc(t, &t->d_zero_bias, C)) || (st = talloc(t, &t->d_dA, P * C)) || (st = talloc(t, &t->d_dA2, P * C)) ||
+            (st = talloc(t, &t->d_dY, P * C)) || (st = talloc(t, &t->d_dZ, P * C)) || (st = talloc(t, &t->d_cols, P * 9 * C)) ||
+            (st = talloc(t, &t->d_G, C * 9 * C)) || (st = talloc(t, &t->d_h, 3 * P)) || (st = talloc(t, &t->d_hn, 3 * P)) ||
+            (st = talloc(t, &t->d_dhn, 3 * P)) || (st = talloc(t, &t->d_dh, 3 * P)) || (st = talloc(t, &t->d_stat, 8)) ||
+            (st = talloc(t, &t->d_hp, N * 128)) || (st = talloc(t, &t->d_hv, N * 64)) || (st = talloc(t, &t->d_policy, N * 65)) ||
+            (st = talloc(t, &t->d_value, N)) || (st = talloc(t, &t->d_dlogits, N * 65)) || (st = talloc(t, &t->d_u, N * Hv)) ||
+            (st = talloc(t, &t->d_dvpre, N)) || (st = talloc(t, &t->d_loss, 4)))
+            break;
+        t->A.resize(L); t->Z.resize(L);
+        for (int l = 0; l < L && !st; ++l) {
+            ConvLayerT &c = t->conv[l];
+            if ((st = talloc(t, &t->A[l], P * C)) || (st = talloc(t, &t->Z[l], P * C)) || (st = talloc(t, &c.wf, (size_t)9 * C * c.cinp))) break;
+            if (l > 0 && (st = talloc(t, &c.wd, (size_t)9 * C * C))) break;
+        }
+    } while (0);
+    if (st) { oz_trainer_destroy(t); return st; }
+    *out = t;
+    return OZ_OK;
+}
+
+void oz_trainer_destroy(oz_trainer *t) {
+    if (!t) return;
+    cudaSetDevice(t->device);
+    if (t->stream) cudaStreamSynchronize(t->stream);
+    if (t->blas && t->cb) t->cb->destroy(t->blas);
+    for (void *p : t->allocs) cudaFree(p);
+    if (t->stream) cudaStreamDestroy(t->stream);
+    delete t;
+}
+
+size_t oz_trainer_num_params(const oz_trainer *t) { return t->n_params; }
+size_t oz_trainer_num_buffers(const oz_trainer *t) { return t->n_buffers; }
+
+int oz_trainer_set_state(oz_trainer *t, const float *params, const float *buffers, const float *momentum) {
+    OZ_CUDA(cudaSetDevice(t->device));
+    OZ_CUDA(cudaStreamSynchronize(t->stream));
+    if (params) OZ_CUDA(cudaMemcpy(t->d_params, params, t->n_params * sizeof(float), cudaMemcpyHostToDevice));
+    if (buffers) OZ_CUDA(cudaMemcpy(t->d_buffers, buffers, t->n_buffers * sizeof(float), cudaMemcpyHostToDevice));
+    if (momentum) OZ_CUDA(cudaMemcpy(t->d_mom, momentum, t->n_params * sizeof(float), cudaMemcpyHostToDevice));
+    return OZ_OK;
+}
+
+int oz_trainer_get_state(oz_trainer *t, float *params, float *buffers, float *momentum, float *grads) {
+    OZ_CUDA(cudaSetDevice(t->device));
+    OZ_CUDA(cudaStreamSynchronize(t->stream));
+    if (params) OZ_CUDA(cudaMemcpy(params, t->d_params, t->n_params * sizeof(float), cudaMemcpyDeviceToHost));
+    if (buffers) OZ_CUDA(cudaMemcpy(buffers, t->d_buffers, t->n_buffers * sizeof(float), cudaMemcpyDeviceToHost));
+    if (momentum) OZ_CUDA(cudaMemcpy(momentum, t->d_mom, t->n_params * sizeof(float), cudaMemcpyDeviceToHost));
+    if (grads) OZ_CUDA(cudaMemcpy(grads, t->d_grads, t->n_params * sizeof(float), cudaMemcpyDeviceToHost));
+    return OZ_OK;
+}
+
+int oz_trainer_step(oz_trainer *t, const float *features, const float *policy, const float *value, int n, const oz_train_config *cfg,
+                    int apply_update, float *losses) {
+    OZ_CUDA(cudaSetDevice(t->device));
+    if (n < 1 || n > t->max_batch) return fail(OZ_ERR_INVALID_ARGUMENT, "Expected 1 <= batch <= max_batch, but got " + std::to_string(n) + ".");
+    OZ_CUDA(cudaMemcpyAsync(t->d_features, features, (size_t)n * t->shape.in_planes * 64 * sizeof(float), cudaMemcpyHostToDevice, t->stream));
+    OZ_CUDA(cudaMemcpyAsync(t->d_tpolicy, policy, (size_t)n * 65 * sizeof(float), cudaMemcpyHostToDevice, t->stream));
+    OZ_CUDA(cudaMemcpyAsync(t->d_tvalue, value, (size_t)n * sizeof(float), cudaMemcpyHostToDevice, t->stream));
+    return step_device(t, t->d_features, t->d_tpolicy, t->d_tvalue, n, cfg, apply_update, losses);
+}
+
+int oz_trainer_step_device(oz_trainer *t, const float *features, const float *policy, const float *value, int n, const oz_train_config *cfg,
+                           int apply_update, float *losses) {
+    OZ_CUDA(cudaSetDevice(t->device));
+    return step_device(t, features, policy, value, n, cfg, apply_update, losses);
+}
+
+int oz_trainer_outputs(oz_trainer *t, int n, float *policy, float *value) {
+    OZ_CUDA(cudaSetDevice(t->device));
+    OZ_CUDA(cudaStreamSynchronize(t->stream));
+    if (n < 1 || n > t->max_batch) return fail(OZ_ERR_INVALID_ARGUMENT, "batch out of range");
+    if (policy) OZ_CUDA(cudaMemcpy(policy, t->d_policy, (size_t)n * 65 * sizeof(float), cudaMemcpyDeviceToHost));
+    if (value) OZ_CUDA(cudaMemcpy(value, t->d_value, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost));
+    return OZ_OK;
+}
+
+void *oz_trainer_stream(oz_trainer *t) { return (void *)t->stream; }
+
+}  // extern "C"

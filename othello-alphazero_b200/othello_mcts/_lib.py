@@ -47,6 +47,10 @@ class OzCounters(C.Structure):
                 ("conv_launches", u64), ("path_nodes", u64), ("children_read", u64)]
 
 
+class OzTrainConfig(C.Structure):
+    _fields_ = [("lr", f32), ("momentum", f32), ("l2_weight", f32), ("bn_momentum", f32), ("bn_eps", f32)]
+
+
 # name -> (restype, argtypes); every symbol include/othello_b200.h declares
 SIGNATURES = {
     "oz_last_error": (C.c_char_p, []),
@@ -116,6 +120,17 @@ SIGNATURES = {
     "oz_engine_finished_records": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, P(C.c_int32)]),
     "oz_engine_set_profiling": (C.c_int, [C.c_void_p, C.c_int]),
     "oz_engine_stream": (C.c_void_p, [C.c_void_p]),
+    "oz_train_config_default": (None, [P(OzTrainConfig)]),
+    "oz_trainer_create": (C.c_int, [C.c_int, P(OzResnetShape), C.c_int, P(C.c_void_p)]),
+    "oz_trainer_destroy": (None, [C.c_void_p]),
+    "oz_trainer_num_params": (C.c_size_t, [C.c_void_p]),
+    "oz_trainer_num_buffers": (C.c_size_t, [C.c_void_p]),
+    "oz_trainer_set_state": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "oz_trainer_get_state": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "oz_trainer_step": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, P(OzTrainConfig), C.c_int, C.c_void_p]),
+    "oz_trainer_step_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, P(OzTrainConfig), C.c_int, C.c_void_p]),
+    "oz_trainer_outputs": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
+    "oz_trainer_stream": (C.c_void_p, [C.c_void_p]),
 }
 
 _lib = None

@@ -1,0 +1,3 @@
+set -x
+O=gpurun_out/r01t1; mkdir -p $O
+timeout 900 python -m pytest tests/test_gpu_training.py -x -q > $O/pytest_train.log 2>&1; echo "pytest rc=$?" >> $O/summary.txt

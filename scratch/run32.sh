@@ -1,0 +1,4 @@
+set -x
+O=gpurun_out/r01t2; mkdir -p $O
+timeout 600 python scratch/train_diag.py > $O/diag.log 2>&1
+timeout 900 python -m pytest tests/test_gpu_training.py -x -q > $O/pytest_train.log 2>&1; echo "pytest rc=$?" >> $O/summary.txt
