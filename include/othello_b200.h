@@ -302,6 +302,9 @@ int oz_trainer_step_device(oz_trainer *t, const float *features, const float *po
                            const oz_train_config *cfg, int apply_update, float *losses);
 /* Network outputs of the last step's forward pass (train mode): policy [n][65], value [n]. */
 int oz_trainer_outputs(oz_trainer *t, int n, float *policy, float *value);
+/* CUDA-graph replay of the whole step (default on): a (batch size, hyper-parameters) combination runs eagerly the first
+ * time, is captured the second time and replayed afterwards.  Results are identical either way. */
+int oz_trainer_set_graphs(oz_trainer *t, int on);
 void *oz_trainer_stream(oz_trainer *t);
 
 #ifdef __cplusplus

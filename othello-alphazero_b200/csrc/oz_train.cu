@@ -33,6 +33,7 @@ struct Cublas {
     cublasStatus_t (*create)(cublasHandle_t *) = nullptr;
     cublasStatus_t (*destroy)(cublasHandle_t) = nullptr;
     cublasStatus_t (*set_stream)(cublasHandle_t, cudaStream_t) = nullptr;
+    cublasStatus_t (*set_workspace)(cublasHandle_t, void *, size_t) = nullptr;
     cublasStatus_t (*gemm_ex)(cublasHandle_t, cublasOperation_t, cublasOperation_t, int, int, int, const void *, const void *, cudaDataType,
                               int, const void *, cudaDataType, int, const void *, void *, cudaDataType, int, cublasComputeType_t,
                               cublasGemmAlgo_t) = nullptr;
@@ -48,6 +49,7 @@ int load_cublas(Cublas **out) {
         cb.destroy = (decltype(cb.destroy))dlsym(cb.lib, "cublasDestroy_v2");
         cb.set_stream = (decltype(cb.set_stream))dlsym(cb.lib, "cublasSetStream_v2");
         cb.gemm_ex = (decltype(cb.gemm_ex))dlsym(cb.lib, "cublasGemmEx");
+        cb.set_workspace = (decltype(cb.set_workspace))dlsym(cb.lib, "cublasSetWorkspace_v2");
         if (!cb.create || !cb.destroy || !cb.set_stream || !cb.gemm_ex) { cb.lib = nullptr; return fail(OZ_ERR_CUDA, "cuBLAS symbols missing"); }
     }
     *out = &cb;
@@ -79,7 +81,12 @@ __device__ float block_sum(float v, float *scratch /* >= 32 floats */) {
 // master fp32 W [C][cin][9] (PyTorch OIHW, tap = ky*3+kx) ->
 //   wf bf16 [9][C][cinp]          forward operand of conv3x3_pair_kernel ([tap][cout][cin], cin zero-padded to cinp)
 //   wd bf16 [9][cin][C] (cin==C)  input-gradient operand: Wd[8 - tap][ci][co] = W[co][ci][tap]
-__global__ void pack_weights_kernel(const float *__restrict__ w, int C, int cin, int cinp, bf16 *__restrict__ wf, bf16 *__restrict__ wd) {
+struct PackDesc { size_t w; int cin, cinp; bf16 *wf, *wd; };      // one per conv layer (blockIdx.y)
+__global__ void pack_weights_kernel(const float *__restrict__ params, const PackDesc *__restrict__ desc, int C) {
+    const PackDesc d = desc[blockIdx.y];
+    const float *w = params + d.w;
+    const int cin = d.cin, cinp = d.cinp;
+    bf16 *wf = d.wf, *wd = d.wd;
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= 9 * C * cinp) return;
     const int ci = idx % cinp, co = (idx / cinp) % C, tap = idx / (cinp * C);
@@ -89,83 +96,136 @@ __global__ void pack_weights_kernel(const float *__restrict__ w, int C, int cin,
 }
 
 // ------------------------------------------------------------------ BatchNorm (train mode), tensors bf16 [P][C]
-// sums[c] += sum z, sums[C + c] += sum z^2.  A thread owns a channel pair; threads with the same pair walk different rows.
-__global__ void bn_stats_kernel(const bf16 *__restrict__ z, size_t P, int C, float *__restrict__ sums) {
-    const int tpr = C / 2, rows = blockDim.x / tpr;
-    const int cp = threadIdx.x % tpr, r0 = threadIdx.x / tpr;
-    if (r0 >= rows) return;
-    float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
-    for (size_t p = (size_t)blockIdx.x * rows + r0; p < P; p += (size_t)gridDim.x * rows) {
-        const float2 v = __bfloat1622float2(*(const __nv_bfloat162 *)(z + p * C + 2 * cp));
-        s0 += v.x; s1 += v.y; q0 += v.x * v.x; q1 += v.y * v.y;
+// All four kernels move 16 bytes (8 channels) per thread and access.
+__device__ __forceinline__ void unpack8(const uint4 &q, float (&f)[8]) {
+    const __nv_bfloat162 *h = (const __nv_bfloat162 *)&q;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { const float2 v = __bfloat1622float2(h[i]); f[2 * i] = v.x; f[2 * i + 1] = v.y; }
+}
+__device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
+    uint4 q;
+    __nv_bfloat162 *h = (__nv_bfloat162 *)&q;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+    return q;
+}
+
+// Shared tail of the two reductions: 16 per-thread partial sums (8 channels x 2 statistics) -> one atomic per channel,
+// statistic and block.  out[c] += first statistic, out[C + c] += second.
+__device__ __forceinline__ void bn_block_reduce(float (&a)[8], float (&b)[8], int C, int tpr, int rows, int cg, int r0, float *out) {
+    __shared__ float red[16][256];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { red[i][threadIdx.x] = a[i]; red[8 + i][threadIdx.x] = b[i]; }
+    __syncthreads();
+    if (r0 == 0) {
+        for (int r = 1; r < rows; ++r)
+#pragma unroll
+            for (int i = 0; i < 8; ++i) { a[i] += red[i][r * tpr + cg]; b[i] += red[8 + i][r * tpr + cg]; }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { atomicAdd(&out[8 * cg + i], a[i]); atomicAdd(&out[C + 8 * cg + i], b[i]); }
     }
-    atomicAdd(&sums[2 * cp], s0); atomicAdd(&sums[2 * cp + 1], s1);
-    atomicAdd(&sums[C + 2 * cp], q0); atomicAdd(&sums[C + 2 * cp + 1], q1);
 }
 
-// mean / invstd from the sums; running statistics as nn.BatchNorm2d updates them (momentum, unbiased variance).  The
-// convolution bias only shifts the mean: the normalised output does not depend on it, the running mean does.
-__global__ void bn_finalize_kernel(const float *__restrict__ sums, float count, int C, const float *__restrict__ conv_bias, float eps, float momentum,
-                                   float *__restrict__ mean, float *__restrict__ invstd, float *__restrict__ run_mean, float *__restrict__ run_var) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= C) return;
-    const float m = sums[c] / count;
-    const float var = fmaxf(sums[C + c] / count - m * m, 0.f);
-    mean[c] = m; invstd[c] = rsqrtf(var + eps);
-    run_mean[c] = (1.f - momentum) * run_mean[c] + momentum * (m + (conv_bias ? conv_bias[c] : 0.f));
-    run_var[c] = (1.f - momentum) * run_var[c] + momentum * var * (count / fmaxf(count - 1.f, 1.f));
+// sums[c] += sum z, sums[C + c] += sum z^2.
+__global__ void __launch_bounds__(256) bn_stats_kernel(const bf16 *__restrict__ z, size_t P, int C, float *__restrict__ sums) {
+    const int tpr = C / 8, rows = blockDim.x / tpr;
+    const int cg = threadIdx.x % tpr, r0 = threadIdx.x / tpr;
+    float s[8], q[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { s[i] = 0.f; q[i] = 0.f; }
+    if (r0 < rows)
+        for (size_t p = (size_t)blockIdx.x * rows + r0; p < P; p += (size_t)gridDim.x * rows) {
+            float v[8];
+            unpack8(*(const uint4 *)(z + p * C + 8 * cg), v);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) { s[i] += v[i]; q[i] += v[i] * v[i]; }
+        }
+    bn_block_reduce(s, q, C, tpr, rows, cg, r0 < rows ? r0 : 1 << 30, sums);
 }
 
-// a = relu(gamma * (z - mean) * invstd + beta [+ skip])
-__global__ void bn_apply_kernel(const bf16 *__restrict__ z, const bf16 *__restrict__ skip, size_t P, int C, const float *__restrict__ mean,
-                                const float *__restrict__ invstd, const float *__restrict__ gamma, const float *__restrict__ beta, bf16 *__restrict__ a) {
-    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;     // one channel pair
-    if (i >= P * (size_t)(C / 2)) return;
-    const int c = 2 * (int)(i % (C / 2));
-    const float2 v = __bfloat1622float2(((const __nv_bfloat162 *)z)[i]);
-    float y0 = gamma[c] * (v.x - mean[c]) * invstd[c] + beta[c], y1 = gamma[c + 1] * (v.y - mean[c + 1]) * invstd[c + 1] + beta[c + 1];
-    if (skip) { const float2 s = __bfloat1622float2(((const __nv_bfloat162 *)skip)[i]); y0 += s.x; y1 += s.y; }
-    ((__nv_bfloat162 *)a)[i] = __floats2bfloat162_rn(fmaxf(y0, 0.f), fmaxf(y1, 0.f));
+// mean / invstd of channel c from the sums (every consumer recomputes them: two flops instead of a kernel launch).
+__device__ __forceinline__ void bn_moments(const float *sums, int C, int c, float count, float eps, float &mean, float &invstd, float &var) {
+    mean = sums[c] / count;
+    var = fmaxf(sums[C + c] / count - mean * mean, 0.f);
+    invstd = rsqrtf(var + eps);
+}
+
+// a = relu(gamma * (z - mean) * invstd + beta [+ skip]).  Block 0 also stores mean / invstd for the backward pass and
+// updates the running statistics as nn.BatchNorm2d does (momentum, unbiased variance).  The convolution bias only shifts
+// the mean: the normalised output does not depend on it, the running mean does.
+__global__ void __launch_bounds__(256) bn_apply_kernel(const bf16 *__restrict__ z, const bf16 *__restrict__ skip, size_t P, int C,
+                                                       const float *__restrict__ sums, const float *__restrict__ gamma, const float *__restrict__ beta,
+                                                       const float *__restrict__ conv_bias, float eps, float momentum, float *__restrict__ mean_out,
+                                                       float *__restrict__ invstd_out, float *__restrict__ run_mean, float *__restrict__ run_var,
+                                                       bf16 *__restrict__ a) {
+    const float count = (float)P;
+    if (blockIdx.x == 0)
+        for (int c = threadIdx.x; c < C; c += blockDim.x) {
+            float m, inv, var;
+            bn_moments(sums, C, c, count, eps, m, inv, var);
+            mean_out[c] = m; invstd_out[c] = inv;
+            run_mean[c] = (1.f - momentum) * run_mean[c] + momentum * (m + conv_bias[c]);
+            run_var[c] = (1.f - momentum) * run_var[c] + momentum * var * (count / fmaxf(count - 1.f, 1.f));
+        }
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;     // one group of 8 channels
+    if (i >= P * (size_t)(C / 8)) return;
+    const int c0 = 8 * (int)(i % (C / 8));
+    float v[8], sk[8];
+    unpack8(((const uint4 *)z)[i], v);
+    if (skip) unpack8(((const uint4 *)skip)[i], sk);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        float m, inv, var;
+        bn_moments(sums, C, c0 + k, count, eps, m, inv, var);
+        float y = gamma[c0 + k] * (v[k] - m) * inv + beta[c0 + k];
+        if (skip) y += sk[k];
+        v[k] = fmaxf(y, 0.f);
+    }
+    ((uint4 *)a)[i] = pack8(v);
 }
 
 // Backward through ReLU and BatchNorm.  dy = da * [a > 0]; s[c] += sum dy, s[C + c] += sum dy * zhat.
-__global__ void bn_bwd_reduce_kernel(const bf16 *__restrict__ da, const bf16 *__restrict__ a, const bf16 *__restrict__ z, size_t P, int C,
-                                     const float *__restrict__ mean, const float *__restrict__ invstd, float *__restrict__ s) {
-    const int tpr = C / 2, rows = blockDim.x / tpr;
-    const int cp = threadIdx.x % tpr, r0 = threadIdx.x / tpr;
-    if (r0 >= rows) return;
-    const float m0 = mean[2 * cp], m1 = mean[2 * cp + 1], i0 = invstd[2 * cp], i1 = invstd[2 * cp + 1];
-    float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
-    for (size_t p = (size_t)blockIdx.x * rows + r0; p < P; p += (size_t)gridDim.x * rows) {
-        const size_t o = p * C + 2 * cp;
-        const float2 g = __bfloat1622float2(*(const __nv_bfloat162 *)(da + o)), av = __bfloat1622float2(*(const __nv_bfloat162 *)(a + o));
-        const float2 zv = __bfloat1622float2(*(const __nv_bfloat162 *)(z + o));
-        const float d0 = av.x > 0.f ? g.x : 0.f, d1 = av.y > 0.f ? g.y : 0.f;
-        s0 += d0; s1 += d1; q0 += d0 * (zv.x - m0) * i0; q1 += d1 * (zv.y - m1) * i1;
-    }
-    atomicAdd(&s[2 * cp], s0); atomicAdd(&s[2 * cp + 1], s1);
-    atomicAdd(&s[C + 2 * cp], q0); atomicAdd(&s[C + 2 * cp + 1], q1);
+__global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const bf16 *__restrict__ da, const bf16 *__restrict__ a, const bf16 *__restrict__ z,
+                                                            size_t P, int C, const float *__restrict__ mean, const float *__restrict__ invstd,
+                                                            float *__restrict__ s) {
+    const int tpr = C / 8, rows = blockDim.x / tpr;
+    const int cg = threadIdx.x % tpr, r0 = threadIdx.x / tpr;
+    float m[8], iv[8], s1[8], s2[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { m[i] = mean[8 * cg + i]; iv[i] = invstd[8 * cg + i]; s1[i] = 0.f; s2[i] = 0.f; }
+    if (r0 < rows)
+        for (size_t p = (size_t)blockIdx.x * rows + r0; p < P; p += (size_t)gridDim.x * rows) {
+            const size_t o = p * C + 8 * cg;
+            float g[8], av[8], zv[8];
+            unpack8(*(const uint4 *)(da + o), g); unpack8(*(const uint4 *)(a + o), av); unpack8(*(const uint4 *)(z + o), zv);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) { const float d = av[i] > 0.f ? g[i] : 0.f; s1[i] += d; s2[i] += d * (zv[i] - m[i]) * iv[i]; }
+        }
+    bn_block_reduce(s1, s2, C, tpr, rows, cg, r0 < rows ? r0 : 1 << 30, s);
 }
 
 // dz = gamma * invstd * (dy - s1 / M - zhat * s2 / M); optionally keeps dy (the gradient that also flows into the skip
 // connection).  Block 0 writes dgamma = s2, dbeta = s1.
-__global__ void bn_bwd_apply_kernel(const bf16 *__restrict__ da, const bf16 *__restrict__ a, const bf16 *__restrict__ z, size_t P, int C,
-                                    const float *__restrict__ mean, const float *__restrict__ invstd, const float *__restrict__ gamma,
-                                    const float *__restrict__ s, bf16 *__restrict__ dz, bf16 *__restrict__ dy_out, float *__restrict__ dgamma,
-                                    float *__restrict__ dbeta) {
+__global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const bf16 *__restrict__ da, const bf16 *__restrict__ a, const bf16 *__restrict__ z,
+                                                           size_t P, int C, const float *__restrict__ mean, const float *__restrict__ invstd,
+                                                           const float *__restrict__ gamma, const float *__restrict__ s, bf16 *__restrict__ dz,
+                                                           bf16 *__restrict__ dy_out, float *__restrict__ dgamma, float *__restrict__ dbeta) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (blockIdx.x == 0) for (int c = threadIdx.x; c < C; c += blockDim.x) { dgamma[c] = s[C + c]; dbeta[c] = s[c]; }
-    if (i >= P * (size_t)(C / 2)) return;
-    const int c = 2 * (int)(i % (C / 2));
+    if (i >= P * (size_t)(C / 8)) return;
+    const int c0 = 8 * (int)(i % (C / 8));
     const float invM = 1.f / (float)P;
-    const float2 g = __bfloat1622float2(((const __nv_bfloat162 *)da)[i]), av = __bfloat1622float2(((const __nv_bfloat162 *)a)[i]);
-    const float2 zv = __bfloat1622float2(((const __nv_bfloat162 *)z)[i]);
-    const float d0 = av.x > 0.f ? g.x : 0.f, d1 = av.y > 0.f ? g.y : 0.f;
-    const float zh0 = (zv.x - mean[c]) * invstd[c], zh1 = (zv.y - mean[c + 1]) * invstd[c + 1];
-    const float r0 = gamma[c] * invstd[c] * (d0 - s[c] * invM - zh0 * s[C + c] * invM);
-    const float r1 = gamma[c + 1] * invstd[c + 1] * (d1 - s[c + 1] * invM - zh1 * s[C + c + 1] * invM);
-    ((__nv_bfloat162 *)dz)[i] = __floats2bfloat162_rn(r0, r1);
-    if (dy_out) ((__nv_bfloat162 *)dy_out)[i] = __floats2bfloat162_rn(d0, d1);
+    float g[8], av[8], zv[8], d[8];
+    unpack8(((const uint4 *)da)[i], g); unpack8(((const uint4 *)a)[i], av); unpack8(((const uint4 *)z)[i], zv);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const int c = c0 + k;
+        d[k] = av[k] > 0.f ? g[k] : 0.f;
+        const float zh = (zv[k] - mean[c]) * invstd[c];
+        g[k] = gamma[c] * invstd[c] * (d[k] - s[c] * invM - zh * s[C + c] * invM);
+    }
+    ((uint4 *)dz)[i] = pack8(g);
+    if (dy_out) ((uint4 *)dy_out)[i] = pack8(d);
 }
 
 // ------------------------------------------------------------------ weight gradient: im2col + (cuBLAS) + scatter
@@ -244,17 +304,24 @@ __global__ void head_fc_fwd_kernel(const float *__restrict__ hp, const float *__
                                    const float *__restrict__ w2, const float *__restrict__ b2, const float *__restrict__ tp,
                                    const float *__restrict__ tv, float *__restrict__ policy, float *__restrict__ value, float *__restrict__ dlogits,
                                    float *__restrict__ u, float *__restrict__ dvpre, float *__restrict__ loss) {
-    const int n = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-    if (n >= N) return;
+    // the FC weights are staged in shared memory once per block (65 x 128 + Hv x 64 floats), boards are strided over warps
+    extern __shared__ float fc_sm[];
+    float *s_lw = fc_sm, *s_w1 = fc_sm + 65 * 128;
+    for (int i = threadIdx.x; i < 65 * 128; i += blockDim.x) s_lw[i] = lw[i];
+    for (int i = threadIdx.x; i < Hv * 64; i += blockDim.x) s_w1[i] = w1[i];
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warps = blockDim.x >> 5;
+    for (int n = blockIdx.x * warps + (threadIdx.x >> 5); n < N; n += gridDim.x * warps) {
     const float *x = hp + (size_t)n * 128;
     float lg[3] = {-INFINITY, -INFINITY, -INFINITY};
-#pragma unroll
-    for (int r = 0; r < 3; ++r) {
-        const int j = lane + 32 * r;
-        if (j < 65) {
-            float acc = lb[j];
-            for (int i = 0; i < 128; ++i) acc += x[i] * lw[j * 128 + i];
-            lg[r] = acc;
+    {
+        // lanes span the 128 inputs, one warp reduction per logit; logit j lives in lane j % 32
+        const float x0 = x[lane], x1 = x[lane + 32], x2 = x[lane + 64], x3 = x[lane + 96];
+        for (int j = 0; j < 65; ++j) {
+            const float *w = s_lw + j * 128;
+            float acc = x0 * w[lane] + x1 * w[lane + 32] + x2 * w[lane + 64] + x3 * w[lane + 96];
+            acc = warp_sum_f(acc) + lb[j];
+            if ((j & 31) == lane) lg[j >> 5] = acc;
         }
     }
     float m = fmaxf(fmaxf(lg[0], lg[1]), lg[2]);
@@ -279,12 +346,13 @@ __global__ void head_fc_fwd_kernel(const float *__restrict__ hp, const float *__
     // value head
     const float *xv = hv + (size_t)n * 64;
     float acc2 = 0.f;
-    for (int k = lane; k < Hv; k += 32) {
-        float a = b1[k];
-        for (int i = 0; i < 64; ++i) a += xv[i] * w1[k * 64 + i];
-        a = fmaxf(a, 0.f);
-        u[(size_t)n * Hv + k] = a;
-        acc2 += a * w2[k];
+    {
+        const float v0 = xv[lane], v1 = xv[lane + 32];
+        for (int k = 0; k < Hv; ++k) {
+            float a = warp_sum_f(v0 * s_w1[k * 64 + lane] + v1 * s_w1[k * 64 + lane + 32]) + b1[k];
+            a = fmaxf(a, 0.f);
+            if (lane == 0) { u[(size_t)n * Hv + k] = a; acc2 += a * w2[k]; }
+        }
     }
     acc2 = warp_sum_f(acc2);
     if (lane == 0) {
@@ -293,6 +361,7 @@ __global__ void head_fc_fwd_kernel(const float *__restrict__ hp, const float *__
         dvpre[n] = 2.f * d / (float)N * (1.f - v * v);
         atomicAdd(&loss[0], ce / (float)N);
         atomicAdd(&loss[1], d * d / (float)N);
+    }
     }
 }
 
@@ -305,9 +374,16 @@ __global__ void head_fc_bwd_params_kernel(const float *__restrict__ hp, const fl
     const int n_lw = 65 * 128, n_w1 = Hv * 64;
     if (idx < n_lw) {
         const int j = idx / 128, i = idx % 128;
-        float acc = 0.f;
-        for (int n = 0; n < N; ++n) acc += dlogits[(size_t)n * 65 + j] * hp[(size_t)n * 128 + i];
-        dlw[idx] = acc;
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+        int n = 0;
+        for (; n + 3 < N; n += 4) {
+            a0 += dlogits[(size_t)n * 65 + j] * hp[(size_t)n * 128 + i];
+            a1 += dlogits[(size_t)(n + 1) * 65 + j] * hp[(size_t)(n + 1) * 128 + i];
+            a2 += dlogits[(size_t)(n + 2) * 65 + j] * hp[(size_t)(n + 2) * 128 + i];
+            a3 += dlogits[(size_t)(n + 3) * 65 + j] * hp[(size_t)(n + 3) * 128 + i];
+        }
+        for (; n < N; ++n) a0 += dlogits[(size_t)n * 65 + j] * hp[(size_t)n * 128 + i];
+        dlw[idx] = (a0 + a1) + (a2 + a3);
     } else if (idx < n_lw + 65) {
         const int j = idx - n_lw;
         float acc = 0.f;
@@ -316,9 +392,14 @@ __global__ void head_fc_bwd_params_kernel(const float *__restrict__ hp, const fl
     } else if (idx < n_lw + 65 + n_w1) {
         const int r = idx - n_lw - 65, k = r / 64, i = r % 64;
         const float wk = w2[k];
-        float acc = 0.f;
-        for (int n = 0; n < N; ++n) acc += (u[(size_t)n * Hv + k] > 0.f ? dvpre[n] * wk : 0.f) * hv[(size_t)n * 64 + i];
-        dw1[r] = acc;
+        float a0 = 0.f, a1 = 0.f;
+        int n = 0;
+        for (; n + 1 < N; n += 2) {
+            a0 += (u[(size_t)n * Hv + k] > 0.f ? dvpre[n] * wk : 0.f) * hv[(size_t)n * 64 + i];
+            a1 += (u[(size_t)(n + 1) * Hv + k] > 0.f ? dvpre[n + 1] * wk : 0.f) * hv[(size_t)(n + 1) * 64 + i];
+        }
+        for (; n < N; ++n) a0 += (u[(size_t)n * Hv + k] > 0.f ? dvpre[n] * wk : 0.f) * hv[(size_t)n * 64 + i];
+        dw1[r] = a0 + a1;
     } else if (idx < n_lw + 65 + n_w1 + Hv) {
         const int k = idx - n_lw - 65 - n_w1;
         const float wk = w2[k];
@@ -448,12 +529,23 @@ struct oz_trainer {
     float *d_mean = nullptr, *d_invstd = nullptr;   // [layers][C]
     float *d_sums = nullptr;      // [2C] scratch
     float *d_zero_bias = nullptr;
+    PackDesc *d_pack = nullptr;
     bf16 *d_dA = nullptr, *d_dA2 = nullptr, *d_dY = nullptr, *d_dZ = nullptr, *d_cols = nullptr;
     float *d_G = nullptr;
     float *d_h = nullptr, *d_hn = nullptr, *d_dhn = nullptr, *d_dh = nullptr, *d_stat = nullptr, *d_hp = nullptr, *d_hv = nullptr;
     float *d_policy = nullptr, *d_value = nullptr, *d_dlogits = nullptr, *d_u = nullptr, *d_dvpre = nullptr, *d_loss = nullptr;
     cublasHandle_t blas = nullptr;
     Cublas *cb = nullptr;
+    void *d_blas_ws = nullptr;
+    // CUDA-graph replay of the whole step: at batch 256 the step is some 250 launches of a few microseconds each, so the
+    // host, not the GPU, sets the pace when every kernel is launched eagerly.  One graph per (batch, hyper-parameters).
+    struct StepKey { int n, apply; oz_train_config cfg; };
+    StepKey last_key{};
+    bool have_last_key = false;
+    cudaGraphExec_t graph = nullptr;
+    StepKey graph_key{};
+    int use_graphs = 1;
+    unsigned long long graph_launches = 0;
     cudaStream_t stream = nullptr;
     std::vector<void *> allocs;
 };
@@ -493,50 +585,47 @@ void layout_params(oz_trainer *t) {
 }
 
 int pack_all_weights(oz_trainer *t) {
-    const int C = t->shape.channels;
-    for (ConvLayerT &c : t->conv) {
-        const int n = 9 * C * c.cinp;
-        pack_weights_kernel<<<grid_for(n, 256), 256, 0, t->stream>>>(t->d_params + c.w, C, c.cin, c.cinp, c.wf, c.wd);
-        count_launch();
-    }
+    const int C = t->shape.channels, L = (int)t->conv.size();
+    pack_weights_kernel<<<dim3(grid_for((size_t)9 * C * C, 256), L), 256, 0, t->stream>>>(t->d_params, t->d_pack, C);
+    count_launch();
     OZ_CUDA(cudaGetLastError());
     return OZ_OK;
 }
 
-// One training step on device-resident inputs.  features: float [n][in_planes][64]; policy targets [n][65]; value [n].
-int step_device(oz_trainer *t, const float *d_features, const float *d_tp, const float *d_tv, int n, const oz_train_config *cfg, int apply,
-                float *losses_host) {
-    if (n < 1 || n > t->max_batch || n % kBoardPad != 0)
-        return fail(OZ_ERR_INVALID_ARGUMENT, "Expected a batch size in [32, " + std::to_string(t->max_batch) + "] that is a multiple of 32, but got " + std::to_string(n) + ".");
+// One training step on the inputs staged in the trainer's own buffers (features float [n][in_planes][64], policy targets
+// [n][65], value targets [n]).  Only stream work: this is what the step graph captures.
+int run_step(oz_trainer *t, int n, const oz_train_config *cfg, int apply) {
+    const float *d_features = t->d_features, *d_tp = t->d_tpolicy, *d_tv = t->d_tvalue;
     const int C = t->shape.channels, Hv = t->shape.value_hidden, L = (int)t->conv.size();
-    const size_t P = (size_t)n * 64, half = P * (size_t)(C / 2);
+    const size_t P = (size_t)n * 64, vec8 = P * (size_t)(C / 8);
     cudaStream_t s = t->stream;
     float *par = t->d_params, *grd = t->d_grads, *buf = t->d_buffers;
     OZ_CUDA(cudaMemsetAsync(grd, 0, t->n_params * sizeof(float), s));
     OZ_CUDA(cudaMemsetAsync(t->d_loss, 0, 4 * sizeof(float), s));
+    OZ_CUDA(cudaMemsetAsync(t->d_sums, 0, (size_t)2 * L * 2 * C * sizeof(float), s));     // reduction slots of every layer, forward and backward
     OZ_TRY(pack_all_weights(t));
     launch_planes_to_nhwc32(d_features, t->shape.in_planes, (size_t)n, (size_t)n, t->d_x0, s);
-    const int bn_block = 256, bn_grid = 296;
+    const int bn_block = 256, bn_grid = (int)std::min<size_t>(592, (P + 127) / 128);
 
     // ---- forward through the tower (neural_net.py:9-65, train mode)
     for (int l = 0; l < L; ++l) {
         ConvLayerT &c = t->conv[l];
         const bf16 *in = l == 0 ? t->d_x0 : t->A[l - 1];
         OZ_TRY(ResNet::conv3x3(in, c.cinp, c.wf, t->d_zero_bias, nullptr, 0, t->Z[l], C, (size_t)n, s));
-        OZ_CUDA(cudaMemsetAsync(t->d_sums, 0, 2 * C * sizeof(float), s));
-        bn_stats_kernel<<<bn_grid, bn_block, 0, s>>>(t->Z[l], P, C, t->d_sums); count_launch();
-        bn_finalize_kernel<<<grid_for(C, 128), 128, 0, s>>>(t->d_sums, (float)P, C, par + c.b, cfg->bn_eps, cfg->bn_momentum, t->d_mean + (size_t)l * C,
-                                                            t->d_invstd + (size_t)l * C, buf + c.rm, buf + c.rv); count_launch();
+        float *fsum = t->d_sums + (size_t)l * 2 * C;
+        bn_stats_kernel<<<bn_grid, bn_block, 0, s>>>(t->Z[l], P, C, fsum); count_launch();
         const bf16 *skip = (l >= 2 && l % 2 == 0) ? t->A[l - 2] : nullptr;     // second conv of a residual block
-        bn_apply_kernel<<<grid_for(half, 256), 256, 0, s>>>(t->Z[l], skip, P, C, t->d_mean + (size_t)l * C, t->d_invstd + (size_t)l * C, par + c.gamma,
-                                                            par + c.beta, t->A[l]); count_launch();
+        bn_apply_kernel<<<grid_for(vec8, 256), 256, 0, s>>>(t->Z[l], skip, P, C, fsum, par + c.gamma, par + c.beta, par + c.b, cfg->bn_eps,
+                                                            cfg->bn_momentum, t->d_mean + (size_t)l * C, t->d_invstd + (size_t)l * C, buf + c.rm,
+                                                            buf + c.rv, t->A[l]); count_launch();
     }
     // ---- heads forward + losses (neural_net.py:68-128, train.py:494-495)
     const bf16 *a_last = t->A[L - 1];
     head_conv_fwd_kernel<<<grid_for(P * 32, 256), 256, 0, s>>>(a_last, P, C, par + t->pcw, par + t->pcb, par + t->vcw, par + t->vcb, t->d_h); count_launch();
     head_bn_fwd_kernel<<<3, 1024, 0, s>>>(t->d_h, P, par + t->pg, par + t->pb, par + t->vg, par + t->vb, cfg->bn_eps, cfg->bn_momentum, buf + t->prm,
                                           buf + t->vrm, t->d_stat, t->d_hn, t->d_hp, t->d_hv); count_launch();
-    head_fc_fwd_kernel<<<grid_for((size_t)n * 32, 128), 128, 0, s>>>(t->d_hp, t->d_hv, n, Hv, par + t->plw, par + t->plb, par + t->v1w, par + t->v1b,
+    const size_t fc_smem = (size_t)(65 * 128 + Hv * 64) * sizeof(float);
+    head_fc_fwd_kernel<<<(unsigned)std::min<size_t>(148, (n + 7) / 8), 256, fc_smem, s>>>(t->d_hp, t->d_hv, n, Hv, par + t->plw, par + t->plb, par + t->v1w, par + t->v1b,
                                                                      par + t->v2w, par + t->v2b, d_tp, d_tv, t->d_policy, t->d_value, t->d_dlogits,
                                                                      t->d_u, t->d_dvpre, t->d_loss); count_launch();
     // ---- heads backward
@@ -557,9 +646,9 @@ int step_device(oz_trainer *t, const float *d_features, const float *d_tp, const
         ConvLayerT &c = t->conv[l];
         const float *mean = t->d_mean + (size_t)l * C, *inv = t->d_invstd + (size_t)l * C;
         const bool block_out = l >= 2 && l % 2 == 0;            // output of a residual block: dy also flows into the skip connection
-        OZ_CUDA(cudaMemsetAsync(t->d_sums, 0, 2 * C * sizeof(float), s));
-        bn_bwd_reduce_kernel<<<bn_grid, bn_block, 0, s>>>(dA, t->A[l], t->Z[l], P, C, mean, inv, t->d_sums); count_launch();
-        bn_bwd_apply_kernel<<<grid_for(half, 256), 256, 0, s>>>(dA, t->A[l], t->Z[l], P, C, mean, inv, par + c.gamma, t->d_sums, t->d_dZ,
+        float *bsum = t->d_sums + (size_t)(L + l) * 2 * C;
+        bn_bwd_reduce_kernel<<<bn_grid, bn_block, 0, s>>>(dA, t->A[l], t->Z[l], P, C, mean, inv, bsum); count_launch();
+        bn_bwd_apply_kernel<<<grid_for(vec8, 256), 256, 0, s>>>(dA, t->A[l], t->Z[l], P, C, mean, inv, par + c.gamma, bsum, t->d_dZ,
                                                                 block_out ? t->d_dY : nullptr, grd + c.gamma, grd + c.beta); count_launch();
         // weight gradient: dW[co][tap][ci] = sum_p dZ[p][co] * cols[p][tap][ci]
         const bf16 *in = l == 0 ? t->d_x0 : t->A[l - 1];
@@ -579,6 +668,53 @@ int step_device(oz_trainer *t, const float *d_features, const float *d_tp, const
     // ---- L2 term, optimizer
     l2_sgd_kernel<<<296, 256, 0, s>>>(par, grd, t->d_mom, t->n_params, cfg->l2_weight, cfg->lr, cfg->momentum, apply, t->d_loss); count_launch();
     OZ_CUDA(cudaGetLastError());
+    return OZ_OK;
+}
+
+bool same_key(const oz_trainer::StepKey &a, const oz_trainer::StepKey &b) {
+    return a.n == b.n && a.apply == b.apply && std::memcmp(&a.cfg, &b.cfg, sizeof(oz_train_config)) == 0;
+}
+
+void drop_step_graph(oz_trainer *t) {
+    if (t->graph) { cudaGraphExecDestroy(t->graph); t->graph = nullptr; }
+    t->have_last_key = false;
+}
+
+// Inputs are staged; run the step eagerly the first time a (batch, hyper-parameter) combination is seen, capture it the
+// second time, replay it from then on.
+int execute_step(oz_trainer *t, int n, const oz_train_config *cfg, int apply, float *losses_host) {
+    if (n < 1 || n > t->max_batch || n % kBoardPad != 0)
+        return fail(OZ_ERR_INVALID_ARGUMENT, "Expected a batch size in [32, " + std::to_string(t->max_batch) + "] that is a multiple of 32, but got " + std::to_string(n) + ".");
+    oz_trainer::StepKey key{};
+    key.n = n; key.apply = apply; key.cfg = *cfg;
+    cudaStream_t s = t->stream;
+    if (t->use_graphs && t->graph && same_key(key, t->graph_key)) {
+        OZ_CUDA(cudaGraphLaunch(t->graph, s));
+        count_launch((int)t->graph_launches);
+    } else if (t->use_graphs && t->have_last_key && same_key(key, t->last_key)) {
+        if (t->graph) { cudaGraphExecDestroy(t->graph); t->graph = nullptr; }
+        cudaGraph_t g = nullptr;
+        const unsigned long long before = g_kernel_launches;
+        OZ_CUDA(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+        const int st = run_step(t, n, cfg, apply);
+        const cudaError_t ce = cudaStreamEndCapture(s, &g);
+        t->graph_launches = g_kernel_launches - before;
+        g_kernel_launches = before;                          // capturing launched nothing
+        if (st || ce != cudaSuccess || !g) {
+            if (g) cudaGraphDestroy(g);
+            cudaGetLastError();
+            return st ? st : fail(OZ_ERR_CUDA, std::string("graph capture of the training step failed: ") + cudaGetErrorString(ce));
+        }
+        const cudaError_t ie = cudaGraphInstantiate(&t->graph, g, 0);
+        cudaGraphDestroy(g);
+        if (ie != cudaSuccess) { t->graph = nullptr; return fail(OZ_ERR_CUDA, std::string("cudaGraphInstantiate: ") + cudaGetErrorString(ie)); }
+        t->graph_key = key;
+        OZ_CUDA(cudaGraphLaunch(t->graph, s));
+        count_launch((int)t->graph_launches);
+    } else {
+        OZ_TRY(run_step(t, n, cfg, apply));
+        t->last_key = key; t->have_last_key = true;
+    }
     if (losses_host) {
         float h[4];
         OZ_CUDA(cudaMemcpyAsync(h, t->d_loss, sizeof(h), cudaMemcpyDeviceToHost, s));
@@ -616,12 +752,16 @@ int oz_trainer_create(int device, const oz_resnet_shape *shape, int max_batch, o
         if (cudaStreamCreateWithFlags(&t->stream, cudaStreamNonBlocking) != cudaSuccess) { st = fail(OZ_ERR_CUDA, "stream creation failed"); break; }
         if (t->cb->create(&t->blas) != CUBLAS_STATUS_SUCCESS) { st = fail(OZ_ERR_CUDA, "cublasCreate failed"); break; }
         t->cb->set_stream(t->blas, t->stream);
+        if (t->cb->set_workspace) {                           // a fixed workspace keeps the GEMMs capturable into the step graph
+            if ((st = talloc(t, (char **)&t->d_blas_ws, (size_t)64 << 20))) break;
+            t->cb->set_workspace(t->blas, t->d_blas_ws, (size_t)64 << 20);
+        }
         const size_t C = shape->channels, Hv = shape->value_hidden, N = max_batch, P = N * 64;
         const int L = (int)t->conv.size();
         if ((st = talloc(t, &t->d_params, t->n_params)) || (st = talloc(t, &t->d_grads, t->n_params)) || (st = talloc(t, &t->d_mom, t->n_params)) ||
             (st = talloc(t, &t->d_buffers, t->n_buffers)) || (st = talloc(t, &t->d_features, N * shape->in_planes * 64)) ||
             (st = talloc(t, &t->d_tpolicy, N * 65)) || (st = talloc(t, &t->d_tvalue, N)) || (st = talloc(t, &t->d_x0, P * 32)) ||
-            (st = talloc(t, &t->d_mean, L * C)) || (st = talloc(t, &t->d_invstd, L * C)) || (st = talloc(t, &t->d_sums, 2 * C)) ||
+            (st = talloc(t, &t->d_mean, L * C)) || (st = talloc(t, &t->d_invstd, L * C)) || (st = talloc(t, &t->d_sums, (size_t)2 * L * 2 * C)) ||
             (st = talloc(t, &t->d_zero_bias, C)) || (st = talloc(t, &t->d_dA, P * C)) || (st = talloc(t, &t->d_dA2, P * C)) ||
             (st = talloc(t, &t->d_dY, P * C)) || (st = talloc(t, &t->d_dZ, P * C)) || (st = talloc(t, &t->d_cols, P * 9 * C)) ||
             (st = talloc(t, &t->d_G, C * 9 * C)) || (st = talloc(t, &t->d_h, 3 * P)) || (st = talloc(t, &t->d_hn, 3 * P)) ||
@@ -630,12 +770,20 @@ int oz_trainer_create(int device, const oz_resnet_shape *shape, int max_batch, o
             (st = talloc(t, &t->d_value, N)) || (st = talloc(t, &t->d_dlogits, N * 65)) || (st = talloc(t, &t->d_u, N * Hv)) ||
             (st = talloc(t, &t->d_dvpre, N)) || (st = talloc(t, &t->d_loss, 4)))
             break;
+        if (cudaFuncSetAttribute(head_fc_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((65 * 128 + Hv * 64) * sizeof(float))) != cudaSuccess) {
+            st = fail(OZ_ERR_CUDA, "value_head_hidden_channels too large for the trainer's head kernel"); break;
+        }
         t->A.resize(L); t->Z.resize(L);
         for (int l = 0; l < L && !st; ++l) {
             ConvLayerT &c = t->conv[l];
             if ((st = talloc(t, &t->A[l], P * C)) || (st = talloc(t, &t->Z[l], P * C)) || (st = talloc(t, &c.wf, (size_t)9 * C * c.cinp))) break;
             if (l > 0 && (st = talloc(t, &c.wd, (size_t)9 * C * C))) break;
         }
+        if (st) break;
+        std::vector<PackDesc> desc(L);
+        for (int l = 0; l < L; ++l) desc[l] = PackDesc{t->conv[l].w, t->conv[l].cin, t->conv[l].cinp, t->conv[l].wf, t->conv[l].wd};
+        if ((st = talloc(t, &t->d_pack, (size_t)L))) break;
+        if (cudaMemcpy(t->d_pack, desc.data(), L * sizeof(PackDesc), cudaMemcpyHostToDevice) != cudaSuccess) { st = fail(OZ_ERR_CUDA, "descriptor upload failed"); break; }
     } while (0);
     if (st) { oz_trainer_destroy(t); return st; }
     *out = t;
@@ -646,6 +794,7 @@ void oz_trainer_destroy(oz_trainer *t) {
     if (!t) return;
     cudaSetDevice(t->device);
     if (t->stream) cudaStreamSynchronize(t->stream);
+    if (t->graph) cudaGraphExecDestroy(t->graph);
     if (t->blas && t->cb) t->cb->destroy(t->blas);
     for (void *p : t->allocs) cudaFree(p);
     if (t->stream) cudaStreamDestroy(t->stream);
@@ -681,13 +830,24 @@ int oz_trainer_step(oz_trainer *t, const float *features, const float *policy, c
     OZ_CUDA(cudaMemcpyAsync(t->d_features, features, (size_t)n * t->shape.in_planes * 64 * sizeof(float), cudaMemcpyHostToDevice, t->stream));
     OZ_CUDA(cudaMemcpyAsync(t->d_tpolicy, policy, (size_t)n * 65 * sizeof(float), cudaMemcpyHostToDevice, t->stream));
     OZ_CUDA(cudaMemcpyAsync(t->d_tvalue, value, (size_t)n * sizeof(float), cudaMemcpyHostToDevice, t->stream));
-    return step_device(t, t->d_features, t->d_tpolicy, t->d_tvalue, n, cfg, apply_update, losses);
+    return execute_step(t, n, cfg, apply_update, losses);
 }
 
 int oz_trainer_step_device(oz_trainer *t, const float *features, const float *policy, const float *value, int n, const oz_train_config *cfg,
                            int apply_update, float *losses) {
     OZ_CUDA(cudaSetDevice(t->device));
-    return step_device(t, features, policy, value, n, cfg, apply_update, losses);
+    if (n < 1 || n > t->max_batch) return fail(OZ_ERR_INVALID_ARGUMENT, "Expected 1 <= batch <= max_batch, but got " + std::to_string(n) + ".");
+    // staged into the trainer's own buffers so that the captured step always reads the same addresses
+    OZ_CUDA(cudaMemcpyAsync(t->d_features, features, (size_t)n * t->shape.in_planes * 64 * sizeof(float), cudaMemcpyDeviceToDevice, t->stream));
+    OZ_CUDA(cudaMemcpyAsync(t->d_tpolicy, policy, (size_t)n * 65 * sizeof(float), cudaMemcpyDeviceToDevice, t->stream));
+    OZ_CUDA(cudaMemcpyAsync(t->d_tvalue, value, (size_t)n * sizeof(float), cudaMemcpyDeviceToDevice, t->stream));
+    return execute_step(t, n, cfg, apply_update, losses);
+}
+
+int oz_trainer_set_graphs(oz_trainer *t, int on) {
+    t->use_graphs = on != 0;
+    if (!on) drop_step_graph(t);
+    return OZ_OK;
 }
 
 int oz_trainer_outputs(oz_trainer *t, int n, float *policy, float *value) {

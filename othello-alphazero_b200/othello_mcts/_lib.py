@@ -130,6 +130,7 @@ SIGNATURES = {
     "oz_trainer_step": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, P(OzTrainConfig), C.c_int, C.c_void_p]),
     "oz_trainer_step_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, P(OzTrainConfig), C.c_int, C.c_void_p]),
     "oz_trainer_outputs": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
+    "oz_trainer_set_graphs": (C.c_int, [C.c_void_p, C.c_int]),
     "oz_trainer_stream": (C.c_void_p, [C.c_void_p]),
 }
 

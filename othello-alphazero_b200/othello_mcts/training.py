@@ -116,6 +116,10 @@ class NativeTrainer:
             check(self._lib.oz_trainer_step(self._h, _ptr(f), _ptr(p), _ptr(v), n, C.byref(self.cfg), int(apply_update), _ptr(losses)))
         return {"total_loss": float(losses[0]), "policy_loss": float(losses[1]), "value_loss": float(losses[2]), "l2_loss": float(losses[3])}
 
+    def set_graphs(self, on: bool) -> None:
+        """CUDA-graph replay of the step (default on; identical results)."""
+        check(self._lib.oz_trainer_set_graphs(self._h, int(on)))
+
     def outputs(self, n: int):
         """(policy [n,65], value [n]) of the last step's forward pass (train mode)."""
         p, v = np.zeros((n, 65), np.float32), np.zeros(n, np.float32)

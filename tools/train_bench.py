@@ -29,6 +29,8 @@ def main():
     ap.add_argument("--channels", type=int, default=128)
     ap.add_argument("--blocks", type=int, default=9)
     ap.add_argument("--hidden", type=int, default=128)
+    ap.add_argument("--skip-pytorch", action="store_true", help="time only the native step (for ncu captures)")
+    ap.add_argument("--graphs", type=int, default=1, help="CUDA-graph replay of the native step")
     ap.add_argument("--tf32", type=int, default=1, help="PyTorch arm: allow TF32 convolutions (the PyTorch default)")
     a = ap.parse_args()
     torch.backends.cudnn.allow_tf32 = bool(a.tf32)
@@ -71,10 +73,11 @@ def main():
     def native_step():
         check(lib.oz_trainer_step_device(h, C.c_void_p(f.data_ptr()), C.c_void_p(p.data_ptr()), C.c_void_p(v.data_ptr()), n, C.byref(tr.cfg), 1, None))
 
-    t_ref = time_it(lambda: ref_step(), a.steps)
+    tr.set_graphs(bool(a.graphs))
+    t_ref = float("nan") if a.skip_pytorch else time_it(lambda: ref_step(), a.steps)
     t_nat = time_it(native_step, a.steps)
     flop = 3 * n * (2 * 576 * a.channels * (17 + 2 * a.blocks * a.channels))       # forward + input gradients + weight gradients of the 3x3 convolutions
-    print(json.dumps({"network": f"{a.channels}x{a.blocks + 1}b", "batch": n, "steps": a.steps,
+    print(json.dumps({"network": f"{a.channels}x{a.blocks + 1}b", "batch": n, "steps": a.steps, "graphs": bool(a.graphs),
                       "native_ms_per_step": 1e3 * t_nat, "native_samples_per_s": n / t_nat, "native_conv_tflops": flop / t_nat / 1e12,
                       "pytorch_ms_per_step": 1e3 * t_ref, "pytorch_samples_per_s": n / t_ref, "pytorch_tf32": bool(a.tf32),
                       "speedup": t_ref / t_nat, "epoch_480k_native_s": 480000 / n * t_nat, "epoch_480k_pytorch_s": 480000 / n * t_ref}))
