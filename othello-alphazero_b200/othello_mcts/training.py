@@ -106,7 +106,7 @@ class NativeTrainer:
         n = int(features.shape[0])
         if isinstance(features, torch.Tensor) and features.is_cuda:
             f, p, v = (t.detach().to(torch.float32).contiguous() for t in (features, policy, value))
-            torch.cuda.current_stream(f.device).synchronize()
+            torch.cuda.current_stream(f.device).synchronize()    # the tensors are complete; the call below blocks until the losses are back
             check(self._lib.oz_trainer_step_device(self._h, C.c_void_p(f.data_ptr()), C.c_void_p(p.data_ptr()), C.c_void_p(v.data_ptr()), n,
                                                    C.byref(self.cfg), int(apply_update), _ptr(losses)))
         else:
@@ -115,6 +115,21 @@ class NativeTrainer:
             v = np.ascontiguousarray(np.asarray(value, dtype=np.float32))
             check(self._lib.oz_trainer_step(self._h, _ptr(f), _ptr(p), _ptr(v), n, C.byref(self.cfg), int(apply_update), _ptr(losses)))
         return {"total_loss": float(losses[0]), "policy_loss": float(losses[1]), "value_loss": float(losses[2]), "l2_loss": float(losses[3])}
+
+    def step_async(self, features, policy, value) -> None:
+        """`step` for CUDA tensors without reading the losses back (no host synchronisation: steps queue up on the
+        trainer's stream).  The inputs are copied into the trainer's own buffers before the call returns control to the
+        stream, so the caller may drop them."""
+        n = int(features.shape[0])
+        f, p, v = (t.detach().to(torch.float32).contiguous() for t in (features, policy, value))
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(f.device))
+        ts = torch.cuda.ExternalStream(self._lib.oz_trainer_stream(self._h), device=f.device)
+        ts.wait_event(ev)                                    # the trainer's stream reads the tensors after they are produced
+        check(self._lib.oz_trainer_step_device(self._h, C.c_void_p(f.data_ptr()), C.c_void_p(p.data_ptr()), C.c_void_p(v.data_ptr()), n,
+                                               C.byref(self.cfg), 1, None))
+        for t in (f, p, v):
+            t.record_stream(ts)                              # keep the allocator from reusing them before the copy has run
 
     def set_graphs(self, on: bool) -> None:
         """CUDA-graph replay of the step (default on; identical results)."""

@@ -128,6 +128,11 @@ def test_training_reduces_the_loss_and_feeds_self_play():
         last = trainer.step(f, p, v)
     # the policy targets are random distributions: their entropy (about 3.3 nats) is the floor of the cross-entropy
     assert last["policy_loss"] < 0.9 * first["policy_loss"] and last["value_loss"] < 0.7 * first["value_loss"], (first, last)
+    fc, pc, vc = f.cuda(), p.cuda(), v.cuda()              # device-resident batches, queued without reading the losses back
+    for _ in range(5):
+        trainer.step_async(fc, pc, vc)
+    after = trainer.step(fc, pc, vc)
+    assert np.isfinite(list(after.values())).all() and after["policy_loss"] <= last["policy_loss"] + 0.05
     trainer.store_to(net)
     eng = SelfPlayEngine(4, history_size=4, num_simulations=32, num_threads=1, batch_size=8, seed=1)
     eng.search(net.eval())
