@@ -36,7 +36,8 @@ MCTS_KW = dict(history_size=8, num_simulations=800, num_threads=2, batch_size=16
 
 
 # dram__bytes_read.sum + dram__bytes_write.sum of a conv launch per board, from one ncu --set full capture of a 128 -> 128
-# layer over 32768 boards (profiles/r01_conv_pair_kernel.json): plain layer 0.537 + 0.497 GB, residual layer 1.074 + 0.496 GB.
+# layer over 32768 boards (profiles/r01_conv_final_kernel.json, same figures as the earlier r01_conv_pair_kernel.json): plain layer
+# 0.537 + 0.496 GB, residual layer 1.074 + 0.496 GB.
 NCU_TRAFFIC_BYTES_PER_BOARD = (0.537230e9 + 0.498725e9 + 1.074230e9 + 0.494879e9) / 2 / 32768
 
 

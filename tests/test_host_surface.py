@@ -133,6 +133,34 @@ def test_no_gpu_fails_loudly():
         MCTS()
     with pytest.raises(RuntimeError):
         movegen_batch(np.array([1], np.uint64), np.array([2], np.uint64))
+    from othello_mcts.neural_net import AlphaZeroNet
+    from othello_mcts.training import NativeTrainer
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        NativeTrainer(AlphaZeroNet(9, conv_channels=128, num_residual_blocks=1, value_head_hidden_channels=32), max_batch=32)
+    from othello_mcts import MatchEngine
+    with pytest.raises(RuntimeError, match="no CUDA device"):
+        MatchEngine(2)
+
+
+def test_trainer_state_vectors_follow_the_module():
+    """The trainer's flat parameter / buffer vectors are the module's parameters() order and its BatchNorm buffers in
+    module order: the element counts the C ABI computes from the shape must equal what PyTorch reports (checked here
+    without a device through the same formulas; oz_trainer_create is exercised by the GPU tests)."""
+    import torch
+    from othello_mcts.neural_net import AlphaZeroNet
+    for blocks, hv in ((1, 32), (9, 128)):
+        net = AlphaZeroNet(17, conv_channels=128, num_residual_blocks=blocks, value_head_hidden_channels=hv)
+        C, L = 128, 1 + 2 * blocks
+        n_params = C * 17 * 9 + 3 * C + (L - 1) * (C * C * 9 + 3 * C) + (2 * C + 2 + 2 + 2 + 65 * 128 + 65) + (C + 1 + 1 + 1 + hv * 64 + hv + hv + 1)
+        assert n_params == sum(p.numel() for p in net.parameters())
+        n_buffers = 2 * C * L + 4 + 2
+        assert n_buffers == sum(2 * m.num_features for m in net.modules() if isinstance(m, torch.nn.BatchNorm2d))
+        names = [n for n, _ in net.named_parameters()]
+        assert names[:4] == ["conv_block.conv.weight", "conv_block.conv.bias", "conv_block.norm.weight", "conv_block.norm.bias"]
+        assert names[-14:-8] == ["policy_head.conv.weight", "policy_head.conv.bias", "policy_head.norm.weight", "policy_head.norm.bias",
+                                 "policy_head.linear.weight", "policy_head.linear.bias"]
+        assert names[-8:] == ["value_head.conv.weight", "value_head.conv.bias", "value_head.norm.weight", "value_head.norm.bias",
+                              "value_head.linear1.weight", "value_head.linear1.bias", "value_head.linear2.weight", "value_head.linear2.bias"]
 
 
 def test_product_does_not_import_oracle():
