@@ -43,6 +43,7 @@ class NativeTrainer:
         if bns:
             self.cfg.bn_momentum, self.cfg.bn_eps = bns[0].momentum, bns[0].eps
         self.max_batch = (max_batch + 31) // 32 * 32
+        self._inflight = []
         self._h = C.c_void_p()
         check(self._lib.oz_trainer_create(cuda_device, C.byref(self.shape), self.max_batch, C.byref(self._h)))
         self.num_params = self._lib.oz_trainer_num_params(self._h)
@@ -52,8 +53,9 @@ class NativeTrainer:
     def __del__(self):
         h = getattr(self, "_h", None)
         if h:
-            self._lib.oz_trainer_destroy(h)
+            self._lib.oz_trainer_destroy(h)                 # synchronises the trainer's stream first
             self._h = None
+        self._inflight = []
 
     # -- state exchange with the torch module ------------------------------------------------------------------
     def load_from(self, net, momentum_buffers=None) -> None:
@@ -118,8 +120,8 @@ class NativeTrainer:
 
     def step_async(self, features, policy, value) -> None:
         """`step` for CUDA tensors without reading the losses back (no host synchronisation: steps queue up on the
-        trainer's stream).  The inputs are copied into the trainer's own buffers before the call returns control to the
-        stream, so the caller may drop them."""
+        trainer's stream).  The trainer keeps the tensors alive until the step that reads them has finished, so the
+        caller may drop them."""
         n = int(features.shape[0])
         f, p, v = (t.detach().to(torch.float32).contiguous() for t in (features, policy, value))
         ev = torch.cuda.Event()
@@ -128,8 +130,12 @@ class NativeTrainer:
         ts.wait_event(ev)                                    # the trainer's stream reads the tensors after they are produced
         check(self._lib.oz_trainer_step_device(self._h, C.c_void_p(f.data_ptr()), C.c_void_p(p.data_ptr()), C.c_void_p(v.data_ptr()), n,
                                                C.byref(self.cfg), 1, None))
-        for t in (f, p, v):
-            t.record_stream(ts)                              # keep the allocator from reusing them before the copy has run
+        # the inputs must outlive the queued copy: hold them until the step that consumed them has finished
+        done = torch.cuda.Event()
+        done.record(ts)
+        self._inflight.append((done, f, p, v))
+        while self._inflight and self._inflight[0][0].query():
+            self._inflight.pop(0)
 
     def set_graphs(self, on: bool) -> None:
         """CUDA-graph replay of the step (default on; identical results)."""

@@ -49,8 +49,8 @@ def _momentum_vector(opt, net):
     return torch.nn.utils.parameters_to_vector(bufs).detach().cpu().numpy()
 
 
-@pytest.mark.parametrize("blocks,hidden,n", [(2, 32, 64), (3, 128, 96)])
-def test_training_step_matches_pytorch_autograd(blocks, hidden, n):
+@pytest.mark.parametrize("channels,blocks,hidden,n", [(128, 2, 32, 64), (128, 3, 128, 96), (256, 1, 64, 32)])
+def test_training_step_matches_pytorch_autograd(channels, blocks, hidden, n):
     """Three consecutive steps of the reference loop; before each one the native trainer takes over the reference's state
     (parameters, BatchNorm buffers, SGD momentum), so every step is compared at identical weights: losses, network outputs,
     the gradient of every parameter tensor, the SGD update and the BatchNorm running statistics.
@@ -65,7 +65,7 @@ def test_training_step_matches_pytorch_autograd(blocks, hidden, n):
     from othello_mcts.training import NativeTrainer
     torch.manual_seed(3)
     planes, lr, mom, l2 = 9, 0.02, 0.9, 1e-4
-    ref = AlphaZeroNet(planes, conv_channels=128, num_residual_blocks=blocks, value_head_hidden_channels=hidden).cuda()
+    ref = AlphaZeroNet(planes, conv_channels=channels, num_residual_blocks=blocks, value_head_hidden_channels=hidden).cuda()
     with torch.no_grad():                                   # non-trivial BatchNorm parameters and biases
         for p in ref.parameters():
             if p.dim() == 1:
