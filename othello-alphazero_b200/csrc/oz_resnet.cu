@@ -789,6 +789,10 @@ int ResNet::forward(const float *d_features, size_t n, float *d_policy, float *d
         planes_to_nhwc32_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, stream>>>(d_features, shape_.in_planes, n, pad, (__nv_bfloat16 *)d_x0_);
         count_launch();
     }
+    // Last layer of a 128-channel tower (pair kernel): the epilogue also applies the three 1x1 head convolutions to its
+    // fp32 values, so the final activation tensor is never written and the head kernel reads 1 KB instead of 16 KB per board.
+    const bool fuse_heads = C == 128 && shape_.blocks > 0 && d_head_pre_ != nullptr;
+    if (fuse_heads) OZ_CUDA(cudaMemsetAsync(d_head_pre_, 0, pad * 64 * 4 * sizeof(float), stream));   // up front: nothing sits between the conv launches
     if (conv_begin) cudaEventRecord(conv_begin, stream);
     ConvParams cp{};
     cp.units = (int)(pad / kBoardsPerUnit); cp.cout_total = C; cp.relu = 1;
@@ -796,17 +800,11 @@ int ResNet::forward(const float *d_features, size_t n, float *d_policy, float *d
     cp.kblocks = 1; cp.skip = nullptr; cp.out = (__nv_bfloat16 *)d_a_; cp.bias = (const float *)(d_blob_ + layout_.conv_b[0]);
     OZ_TRY(launch_conv(map_x0_, map_w_[0], cp, stream, pdl_));
     cp.kblocks = C / kKBlock;
-    // Last layer of a 128-channel tower (pair kernel): the epilogue also applies the three 1x1 head convolutions to its
-    // fp32 values, so the final activation tensor is never written and the head kernel reads 1 KB instead of 16 KB per board.
-    const bool fuse_heads = C == 128 && shape_.blocks > 0 && d_head_pre_ != nullptr;
     for (int b = 0; b < shape_.blocks; ++b) {   // residual tower (neural_net.py:32-65)
         cp.skip = nullptr; cp.out = (__nv_bfloat16 *)d_t_; cp.bias = (const float *)(d_blob_ + layout_.conv_b[1 + 2 * b]);
         OZ_TRY(launch_conv(map_a_, map_w_[1 + 2 * b], cp, stream, pdl_));
         cp.skip = (const __nv_bfloat16 *)d_a_; cp.out = (__nv_bfloat16 *)d_a_; cp.bias = (const float *)(d_blob_ + layout_.conv_b[2 + 2 * b]);
-        if (fuse_heads && b == shape_.blocks - 1) {
-            OZ_CUDA(cudaMemsetAsync(d_head_pre_, 0, pad * 64 * 4 * sizeof(float), stream));
-            cp.out = nullptr; cp.head_w = (const float *)(d_blob_ + layout_.head_w); cp.head_out = d_head_pre_;
-        }
+        if (fuse_heads && b == shape_.blocks - 1) { cp.out = nullptr; cp.head_w = (const float *)(d_blob_ + layout_.head_w); cp.head_out = d_head_pre_; }
         OZ_TRY(launch_conv(map_t_, map_w_[2 + 2 * b], cp, stream, pdl_));
         cp.head_w = nullptr; cp.head_out = nullptr;
     }
