@@ -81,8 +81,18 @@ class ClockSampler:
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
-        sm = sorted(float(r[1]) for r in self.rows if len(r) > 8 and r[1].replace(".", "").isdigit())
-        mx = [float(r[2]) for r in self.rows if len(r) > 8 and r[2].replace(".", "").isdigit()]
+        rows = [r for r in self.rows if len(r) > 8 and r[1].replace(".", "").isdigit()]
+        # "under load" = samples whose power draw is at least half of the highest one seen: the sampler also runs while
+        # the ranks wait for each other at the barriers around the timed region
+        def _f(x):
+            try:
+                return float(x)
+            except ValueError:
+                return 0.0
+        pmax = max((_f(r[3]) for r in rows), default=0.0)
+        loaded = [r for r in rows if _f(r[3]) >= 0.5 * pmax] or rows
+        sm = sorted(float(r[1]) for r in loaded)
+        mx = [float(r[2]) for r in rows if r[2].replace(".", "").isdigit()]
         reasons = set()
         for r in self.rows:
             if len(r) > 8:
@@ -90,7 +100,7 @@ class ClockSampler:
                     if v.lower().startswith("active"):
                         reasons.add(name)
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons),
-                "samples": len(sm)}
+                "samples": len(rows), "samples_under_load": len(sm), "power_w_max": pmax}
 
 
 # ----------------------------------------------------------------------------------------------

@@ -34,6 +34,9 @@ def _gather_tensor(t: torch.Tensor, dst: int, group) -> torch.Tensor | None:
     """Concatenate per-rank tensors (dim 0 may differ) on `dst`.  Works on gloo (CPU) and nccl (CUDA)."""
     import torch.distributed as dist
     world, rank = dist.get_world_size(group), dist.get_rank(group)
+    home = t.device
+    if dist.get_backend(group) == "nccl" and not t.is_cuda:      # NCCL moves device memory: stage host tensors on this rank's GPU
+        t = t.cuda()
     n = torch.tensor([t.shape[0]], dtype=torch.int64, device=t.device)
     sizes = [torch.zeros_like(n) for _ in range(world)]
     dist.all_gather(sizes, n, group=group)
@@ -44,7 +47,7 @@ def _gather_tensor(t: torch.Tensor, dst: int, group) -> torch.Tensor | None:
     if rank == dst:
         bufs = [torch.empty_like(padded) for _ in range(world)]
         dist.gather(padded, bufs, dst=dst, group=group)
-        return torch.cat([b[:k] for b, k in zip(bufs, sizes)], dim=0)
+        return torch.cat([b[:k] for b, k in zip(bufs, sizes)], dim=0).to(home)
     dist.gather(padded, None, dst=dst, group=group)
     return None
 
