@@ -27,6 +27,23 @@ namespace {
 
 typedef __nv_bfloat16 bf16;
 
+// Programmatic dependent launch for the many small kernels of a step: every kernel lets its successor become resident at
+// once and waits for its predecessor's results before touching memory, so the launch latency of a kernel overlaps the
+// execution of the one before it (a kernel completes only after its own wait, hence completion stays transitive).
+#define OZ_PDL_PROLOGUE() asm volatile("griddepcontrol.launch_dependents;\n\tgriddepcontrol.wait;" ::: "memory")
+
+template <typename... KArgs, typename... Args>
+inline void launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+    count_launch();
+}
+
 // ------------------------------------------------------------------ cuBLAS through dlopen
 struct Cublas {
     void *lib = nullptr;
@@ -83,6 +100,7 @@ __device__ float block_sum(float v, float *scratch /* >= 32 floats */) {
 //   wd bf16 [9][cin][C] (cin==C)  input-gradient operand: Wd[8 - tap][ci][co] = W[co][ci][tap]
 struct PackDesc { size_t w; int cin, cinp; bf16 *wf, *wd; };      // one per conv layer (blockIdx.y)
 __global__ void pack_weights_kernel(const float *__restrict__ params, const PackDesc *__restrict__ desc, int C) {
+    OZ_PDL_PROLOGUE();
     const PackDesc d = desc[blockIdx.y];
     const float *w = params + d.w;
     const int cin = d.cin, cinp = d.cinp;
@@ -128,6 +146,7 @@ __device__ __forceinline__ void bn_block_reduce(float (&a)[8], float (&b)[8], in
 
 // sums[c] += sum z, sums[C + c] += sum z^2.
 __global__ void __launch_bounds__(256) bn_stats_kernel(const bf16 *__restrict__ z, size_t P, int C, float *__restrict__ sums) {
+    OZ_PDL_PROLOGUE();
     const int tpr = C / 8, rows = blockDim.x / tpr;
     const int cg = threadIdx.x % tpr, r0 = threadIdx.x / tpr;
     float s[8], q[8];
@@ -158,6 +177,7 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(const bf16 *__restrict__ 
                                                        const float *__restrict__ conv_bias, float eps, float momentum, float *__restrict__ mean_out,
                                                        float *__restrict__ invstd_out, float *__restrict__ run_mean, float *__restrict__ run_var,
                                                        bf16 *__restrict__ a) {
+    OZ_PDL_PROLOGUE();
     const float count = (float)P;
     if (blockIdx.x == 0)
         for (int c = threadIdx.x; c < C; c += blockDim.x) {
@@ -188,6 +208,7 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(const bf16 *__restrict__ 
 __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const bf16 *__restrict__ da, const bf16 *__restrict__ a, const bf16 *__restrict__ z,
                                                             size_t P, int C, const float *__restrict__ mean, const float *__restrict__ invstd,
                                                             float *__restrict__ s) {
+    OZ_PDL_PROLOGUE();
     const int tpr = C / 8, rows = blockDim.x / tpr;
     const int cg = threadIdx.x % tpr, r0 = threadIdx.x / tpr;
     float m[8], iv[8], s1[8], s2[8];
@@ -210,6 +231,7 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const bf16 *__restric
                                                            size_t P, int C, const float *__restrict__ mean, const float *__restrict__ invstd,
                                                            const float *__restrict__ gamma, const float *__restrict__ s, bf16 *__restrict__ dz,
                                                            bf16 *__restrict__ dy_out, float *__restrict__ dgamma, float *__restrict__ dbeta) {
+    OZ_PDL_PROLOGUE();
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (blockIdx.x == 0) for (int c = threadIdx.x; c < C; c += blockDim.x) { dgamma[c] = s[C + c]; dbeta[c] = s[c]; }
     if (i >= P * (size_t)(C / 8)) return;
@@ -231,6 +253,7 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const bf16 *__restric
 // ------------------------------------------------------------------ weight gradient: im2col + (cuBLAS) + scatter
 // x bf16 [N][8][8][cinp] -> cols bf16 [P][9][cinp], zero outside the board; one thread per 16-byte channel group.
 __global__ void im2col_kernel(const bf16 *__restrict__ x, size_t P, int cinp, bf16 *__restrict__ cols) {
+    OZ_PDL_PROLOGUE();
     const int gpt = cinp / 8;
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= P * 9 * gpt) return;
@@ -244,6 +267,7 @@ __global__ void im2col_kernel(const bf16 *__restrict__ x, size_t P, int cinp, bf
 
 // G fp32 [C][9][cinp] (GEMM output) -> dW fp32 [C][cin][9] (OIHW)
 __global__ void wgrad_scatter_kernel(const float *__restrict__ G, int C, int cin, int cinp, float *__restrict__ dw) {
+    OZ_PDL_PROLOGUE();
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= C * cin * 9) return;
     const int tap = idx % 9, ci = (idx / 9) % cin, co = idx / (9 * cin);
@@ -254,6 +278,7 @@ __global__ void wgrad_scatter_kernel(const float *__restrict__ G, int C, int cin
 // h[k][p] = sum_c a[p][c] * w[k][c] + b[k], k = 0, 1 (policy), 2 (value); one warp per position.
 __global__ void head_conv_fwd_kernel(const bf16 *__restrict__ a, size_t P, int C, const float *__restrict__ pw, const float *__restrict__ pb,
                                      const float *__restrict__ vw, const float *__restrict__ vb, float *__restrict__ h) {
+    OZ_PDL_PROLOGUE();
     const size_t p = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (p >= P) return;
@@ -272,6 +297,7 @@ __global__ void head_bn_fwd_kernel(const float *__restrict__ h, size_t P, const 
                                    const float *__restrict__ gamma_v, const float *__restrict__ beta_v, float eps, float momentum,
                                    float *__restrict__ run_p /* mean[2], var[2] */, float *__restrict__ run_v /* mean[1], var[1] */,
                                    float *__restrict__ stat, float *__restrict__ hn, float *__restrict__ hp, float *__restrict__ hv) {
+    OZ_PDL_PROLOGUE();
     __shared__ float scratch[32];
     __shared__ float sh_mean, sh_inv;
     const int k = blockIdx.x;
@@ -304,6 +330,7 @@ __global__ void head_fc_fwd_kernel(const float *__restrict__ hp, const float *__
                                    const float *__restrict__ w2, const float *__restrict__ b2, const float *__restrict__ tp,
                                    const float *__restrict__ tv, float *__restrict__ policy, float *__restrict__ value, float *__restrict__ dlogits,
                                    float *__restrict__ u, float *__restrict__ dvpre, float *__restrict__ loss) {
+    OZ_PDL_PROLOGUE();
     // the FC weights are staged in shared memory once per block (65 x 128 + Hv x 64 floats), boards are strided over warps
     extern __shared__ float fc_sm[];
     float *s_lw = fc_sm, *s_w1 = fc_sm + 65 * 128;
@@ -370,6 +397,7 @@ __global__ void head_fc_bwd_params_kernel(const float *__restrict__ hp, const fl
                                           const float *__restrict__ u, const float *__restrict__ dvpre, const float *__restrict__ w2, int N, int Hv,
                                           float *__restrict__ dlw, float *__restrict__ dlb, float *__restrict__ dw1, float *__restrict__ db1,
                                           float *__restrict__ dw2, float *__restrict__ db2) {
+    OZ_PDL_PROLOGUE();
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     const int n_lw = 65 * 128, n_w1 = Hv * 64;
     if (idx < n_lw) {
@@ -417,6 +445,7 @@ __global__ void head_fc_bwd_params_kernel(const float *__restrict__ hp, const fl
 __global__ void head_fc_bwd_input_kernel(const float *__restrict__ dlogits, const float *__restrict__ lw, const float *__restrict__ u,
                                          const float *__restrict__ dvpre, const float *__restrict__ w1, const float *__restrict__ w2,
                                          const float *__restrict__ hn, size_t P, int Hv, float *__restrict__ dhn) {
+    OZ_PDL_PROLOGUE();
     const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= 3 * P) return;
     const int k = (int)(idx / P);
@@ -437,6 +466,7 @@ __global__ void head_fc_bwd_input_kernel(const float *__restrict__ dlogits, cons
 __global__ void head_bn_bwd_kernel(const float *__restrict__ h, const float *__restrict__ dhn, size_t P, const float *__restrict__ stat,
                                    const float *__restrict__ gamma_p, const float *__restrict__ gamma_v, float *__restrict__ dh,
                                    float *__restrict__ dgamma_p, float *__restrict__ dbeta_p, float *__restrict__ dgamma_v, float *__restrict__ dbeta_v) {
+    OZ_PDL_PROLOGUE();
     __shared__ float scratch[32];
     __shared__ float sh1, sh2;
     const int k = blockIdx.x;
@@ -460,6 +490,7 @@ __global__ void head_bn_bwd_kernel(const float *__restrict__ h, const float *__r
 __global__ void head_conv_bwd_kernel(const bf16 *__restrict__ a, const float *__restrict__ dh, size_t P, int C, const float *__restrict__ pw,
                                      const float *__restrict__ vw, bf16 *__restrict__ da, float *__restrict__ dpw, float *__restrict__ dpb,
                                      float *__restrict__ dvw, float *__restrict__ dvb) {
+    OZ_PDL_PROLOGUE();
     __shared__ float sd[3][64];
     const size_t p0 = (size_t)blockIdx.x * 64;
     for (int i = threadIdx.x; i < 3 * 64; i += blockDim.x) sd[i / 64][i % 64] = p0 + (i % 64) < P ? dh[(size_t)(i / 64) * P + p0 + (i % 64)] : 0.f;
@@ -485,6 +516,7 @@ __global__ void head_conv_bwd_kernel(const bf16 *__restrict__ a, const float *__
 // g += 2 * l2 * p; loss[2] += l2 * sum p^2; if (apply) { buf = momentum * buf + g; p -= lr * buf; }
 __global__ void l2_sgd_kernel(float *__restrict__ p, float *__restrict__ g, float *__restrict__ buf, size_t n, float l2, float lr, float momentum,
                               int apply, float *__restrict__ loss) {
+    OZ_PDL_PROLOGUE();
     __shared__ float scratch[32];
     float sq = 0.f;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
@@ -586,8 +618,7 @@ void layout_params(oz_trainer *t) {
 
 int pack_all_weights(oz_trainer *t) {
     const int C = t->shape.channels, L = (int)t->conv.size();
-    pack_weights_kernel<<<dim3(grid_for((size_t)9 * C * C, 256), L), 256, 0, t->stream>>>(t->d_params, t->d_pack, C);
-    count_launch();
+    launch_pdl(pack_weights_kernel, dim3(dim3(grid_for((size_t)9 * C * C, 256), L)), dim3(256), 0, t->stream, t->d_params, t->d_pack, C);
     OZ_CUDA(cudaGetLastError());
     return OZ_OK;
 }
@@ -613,33 +644,33 @@ int run_step(oz_trainer *t, int n, const oz_train_config *cfg, int apply) {
         const bf16 *in = l == 0 ? t->d_x0 : t->A[l - 1];
         OZ_TRY(ResNet::conv3x3(in, c.cinp, c.wf, t->d_zero_bias, nullptr, 0, t->Z[l], C, (size_t)n, s));
         float *fsum = t->d_sums + (size_t)l * 2 * C;
-        bn_stats_kernel<<<bn_grid, bn_block, 0, s>>>(t->Z[l], P, C, fsum); count_launch();
+        launch_pdl(bn_stats_kernel, dim3(bn_grid), dim3(bn_block), 0, s, t->Z[l], P, C, fsum);
         const bf16 *skip = (l >= 2 && l % 2 == 0) ? t->A[l - 2] : nullptr;     // second conv of a residual block
-        bn_apply_kernel<<<grid_for(vec8, 256), 256, 0, s>>>(t->Z[l], skip, P, C, fsum, par + c.gamma, par + c.beta, par + c.b, cfg->bn_eps,
+        launch_pdl(bn_apply_kernel, dim3(grid_for(vec8, 256)), dim3(256), 0, s, t->Z[l], skip, P, C, fsum, par + c.gamma, par + c.beta, par + c.b, cfg->bn_eps,
                                                             cfg->bn_momentum, t->d_mean + (size_t)l * C, t->d_invstd + (size_t)l * C, buf + c.rm,
-                                                            buf + c.rv, t->A[l]); count_launch();
+                                                            buf + c.rv, t->A[l]);
     }
     // ---- heads forward + losses (neural_net.py:68-128, train.py:494-495)
     const bf16 *a_last = t->A[L - 1];
-    head_conv_fwd_kernel<<<grid_for(P * 32, 256), 256, 0, s>>>(a_last, P, C, par + t->pcw, par + t->pcb, par + t->vcw, par + t->vcb, t->d_h); count_launch();
-    head_bn_fwd_kernel<<<3, 1024, 0, s>>>(t->d_h, P, par + t->pg, par + t->pb, par + t->vg, par + t->vb, cfg->bn_eps, cfg->bn_momentum, buf + t->prm,
-                                          buf + t->vrm, t->d_stat, t->d_hn, t->d_hp, t->d_hv); count_launch();
+    launch_pdl(head_conv_fwd_kernel, dim3(grid_for(P * 32, 256)), dim3(256), 0, s, a_last, P, C, par + t->pcw, par + t->pcb, par + t->vcw, par + t->vcb, t->d_h);
+    launch_pdl(head_bn_fwd_kernel, dim3(3), dim3(1024), 0, s, t->d_h, P, par + t->pg, par + t->pb, par + t->vg, par + t->vb, cfg->bn_eps, cfg->bn_momentum, buf + t->prm,
+                                          buf + t->vrm, t->d_stat, t->d_hn, t->d_hp, t->d_hv);
     const size_t fc_smem = (size_t)(65 * 128 + Hv * 64) * sizeof(float);
-    head_fc_fwd_kernel<<<(unsigned)std::min<size_t>(148, (n + 7) / 8), 256, fc_smem, s>>>(t->d_hp, t->d_hv, n, Hv, par + t->plw, par + t->plb, par + t->v1w, par + t->v1b,
+    launch_pdl(head_fc_fwd_kernel, dim3((unsigned)std::min<size_t>(148, (n + 7) / 8)), dim3(256), fc_smem, s, t->d_hp, t->d_hv, n, Hv, par + t->plw, par + t->plb, par + t->v1w, par + t->v1b,
                                                                      par + t->v2w, par + t->v2b, d_tp, d_tv, t->d_policy, t->d_value, t->d_dlogits,
-                                                                     t->d_u, t->d_dvpre, t->d_loss); count_launch();
+                                                                     t->d_u, t->d_dvpre, t->d_loss);
     // ---- heads backward
     const int n_head_params = 65 * 128 + 65 + Hv * 64 + Hv + 1;
-    head_fc_bwd_params_kernel<<<grid_for(n_head_params, 128), 128, 0, s>>>(t->d_hp, t->d_hv, t->d_dlogits, t->d_u, t->d_dvpre, par + t->v2w, n, Hv,
+    launch_pdl(head_fc_bwd_params_kernel, dim3(grid_for(n_head_params, 128)), dim3(128), 0, s, t->d_hp, t->d_hv, t->d_dlogits, t->d_u, t->d_dvpre, par + t->v2w, n, Hv,
                                                                            grd + t->plw, grd + t->plb, grd + t->v1w, grd + t->v1b, grd + t->v2w,
-                                                                           grd + t->v2b); count_launch();
-    head_fc_bwd_input_kernel<<<grid_for(3 * P, 256), 256, 0, s>>>(t->d_dlogits, par + t->plw, t->d_u, t->d_dvpre, par + t->v1w, par + t->v2w, t->d_hn, P,
-                                                                  Hv, t->d_dhn); count_launch();
-    head_bn_bwd_kernel<<<3, 1024, 0, s>>>(t->d_h, t->d_dhn, P, t->d_stat, par + t->pg, par + t->vg, t->d_dh, grd + t->pg, grd + t->pb, grd + t->vg,
-                                          grd + t->vb); count_launch();
+                                                                           grd + t->v2b);
+    launch_pdl(head_fc_bwd_input_kernel, dim3(grid_for(3 * P, 256)), dim3(256), 0, s, t->d_dlogits, par + t->plw, t->d_u, t->d_dvpre, par + t->v1w, par + t->v2w, t->d_hn, P,
+                                                                  Hv, t->d_dhn);
+    launch_pdl(head_bn_bwd_kernel, dim3(3), dim3(1024), 0, s, t->d_h, t->d_dhn, P, t->d_stat, par + t->pg, par + t->vg, t->d_dh, grd + t->pg, grd + t->pb, grd + t->vg,
+                                          grd + t->vb);
     bf16 *dA = t->d_dA, *dA_other = t->d_dA2;
-    head_conv_bwd_kernel<<<grid_for(P, 64), 128, 0, s>>>(a_last, t->d_dh, P, C, par + t->pcw, par + t->vcw, dA, grd + t->pcw, grd + t->pcb, grd + t->vcw,
-                                                         grd + t->vcb); count_launch();
+    launch_pdl(head_conv_bwd_kernel, dim3(grid_for(P, 64)), dim3(128), 0, s, a_last, t->d_dh, P, C, par + t->pcw, par + t->vcw, dA, grd + t->pcw, grd + t->pcb, grd + t->vcw,
+                                                         grd + t->vcb);
     // ---- tower backward
     const float one = 1.f, zero = 0.f;
     for (int l = L - 1; l >= 0; --l) {
@@ -647,17 +678,17 @@ int run_step(oz_trainer *t, int n, const oz_train_config *cfg, int apply) {
         const float *mean = t->d_mean + (size_t)l * C, *inv = t->d_invstd + (size_t)l * C;
         const bool block_out = l >= 2 && l % 2 == 0;            // output of a residual block: dy also flows into the skip connection
         float *bsum = t->d_sums + (size_t)(L + l) * 2 * C;
-        bn_bwd_reduce_kernel<<<bn_grid, bn_block, 0, s>>>(dA, t->A[l], t->Z[l], P, C, mean, inv, bsum); count_launch();
-        bn_bwd_apply_kernel<<<grid_for(vec8, 256), 256, 0, s>>>(dA, t->A[l], t->Z[l], P, C, mean, inv, par + c.gamma, bsum, t->d_dZ,
-                                                                block_out ? t->d_dY : nullptr, grd + c.gamma, grd + c.beta); count_launch();
+        launch_pdl(bn_bwd_reduce_kernel, dim3(bn_grid), dim3(bn_block), 0, s, dA, t->A[l], t->Z[l], P, C, mean, inv, bsum);
+        launch_pdl(bn_bwd_apply_kernel, dim3(grid_for(vec8, 256)), dim3(256), 0, s, dA, t->A[l], t->Z[l], P, C, mean, inv, par + c.gamma, bsum, t->d_dZ,
+                                                                block_out ? t->d_dY : nullptr, grd + c.gamma, grd + c.beta);
         // weight gradient: dW[co][tap][ci] = sum_p dZ[p][co] * cols[p][tap][ci]
         const bf16 *in = l == 0 ? t->d_x0 : t->A[l - 1];
         const int K9 = 9 * c.cinp;
-        im2col_kernel<<<grid_for(P * 9 * (c.cinp / 8), 256), 256, 0, s>>>(in, P, c.cinp, t->d_cols); count_launch();
+        launch_pdl(im2col_kernel, dim3(grid_for(P * 9 * (c.cinp / 8), 256)), dim3(256), 0, s, in, P, c.cinp, t->d_cols);
         cublasStatus_t bs = t->cb->gemm_ex(t->blas, CUBLAS_OP_N, CUBLAS_OP_T, K9, C, (int)P, &one, t->d_cols, CUDA_R_16BF, K9, t->d_dZ, CUDA_R_16BF, C,
                                            &zero, t->d_G, CUDA_R_32F, K9, CUBLAS_COMPUTE_32F, CUBLAS_GEMM_DEFAULT);
         if (bs != CUBLAS_STATUS_SUCCESS) return fail(OZ_ERR_CUDA, "cublasGemmEx (weight gradient) failed: " + std::to_string((int)bs));
-        wgrad_scatter_kernel<<<grid_for((size_t)C * c.cin * 9, 256), 256, 0, s>>>(t->d_G, C, c.cin, c.cinp, grd + c.w); count_launch();
+        launch_pdl(wgrad_scatter_kernel, dim3(grid_for((size_t)C * c.cin * 9, 256)), dim3(256), 0, s, t->d_G, C, c.cin, c.cinp, grd + c.w);
         // (the conv bias has no gradient besides the L2 term: BatchNorm removes it)
         if (l == 0) break;
         // input gradient: the same convolution with rotated taps; the second-to-last layer of a block adds the skip gradient
@@ -666,7 +697,7 @@ int run_step(oz_trainer *t, int n, const oz_train_config *cfg, int apply) {
         std::swap(dA, dA_other);
     }
     // ---- L2 term, optimizer
-    l2_sgd_kernel<<<296, 256, 0, s>>>(par, grd, t->d_mom, t->n_params, cfg->l2_weight, cfg->lr, cfg->momentum, apply, t->d_loss); count_launch();
+    launch_pdl(l2_sgd_kernel, dim3(296), dim3(256), 0, s, par, grd, t->d_mom, t->n_params, cfg->l2_weight, cfg->lr, cfg->momentum, apply, t->d_loss);
     OZ_CUDA(cudaGetLastError());
     return OZ_OK;
 }
