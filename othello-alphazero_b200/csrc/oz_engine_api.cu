@@ -60,8 +60,6 @@ struct oz_engine {
     oz_counters ctr{};
     bool profiling = false;
     std::vector<cudaEvent_t> ev;          // phase boundaries of one search
-    std::vector<char> pool;               // keeps allocation list
-    std::vector<void *> allocs;
 };
 
 namespace {
