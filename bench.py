@@ -342,14 +342,14 @@ def run_ours(args):
                   "expand_backup": exp_ms,
                   "rest_of_ply (choose, record, re-root, syncs)": (ms - eval_ms) / args.steps - sel_ms - exp_ms}
     # Tree traffic: algorithmic bytes of select / encode / expand from the engine's counters, per simulation:
-    # select reads a (N, Q, P, meta, child) row = 20 B per child per level and 12 B of node header, then writes the virtual
-    # loss along the path (read N, W; write N, W, Q; path entry = 24 B per node); expand reads the leaf (20 B), writes 44 B
+    # select reads a (N, W, Q, P, meta, child) row = 24 B per child per level below the root (the root's children once per
+    # round), then writes the virtual loss along the path (N, W, Q and the path entry = 16 B per node); expand reads the leaf (20 B), writes 44 B
     # per new node (+ 4 B prior gathered from the 260 B policy row), and backs up along the path (read N, W; write W, Q;
-    # path entry = 20 B per node); encode gathers 16 B per history position and writes the 4 352 B float32 planes.
+    # path entry = 20 B per node); encode gathers 16 B per history position and writes the 4 096 B bf16 NHWC input.
     d_sims = max(1, c1["simulations"] - c0["simulations"])
     d_path, d_child, d_nodes = c1["path_nodes"] - c0["path_nodes"], c1["children_read"] - c0["children_read"], c1["nodes_expanded"] - c0["nodes_expanded"]
-    planes_bytes = (1 + 2 * MCTS_KW["history_size"]) * 64 * 4
-    tree_bytes = 20 * d_child + 12 * (d_path + d_sims) + 24 * d_path + 20 * d_path + 48 * d_nodes + d_sims * (20 + 4 + 16 * MCTS_KW["history_size"] + planes_bytes)
+    planes_bytes = 64 * 32 * 2                                   # the network's bf16 NHWC input, written by encode_kernel
+    tree_bytes = 24 * d_child + 16 * d_path + 20 * d_path + 48 * d_nodes + d_sims * (20 + 4 + 16 * MCTS_KW["history_size"] + planes_bytes)
     tree_ms = (c1["select_ms"] - c0["select_ms"]) + (c1["expand_ms"] - c0["expand_ms"])
     if rank == 0:
         f_all, f_conv = flops_per_eval(c=args.channels, blocks=args.blocks, hv=args.hidden)
@@ -417,7 +417,7 @@ def main():
     ap.add_argument("--hidden", type=int, default=128, help="value head hidden units (config 5: 256)")
     ap.add_argument("--pipeline", type=int, default=0, help="game groups of the pipelined search: 0 auto, 1 off, 2..4")
     ap.add_argument("--pipeline-pdl", type=int, default=1, help="keep programmatic dependent launch while pipelined")
-    ap.add_argument("--cpu-steps", type=int, default=12)
+    ap.add_argument("--cpu-steps", type=int, default=36, help="searches of the CPU baseline sample (about 10-15 s on 16 host cores)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--midgame-ply", type=int, default=24, help="also time 2 plies after fast-forwarding every game this far (0 = skip)")
     args = ap.parse_args()

@@ -90,8 +90,23 @@ __global__ void reset_kernel(Tree t) {
 // of single-warp blocks without shared memory: they fit into the registers a resident convolution CTA leaves free on
 // its SM (6 400 of 65 536), so one game group's tree work runs underneath the other group's network and never keeps a
 // convolution CTA off an SM.  The path of a selection lives in registers (lane k holds nodes k, k + 32, ...).
+//
+// A selection is a chain of dependent memory round trips, one per tree level, and the B selections of a game are
+// sequential by the reference's semantics; the chain is kept as short as it can be:
+//   * the root's header and the statistics of its children stay in registers for all B selections of the round (every
+//     selection starts there), updated in place and written through;
+//   * a level's read brings N, W, Q, P AND the header of every child, so the chosen child's header needs no second read;
+//   * the virtual loss (N += 1, W -= 1, Q = W / N, search_thread.cpp:70-76) is applied on the way down by the lane that
+//     already holds the chosen child's N and W -- the reference applies it after the descent, which gives the same
+//     numbers because a selection visits every node of its path once -- so there is no read-modify-write pass afterwards.
+//   * the Dirichlet draws of a selection depend on (game, search, simulation, child) only, not on the tree: instead of one
+//     Gamma draw per lane inside every selection (a few hundred dependent instructions on the critical path, 32 times per
+//     round), lane s draws the noise of simulation s for all root children up front -- 32 selections in parallel, each a
+//     loop over the handful of children -- into shared memory, together with the sequential child-order sum.
 template <int WARPS>
 __global__ void __launch_bounds__(WARPS * 32) select_kernel(Tree t) {
+    __shared__ float s_gamma[WARPS][32][33];                   // [selection of the chunk][root child]
+    __shared__ float s_gsum[WARPS][32];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int B = t.inflight, round = *t.round;
     unsigned long long path_nodes = 0, children_read = 0;      // traffic counters (oz_counters)
@@ -104,48 +119,74 @@ __global__ void __launch_bounds__(WARPS * 32) select_kernel(Tree t) {
     const size_t base = arena_base(t, g);
     const int root = t.g_root[g];
     const uint32_t game_id = t.g_gameid[g], search = t.g_search[g];
+    // root header and root children, cached for the round
+    const int rm = t.n_meta[base + root], rfc = t.n_child[base + root];
+    int root_n = t.n_N[base + root];
+    int rn0 = 0, rn1 = 0, rcm0 = 0, rcm1 = 0, rcf0 = -1, rcf1 = -1;
+    float rw0 = 0.f, rw1 = 0.f, rq0 = 0.f, rq1 = 0.f, rp0 = 0.f, rp1 = 0.f;
+    if ((rm & 3) != 0) {
+        const int rnch = rm >> 8;
+        children_read += (unsigned)rnch;
+        if (lane < rnch) { const size_t a = base + rfc + lane; rn0 = t.n_N[a]; rw0 = t.n_W[a]; rq0 = t.n_Q[a]; rp0 = t.n_P[a]; rcm0 = t.n_meta[a]; rcf0 = t.n_child[a]; }
+        if (lane + 32 < rnch) { const size_t a = base + rfc + lane + 32; rn1 = t.n_N[a]; rw1 = t.n_W[a]; rq1 = t.n_Q[a]; rp1 = t.n_P[a]; rcm1 = t.n_meta[a]; rcf1 = t.n_child[a]; }
+    }
 
+    const bool noisy = t.eps > 0.0f && (rm & 3) != 0 && (rm >> 8) > 1;    // noise is only drawn where PUCT runs at the root
     for (int i = 0; i < B; ++i) {
         const uint32_t sim = (uint32_t)(round * B + i);
+        if (noisy && (i & 31) == 0) {                // the next 32 selections' draws, one selection per lane
+            __syncwarp();
+            const int rnch = rm >> 8;
+            if (i + lane < B) {
+                float sum = 0.0f;                    // sequential float sum in child order (:236-241)
+                for (int c = 0; c < rnch; ++c) {
+                    const float gc = gamma_draw(t, game_id, search, sim + (uint32_t)lane, c);
+                    s_gamma[wib][lane][c] = gc;
+                    sum = __fadd_rn(sum, gc);
+                }
+                s_gsum[wib][lane] = sum == 0.0f ? 1.0f : sum;
+            }
+            __syncwarp();
+        }
         int node = root, depth = 0;
         int pr0 = 0, pr1 = 0, pr2 = 0, pr3 = 0;      // path nodes lane, lane + 32, lane + 64, lane + 96
-        // Header of the current node (meta, first child, visit count).  Below the root it comes from the
-        // child-statistics read of the level above (the winning lane already holds it), so a level costs
-        // one dependent memory round trip instead of two.
-        int m = t.n_meta[base + node], fc = t.n_child[base + node], nn = t.n_N[base + node];
+        int m = rm, fc = rfc, nn = root_n;           // header of the current node (meta, first child, visit count)
         while (true) {
             const int nch = m >> 8;
             if ((m & 3) == 0 || nch == 0) break;     // terminal or childless (search_thread.cpp:65)
-            int next = fc, nm, nfc, nnn;
+            const bool at_root = depth == 0;
+            const int c0 = lane, c1 = lane + 32;
+            const bool v0 = c0 < nch, v1 = c1 < nch;
+            int n0, n1, cm0, cm1, cf0, cf1;
+            float w0, w1, q0, q1, p0, p1;
+            if (at_root) {
+                n0 = rn0; n1 = rn1; w0 = rw0; w1 = rw1; q0 = rq0; q1 = rq1; p0 = rp0; p1 = rp1; cm0 = rcm0; cm1 = rcm1; cf0 = rcf0; cf1 = rcf1;
+            } else {                                 // one round trip: statistics and headers of all children
+                const size_t a0 = base + fc + c0, a1 = base + fc + c1;
+                n0 = v0 ? t.n_N[a0] : 0; n1 = v1 ? t.n_N[a1] : 0;
+                w0 = v0 ? t.n_W[a0] : 0.f; w1 = v1 ? t.n_W[a1] : 0.f;
+                q0 = v0 ? t.n_Q[a0] : 0.f; q1 = v1 ? t.n_Q[a1] : 0.f;
+                p0 = v0 ? t.n_P[a0] : 0.f; p1 = v1 ? t.n_P[a1] : 0.f;
+                cm0 = v0 ? t.n_meta[a0] : 0; cm1 = v1 ? t.n_meta[a1] : 0;
+                cf0 = v0 ? t.n_child[a0] : -1; cf1 = v1 ? t.n_child[a1] : -1;
+            }
+            int idx = 0;                             // a single child is taken without any arithmetic (:194-196)
             if (nch > 1) {
                 if (nn >= t.rate_len) { if (lane == 0) atomicOr(t.error, kErrRateTable); nn = t.rate_len - 1; }
                 const float rate = t.rate[nn];       // logf((1 + N + c_base) / c_base) + c_init, host libm
-                const int c0 = lane, c1 = lane + 32;
-                const bool v0 = c0 < nch, v1 = c1 < nch;
-                const size_t a0 = base + fc + c0, a1 = base + fc + c1;
-                const int n0 = v0 ? t.n_N[a0] : 0, n1 = v1 ? t.n_N[a1] : 0;
-                const float q0 = v0 ? t.n_Q[a0] : 0.f, q1 = v1 ? t.n_Q[a1] : 0.f;
-                float p0 = v0 ? t.n_P[a0] : 0.f, p1 = v1 ? t.n_P[a1] : 0.f;
-                const int cm0 = v0 ? t.n_meta[a0] : 0, cm1 = v1 ? t.n_meta[a1] : 0;
-                const int cf0 = v0 ? t.n_child[a0] : -1, cf1 = v1 ? t.n_child[a1] : -1;
                 const int total = warp_sum(n0 + n1);
-                children_read += (unsigned)nch;
+                if (!at_root) children_read += (unsigned)nch;   // the root's children were read once for the round
                 const float mult = __fmul_rn(rate, __fsqrt_rn((float)total));
-                if (node == root && t.eps > 0.0f) {  // Dirichlet noise, re-drawn per selection (:230-249)
-                    const float g0 = v0 ? gamma_draw(t, game_id, search, sim, c0) : 0.f;
-                    const float g1 = v1 ? gamma_draw(t, game_id, search, sim, c1) : 0.f;
-                    float sum = 0.0f;                // sequential float sum in child order
-                    for (int j = 0; j < nch; ++j) {
-                        const float gj = __shfl_sync(0xffffffffu, j < 32 ? g0 : g1, j & 31);
-                        sum = __fadd_rn(sum, gj);
-                    }
-                    if (sum == 0.0f) sum = 1.0f;
+                if (at_root && noisy) {              // Dirichlet noise, re-drawn per selection (:230-249)
+                    const float g0 = v0 ? s_gamma[wib][i & 31][c0] : 0.f;
+                    const float g1 = v1 ? s_gamma[wib][i & 31][c1] : 0.f;
+                    const float sum = s_gsum[wib][i & 31];
                     const float pm = __fsub_rn(1.0f, t.eps), nm2 = __fdiv_rn(t.eps, sum);
                     p0 = __fadd_rn(__fmul_rn(p0, pm), __fmul_rn(g0, nm2));
                     p1 = __fadd_rn(__fmul_rn(p1, pm), __fmul_rn(g1, nm2));
                 }
                 // ucb = Q + (mult * P) / (1 + N)
-                float u = -INFINITY; int idx = INT_MAX;
+                float u = -INFINITY; idx = INT_MAX;
                 if (v0) { u = __fadd_rn(q0, __fdiv_rn(__fmul_rn(mult, p0), __fadd_rn(1.0f, (float)n0))); idx = c0; }
                 if (v1) {
                     const float u1 = __fadd_rn(q1, __fdiv_rn(__fmul_rn(mult, p1), __fadd_rn(1.0f, (float)n1)));
@@ -157,13 +198,18 @@ __global__ void __launch_bounds__(WARPS * 32) select_kernel(Tree t) {
                     const int oi = __shfl_xor_sync(0xffffffffu, idx, o);
                     if (ou > u || (ou == u && oi < idx)) { u = ou; idx = oi; }
                 }
-                next = fc + idx;
-                const bool hi = idx >= 32;
-                nm = __shfl_sync(0xffffffffu, hi ? cm1 : cm0, idx & 31);
-                nfc = __shfl_sync(0xffffffffu, hi ? cf1 : cf0, idx & 31);
-                nnn = __shfl_sync(0xffffffffu, hi ? n1 : n0, idx & 31);
-            } else {
-                nm = t.n_meta[base + next]; nfc = t.n_child[base + next]; nnn = t.n_N[base + next];
+            }
+            const int next = fc + idx;
+            const bool hi = idx >= 32;
+            const int nm = __shfl_sync(0xffffffffu, hi ? cm1 : cm0, idx & 31);
+            const int nfc = __shfl_sync(0xffffffffu, hi ? cf1 : cf0, idx & 31);
+            const int nnn = __shfl_sync(0xffffffffu, hi ? n1 : n0, idx & 31);     // the child's count BEFORE this selection's virtual loss
+            if (lane == (idx & 31)) {                // virtual loss by the lane that holds the chosen child
+                const int nv = (hi ? n1 : n0) + 1;
+                const float wv = __fsub_rn(hi ? w1 : w0, 1.0f), qv = __fdiv_rn(wv, (float)nv);
+                const size_t a = base + next;
+                t.n_N[a] = nv; t.n_W[a] = wv; t.n_Q[a] = qv;
+                if (at_root) { if (hi) { rn1 = nv; rw1 = wv; rq1 = qv; } else { rn0 = nv; rw0 = wv; rq0 = qv; } }
             }
             if (depth < kMaxDepth) {
                 if (lane == (depth & 31)) {
@@ -176,23 +222,17 @@ __global__ void __launch_bounds__(WARPS * 32) select_kernel(Tree t) {
         }
         if (depth > kMaxDepth) depth = kMaxDepth;
         path_nodes += (unsigned)depth;
-        // virtual loss on the path (root excluded), root visit count (:70-78)
-        int *gpath = t.s_path + ((size_t)g * B + i) * kMaxDepth;
+        int *gpath = t.s_path + ((size_t)g * B + i) * kMaxDepth;     // the path, for the backup of expand_kernel
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
             const int k = lane + 32 * q;
-            if (k < depth) {
-                const int nd = q == 0 ? pr0 : (q == 1 ? pr1 : (q == 2 ? pr2 : pr3));
-                gpath[k] = nd;
-                const size_t a = base + nd;
-                const int n = t.n_N[a] + 1;
-                const float w = __fsub_rn(t.n_W[a], 1.0f);
-                t.n_N[a] = n; t.n_W[a] = w; t.n_Q[a] = __fdiv_rn(w, (float)n);
-            }
+            if (k < depth) gpath[k] = q == 0 ? pr0 : (q == 1 ? pr1 : (q == 2 ? pr2 : pr3));
         }
-        if (lane == 0) { t.n_N[base + root] += 1; leaf_out[i] = node; t.s_len[(size_t)g * B + i] = depth; }
-        __syncwarp();
+        root_n += 1;                                 // root visit count (:78)
+        if (lane == 0) { leaf_out[i] = node; t.s_len[(size_t)g * B + i] = depth; }
+        __syncwarp();                                // the virtual-loss stores are ordered before the next selection's reads
     }
+    if (lane == 0) t.n_N[base + root] = root_n;
     }
     if (lane == 0 && path_nodes) { atomicAdd(&t.stats[1], path_nodes); atomicAdd(&t.stats[2], children_read); }
 }
