@@ -332,21 +332,36 @@ __global__ void __launch_bounds__(WARPS * 32) expand_kernel(Tree t, const float 
     for (int g = blockIdx.x * WARPS + wib; g < t.G; g += gridDim.x * WARPS) {
     if (t.g_status[g] & 1) continue;
     const size_t base = arena_base(t, g);
+    int count = t.g_count[g];                            // nodes in the arena; kept in a register, written back once
+    // Per-slot inputs of 32 slots at a time, one slot per lane: two memory round trips for the chunk instead of two per
+    // slot on the sequential chain below (slots are processed in order: backups add floats to shared ancestors).
+    int c_leaf = 0, c_len = 0, c_tf = 0, c_meta = 0;
+    float c_val = 0.f;
+    uint64_t c_p1 = 0, c_p2 = 0;
     for (int i = 0; i < B; ++i) {
         const size_t slot = (size_t)g * B + i;
-        const int leaf = t.s_leaf[slot];
-        const int m = t.n_meta[base + leaf];
+        const int li = i & 31;
+        if (li == 0) {
+            __syncwarp();
+            if (i + lane < B) {
+                const size_t sl = slot + lane;
+                c_leaf = t.s_leaf[sl]; c_len = t.s_len[sl]; c_tf = t.s_tf[sl]; c_val = value[sl];
+                c_meta = t.n_meta[base + c_leaf]; c_p1 = t.n_p1[base + c_leaf]; c_p2 = t.n_p2[base + c_leaf];
+            }
+        }
+        const int leaf = __shfl_sync(0xffffffffu, c_leaf, li);
+        const int m = __shfl_sync(0xffffffffu, c_meta, li);
         const int player = m & 3;
-        const uint64_t lp1 = t.n_p1[base + leaf], lp2 = t.n_p2[base + leaf];
+        const uint64_t lp1 = __shfl_sync(0xffffffffu, c_p1, li), lp2 = __shfl_sync(0xffffffffu, c_p2, li);
         if (player != 0 && (m >> 8) == 0) {           // still childless (:135)
             const uint64_t me = player == 1 ? lp1 : lp2, opp = player == 1 ? lp2 : lp1;
             const uint64_t legal = legal_moves(me, opp);
             const int n = legal ? __popcll(legal) : 1;
-            const int first = t.g_count[g];
+            const int first = count;
             if (first + n > t.cap) {
                 if (lane == 0) atomicOr(t.error, kErrArenaFull);
             } else {
-                const int tf = t.s_tf[slot];
+                const int tf = __shfl_sync(0xffffffffu, c_tf, li);
                 const float *pol = policy + slot * 65;
                 Position s; s.player = player; s.p1 = lp1; s.p2 = lp2; s.legal = legal;
                 s.next_legal = legal ? 0 : legal_moves(opp, me);
@@ -359,13 +374,15 @@ __global__ void __launch_bounds__(WARPS * 32) expand_kernel(Tree t, const float 
                     t.n_N[d] = 0; t.n_W[d] = 0.f; t.n_Q[d] = 0.f;
                     t.n_P[d] = pol[transform_action(a, tf)];   // raw softmax output, no renormalisation (:139-149)
                 }
-                if (lane == 0) { t.n_child[base + leaf] = first; t.n_meta[base + leaf] = player | (n << 8); t.g_count[g] = first + n; }
+                if (lane == 0) { t.n_child[base + leaf] = first; t.n_meta[base + leaf] = player | (n << 8); }
+                count = first + n;
+                if (c_leaf == leaf) c_meta = player | (n << 8);   // later slots of the chunk that hold the same leaf see it expanded (:135)
                 expanded += (unsigned)n;
             }
         }
         float v;
         if (player != 0) {
-            v = -value[slot];                          // edge value is from the parent's view (:156-157)
+            v = -__shfl_sync(0xffffffffu, c_val, li);  // edge value is from the parent's view (:156-157)
         } else {                                       // terminal: disc count from the parent's side (:158-177)
             const int par = t.n_parent[base + leaf];
             const int pp = par >= 0 ? (t.n_meta[base + par] & 3) : t.h_player[(size_t)g * kMaxHist];
@@ -373,7 +390,7 @@ __global__ void __launch_bounds__(WARPS * 32) expand_kernel(Tree t, const float 
             v = pc > oc ? 1.0f : (pc < oc ? -1.0f : 0.0f);
         }
         // backup along the stored path (leaf last); the sign alternates towards the root
-        const int len = t.s_len[slot];
+        const int len = __shfl_sync(0xffffffffu, c_len, li);
         const int *gpath = t.s_path + slot * kMaxDepth;
         for (int k = lane; k < len; k += 32) {
             const size_t a = base + gpath[k];
@@ -383,6 +400,7 @@ __global__ void __launch_bounds__(WARPS * 32) expand_kernel(Tree t, const float 
         }
         __syncwarp();
     }
+    if (lane == 0) t.g_count[g] = count;
     }
     if (lane == 0 && expanded) atomicAdd(&t.stats[0], expanded);
 }
