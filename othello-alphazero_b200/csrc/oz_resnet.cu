@@ -131,27 +131,10 @@ __device__ __forceinline__ void mbar_wait_b(uint32_t bar, uint32_t parity) {
         }
     }
 }
-// Activations stream through the L2 once per layer (0.5 GB per tensor at the benchmark batch, four times the L2), so their
-// loads and stores carry an evict-first policy: what they would otherwise push out between two search rounds are the
-// search trees, whose nodes the tree kernels then fetch from HBM one dependent miss at a time.
-__device__ __forceinline__ uint64_t policy_evict_first() {
-    uint64_t p;
-    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
-    return p;
-}
-__device__ __forceinline__ void tma_load_4d_pair(uint32_t dst, const CUtensorMap *map, uint32_t bar_cluster, int c0, int c1, int c2, int c3,
-                                                 uint64_t policy) {
+__device__ __forceinline__ void tma_load_4d_pair(uint32_t dst, const CUtensorMap *map, uint32_t bar_cluster, int c0, int c1, int c2, int c3) {
     asm volatile(
-        "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4, %5, %6}], [%2], %7;"
-        ::"r"(dst), "l"(map), "r"(bar_cluster), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "l"(policy) : "memory");
-}
-__device__ __forceinline__ void ldg256_stream(const void *ptr, uint32_t *v, uint64_t policy) {
-    asm volatile("ld.global.L2::cache_hint.v8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8], %9;"
-                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]) : "l"(ptr), "l"(policy) : "memory");
-}
-__device__ __forceinline__ void stg256_stream(void *ptr, const uint32_t *v, uint64_t policy) {
-    asm volatile("st.global.L2::cache_hint.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8}, %9;"
-                 ::"l"(ptr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "l"(policy) : "memory");
+        "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+        ::"r"(dst), "l"(map), "r"(bar_cluster), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
 }
 // 256-bit global accesses (sm_100): one full 32-byte sector per lane per instruction.
 __device__ __forceinline__ void ldg256(const void *ptr, uint32_t *v) {
@@ -239,7 +222,6 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap map_act, const __grid_co
         // ===== activation TMA producer (one per CTA; bytes complete on the LEADER's barrier) =====
         uint32_t it = 0;
         const uint32_t full0 = mapa_rank(bar_act_full, 0);
-        const uint64_t stream_policy = policy_evict_first();
         griddep_wait();                                   // the previous layer's output is complete and visible
         for (int pp = cluster_id; pp < num_pp; pp += num_clusters) {
             const int up = pp / ntiles, unit = 2 * (up >> 2) + (int)rank, yp = up & 3;
@@ -249,7 +231,7 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap map_act, const __grid_co
                 if (elect_one()) {
                     if (leader) mbar_expect_tx(bar_act_full + 8 * s, 2 * kActBoxBytesP);
                     tma_load_4d_pair(act0 + s * kActStageBytesP + kSlotBytes, &map_act, full0 + 8 * s,
-                                     kb * kKBlock, unit * kBoardsPerUnit, 0, yp * kYPerPass - 1, stream_policy);
+                                     kb * kKBlock, unit * kBoardsPerUnit, 0, yp * kYPerPass - 1);
                 }
                 __syncwarp();
             }
@@ -348,7 +330,6 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap map_act, const __grid_co
         const int quad = warp & 3, half = (warp - 3) >> 2;
         const int row = quad * 32 + lane, x = row >> 4, bl = row & 15;     // row in tile = x * 16 + board
         const uint32_t empty_remote = mapa_rank(bar_tmem_empty, 0);
-        const uint64_t stream_policy = policy_evict_first();
         uint32_t np = 0;
         griddep_wait();
         for (int pp = cluster_id; pp < num_pp; pp += num_clusters, ++np) {
@@ -362,7 +343,7 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap map_act, const __grid_co
 #pragma unroll
                 for (int r = 0; r < kYPerPass; ++r) {
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) ldg256_stream(p.skip + off0 + r * ystride + i * 16, &sk[r][i * 8], stream_policy);
+                    for (int i = 0; i < 4; ++i) ldg256(p.skip + off0 + r * ystride + i * 16, &sk[r][i * 8]);
                 }
                 if (pp + num_clusters < num_pp) {               // next pass's residual rows: HBM -> L2 ahead of use
                     const int ppn = pp + num_clusters, ntn = ppn % ntiles, un = ppn / ntiles;
@@ -406,8 +387,8 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap map_act, const __grid_co
                     }
                     if (p.out) {
                         __nv_bfloat16 *op = p.out + off0 + r * ystride + ch * 32;   // full 32-byte sectors per store
-                        stg256_stream(op, &ow[0], stream_policy);
-                        stg256_stream(op + 16, &ow[8], stream_policy);
+                        stg256(op, &ow[0]);
+                        stg256(op + 16, &ow[8]);
                     }
                 }
                 if (p.head_out) {                            // the two column halves of a row add into zeroed memory: order-free

@@ -174,7 +174,7 @@ __global__ void __launch_bounds__(WARPS * 32) select_kernel(Tree t) {
             if (nch > 1) {
                 if (nn >= t.rate_len) { if (lane == 0) atomicOr(t.error, kErrRateTable); nn = t.rate_len - 1; }
                 const float rate = t.rate[nn];       // logf((1 + N + c_base) / c_base) + c_init, host libm
-                const int total = warp_sum(n0 + n1);
+                const int total = __reduce_add_sync(0xffffffffu, n0 + n1);
                 if (!at_root) children_read += (unsigned)nch;   // the root's children were read once for the round
                 const float mult = __fmul_rn(rate, __fsqrt_rn((float)total));
                 if (at_root && noisy) {              // Dirichlet noise, re-drawn per selection (:230-249)
@@ -192,12 +192,12 @@ __global__ void __launch_bounds__(WARPS * 32) select_kernel(Tree t) {
                     const float u1 = __fadd_rn(q1, __fdiv_rn(__fmul_rn(mult, p1), __fadd_rn(1.0f, (float)n1)));
                     if (u1 > u) { u = u1; idx = c1; }
                 }
-#pragma unroll
-                for (int o = 16; o; o >>= 1) {       // first maximum wins (strict > in the reference)
-                    const float ou = __shfl_xor_sync(0xffffffffu, u, o);
-                    const int oi = __shfl_xor_sync(0xffffffffu, idx, o);
-                    if (ou > u || (ou == u && oi < idx)) { u = ou; idx = oi; }
-                }
+                // First maximum wins (strict > in the reference): the largest value through an order-preserving integer key
+                // (-0 folded into +0 first, they compare equal as floats), then the smallest index that holds it.
+                uint32_t key = __float_as_uint(__fadd_rn(u, 0.0f));
+                key ^= (uint32_t)((int32_t)key >> 31) | 0x80000000u;
+                const uint32_t kmax = __reduce_max_sync(0xffffffffu, key);
+                idx = __reduce_min_sync(0xffffffffu, key == kmax ? idx : INT_MAX);
             }
             const int next = fc + idx;
             const bool hi = idx >= 32;
