@@ -163,9 +163,16 @@ __device__ __forceinline__ void tc_mma_pair(uint32_t d_tmem, uint64_t adesc, uin
         ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
 }
 
+// YPP = board rows per pass (and accumulator tiles per pass).  2 is the throughput configuration described above; 1 halves
+// the serial MMA chain of a pass and doubles the number of passes, for batches that cannot give every CTA pair a pass
+// otherwise (the single-game MCTS of the reference's CLIs: 32 boards are 4 pair-passes at YPP = 2).
+template <int YPP>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(pair::kThreadsP, 1)
 conv3x3_pair_kernel(const __grid_constant__ CUtensorMap map_act, const __grid_constant__ CUtensorMap map_w, const ConvParams p) {
     using namespace pair;
+    constexpr int kYPerPass = YPP, kRowPasses = 8 / YPP;                      // passes per board column of rows
+    constexpr int kActBoxBytesP = kBoxX * (YPP + 2) * kSlotBytes;            // the box carries one halo row above and below
+    constexpr int kActStageBytesP = kSlotBytes + kActBoxBytesP;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t *gen = smem_raw + (base - smem_u32(smem_raw));
@@ -183,7 +190,7 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap map_act, const __grid_co
     const uint32_t rank = cluster_ctarank();
     const bool leader = rank == 0;
     const int ntiles = p.cout_total >> 7;
-    const int num_pp = p.units * 2 * ntiles;                 // pair-passes: two spatial passes x one cout tile
+    const int num_pp = (p.units / 2) * kRowPasses * ntiles;  // pair-passes: (unit pair, row group, cout tile)
     const int cluster_id = blockIdx.x >> 1, num_clusters = gridDim.x >> 1;
     const int wtiles = p.kblocks * 9;
     const bool resident = ntiles == 1 && wtiles <= kWSlots;
@@ -224,7 +231,7 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap map_act, const __grid_co
         const uint32_t full0 = mapa_rank(bar_act_full, 0);
         griddep_wait();                                   // the previous layer's output is complete and visible
         for (int pp = cluster_id; pp < num_pp; pp += num_clusters) {
-            const int up = pp / ntiles, unit = 2 * (up >> 2) + (int)rank, yp = up & 3;
+            const int up = pp / ntiles, unit = 2 * (up / kRowPasses) + (int)rank, yp = up % kRowPasses;
             for (int kb = 0; kb < p.kblocks; ++kb, ++it) {
                 const uint32_t s = it % kActStagesP, ph = (it / kActStagesP) & 1;
                 mbar_wait_b(bar_act_empty + 8 * s, ph ^ 1);
@@ -266,8 +273,8 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap map_act, const __grid_co
                 const uint32_t dcol = tmem_base + acc * 256;
                 // Board rows -1 and 8 are zero padding: for the first / last row pair, three taps of one tile
                 // multiply an all-zero operand and are not issued (both CTAs of the pair work on the same rows).
-                const int yp = (pp / ntiles) & 3;
-                const bool skip_top = yp == 0, skip_bot = yp == 3;
+                const int yp = (pp / ntiles) % kRowPasses;
+                const bool skip_top = yp == 0, skip_bot = yp == kRowPasses - 1;
                 for (int kb = 0; kb < p.kblocks; ++kb, ++ait) {
                     const uint32_t as = ait % kActStagesP;
                     mbar_wait_b(bar_act_full + 8 * as, (ait / kActStagesP) & 1);
@@ -333,7 +340,7 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap map_act, const __grid_co
         uint32_t np = 0;
         griddep_wait();
         for (int pp = cluster_id; pp < num_pp; pp += num_clusters, ++np) {
-            const int nt = pp % ntiles, up = pp / ntiles, unit = 2 * (up >> 2) + (int)rank, yp = up & 3;
+            const int nt = pp % ntiles, up = pp / ntiles, unit = 2 * (up / kRowPasses) + (int)rank, yp = up % kRowPasses;
             const uint32_t acc = np & 1;
             const size_t board = (size_t)unit * kBoardsPerUnit + bl;
             const size_t off0 = ((board * 8 + yp * kYPerPass) * 8 + x) * (size_t)p.cout_total + nt * 128 + half * 64;
@@ -347,8 +354,8 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap map_act, const __grid_co
                 }
                 if (pp + num_clusters < num_pp) {               // next pass's residual rows: HBM -> L2 ahead of use
                     const int ppn = pp + num_clusters, ntn = ppn % ntiles, un = ppn / ntiles;
-                    const size_t board_n = (size_t)(2 * (un >> 2) + (int)rank) * kBoardsPerUnit + bl;
-                    const size_t offn = ((board_n * 8 + (un & 3) * kYPerPass) * 8 + x) * (size_t)p.cout_total + ntn * 128 + half * 64;
+                    const size_t board_n = (size_t)(2 * (un / kRowPasses) + (int)rank) * kBoardsPerUnit + bl;
+                    const size_t offn = ((board_n * 8 + (un % kRowPasses) * kYPerPass) * 8 + x) * (size_t)p.cout_total + ntn * 128 + half * 64;
 #pragma unroll
                     for (int r = 0; r < kYPerPass; ++r)
                         asm volatile("prefetch.global.L2 [%0];" ::"l"(p.skip + offn + r * ystride));
@@ -678,16 +685,24 @@ static int make_w_map(CUtensorMap *m, void *ptr, int cin, int cout, int box_rows
     return OZ_OK;
 }
 
-static int launch_conv(const CUtensorMap &ma, const CUtensorMap &mw, const ConvParams &cp, cudaStream_t stream, bool pdl = true) {
+// ma = activation map with a 4-row box (two board rows per pass), ma1 = the same tensor with a 3-row box (one row per pass)
+// or null.  One row per pass is used when that still leaves every CTA pair with at most one pass: the pass is half as
+// long and twice as many pairs work.  (Beyond that it only costs: a pair would run two half passes instead of one, and
+// with streamed weights -- 256 channels -- load every weight tile twice.)
+static int launch_conv(const CUtensorMap &ma, const CUtensorMap *ma1, const CUtensorMap &mw, const ConvParams &cp, cudaStream_t stream,
+                       bool pdl = true) {
     static bool attr_set = false;
     if (!attr_set) {
-        OZ_CUDA(cudaFuncSetAttribute(conv3x3_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, pair::kSmemBytesP));
+        OZ_CUDA(cudaFuncSetAttribute(conv3x3_pair_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, pair::kSmemBytesP));
+        OZ_CUDA(cudaFuncSetAttribute(conv3x3_pair_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, pair::kSmemBytesP));
         attr_set = true;
     }
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    const int num_pp = cp.units * 2 * (cp.cout_total >> 7);
+    const int pp2 = cp.units * 2 * (cp.cout_total >> 7);
+    const bool one_row = ma1 != nullptr && 2 * pp2 <= sms / 2;   // every pair still gets at most one pass, half as long
+    const int num_pp = one_row ? 2 * pp2 : pp2;
     const int clusters = num_pp < sms / 2 ? num_pp : sms / 2;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(2 * clusters); cfg.blockDim = dim3(pair::kThreadsP); cfg.dynamicSmemBytes = pair::kSmemBytesP; cfg.stream = stream;
@@ -695,7 +710,8 @@ static int launch_conv(const CUtensorMap &ma, const CUtensorMap &mw, const ConvP
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr; cfg.numAttrs = pdl ? 1 : 0;
-    OZ_CUDA(cudaLaunchKernelEx(&cfg, conv3x3_pair_kernel, ma, mw, cp));
+    if (one_row) OZ_CUDA(cudaLaunchKernelEx(&cfg, conv3x3_pair_kernel<1>, *ma1, mw, cp));
+    else OZ_CUDA(cudaLaunchKernelEx(&cfg, conv3x3_pair_kernel<2>, ma, mw, cp));
     count_launch();
     OZ_CUDA(cudaGetLastError());
     return OZ_OK;
@@ -762,6 +778,9 @@ int ResNet::reserve(size_t boards, int ws) {
     OZ_TRY(make_act_map(&w.map_x0, w.x0, pad, 32, pair::kBoxYp));
     OZ_TRY(make_act_map(&w.map_a, w.a, pad, (int)C, pair::kBoxYp));
     OZ_TRY(make_act_map(&w.map_t, w.t, pad, (int)C, pair::kBoxYp));
+    OZ_TRY(make_act_map(&w.map_x0_1, w.x0, pad, 32, 3));          // one board row per pass (small batches)
+    OZ_TRY(make_act_map(&w.map_a_1, w.a, pad, (int)C, 3));
+    OZ_TRY(make_act_map(&w.map_t_1, w.t, pad, (int)C, 3));
     w.cap = pad;
     return OZ_OK;
 }
@@ -782,6 +801,7 @@ int ResNet::forward(const float *d_features, size_t n, float *d_policy, float *d
     void *const d_x0_ = w.x0, *const d_a_ = w.a, *const d_t_ = w.t;
     float *const d_head_pre_ = w.head_pre;
     const CUtensorMap &map_x0_ = w.map_x0, &map_a_ = w.map_a, &map_t_ = w.map_t;
+    const CUtensorMap *map_x0_1 = &w.map_x0_1, *map_a_1 = &w.map_a_1, *map_t_1 = &w.map_t_1;
     const size_t pad = (n + kBoardPad - 1) / kBoardPad * kBoardPad;
     const int C = shape_.channels;
     if (d_features) {                                   // nullptr: the caller staged the input in input_buffer()
@@ -798,14 +818,14 @@ int ResNet::forward(const float *d_features, size_t n, float *d_policy, float *d
     cp.units = (int)(pad / kBoardsPerUnit); cp.cout_total = C; cp.relu = 1;
     // conv block (neural_net.py:9-29)
     cp.kblocks = 1; cp.skip = nullptr; cp.out = (__nv_bfloat16 *)d_a_; cp.bias = (const float *)(d_blob_ + layout_.conv_b[0]);
-    OZ_TRY(launch_conv(map_x0_, map_w_[0], cp, stream, pdl_));
+    OZ_TRY(launch_conv(map_x0_, map_x0_1, map_w_[0], cp, stream, pdl_));
     cp.kblocks = C / kKBlock;
     for (int b = 0; b < shape_.blocks; ++b) {   // residual tower (neural_net.py:32-65)
         cp.skip = nullptr; cp.out = (__nv_bfloat16 *)d_t_; cp.bias = (const float *)(d_blob_ + layout_.conv_b[1 + 2 * b]);
-        OZ_TRY(launch_conv(map_a_, map_w_[1 + 2 * b], cp, stream, pdl_));
+        OZ_TRY(launch_conv(map_a_, map_a_1, map_w_[1 + 2 * b], cp, stream, pdl_));
         cp.skip = (const __nv_bfloat16 *)d_a_; cp.out = (__nv_bfloat16 *)d_a_; cp.bias = (const float *)(d_blob_ + layout_.conv_b[2 + 2 * b]);
         if (fuse_heads && b == shape_.blocks - 1) { cp.out = nullptr; cp.head_w = (const float *)(d_blob_ + layout_.head_w); cp.head_out = d_head_pre_; }
-        OZ_TRY(launch_conv(map_t_, map_w_[2 + 2 * b], cp, stream, pdl_));
+        OZ_TRY(launch_conv(map_t_, map_t_1, map_w_[2 + 2 * b], cp, stream, pdl_));
         cp.head_w = nullptr; cp.head_out = nullptr;
     }
     if (conv_end) cudaEventRecord(conv_end, stream);
@@ -833,13 +853,14 @@ int ResNet::conv3x3(const void *d_in, int cin, const void *d_w, const float *d_b
                     void *d_out, int cout, size_t boards_padded, cudaStream_t stream) {
     if (cin % kKBlock || cout % 128 || boards_padded % kBoardPad)
         return fail(OZ_ERR_INVALID_ARGUMENT, "conv3x3: cin % 32, cout % 128, boards % 32 must be 0");
-    CUtensorMap ma, mw;
+    CUtensorMap ma, ma1, mw;
     OZ_TRY(make_act_map(&ma, const_cast<void *>(d_in), boards_padded, cin, pair::kBoxYp));
+    OZ_TRY(make_act_map(&ma1, const_cast<void *>(d_in), boards_padded, cin, 3));
     OZ_TRY(make_w_map(&mw, const_cast<void *>(d_w), cin, cout, 64));
     ConvParams cp{};
     cp.skip = (const __nv_bfloat16 *)d_skip; cp.out = (__nv_bfloat16 *)d_out; cp.bias = d_bias;
     cp.units = (int)(boards_padded / kBoardsPerUnit); cp.kblocks = cin / kKBlock; cp.cout_total = cout; cp.relu = relu;
-    return launch_conv(ma, mw, cp, stream);
+    return launch_conv(ma, &ma1, mw, cp, stream);
 }
 
 }  // namespace oz

@@ -68,7 +68,8 @@ class ResNet {
         size_t cap = 0;
         void *x0 = nullptr, *a = nullptr, *t = nullptr;       // bf16 NHWC activations
         float *head_pre = nullptr;                            // [boards][64][4] fused head-conv pre-activations
-        CUtensorMap map_x0, map_a, map_t;
+        CUtensorMap map_x0, map_a, map_t;                     // 4-row boxes: two board rows per pass
+        CUtensorMap map_x0_1, map_a_1, map_t_1;               // 3-row boxes: one board row per pass (small batches)
     };
     void free_workspaces();
     std::vector<Workspace> ws_;

@@ -28,6 +28,10 @@ def _from_bits(a: np.ndarray) -> torch.Tensor:
     (128, 128, 50, True, True),      # ragged board count (padded to 64 inside), several passes per CTA
     (128, 128, 16 * 160, False, False),   # more passes than SMs: persistent loop + barrier phase wrap
     (256, 256, 32, True, True),      # 256-channel tower: two cout tiles, 8 K blocks
+    (128, 128, 16 * 18, True, True),      # 36 pair-passes at two rows per pass: the one-row-per-pass kernel, 72 passes on 74 CTA pairs
+    (128, 128, 16 * 20, True, True),      # 40 pair-passes: just above the switch, the two-rows-per-pass kernel
+    (256, 256, 16 * 8, True, True),       # 256 channels, 32 pair-passes at two rows per pass: one-row kernel with streamed weights
+    (256, 256, 16 * 12, False, True),     # ... and 48: two-row kernel
 ])
 def test_conv3x3_vs_torch(cin, cout, boards, skip, relu):
     from othello_mcts import _lib

@@ -58,7 +58,7 @@ def test_training_step_matches_pytorch_autograd(channels, blocks, hidden, n):
     tensor and >= 0.98 over the whole parameter vector, norms within 10 % -- torch.autocast(bfloat16) of the same network
     reaches 0.976-0.990 per tensor and 0.985 overall against true fp32, the native step 0.986-0.992 and 0.989
     (tools/train_grad_check.py) --; the one- and two-element BatchNorm tensors of the heads, sums with heavy
-    cancellation, are compared absolutely (5e-3 + 10 %); update direction cosine >= 0.97, length within 5 %."""
+    cancellation whose terms are of order 0.1, are compared absolutely (2e-2 + 10 %); update direction cosine >= 0.97, length within 5 %."""
     import copy
     import torch
     from othello_mcts.neural_net import AlphaZeroNet
@@ -94,7 +94,7 @@ def test_training_step_matches_pytorch_autograd(channels, blocks, hidden, n):
                 # conv biases in front of a BatchNorm only get the L2 term (their data gradient is exactly zero)
                 assert np.abs(a - b).max() <= 1e-3 + 0.05 * np.abs(b).max(), (step, name)
             elif b.size <= 4:
-                assert np.abs(a - b).max() <= 5e-3 + 0.1 * np.abs(b).max(), (step, name, a, b)
+                assert np.abs(a - b).max() <= 2e-2 + 0.1 * np.abs(b).max(), (step, name, a, b)
             else:
                 cos = float(a @ b / (np.linalg.norm(a) * nb + 1e-30))
                 assert cos >= 0.95, (step, name, cos)
