@@ -227,7 +227,7 @@ def run_ours(args):
     # games are partitioned contiguously by id: rank r owns [r*G, (r+1)*G); no collective on the hot path
     eng = om.SelfPlayEngine(G, seed=args.seed, first_game_id=rank * G, cuda_device=local, **kw)
     eng.prepare(net)
-    eng.set_profiling(True)
+    eng.set_profiling(not args.no_profiling)
     eng.set_pipeline(args.pipeline, bool(args.pipeline_pdl))
     lib = _lib.load()
     stream = torch.cuda.ExternalStream(lib.oz_engine_stream(eng._h), device=torch.device("cuda", local))
@@ -415,6 +415,7 @@ def main():
     ap.add_argument("--channels", type=int, default=128, help="conv_channels (BASELINE config 5: 256)")
     ap.add_argument("--blocks", type=int, default=9, help="residual blocks (config 5: 19)")
     ap.add_argument("--hidden", type=int, default=128, help="value head hidden units (config 5: 256)")
+    ap.add_argument("--no-profiling", action="store_true", help="no per-phase CUDA events inside the searches (roofline fields stay empty)")
     ap.add_argument("--pipeline", type=int, default=0, help="game groups of the pipelined search: 0 auto, 1 off, 2..4")
     ap.add_argument("--pipeline-pdl", type=int, default=1, help="keep programmatic dependent launch while pipelined")
     ap.add_argument("--cpu-steps", type=int, default=36, help="searches of the CPU baseline sample (about 10-15 s on 16 host cores)")

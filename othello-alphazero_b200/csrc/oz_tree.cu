@@ -542,10 +542,21 @@ __global__ void __launch_bounds__(128) apply_kernel(Tree t, const int32_t *__res
             const int total = __shfl_sync(0xffffffffu, incl, 31);
             const int off = incl - nc;
             if (nc > 0) t.n_child[dst + my] = new_count + off;
-            for (int s = 0; s < batch; ++s) {
-                const int f = __shfl_sync(0xffffffffu, fc_old, s), c2 = __shfl_sync(0xffffffffu, nc, s), o2 = __shfl_sync(0xffffffffu, off, s);
-                for (int j = lane; j < c2; j += 32) {
-                    const size_t a = src + f + j, d = dst + new_count + o2 + j;
+            // All children of the batch as one flat range, 32 at a time with every lane busy: child k of the batch belongs
+            // to the first parent whose inclusive prefix exceeds k (a 5-step search over the lanes' prefixes) and lands at
+            // new_count + k -- the same order as copying parent by parent, a quarter of the dependent round trips.
+            for (int k0 = 0; k0 < total; k0 += 32) {
+                const int k = k0 + lane;
+                int s = 0;
+#pragma unroll
+                for (int step = 16; step; step >>= 1) {
+                    const int cand = s + step;
+                    const int v = __shfl_sync(0xffffffffu, incl, (cand - 1) & 31);
+                    if (cand <= 31 && v <= k) s = cand;
+                }
+                const int f = __shfl_sync(0xffffffffu, fc_old, s), o2 = __shfl_sync(0xffffffffu, off, s);
+                if (k < total) {
+                    const size_t a = src + f + (k - o2), d = dst + new_count + k;
                     t.n_p1[d] = t.n_p1[a]; t.n_p2[d] = t.n_p2[a]; t.n_meta[d] = t.n_meta[a]; t.n_parent[d] = head + s;
                     t.n_child[d] = t.n_child[a]; t.n_N[d] = t.n_N[a]; t.n_W[d] = t.n_W[a]; t.n_Q[d] = t.n_Q[a]; t.n_P[d] = t.n_P[a];
                 }
