@@ -323,6 +323,17 @@ __global__ void __launch_bounds__(WARPS * 32) encode_kernel(Tree t, float *featu
 }
 
 // ------------------------------------------------------------------ expand + backup (search_thread.cpp:130-190)
+// The reference handles the slots of a batch one after another: expand the leaf if it is still childless, then back its
+// value up.  Backups must stay in slot order (they add floats to shared ancestors), expansions need not: creating the
+// children of a leaf touches nothing a backup reads or writes.  So a chunk of 32 slots is processed as
+//   1. one slot per lane: leaf, path length, symmetry, value, the leaf's header and discs (two memory round trips for the
+//      chunk), which slots expand (non-terminal, childless, FIRST slot of the chunk holding that leaf -- later copies skip
+//      the expansion, search_thread.cpp:135), the legal moves and child count of every expanding leaf (one SIMT pass of
+//      the move generator for 32 leaves instead of 32 passes), a prefix sum that gives every leaf the node ids the
+//      sequential order would have given it;
+//   2. all new children of the chunk as one flat range, 32 per step with every lane busy: position after the move
+//      (flips + the mover's next legal moves), prior gathered from the policy row through the symmetry;
+//   3. the 32 backups in slot order.
 template <int WARPS>
 __global__ void __launch_bounds__(WARPS * 32) expand_kernel(Tree t, const float *__restrict__ policy, const float *__restrict__ value) {
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
@@ -333,72 +344,91 @@ __global__ void __launch_bounds__(WARPS * 32) expand_kernel(Tree t, const float 
     if (t.g_status[g] & 1) continue;
     const size_t base = arena_base(t, g);
     int count = t.g_count[g];                            // nodes in the arena; kept in a register, written back once
-    // Per-slot inputs of 32 slots at a time, one slot per lane: two memory round trips for the chunk instead of two per
-    // slot on the sequential chain below (slots are processed in order: backups add floats to shared ancestors).
-    int c_leaf = 0, c_len = 0, c_tf = 0, c_meta = 0;
-    float c_val = 0.f;
-    uint64_t c_p1 = 0, c_p2 = 0;
-    for (int i = 0; i < B; ++i) {
-        const size_t slot = (size_t)g * B + i;
-        const int li = i & 31;
-        if (li == 0) {
-            __syncwarp();
-            if (i + lane < B) {
-                const size_t sl = slot + lane;
-                c_leaf = t.s_leaf[sl]; c_len = t.s_len[sl]; c_tf = t.s_tf[sl]; c_val = value[sl];
-                c_meta = t.n_meta[base + c_leaf]; c_p1 = t.n_p1[base + c_leaf]; c_p2 = t.n_p2[base + c_leaf];
-            }
-        }
-        const int leaf = __shfl_sync(0xffffffffu, c_leaf, li);
-        const int m = __shfl_sync(0xffffffffu, c_meta, li);
-        const int player = m & 3;
-        const uint64_t lp1 = __shfl_sync(0xffffffffu, c_p1, li), lp2 = __shfl_sync(0xffffffffu, c_p2, li);
-        if (player != 0 && (m >> 8) == 0) {           // still childless (:135)
-            const uint64_t me = player == 1 ? lp1 : lp2, opp = player == 1 ? lp2 : lp1;
-            const uint64_t legal = legal_moves(me, opp);
-            const int n = legal ? __popcll(legal) : 1;
-            const int first = count;
-            if (first + n > t.cap) {
-                if (lane == 0) atomicOr(t.error, kErrArenaFull);
-            } else {
-                const int tf = __shfl_sync(0xffffffffu, c_tf, li);
-                const float *pol = policy + slot * 65;
-                Position s; s.player = player; s.p1 = lp1; s.p2 = lp2; s.legal = legal;
-                s.next_legal = legal ? 0 : legal_moves(opp, me);
-                for (int j = lane; j < n; j += 32) {   // one child position per lane
-                    const int a = legal ? nth_action(legal, j) : 64;
-                    const Position c = apply_action(s, a);
-                    const size_t d = base + first + j;
-                    t.n_p1[d] = c.p1; t.n_p2[d] = c.p2; t.n_meta[d] = c.player;
-                    t.n_parent[d] = leaf; t.n_child[d] = -1;
-                    t.n_N[d] = 0; t.n_W[d] = 0.f; t.n_Q[d] = 0.f;
-                    t.n_P[d] = pol[transform_action(a, tf)];   // raw softmax output, no renormalisation (:139-149)
-                }
-                if (lane == 0) { t.n_child[base + leaf] = first; t.n_meta[base + leaf] = player | (n << 8); }
-                count = first + n;
-                if (c_leaf == leaf) c_meta = player | (n << 8);   // later slots of the chunk that hold the same leaf see it expanded (:135)
-                expanded += (unsigned)n;
-            }
-        }
-        float v;
-        if (player != 0) {
-            v = -__shfl_sync(0xffffffffu, c_val, li);  // edge value is from the parent's view (:156-157)
-        } else {                                       // terminal: disc count from the parent's side (:158-177)
-            const int par = t.n_parent[base + leaf];
-            const int pp = par >= 0 ? (t.n_meta[base + par] & 3) : t.h_player[(size_t)g * kMaxHist];
-            const int pc = __popcll(pp == 1 ? lp1 : lp2), oc = __popcll(pp == 1 ? lp2 : lp1);
-            v = pc > oc ? 1.0f : (pc < oc ? -1.0f : 0.0f);
-        }
-        // backup along the stored path (leaf last); the sign alternates towards the root
-        const int len = __shfl_sync(0xffffffffu, c_len, li);
-        const int *gpath = t.s_path + slot * kMaxDepth;
-        for (int k = lane; k < len; k += 32) {
-            const size_t a = base + gpath[k];
-            const float vk = ((len - 1 - k) & 1) ? -v : v;
-            const float w = __fadd_rn(t.n_W[a], __fadd_rn(1.0f, vk));   // W += 1 + v cancels the virtual loss (:184)
-            t.n_W[a] = w; t.n_Q[a] = __fdiv_rn(w, (float)t.n_N[a]);
-        }
+    for (int i0 = 0; i0 < B; i0 += 32) {
+        const int chunk = min(32, B - i0);
+        const size_t slot0 = (size_t)g * B + i0;
+        // ---- 1. per-slot inputs, one slot per lane
         __syncwarp();
+        const bool c_valid = lane < chunk;
+        int c_leaf = -1 - lane, c_len = 0, c_tf = 0, c_meta = 0;
+        float c_val = 0.f;
+        uint64_t c_p1 = 0, c_p2 = 0;
+        if (c_valid) {
+            const size_t sl = slot0 + lane;
+            c_leaf = t.s_leaf[sl]; c_len = t.s_len[sl]; c_tf = t.s_tf[sl]; c_val = value[sl];
+            c_meta = t.n_meta[base + c_leaf]; c_p1 = t.n_p1[base + c_leaf]; c_p2 = t.n_p2[base + c_leaf];
+        }
+        const int c_player = c_meta & 3;
+        const unsigned same = __match_any_sync(0xffffffffu, c_leaf);          // lanes holding the same leaf
+        const bool expands = c_valid && c_player != 0 && (c_meta >> 8) == 0 && (__ffs(same) - 1) == lane;
+        const uint64_t c_me = c_player == 1 ? c_p1 : c_p2, c_opp = c_player == 1 ? c_p2 : c_p1;
+        const uint64_t c_legal = expands ? legal_moves(c_me, c_opp) : 0;
+        const uint64_t c_next = (expands && !c_legal) ? legal_moves(c_opp, c_me) : 0;
+        const int c_n = expands ? (c_legal ? __popcll(c_legal) : 1) : 0;
+        int incl = c_n;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+        int total = __shfl_sync(0xffffffffu, incl, 31);
+        const int c_off = incl - c_n;
+        if (count + total > t.cap) {                     // cannot happen after oz_engine's capacity check; reported, nothing expanded
+            if (lane == 0) atomicOr(t.error, kErrArenaFull);
+            total = 0;
+        }
+        // ---- 2. the children of the chunk, flat
+        for (int k0 = 0; k0 < total; k0 += 32) {
+            const int k = k0 + lane;
+            int sidx = 0;                                // first lane whose inclusive prefix exceeds k
+#pragma unroll
+            for (int step = 16; step; step >>= 1) {
+                const int cand = sidx + step;
+                const int v = __shfl_sync(0xffffffffu, incl, (cand - 1) & 31);
+                if (cand <= 31 && v <= k) sidx = cand;
+            }
+            Position sp;
+            sp.player = __shfl_sync(0xffffffffu, c_player, sidx);
+            sp.p1 = __shfl_sync(0xffffffffu, c_p1, sidx); sp.p2 = __shfl_sync(0xffffffffu, c_p2, sidx);
+            sp.legal = __shfl_sync(0xffffffffu, c_legal, sidx); sp.next_legal = __shfl_sync(0xffffffffu, c_next, sidx);
+            const int leaf_s = __shfl_sync(0xffffffffu, c_leaf, sidx), tf_s = __shfl_sync(0xffffffffu, c_tf, sidx);
+            const int j = k - __shfl_sync(0xffffffffu, c_off, sidx);
+            if (k < total) {
+                const int a = sp.legal ? nth_action(sp.legal, j) : 64;
+                const Position c = apply_action(sp, a);
+                const size_t d = base + count + k;
+                t.n_p1[d] = c.p1; t.n_p2[d] = c.p2; t.n_meta[d] = c.player;
+                t.n_parent[d] = leaf_s; t.n_child[d] = -1;
+                t.n_N[d] = 0; t.n_W[d] = 0.f; t.n_Q[d] = 0.f;
+                t.n_P[d] = policy[(slot0 + sidx) * 65 + transform_action(a, tf_s)];   // raw softmax output, no renormalisation (:139-149)
+            }
+        }
+        if (expands && total > 0) { t.n_child[base + c_leaf] = count + c_off; t.n_meta[base + c_leaf] = c_player | (c_n << 8); }
+        count += total;
+        expanded += (unsigned)total;
+        __syncwarp();
+        // ---- 3. backups in slot order
+        for (int li = 0; li < chunk; ++li) {
+            const int leaf = __shfl_sync(0xffffffffu, c_leaf, li);
+            const int player = __shfl_sync(0xffffffffu, c_player, li);
+            float v;
+            if (player != 0) {
+                v = -__shfl_sync(0xffffffffu, c_val, li);  // edge value is from the parent's view (:156-157)
+            } else {                                       // terminal: disc count from the parent's side (:158-177)
+                const uint64_t lp1 = __shfl_sync(0xffffffffu, c_p1, li), lp2 = __shfl_sync(0xffffffffu, c_p2, li);
+                const int par = t.n_parent[base + leaf];
+                const int pp = par >= 0 ? (t.n_meta[base + par] & 3) : t.h_player[(size_t)g * kMaxHist];
+                const int pc = __popcll(pp == 1 ? lp1 : lp2), oc = __popcll(pp == 1 ? lp2 : lp1);
+                v = pc > oc ? 1.0f : (pc < oc ? -1.0f : 0.0f);
+            }
+            // along the stored path (leaf last); the sign alternates towards the root
+            const int len = __shfl_sync(0xffffffffu, c_len, li);
+            const int *gpath = t.s_path + (slot0 + li) * kMaxDepth;
+            for (int k = lane; k < len; k += 32) {
+                const size_t a = base + gpath[k];
+                const float vk = ((len - 1 - k) & 1) ? -v : v;
+                const float w = __fadd_rn(t.n_W[a], __fadd_rn(1.0f, vk));   // W += 1 + v cancels the virtual loss (:184)
+                t.n_W[a] = w; t.n_Q[a] = __fdiv_rn(w, (float)t.n_N[a]);
+            }
+            __syncwarp();
+        }
     }
     if (lane == 0) t.g_count[g] = count;
     }
