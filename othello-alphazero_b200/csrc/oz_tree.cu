@@ -404,7 +404,16 @@ __global__ void __launch_bounds__(WARPS * 32) expand_kernel(Tree t, const float 
         count += total;
         expanded += (unsigned)total;
         __syncwarp();
-        // ---- 3. backups in slot order
+        // ---- 3. backups in slot order.  The first eight path entries of every slot are fetched up front, transposed over
+        // the warp (lane 8 * (s % 4) + k holds entry k of slots s = 4 r + ..., r = 0..7), so the sequential part below
+        // starts with the nodes' W and N instead of a dependent read of the path; longer paths read the rest from memory.
+        int pa[8];
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+            const int sl = 4 * r + (lane >> 3), k = lane & 7;
+            const int ln = __shfl_sync(0xffffffffu, c_len, sl);
+            pa[r] = (sl < chunk && k < ln) ? t.s_path[(slot0 + sl) * kMaxDepth + k] : -1;
+        }
         for (int li = 0; li < chunk; ++li) {
             const int leaf = __shfl_sync(0xffffffffu, c_leaf, li);
             const int player = __shfl_sync(0xffffffffu, c_player, li);
@@ -421,8 +430,12 @@ __global__ void __launch_bounds__(WARPS * 32) expand_kernel(Tree t, const float 
             // along the stored path (leaf last); the sign alternates towards the root
             const int len = __shfl_sync(0xffffffffu, c_len, li);
             const int *gpath = t.s_path + (slot0 + li) * kMaxDepth;
+            int par_r = pa[0];
+#pragma unroll
+            for (int r = 1; r < 8; ++r) if ((li >> 2) == r) par_r = pa[r];
+            const int pre = __shfl_sync(0xffffffffu, par_r, ((li & 3) << 3) + (lane & 7));
             for (int k = lane; k < len; k += 32) {
-                const size_t a = base + gpath[k];
+                const size_t a = base + (k < 8 ? pre : gpath[k]);
                 const float vk = ((len - 1 - k) & 1) ? -v : v;
                 const float w = __fadd_rn(t.n_W[a], __fadd_rn(1.0f, vk));   // W += 1 + v cancels the virtual loss (:184)
                 t.n_W[a] = w; t.n_Q[a] = __fdiv_rn(w, (float)t.n_N[a]);
