@@ -238,18 +238,22 @@ __global__ void __launch_bounds__(WARPS * 32) select_kernel(Tree t) {
 }
 
 // ------------------------------------------------------------------ encode (search_thread.cpp:87-100, transformation.h:83-116)
-// Positions of `node` and its ancestors, newest first: the chain inside the arena, then the
-// retired ancestors of the root (position_iterator.h:49-52 crosses the root the same way).
-__device__ __forceinline__ int gather_history(const Tree &t, int g, size_t base, int node, int lane,
-                                              uint64_t *sp1, uint64_t *sp2) {
-    int n = 0;
-    if (lane == 0) {
-        int nd = node;
-        while (n < t.H && nd >= 0) { sp1[n] = t.n_p1[base + nd]; sp2[n] = t.n_p2[base + nd]; nd = t.n_parent[base + nd]; ++n; }
-        const int hn = t.h_n[g];
-        for (int r = 0; n < t.H && r < hn; ++r, ++n) { sp1[n] = t.h_p1[(size_t)g * kMaxHist + r]; sp2[n] = t.h_p2[(size_t)g * kMaxHist + r]; }
+// Positions of the leaf of `slot` and its ancestors, newest first: the chain inside the arena, then the retired
+// ancestors of the root (position_iterator.h:49-52 crosses the root the same way).  The chain is not walked through the
+// parent links (one dependent read per ply of history): the selection stored its path, which IS the chain -- entry
+// len - 1 is the leaf, entry 0 the root's child -- so lane k reads the k-th position back directly.
+__device__ __forceinline__ int gather_history(const Tree &t, int g, size_t base, size_t slot, int lane, uint64_t *sp1, uint64_t *sp2) {
+    const int len = t.s_len[slot], hn = t.h_n[g];
+    const int n = min(t.H, len + 1 + hn);
+    if (lane < n) {
+        if (lane <= len) {
+            const int nd = lane < len ? t.s_path[slot * kMaxDepth + (len - 1 - lane)] : t.g_root[g];
+            sp1[lane] = t.n_p1[base + nd]; sp2[lane] = t.n_p2[base + nd];
+        } else {
+            const int r = lane - len - 1;
+            sp1[lane] = t.h_p1[(size_t)g * kMaxHist + r]; sp2[lane] = t.h_p2[(size_t)g * kMaxHist + r];
+        }
     }
-    n = __shfl_sync(0xffffffffu, n, 0);
     __syncwarp();
     return n;
 }
@@ -315,7 +319,7 @@ __global__ void __launch_bounds__(WARPS * 32) encode_kernel(Tree t, float *featu
             tf = (int)(r[0] & 7u);
         }
         if (lane == 0) t.s_tf[slot] = tf;
-        const int nh = gather_history(t, g, base, leaf, lane, s1[wib], s2[wib]);
+        const int nh = gather_history(t, g, base, slot, lane, s1[wib], s2[wib]);
         if (nhwc) write_planes_nhwc(nhwc + slot * 64 * 32, nh, s1[wib], s2[wib], player, tf, lane);
         else write_planes(features + slot * (size_t)(1 + 2 * t.H) * 64, t.H, nh, s1[wib], s2[wib], (float)player - 1.0f, tf, lane);
         __syncwarp();                                     // the history buffer is reused by the next slot
@@ -704,10 +708,12 @@ __global__ void self_play_data_kernel(Tree t, int g, float *features, float *pol
     const int root = t.g_root[g];
     const int m = t.n_meta[base + root];
     const int player = m & 3, nch = m >> 8, fc = t.n_child[base + root];
-    if (tf == 0) gather_history(t, g, base, root, lane, s1, s2);
+    const int nh = min(t.H, 1 + t.h_n[g]);                      // the root, then its retired ancestors
+    if (tf == 0 && lane < nh) {
+        s1[lane] = lane == 0 ? t.n_p1[base + root] : t.h_p1[(size_t)g * kMaxHist + lane - 1];
+        s2[lane] = lane == 0 ? t.n_p2[base + root] : t.h_p2[(size_t)g * kMaxHist + lane - 1];
+    }
     __syncthreads();
-    int nh = 0;
-    { int nd = root; while (nh < t.H && nd >= 0) { nd = t.n_parent[base + nd]; ++nh; } nh = min(t.H, nh + t.h_n[g]); }
     write_planes(features + (size_t)tf * (1 + 2 * t.H) * 64, t.H, nh, s1, s2, (float)player - 1.0f, tf, lane);
     float *pol = policy + tf * 65;
     for (int i = lane; i < 65; i += 32) pol[i] = 0.f;
