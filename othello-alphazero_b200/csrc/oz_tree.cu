@@ -163,12 +163,13 @@ __global__ void __launch_bounds__(WARPS * 32) select_kernel(Tree t) {
                 n0 = rn0; n1 = rn1; w0 = rw0; w1 = rw1; q0 = rq0; q1 = rq1; p0 = rp0; p1 = rp1; cm0 = rcm0; cm1 = rcm1; cf0 = rcf0; cf1 = rcf1;
             } else {                                 // one round trip: statistics and headers of all children
                 const size_t a0 = base + fc + c0, a1 = base + fc + c1;
-                n0 = v0 ? t.n_N[a0] : 0; n1 = v1 ? t.n_N[a1] : 0;
-                w0 = v0 ? t.n_W[a0] : 0.f; w1 = v1 ? t.n_W[a1] : 0.f;
-                q0 = v0 ? t.n_Q[a0] : 0.f; q1 = v1 ? t.n_Q[a1] : 0.f;
-                p0 = v0 ? t.n_P[a0] : 0.f; p1 = v1 ? t.n_P[a1] : 0.f;
-                cm0 = v0 ? t.n_meta[a0] : 0; cm1 = v1 ? t.n_meta[a1] : 0;
-                cf0 = v0 ? t.n_child[a0] : -1; cf1 = v1 ? t.n_child[a1] : -1;
+                n0 = v0 ? t.n_N[a0] : 0; w0 = v0 ? t.n_W[a0] : 0.f; q0 = v0 ? t.n_Q[a0] : 0.f; p0 = v0 ? t.n_P[a0] : 0.f;
+                cm0 = v0 ? t.n_meta[a0] : 0; cf0 = v0 ? t.n_child[a0] : -1;
+                n1 = 0; w1 = 0.f; q1 = 0.f; p1 = 0.f; cm1 = 0; cf1 = -1;
+                if (nch > 32) {                      // a 33rd child exists in a handful of positions only: warp-uniform branch
+                    n1 = v1 ? t.n_N[a1] : 0; w1 = v1 ? t.n_W[a1] : 0.f; q1 = v1 ? t.n_Q[a1] : 0.f; p1 = v1 ? t.n_P[a1] : 0.f;
+                    cm1 = v1 ? t.n_meta[a1] : 0; cf1 = v1 ? t.n_child[a1] : -1;
+                }
             }
             int idx = 0;                             // a single child is taken without any arithmetic (:194-196)
             if (nch > 1) {
@@ -179,16 +180,16 @@ __global__ void __launch_bounds__(WARPS * 32) select_kernel(Tree t) {
                 const float mult = __fmul_rn(rate, __fsqrt_rn((float)total));
                 if (at_root && noisy) {              // Dirichlet noise, re-drawn per selection (:230-249)
                     const float g0 = v0 ? s_gamma[wib][i & 31][c0] : 0.f;
-                    const float g1 = v1 ? s_gamma[wib][i & 31][c1] : 0.f;
+                    const float g1 = (nch > 32 && v1) ? s_gamma[wib][i & 31][c1] : 0.f;
                     const float sum = s_gsum[wib][i & 31];
                     const float pm = __fsub_rn(1.0f, t.eps), nm2 = __fdiv_rn(t.eps, sum);
                     p0 = __fadd_rn(__fmul_rn(p0, pm), __fmul_rn(g0, nm2));
-                    p1 = __fadd_rn(__fmul_rn(p1, pm), __fmul_rn(g1, nm2));
+                    if (nch > 32) p1 = __fadd_rn(__fmul_rn(p1, pm), __fmul_rn(g1, nm2));
                 }
                 // ucb = Q + (mult * P) / (1 + N)
                 float u = -INFINITY; idx = INT_MAX;
                 if (v0) { u = __fadd_rn(q0, __fdiv_rn(__fmul_rn(mult, p0), __fadd_rn(1.0f, (float)n0))); idx = c0; }
-                if (v1) {
+                if (nch > 32 && v1) {
                     const float u1 = __fadd_rn(q1, __fdiv_rn(__fmul_rn(mult, p1), __fadd_rn(1.0f, (float)n1)));
                     if (u1 > u) { u = u1; idx = c1; }
                 }
