@@ -117,6 +117,9 @@ typedef struct {
     int32_t  sym_mode;           /* OZ_SYM_* (reference: uniform_int_distribution(0,7), search_thread.cpp:24) */
     int32_t  temperature_plies;  /* plies sampled proportionally to visits (train.py:422: 12) */
     int32_t  max_nodes_per_game; /* 0 = derive from num_simulations */
+    float    self_play_temperature; /* > 0; sampling weights are visit_counts ** (1 / T) while ply < temperature_plies
+                                       (train.py:423, --self-play-temperature; default 1) */
+    int32_t  reserved;           /* 0 */
 } oz_config;
 
 void oz_config_default(oz_config *cfg);

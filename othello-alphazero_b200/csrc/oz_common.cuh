@@ -17,6 +17,18 @@ int fail(int status, const std::string &msg);
 extern unsigned long long g_kernel_launches;
 inline void count_launch(int n = 1) { g_kernel_launches += (unsigned long long)n; }
 
+// cudaFuncSetAttribute applies to the CURRENT device only, so "already set" is tracked per device ordinal (a process
+// may own engines on several GPUs, e.g. MCTS(torch_device="cuda:1") after one on cuda:0).  True the first time it is
+// called for `mask` on the current device.
+inline bool first_use_on_device(unsigned long long &mask) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    const unsigned long long bit = 1ull << (dev & 63);
+    if (mask & bit) return false;
+    mask |= bit;
+    return true;
+}
+
 }  // namespace oz
 
 #define OZ_CUDA(expr)                                                                     \

@@ -57,6 +57,7 @@ struct oz_engine {
     cudaEvent_t ev_fork = nullptr, ev_join[kMaxGroups] = {}, ev_sel[kMaxGroups] = {}, ev_net[kMaxGroups] = {};
     int active = 0;                       // games not finished
     long tree_bound = 1;                  // upper bound on the nodes of the largest live tree
+    long rootn_bound = 0;                 // upper bound on any node's visit count (index into the exploration-rate table)
     oz_counters ctr{};
     bool profiling = false;
     std::vector<cudaEvent_t> ev;          // phase boundaries of one search
@@ -84,6 +85,7 @@ int check_config(const oz_config &c) {
 int check_engine_limits(const oz_config &c) {
     if (c.num_games < 1) return fail(OZ_ERR_INVALID_ARGUMENT, "Expected num_games >= 1, but got " + std::to_string(c.num_games) + ".");
     if (c.history_size > kMaxHist) return fail(OZ_ERR_INVALID_ARGUMENT, "history_size above " + std::to_string(kMaxHist) + " is not supported by the device engine.");
+    if (!(c.self_play_temperature > 0.0f)) return fail(OZ_ERR_INVALID_ARGUMENT, "Expected self_play_temperature > 0.0, but got " + std::to_string(c.self_play_temperature) + ".");
     return OZ_OK;
 }
 
@@ -160,9 +162,9 @@ int alloc_slots(oz_engine *e) {
 
 // Exploration rate by visit count, computed with the host libm the reference links
 // (search_thread.cpp:198-203): logf((1 + N + c_base) / c_base) + c_init.
-int build_rate_table(oz_engine *e) {
+int build_rate_table(oz_engine *e, long min_len = 0) {
     const long sims = (long)rounds_of(e->cfg) * e->cfg.num_threads * e->cfg.batch_size;
-    const long len = std::min<long>(std::max<long>(sims * 140 + 1024, 4096), 1L << 24);
+    const long len = std::min<long>(std::max<long>({sims * 140 + 1024, 4096L, min_len, (long)e->t.rate_len}), 1L << 26);   // never shrinks
     std::vector<float> tab((size_t)len);
     const float cb = e->cfg.c_puct_base, ci = e->cfg.c_puct_init;
     for (long n = 0; n < len; ++n) tab[(size_t)n] = std::log(((float)(1 + (int)n) + cb) / cb) + ci;
@@ -178,6 +180,7 @@ void sync_params(oz_engine *e) {
     t.eps = e->cfg.dirichlet_epsilon; t.alpha = e->cfg.dirichlet_alpha;
     t.seed_lo = (uint32_t)e->cfg.seed; t.seed_hi = (uint32_t)(e->cfg.seed >> 32);
     t.first_game_id = e->cfg.first_game_id; t.sym_mode = e->cfg.sym_mode; t.temperature_plies = e->cfg.temperature_plies;
+    t.inv_temperature = 1.0f / e->cfg.self_play_temperature;
 }
 
 int check_device_errors(oz_engine *e) {
@@ -236,6 +239,29 @@ int ensure_capacity(oz_engine *e) {
     return OZ_OK;
 }
 
+// The reference evaluates logf((1 + N + c_base) / c_base) for any N (search_thread.cpp:198-203) and allows any number
+// of searches from the same root; the table indexed by N is therefore extended when the largest visit count a search
+// can reach would leave it.  rootn_bound is a host-side bound (every search adds its simulations to the root; a child
+// never has more visits than its parent); it is tightened with one read-back before paying for a rebuild.
+int ensure_rate_table(oz_engine *e) {
+    const long sims = (long)rounds_of(e->cfg) * e->cfg.num_threads * e->cfg.batch_size;
+    if (e->rootn_bound + sims + 2 > e->t.rate_len) {
+        std::vector<int32_t> rn((size_t)e->t.G);
+        launch_root_stats(e->t, nullptr, nullptr, nullptr, e->d_stat_rootn, e->stream);
+        OZ_CUDA(cudaMemcpyAsync(rn.data(), e->d_stat_rootn, rn.size() * sizeof(int32_t), cudaMemcpyDeviceToHost, e->stream));
+        OZ_CUDA(cudaStreamSynchronize(e->stream));
+        e->rootn_bound = *std::max_element(rn.begin(), rn.end());
+    }
+    if (e->rootn_bound + sims + 2 > e->t.rate_len) {
+        if (e->rootn_bound + sims + 2 > (1L << 26)) return fail(OZ_ERR_CAPACITY, "visit count beyond 64 M: the exploration-rate table cannot grow further");
+        drop_graph(e);
+        OZ_CUDA(cudaStreamSynchronize(e->stream));
+        OZ_TRY(build_rate_table(e, 2 * (e->rootn_bound + sims + 2)));
+    }
+    e->rootn_bound += sims;
+    return OZ_OK;
+}
+
 // One evaluator call over `n` leaf slots starting at slot `first` (ws = network workspace = pipeline group).
 // staged = the encode kernel already wrote the network's own input tensor (encode_target).
 int eval_slots(oz_engine *e, size_t first, size_t n, cudaStream_t stream, int ws, cudaEvent_t conv_begin = nullptr, cudaEvent_t conv_end = nullptr,
@@ -277,6 +303,7 @@ int begin_search(oz_engine *e) {
     if (e->cfg.evaluator == OZ_EVAL_RESNET && !e->net.loaded()) return fail(OZ_ERR_STATE, "no network weights loaded");
     sync_params(e);
     OZ_TRY(ensure_capacity(e));
+    OZ_TRY(ensure_rate_table(e));
     // New SearchThread per search: feature slots start from zeros (search_thread.cpp:37-39).  Only slots of terminal
     // leaves keep them, and their network outputs are never read, so the native network's own input tensor is not re-zeroed.
     if (e->cfg.evaluator != OZ_EVAL_RESNET)
@@ -407,7 +434,7 @@ void oz_config_default(oz_config *c) {
     c->num_games = 1; c->history_size = 4; c->num_simulations = 800; c->num_threads = 2; c->batch_size = 16;
     c->c_puct_base = 20000.0f; c->c_puct_init = 2.5f; c->dirichlet_epsilon = 0.25f; c->dirichlet_alpha = 0.5f;
     c->seed = 0; c->first_game_id = 0; c->device = 0; c->evaluator = OZ_EVAL_EXTERNAL; c->sym_mode = OZ_SYM_RANDOM;
-    c->temperature_plies = 12; c->max_nodes_per_game = 0;
+    c->temperature_plies = 12; c->max_nodes_per_game = 0; c->self_play_temperature = 1.0f; c->reserved = 0;
 }
 
 int oz_engine_create(const oz_config *cfg, oz_engine **out) {
@@ -527,6 +554,7 @@ int oz_engine_reset(oz_engine *e) {
     launch_reset(e->t, e->stream);
     e->active = e->t.G;
     e->tree_bound = 1;
+    e->rootn_bound = 0;
     if (e->done.capacity > 0) {
         const int32_t init[3] = {0, e->t.G, 0};
         OZ_CUDA(cudaMemcpyAsync(e->done.counters, init, sizeof(init), cudaMemcpyHostToDevice, e->stream));
@@ -771,7 +799,7 @@ static int search_games(oz_engine *e, int g0, int g1) {
         const uint64_t evals_before = e->ctr.evaluations;
         void *gx0 = nullptr;
         if ((st = encode_target(e, boards, 0, &gx0))) { e->in_search = false; return st; }
-        OZ_CUDA(cudaStreamBeginCapture(e->stream, cudaStreamCaptureModeThreadLocal));
+        if (cudaStreamBeginCapture(e->stream, cudaStreamCaptureModeThreadLocal) != cudaSuccess) { e->in_search = false; return fail(OZ_ERR_CUDA, "cudaStreamBeginCapture failed"); }
         launch_select(e->t, e->stream);
         launch_encode(e->t, e->d_features, e->stream, false, gx0);
         st = eval_slots(e, 0, boards, e->stream, 0, nullptr, nullptr, gx0 != nullptr);
@@ -792,7 +820,8 @@ static int search_games(oz_engine *e, int g0, int g1) {
     }
     if (want_graph) {
         for (int r = 0; r < rounds; ++r) {
-            OZ_CUDA(cudaGraphLaunch(e->round_graph, e->stream));
+            const cudaError_t ge = cudaGraphLaunch(e->round_graph, e->stream);
+            if (ge != cudaSuccess) { e->in_search = false; return fail(OZ_ERR_CUDA, std::string("cudaGraphLaunch: ") + cudaGetErrorString(ge)); }
             count_launch((int)e->graph_launches);
             e->ctr.evaluations += boards;
         }

@@ -691,11 +691,10 @@ static int make_w_map(CUtensorMap *m, void *ptr, int cin, int cout, int box_rows
 // with streamed weights -- 256 channels -- load every weight tile twice.)
 static int launch_conv(const CUtensorMap &ma, const CUtensorMap *ma1, const CUtensorMap &mw, const ConvParams &cp, cudaStream_t stream,
                        bool pdl = true) {
-    static bool attr_set = false;
-    if (!attr_set) {
+    static unsigned long long attr_devices = 0;
+    if (first_use_on_device(attr_devices)) {
         OZ_CUDA(cudaFuncSetAttribute(conv3x3_pair_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, pair::kSmemBytesP));
         OZ_CUDA(cudaFuncSetAttribute(conv3x3_pair_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, pair::kSmemBytesP));
-        attr_set = true;
     }
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
@@ -839,8 +838,10 @@ int ResNet::forward(const float *d_features, size_t n, float *d_policy, float *d
     hp.pre = fuse_heads ? d_head_pre_ : nullptr;
     hp.policy = d_policy; hp.value = d_value; hp.C = C; hp.Hv = shape_.value_hidden; hp.n = n;
     const size_t hsm = (size_t)heads_smem_floats(C, hp.Hv) * sizeof(float);
-    static size_t hsm_set = 0;
-    if (hsm > hsm_set) { OZ_CUDA(cudaFuncSetAttribute(heads_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hsm)); hsm_set = hsm; }
+    static size_t hsm_set[64] = {};                      // per device ordinal: the attribute belongs to the current device
+    int hdev = 0;
+    cudaGetDevice(&hdev);
+    if (hsm > hsm_set[hdev & 63]) { OZ_CUDA(cudaFuncSetAttribute(heads_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hsm)); hsm_set[hdev & 63] = hsm; }
     const size_t want = (n + kHeadWarps * kHeadBoards - 1) / (kHeadWarps * kHeadBoards);
     const unsigned grid = (unsigned)(want < 148 * 2 ? want : 148 * 2);
     heads_kernel<<<grid, kHeadWarps * 32, hsm, stream>>>(hp);

@@ -192,7 +192,7 @@ using namespace oz;
 extern "C" {
 
 const char *oz_last_error(void) { return t_error.c_str(); }
-int oz_abi_version(void) { return 3; }
+int oz_abi_version(void) { return 4; }
 
 uint64_t oz_get_legal_moves(uint64_t a, uint64_t b) { return legal_moves(a, b); }
 uint64_t oz_get_flips(uint64_t m, uint64_t a, uint64_t b) { return flips(m, a, b); }

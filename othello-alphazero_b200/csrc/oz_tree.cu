@@ -87,7 +87,7 @@ __global__ void reset_kernel(Tree t) {
 
 // ------------------------------------------------------------------ select (search_thread.cpp:60-79, 192-260)
 // WARPS = warps (games) per block; a warp walks games g, g + stride, ...  The pipelined search launches a bounded grid
-// of single-warp blocks without shared memory: they fit into the registers a resident convolution CTA leaves free on
+// of single-warp blocks (4.3 KB of static shared memory for the precomputed noise): they fit into the registers a resident convolution CTA leaves free on
 // its SM (6 400 of 65 536), so one game group's tree work runs underneath the other group's network and never keeps a
 // convolution CTA off an SM.  The path of a selection lives in registers (lane k holds nodes k, k + 32, ...).
 //
@@ -489,7 +489,18 @@ __global__ void choose_kernel(Tree t, int32_t *actions) {
     philox(t.g_gameid[g], (uint32_t)t.g_ply[g], 0xFFFFFFFFu, 2u, t.seed_lo, t.seed_hi, r);
     int pick_j = 0;
     if (nch != 0) {
-        if (t.g_ply[g] < t.temperature_plies) {      // proportional to visit counts (tau = 1)
+        if (t.g_ply[g] < t.temperature_plies && t.inv_temperature != 1.0f) {
+            // visit_counts ** (1 / tau), normalised, then one draw (train.py:423-425; np.random.choice walks the cumulative sum)
+            float wsum = 0.f;
+            for (int j = 0; j < n; ++j) wsum += powf((float)t.n_N[base + fc + j], t.inv_temperature);
+            if (!(wsum > 0.f)) pick_j = (int)(((uint64_t)r[0] * (uint32_t)n) >> 32);
+            else {
+                const float pick = ((float)(r[0] >> 8) * (1.0f / 16777216.0f)) * wsum;
+                float acc = 0.f;
+                pick_j = n - 1;
+                for (int j = 0; j < n; ++j) { acc += powf((float)t.n_N[base + fc + j], t.inv_temperature); if (pick < acc) { pick_j = j; break; } }
+            }
+        } else if (t.g_ply[g] < t.temperature_plies) {      // tau = 1: proportional to visit counts, in integers
             uint32_t sum = 0;
             for (int j = 0; j < n; ++j) sum += (uint32_t)t.n_N[base + fc + j];
             if (sum == 0) pick_j = (int)(((uint64_t)r[0] * (uint32_t)n) >> 32);
@@ -830,12 +841,11 @@ constexpr unsigned kNarrowGrid = 2 * 148;
 // kernel that prefers another split cannot share the SM with it (the SM drains first), so the narrow kernels ask for
 // the same carve-out although they use next to no shared memory.
 static void narrow_attributes() {
-    static bool done = false;
-    if (done) return;
+    static unsigned long long done_devices = 0;
+    if (!first_use_on_device(done_devices)) return;
     cudaFuncSetAttribute(select_kernel<1>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     cudaFuncSetAttribute(encode_kernel<2>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     cudaFuncSetAttribute(expand_kernel<1>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-    done = true;
 }
 
 void launch_reset(const Tree &t, cudaStream_t s) { reset_kernel<<<blocks(t.G, 128), 128, 0, s>>>(t); count_launch(); }

@@ -52,6 +52,7 @@ struct Tree {
     float eps, alpha;
     uint32_t seed_lo, seed_hi, first_game_id;
     int sym_mode, temperature_plies;
+    float inv_temperature;               // 1 / self_play_temperature (train.py:423)
 };
 
 struct PlyRecordDev {     // matches oz_ply_record

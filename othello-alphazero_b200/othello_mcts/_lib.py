@@ -28,7 +28,8 @@ class OzConfig(C.Structure):
     _fields_ = [("num_games", i32), ("history_size", i32), ("num_simulations", i32), ("num_threads", i32),
                 ("batch_size", i32), ("c_puct_base", f32), ("c_puct_init", f32), ("dirichlet_epsilon", f32),
                 ("dirichlet_alpha", f32), ("seed", u64), ("first_game_id", C.c_uint32), ("device", i32),
-                ("evaluator", i32), ("sym_mode", i32), ("temperature_plies", i32), ("max_nodes_per_game", i32)]
+                ("evaluator", i32), ("sym_mode", i32), ("temperature_plies", i32), ("max_nodes_per_game", i32),
+                ("self_play_temperature", C.c_float), ("reserved", i32)]
 
 
 class OzResnetShape(C.Structure):

@@ -30,7 +30,8 @@ class _Engine:
 
     def __init__(self, num_games, history_size, torch_device, torch_pin_memory, num_simulations, num_threads,
                  batch_size, c_puct_base, c_puct_init, dirichlet_epsilon, dirichlet_alpha, seed=0, first_game_id=0,
-                 sym_mode=_lib.SYM_RANDOM, temperature_plies=12, max_nodes_per_game=0, cuda_device=None):
+                 sym_mode=_lib.SYM_RANDOM, temperature_plies=12, max_nodes_per_game=0, cuda_device=None,
+                 self_play_temperature=1.0):
         self._lib = _lib.load()
         self._torch_device = str(torch_device)
         self._torch_pin_memory = bool(torch_pin_memory)
@@ -43,6 +44,7 @@ class _Engine:
         cfg.dirichlet_epsilon, cfg.dirichlet_alpha = dirichlet_epsilon, dirichlet_alpha
         cfg.seed, cfg.first_game_id = seed, first_game_id
         cfg.sym_mode, cfg.temperature_plies, cfg.max_nodes_per_game = sym_mode, temperature_plies, max_nodes_per_game
+        cfg.self_play_temperature = self_play_temperature
         cfg.evaluator = EVAL_EXTERNAL
         if cuda_device is None:
             dev = torch.device(self._torch_device)
@@ -245,11 +247,13 @@ class SelfPlayEngine(_Engine):
                  num_simulations: int = 800, num_threads: int = 2, batch_size: int = 16, c_puct_base: float = 20000.0,
                  c_puct_init: float = 2.5, dirichlet_epsilon: float = 0.25, dirichlet_alpha: float = 0.5, *, seed: int = 0,
                  first_game_id: int = 0, sym_mode: int = _lib.SYM_RANDOM, temperature_plies: int = 12,
-                 max_nodes_per_game: int = 0, cuda_device: int | None = None) -> None:
+                 max_nodes_per_game: int = 0, cuda_device: int | None = None, self_play_temperature: float = 1.0) -> None:
+        # self_play_temperature: train.py:423 (--self-play-temperature): sampling weights visit_counts ** (1 / T) while
+        # ply < temperature_plies
         super().__init__(num_games, history_size, torch_device, torch_pin_memory, num_simulations, num_threads, batch_size,
                          c_puct_base, c_puct_init, dirichlet_epsilon, dirichlet_alpha, seed=seed, first_game_id=first_game_id,
                          sym_mode=sym_mode, temperature_plies=temperature_plies, max_nodes_per_game=max_nodes_per_game,
-                         cuda_device=cuda_device)
+                         cuda_device=cuda_device, self_play_temperature=self_play_temperature)
         self.num_games = num_games
 
     def reset(self) -> None:

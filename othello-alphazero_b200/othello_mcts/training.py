@@ -44,6 +44,7 @@ class NativeTrainer:
             self.cfg.bn_momentum, self.cfg.bn_eps = bns[0].momentum, bns[0].eps
         self.max_batch = (max_batch + 31) // 32 * 32
         self._inflight = []
+        self._steps_since_store = 0      # train-mode forwards since load_from / store_to (BatchNorm num_batches_tracked)
         self._h = C.c_void_p()
         check(self._lib.oz_trainer_create(cuda_device, C.byref(self.shape), self.max_batch, C.byref(self._h)))
         self.num_params = self._lib.oz_trainer_num_params(self._h)
@@ -72,6 +73,7 @@ class NativeTrainer:
         p = np.ascontiguousarray(p, np.float32)
         mom = None if momentum_buffers is None else np.ascontiguousarray(momentum_buffers, np.float32)
         check(self._lib.oz_trainer_set_state(self._h, _ptr(p), _ptr(b), None if mom is None else _ptr(mom)))
+        self._steps_since_store = 0
 
     def store_to(self, net) -> None:
         """Write parameters and running statistics back into `net` (e.g. before self-play or a checkpoint)."""
@@ -79,14 +81,20 @@ class NativeTrainer:
         p, b = np.zeros(self.num_params, np.float32), np.zeros(self.num_buffers, np.float32)
         check(self._lib.oz_trainer_get_state(self._h, _ptr(p), _ptr(b), None, None))
         with torch.no_grad():
-            params = list(net.parameters())
-            torch.nn.utils.vector_to_parameters(torch.from_numpy(p).to(params[0].device, params[0].dtype), params)
+            # in-place copies (p.copy_), not vector_to_parameters: that rebinds .data without bumping _version, and the
+            # engine's re-fold trigger (weights.weights_fingerprint) keys on (data_ptr, _version)
+            flat, o = torch.from_numpy(p), 0
+            for q in net.parameters():
+                k = q.numel()
+                q.copy_(flat[o:o + k].view_as(q))
+                o += k
             o = 0
             for m in _batch_norms(net):
                 c = m.num_features
                 m.running_mean.copy_(torch.from_numpy(b[o:o + c])); m.running_var.copy_(torch.from_numpy(b[o + c:o + 2 * c]))
-                m.num_batches_tracked += 0
+                m.num_batches_tracked += self._steps_since_store      # what BatchNorm2d.forward counts in train mode
                 o += 2 * c
+        self._steps_since_store = 0
 
     def gradients(self) -> np.ndarray:
         """Gradients of the last step (flat, parameter order), L2 term included."""
@@ -106,6 +114,7 @@ class NativeTrainer:
         Returns the four losses train.py:504-507 logs."""
         losses = np.zeros(4, np.float32)
         n = int(features.shape[0])
+        self._steps_since_store += 1
         if isinstance(features, torch.Tensor) and features.is_cuda:
             f, p, v = (t.detach().to(torch.float32).contiguous() for t in (features, policy, value))
             torch.cuda.current_stream(f.device).synchronize()    # the tensors are complete; the call below blocks until the losses are back
@@ -123,6 +132,7 @@ class NativeTrainer:
         trainer's stream).  The trainer keeps the tensors alive until the step that reads them has finished, so the
         caller may drop them."""
         n = int(features.shape[0])
+        self._steps_since_store += 1
         f, p, v = (t.detach().to(torch.float32).contiguous() for t in (features, policy, value))
         ev = torch.cuda.Event()
         ev.record(torch.cuda.current_stream(f.device))

@@ -22,14 +22,14 @@ def test_library_exports_every_declared_symbol():
     assert not missing, f"declared in include/othello_b200.h but not exported: {missing}"
     unbound = sorted(declared - set(_lib.SIGNATURES))
     assert not unbound, f"no ctypes signature for: {unbound}"
-    assert _lib.load().oz_abi_version() == 3
+    assert _lib.load().oz_abi_version() == 4
 
 
 def test_struct_sizes_match_abi():
     from othello_mcts import _lib
     assert C.sizeof(_lib.OzPosition) == 40
     assert C.sizeof(_lib.OzPlyRecord) == 176
-    assert C.sizeof(_lib.OzConfig) == 72
+    assert C.sizeof(_lib.OzConfig) == 80
     assert C.sizeof(_lib.OzCounters) == 120
 
 
