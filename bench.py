@@ -12,6 +12,11 @@ trees, weights and all inputs resident in HBM.  `e2e` drives the same plies thro
 reference-shaped API (search / visit counts to the host / host-side action choice / apply_action from
 host buffers), copies inside the timed region.  Timing: CUDA events on the engine stream, barrier +
 synchronize on both sides, max over ranks.  Rank 0 prints one JSON line.
+
+Beside the headline (BASELINE.json configs[2], 1 000 lockstep games per GPU = weak scaling) the same line carries two
+sub-records so that the driver's own runs hold BASELINE configs 4 and 5 (skip them with --no-extra-configs):
+  "config4": 8 192 lockstep games partitioned over the N GPUs (8192/N per GPU; N = 1 is the strong-scaling denominator),
+  "config5": 256x20b, 1 600 sims/move, leaf batch 64 ... 4096 per network call and GPU, on the N GPUs.
 """
 from __future__ import annotations
 
@@ -46,6 +51,14 @@ def flops_per_eval(cin=17, c=128, blocks=9, hv=128):
     conv = 2 * 576 * c * (cin + 2 * blocks * c)
     heads = 2 * (c * 2 * 64 + 128 * 65) + 2 * (c * 64 + 64 * hv + hv)
     return conv + heads, conv
+
+
+# The kernel legitimately skips the tile-taps that only see the zero rows -1 / 8 (6 of 72 per board); the dense FLOP
+# convention of SURVEY.md 8(d) still counts them, so the issued tensor work is this fraction of the dense figure.
+ISSUED_MMA_FRACTION = 66.0 / 72.0
+# thread-instructions per perft node of dfs_kernel<3> at depth 11: smsp__inst_executed.sum x 32 / nodes from the ncu
+# capture profiles/r01_perft_dfs_kernel.json (8 140 593 608 warp instructions for 212 258 800 leaves, 95.7 % on the ALU pipe)
+PERFT_THREAD_INST_PER_NODE = 8140593608 * 32 / 212258800
 
 
 def peaks():
@@ -104,9 +117,20 @@ class ClockSampler:
 
 
 # ----------------------------------------------------------------------------------------------
-def make_net(net_kw=None):
+def make_net(net_kw=None, reference_class=False):
+    """Random-init network (torch.manual_seed(0), default PyTorch init, eval mode).  Our arm builds the repo's class
+    (pinned bit for bit to the reference class by tests/test_net_golden.py); the reference arm builds the reference's own
+    class from oracle/_ref/python when build() has placed it there."""
     import torch
-    from othello_mcts.neural_net import AlphaZeroNet
+    AlphaZeroNet = None
+    if reference_class and (ROOT / "oracle" / "_ref" / "python" / "othello_alphazero" / "neural_net.py").exists():
+        sys.path.insert(0, str(ROOT / "oracle" / "_ref" / "python"))
+        try:
+            from othello_alphazero.neural_net import AlphaZeroNet
+        except Exception:
+            AlphaZeroNet = None
+    if AlphaZeroNet is None:
+        from othello_mcts.neural_net import AlphaZeroNet
     torch.manual_seed(0)
     return AlphaZeroNet(**(net_kw or NET)).eval()
 
@@ -129,7 +153,7 @@ def reference_search_rate(steps: int, warmup: int, threads: int):
     import numpy as np
     import torch
     torch.set_num_threads(threads)
-    net = make_net()
+    net = make_net(reference_class=True)
     kind = "port"
     mcts = None
     ref_dir = ROOT / "oracle" / "_ref"
@@ -184,18 +208,57 @@ def run_reference(args):
     if rank != 0:
         return
     cores = os.cpu_count() or 1
-    steps, warmup = max(1, args.steps), max(1, min(args.warmup, 3))
+    steps, warmup = max(1, args.steps), max(args.warmup, 3)           # same --steps / --warmup handling as our arm
     rate, t, kind = reference_search_rate(steps, warmup, cores)
     line = {"metric": "mcts_simulations_per_second", "value": rate, "unit": "sims/s", "n_gpus": args.gpus, "steps": steps,
             "warmup": warmup, "ms_per_step": 1e3 * t / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic", "impl": "reference",
-            "config": dict(workload_config(args, max(1, args.gpus)),
-                           reference_sample="the reference plays the games one at a time (train.py:394-398): each step = one 800-simulation "
-                                            "search of one game, C++ MCTS (T=2 x B=16) + LibTorch CPU on all host cores"),
+            "config": workload_config(args, max(1, args.gpus)),
+            "reference_sample": "the reference plays the games one at a time (train.py:394-398): each step = one 800-simulation "
+                                "search of one game, C++ MCTS (T=2 x B=16) + LibTorch CPU on all host cores",
             "cpu_baseline": {"value": rate, "unit": "sims/s", "cores": cores, "kind": kind,
                              "sample": f"{steps} searches x 800 sims, one game, after {warmup} warm-up searches"},
             "e2e": {"value": rate, "unit": "sims/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
     print(json.dumps(line))
+
+
+def perft_cpu_baseline(cores: int) -> dict | None:
+    """perft through the REFERENCE's own Position code (position.h:202-262 behind
+    oracle/_ref/libref_shim.so; the oracle's C port if that was never built) on the host: depth 10 on one thread, depth 11
+    over a depth-4 frontier (244 positions) on `cores` threads (ctypes releases the GIL)."""
+    from concurrent.futures import ThreadPoolExecutor
+    try:
+        import pyoracle as po
+        lib, pre, kind = po.ref_shim(), "ref_", "reference"
+        if lib is None:
+            lib, pre, kind = po.lib(), "ozo_", "port"
+        fn = lambda name: getattr(lib, pre + name)
+        start = po.Pos()
+        fn("initial_position")(C.byref(start))
+        t0 = time.perf_counter()
+        n1 = int(fn("perft")(C.byref(start), 10))
+        t1 = time.perf_counter() - t0
+        frontier = [start]
+        for _ in range(4):
+            nxt = []
+            for p in frontier:
+                acts = (C.c_int * 40)()
+                for a in list(acts[: fn("legal_actions")(C.byref(p), acts)]):
+                    q = po.Pos()
+                    fn("apply_action")(C.byref(p), a, C.byref(q))
+                    nxt.append(q)
+            frontier = nxt
+        t0 = time.perf_counter()
+        with ThreadPoolExecutor(max_workers=cores) as pool:
+            nN = sum(pool.map(lambda q: int(fn("perft")(C.byref(q), 7)), frontier))
+        tN = time.perf_counter() - t0
+        return {"kind": kind, "unit": "nodes/s", "one_thread": {"depth": 10, "nodes": n1, "nodes_per_s": n1 / t1, "seconds": t1},
+                "all_threads": {"depth": 11, "nodes": nN, "threads": cores, "nodes_per_s": nN / tN, "seconds": tN,
+                                "split": f"{len(frontier)} depth-4 frontier positions"},
+                "value": nN / tN, "cores": cores,
+                "sample": "reference Position code (position.h) compiled -O3: perft(10) on 1 thread, perft(11) over the depth-4 frontier on all threads"}
+    except Exception as exc:  # the baseline is reported beside the GPU number, never a reason to lose the line
+        return {"error": repr(exc)}
 
 
 def run_ours(args):
@@ -222,15 +285,9 @@ def run_ours(args):
     inflight = args.threads * args.batch
     sims_per_search = -(-args.sims // inflight) * inflight
     net_kw = dict(NET, conv_channels=args.channels, num_residual_blocks=args.blocks, value_head_hidden_channels=args.hidden)
-    net_name = f"{args.channels}x{args.blocks + 1}b"
     net = make_net(net_kw)
-    # games are partitioned contiguously by id: rank r owns [r*G, (r+1)*G); no collective on the hot path
-    eng = om.SelfPlayEngine(G, seed=args.seed, first_game_id=rank * G, cuda_device=local, **kw)
-    eng.prepare(net)
-    eng.set_profiling(not args.no_profiling)
-    eng.set_pipeline(args.pipeline, bool(args.pipeline_pdl))
     lib = _lib.load()
-    stream = torch.cuda.ExternalStream(lib.oz_engine_stream(eng._h), device=torch.device("cuda", local))
+    steps, warmup = max(1, args.steps), max(args.warmup, 3)
 
     def barrier():
         torch.cuda.synchronize()
@@ -238,11 +295,13 @@ def run_ours(args):
             dist.barrier()
             torch.cuda.synchronize()
 
-    def timed(fn, steps):
+    def timed(eng, fn, n_steps):
+        """CUDA events on the engine's stream around n_steps calls, barrier + synchronize on both sides, max over ranks."""
+        stream = torch.cuda.ExternalStream(lib.oz_engine_stream(eng._h), device=torch.device("cuda", local))
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(stream)
-        for _ in range(steps):
+        for _ in range(n_steps):
             fn()
         e1.record(stream)
         barrier()
@@ -253,12 +312,23 @@ def run_ours(args):
             ms = float(t.item())
         return ms
 
+    def allsum(*vals):
+        t = torch.tensor([float(v) for v in vals], device="cuda", dtype=torch.float64)
+        if dist is not None:
+            dist.all_reduce(t)
+        return [float(x) for x in t.tolist()]
+
+    # games are partitioned contiguously by id: rank r owns [r*G, (r+1)*G); no collective on the hot path
+    eng = om.SelfPlayEngine(G, seed=args.seed, first_game_id=rank * G, cuda_device=local, **kw)
+    eng.prepare(net)
+    eng.set_profiling(not args.no_profiling)
+    eng.set_pipeline(args.pipeline, bool(args.pipeline_pdl))
+
     def dev_step():
         eng.play_ply(want_counts=False)
 
     rng = np.random.default_rng(args.seed + rank)
     h2d = d2h = 0
-
     sq = np.arange(64, dtype=np.uint64)
 
     def e2e_step():
@@ -273,21 +343,21 @@ def run_ours(args):
         pick = (rng.random(G) * tot_c)[:, None]
         j = np.minimum((np.cumsum(c, axis=1) <= pick).sum(axis=1), np.maximum(n - 1, 0))     # sampled child index
         bits = ((pos["legal"][:, None] >> (np.uint64(63) - sq)[None, :]) & np.uint64(1)).astype(np.int32)   # [G,64] by action
-        rank = np.cumsum(bits, axis=1) * bits                     # 1-based rank of every legal action
-        acts = np.argmax(rank == (j + 1)[:, None], axis=1).astype(np.int32)
+        rk = np.cumsum(bits, axis=1) * bits                       # 1-based rank of every legal action
+        acts = np.argmax(rk == (j + 1)[:, None], axis=1).astype(np.int32)
         acts[pos["legal"] == 0] = 64                              # pass
         acts[(n == 0) | (pos["player"] == 0)] = -1                # finished games
         eng.apply_actions(acts)                                   # H2D: actions (+ D2H of positions for validation)
         h2d = G * 4
         d2h = G * (4 + 36 * 4 + 36 * 4 + 4) + 2 * G * 40
 
-    for _ in range(max(args.warmup, 3)):
+    for _ in range(warmup):
         dev_step()
     c0 = eng.counters()
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    ms = timed(dev_step, args.steps)
+    ms = timed(eng, dev_step, steps)
     clocks = sampler.stop() if rank == 0 else None
     c1 = eng.counters()
     sims = (c1["simulations"] - c0["simulations"])
@@ -296,10 +366,8 @@ def run_ours(args):
     eval_ms = c1["eval_ms"] - c0["eval_ms"]
     conv_ms = c1["conv_ms"] - c0["conv_ms"]
     conv_launches = c1["conv_launches"] - c0["conv_launches"]
-    tot = torch.tensor([float(sims), float(evals), float(launches)], device="cuda", dtype=torch.float64)
-    if dist is not None:
-        dist.all_reduce(tot)                                      # the only collective: final counters
-    value = float(tot[0].item()) / (ms * 1e-3)
+    tot = allsum(sims, evals, launches)                           # the only collective: final counters
+    value = tot[0] / (ms * 1e-3)
 
     # Same device-resident step measured in the middle game: every game is fast-forwarded to ply `--midgame-ply` with
     # full-width searches on the built-in hash evaluator (tree kernels only), then the network is switched back.
@@ -312,12 +380,10 @@ def run_ours(args):
         eng.prepare(net)
         dev_step()
         m0 = eng.counters()
-        ms_mid = timed(dev_step, 2)
+        ms_mid = timed(eng, dev_step, 2)
         m1 = eng.counters()
-        mid_sims = torch.tensor([float(m1["simulations"] - m0["simulations"])], device="cuda", dtype=torch.float64)
-        if dist is not None:
-            dist.all_reduce(mid_sims)
-        mid = {"ply": args.midgame_ply + 1, "steps": 2, "value": float(mid_sims.item()) / (ms_mid * 1e-3), "unit": "sims/s",
+        mid_sims = allsum(m1["simulations"] - m0["simulations"])[0]
+        mid = {"ply": args.midgame_ply + 1, "steps": 2, "value": mid_sims / (ms_mid * 1e-3), "unit": "sims/s",
                "ms_per_step": ms_mid / 2, "select_ms_per_step": (m1["select_ms"] - m0["select_ms"]) / 2,
                "expand_ms_per_step": (m1["expand_ms"] - m0["expand_ms"]) / 2}
         eng.reset()
@@ -325,22 +391,23 @@ def run_ours(args):
         for _ in range(2):
             dev_step()
 
-    ms_e2e = timed(e2e_step, max(1, min(args.steps, 3)))
-    e2e_steps = max(1, min(args.steps, 3))
-    active_sims = e2e_steps * G * sims_per_search * world
+    # end to end through the reference-shaped calls with host buffers, over ALL --steps plies
+    e2e_step()                                                    # host-path warm-up (NumPy buffers, pinned staging)
+    ms_e2e = timed(eng, e2e_step, steps)
+    active_sims = steps * G * sims_per_search * world
     e2e_value = active_sims / (ms_e2e * 1e-3)
 
     groups = max(1, args.pipeline)
-    sel_ms, exp_ms = (c1["select_ms"] - c0["select_ms"]) / args.steps, (c1["expand_ms"] - c0["expand_ms"]) / args.steps
+    sel_ms, exp_ms = (c1["select_ms"] - c0["select_ms"]) / steps, (c1["expand_ms"] - c0["expand_ms"]) / steps
     if groups > 1:     # phases of different game groups overlap: network / conv = time at least one group spent there
-        phases = {"pipeline_groups": groups, "network (union over groups)": eval_ms / args.steps, "of_which_conv": conv_ms / args.steps,
+        phases = {"pipeline_groups": groups, "network (union over groups)": eval_ms / steps, "of_which_conv": conv_ms / steps,
                   "select_encode (sum over groups, runs under the other group's network)": sel_ms,
                   "expand_backup (sum over groups, runs under the other group's network)": exp_ms,
-                  "step time with no network running": (ms - eval_ms) / args.steps}
+                  "step time with no network running": (ms - eval_ms) / steps}
     else:
-        phases = {"pipeline_groups": 1, "select_encode": sel_ms, "network": eval_ms / args.steps, "of_which_conv": conv_ms / args.steps,
+        phases = {"pipeline_groups": 1, "select_encode": sel_ms, "network": eval_ms / steps, "of_which_conv": conv_ms / steps,
                   "expand_backup": exp_ms,
-                  "rest_of_ply (choose, record, re-root, syncs)": (ms - eval_ms) / args.steps - sel_ms - exp_ms}
+                  "rest_of_ply (choose, record, re-root, syncs)": (ms - eval_ms) / steps - sel_ms - exp_ms}
     # Tree traffic: algorithmic bytes of select / encode / expand from the engine's counters, per simulation:
     # select reads a (N, W, Q, P, meta, child) row = 24 B per child per level below the root (the root's children once per
     # round), then writes the virtual loss along the path (N, W, Q and the path entry = 16 B per node); expand reads the leaf (20 B), writes 44 B
@@ -351,6 +418,13 @@ def run_ours(args):
     planes_bytes = 64 * 32 * 2                                   # the network's bf16 NHWC input, written by encode_kernel
     tree_bytes = 24 * d_child + 16 * d_path + 20 * d_path + 48 * d_nodes + d_sims * (20 + 4 + 16 * MCTS_KW["history_size"] + planes_bytes)
     tree_ms = (c1["select_ms"] - c0["select_ms"]) + (c1["expand_ms"] - c0["expand_ms"])
+
+    del eng                                                       # free the arenas before the sub-records allocate theirs
+    extra = {}
+    if not args.no_extra_configs:
+        extra["config4"] = run_config4(args, om, net, kw, rank, world, local, timed, allsum)
+        extra["config5"] = run_config5(args, om, rank, world, local, timed, allsum)
+
     if rank == 0:
         f_all, f_conv = flops_per_eval(c=args.channels, blocks=args.blocks, hv=args.hidden)
         pk = peaks()
@@ -358,29 +432,49 @@ def run_ours(args):
         # dominant kernel: the 3x3 convolution.  Algorithmic FLOPs of this rank's conv launches in the timed region
         # (dense 2*MAC, zero-padding taps counted: SURVEY.md 8d) / their CUDA-event time on the engine stream.
         achieved = (evals * f_conv) / (conv_ms * 1e-3) / 1e12 if conv_ms > 0 else None
+        frac = (achieved / pk["bf16_sustained"]) if achieved else None
         # best of 3: the event window of oz_perft spans the host round trips between its breadth-first levels
         perft_nodes, perft_ms = min((om.perft(11, return_ms=True) for _ in range(3)), key=lambda r: r[1])
+        perft_rate = perft_nodes / (perft_ms * 1e-3) if perft_ms > 0 else None
+        int_ops, int_ms = C.c_double(), C.c_double()
+        _lib.check(lib.oz_debug_int_peak(C.byref(int_ops), C.byref(int_ms)))
+        cores = os.cpu_count() or 1
         line = {
-            "metric": "mcts_simulations_per_second", "value": value, "unit": "sims/s", "n_gpus": world, "steps": args.steps,
-            "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "metric": "mcts_simulations_per_second", "value": value, "unit": "sims/s", "n_gpus": world, "steps": steps,
+            "warmup": warmup, "ms_per_step": ms / steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": workload_config(args, world),
             "e2e": {"value": e2e_value, "unit": "sims/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "steps": e2e_steps, "path": "SelfPlayEngine.search(net) -> root_stats (host) -> numpy action choice -> apply_actions (host buffers)"},
-            "gpu_launches": int(tot[2].item()),
-            "nn_evals_per_second": float(tot[1].item()) / (ms * 1e-3),
+                    "steps": steps, "ms_per_step": ms_e2e / steps,
+                    "path": "SelfPlayEngine.search(net) -> root_stats (host) -> numpy action choice -> apply_actions (host buffers)"},
+            "gpu_launches": int(tot[2]),
+            "nn_evals_per_second": tot[1] / (ms * 1e-3),
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": pk["bf16_sustained"], "unit": "TFLOP/s",
-                         "frac": (achieved / pk["bf16_sustained"]) if achieved else None, "traffic": NCU_TRAFFIC_BYTES_PER_BOARD * G * inflight if args.channels == 128 else None,
+                         "frac": frac, "traffic": NCU_TRAFFIC_BYTES_PER_BOARD * G * inflight if args.channels == 128 else None,
                          "kernel": "conv3x3_pair_kernel (tcgen05.mma cta_group::2 implicit GEMM)",
                          "flop_per_launch": (evals * f_conv / conv_launches) if conv_launches else None,
                          "us_per_launch": (1e3 * conv_ms / conv_launches) if conv_launches else None,
                          "launches_timed": int(conv_launches), "conv_share_of_step": conv_ms / ms if ms > 0 else None,
                          "nn_share_of_step": nn_share, "frac_of_burst_peak": (achieved / pk["bf16_burst"]) if achieved else None,
-                         "traffic_note": "dram read+write bytes per launch (mean of a plain and a residual 128->128 layer, ncu --set full capture in "
-                                         "profiles/ scaled to this leaf batch); algorithmic: 32 KB / 48 KB per board",
+                         "issued_mma_fraction": ISSUED_MMA_FRACTION,
+                         "frac_issued_work": frac * ISSUED_MMA_FRACTION if frac else None,
+                         "issued_note": "the dense convention (SURVEY 8d) counts the 6 of 72 tile-taps per board the kernel skips because they "
+                                        "only see the zero rows -1 / 8; frac_issued_work = frac x 66/72 is the tensor work actually issued",
+                         "whole_step_frac": (tot[1] / world * f_all) / (ms * 1e-3) / 1e12 / pk["bf16_sustained"] if ms > 0 else None,
+                         "traffic_source": "constant from the stored ncu --set full capture profiles/r01_conv_final_kernel.json "
+                                           "(dram read+write bytes per launch, mean of a plain and a residual 128->128 layer, scaled to this "
+                                           "leaf batch), not measured in this run; algorithmic: 32 KB / 48 KB per board",
                          "peak_source": pk["source"] + ", sustained bf16 (kernel timed inside a long step)"},
-            "perft": {"depth": 11, "nodes": int(perft_nodes), "nodes_per_s": perft_nodes / (perft_ms * 1e-3) if perft_ms > 0 else None,
-                      "device_ms": perft_ms},
+            "perft": {"depth": 11, "nodes": int(perft_nodes), "nodes_per_s": perft_rate, "device_ms": perft_ms,
+                      "roofline": {"bound": "integer ALU issue (LOP3 / SHF)", "unit": "G thread-inst/s",
+                                   "achieved": perft_rate * PERFT_THREAD_INST_PER_NODE / 1e9 if perft_rate else None,
+                                   "peak": int_ops.value / 1e9,
+                                   "frac": perft_rate * PERFT_THREAD_INST_PER_NODE / int_ops.value if perft_rate and int_ops.value else None,
+                                   "inst_per_node": PERFT_THREAD_INST_PER_NODE,
+                                   "peak_source": "measured in this run: oz_debug_int_peak (8 independent LOP3 + SHF chains per thread, "
+                                                  f"{int_ms.value:.3f} ms); inst_per_node from profiles/r01_perft_dfs_kernel.json; the event window "
+                                                  "of oz_perft includes the breadth-first frontier levels in front of dfs_kernel"},
+                      "cpu_baseline": None if (world > 1 or args.no_cpu_baseline) else perft_cpu_baseline(cores)},
             "phases_ms_per_step": phases,
             "tree": {"bound": "latency (HBM pointer chasing, sequential within a game)", "bytes_per_sim": tree_bytes / d_sims,
                      "mean_path_nodes": d_path / d_sims, "mean_children_per_level": d_child / max(1, d_path),
@@ -390,8 +484,8 @@ def run_ours(args):
             "midgame": mid,
             "clocks": clocks,
         }
+        line.update(extra)
         if world == 1 and not args.no_cpu_baseline:
-            cores = os.cpu_count() or 1
             rate, t, kind = reference_search_rate(args.cpu_steps, 1, cores)
             line["cpu_baseline"] = {"value": rate, "unit": "sims/s", "cores": cores, "kind": kind,
                                     "sample": f"{args.cpu_steps} searches x 800 sims of one game (T=2 x B=16, LibTorch CPU 128x10b), {t:.1f} s"}
@@ -399,6 +493,68 @@ def run_ours(args):
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def run_config4(args, om, net, kw, rank, world, local, timed, allsum) -> dict:
+    """BASELINE.json configs[3]: 128x10b self-play, 8 192 lockstep games partitioned over the N GPUs (no collective on
+    the hot path).  Total work is fixed, so the N = 1 run of the same record is the strong-scaling denominator."""
+    total = args.config4_games
+    G = total // world
+    steps, warmup = max(1, min(args.steps, args.config4_steps)), 2
+    try:
+        eng = om.SelfPlayEngine(G, seed=args.seed, first_game_id=rank * G, cuda_device=local, **kw)
+        eng.prepare(net)
+        step = lambda: eng.play_ply(want_counts=False)
+        for _ in range(warmup):
+            step()
+        c0 = eng.counters()
+        ms = timed(eng, step, steps)
+        c1 = eng.counters()
+        sims = allsum(c1["simulations"] - c0["simulations"])[0]
+        del eng
+        inflight = kw["num_threads"] * kw["batch_size"]
+        return {"workload": f"BASELINE configs[3]: 128x10b self-play, {G * world} lockstep games partitioned by id over {world} GPU(s) "
+                            f"({G} per GPU, leaf batch {G * inflight} per network call), {kw['num_simulations']} sims/move",
+                "metric": "mcts_simulations_per_second", "value": sims / (ms * 1e-3), "unit": "sims/s", "n_gpus": world,
+                "games_total": G * world, "games_per_gpu": G, "steps": steps, "warmup": warmup, "ms_per_step": ms / steps,
+                "scaling": "strong", "collectives_on_hot_path": 0}
+    except Exception as exc:
+        return {"error": repr(exc)}
+
+
+def run_config5(args, om, rank, world, local, timed, allsum) -> dict:
+    """BASELINE.json configs[4]: 256x20b (AlphaZeroNet(17, 64, 65, 256, 19, 256)), 1 600 sims/move, leaf batch per network
+    call swept 64 ... 4096 on every one of the N GPUs (games per GPU = leaf batch / (T x B))."""
+    try:
+        net_kw = dict(NET, conv_channels=256, num_residual_blocks=19, value_head_hidden_channels=256)
+        net = make_net(net_kw)
+        kw = dict(MCTS_KW, num_simulations=1600)
+        inflight = kw["num_threads"] * kw["batch_size"]
+        f_all, _ = flops_per_eval(c=256, blocks=19, hv=256)
+        pk = peaks()
+        steps, warmup = max(1, args.config5_steps), 3
+        points = []
+        for leaf in args.config5_leaf:
+            G = max(1, leaf // inflight)
+            eng = om.SelfPlayEngine(G, seed=args.seed, first_game_id=rank * G, cuda_device=local, **kw)
+            eng.prepare(net)
+            step = lambda: eng.play_ply(want_counts=False)
+            for _ in range(warmup):
+                step()
+            c0 = eng.counters()
+            ms = timed(eng, step, steps)
+            c1 = eng.counters()
+            sims, evals = allsum(c1["simulations"] - c0["simulations"], c1["evaluations"] - c0["evaluations"])
+            del eng
+            rate = sims / (ms * 1e-3)
+            tf = evals / world * f_all / (ms * 1e-3) / 1e12
+            points.append({"leaf_batch_per_gpu": G * inflight, "games_per_gpu": G, "value": rate, "unit": "sims/s", "steps": steps,
+                           "ms_per_step": ms / steps, "tflops_per_gpu": tf, "frac_of_sustained_peak": tf / pk["bf16_sustained"]})
+        return {"workload": "BASELINE configs[4]: 256x20b random-init ResNet self-play, 1600 sims/move, leaf batch per network call and GPU "
+                            f"swept over {list(args.config5_leaf)}, {world} GPU(s), games partitioned by id",
+                "metric": "mcts_simulations_per_second", "n_gpus": world, "flop_per_eval": f_all, "warmup": warmup, "points": points}
+    except Exception as exc:
+        return {"error": repr(exc)}
 
 
 def main():
@@ -421,6 +577,11 @@ def main():
     ap.add_argument("--cpu-steps", type=int, default=36, help="searches of the CPU baseline sample (about 10-15 s on 16 host cores)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--midgame-ply", type=int, default=24, help="also time 2 plies after fast-forwarding every game this far (0 = skip)")
+    ap.add_argument("--no-extra-configs", action="store_true", help="skip the config4 / config5 sub-records")
+    ap.add_argument("--config4-games", type=int, default=8192, help="total lockstep games of the config4 sub-record")
+    ap.add_argument("--config4-steps", type=int, default=4)
+    ap.add_argument("--config5-steps", type=int, default=10)
+    ap.add_argument("--config5-leaf", type=int, nargs="*", default=[64, 128, 256, 512, 1024, 2048, 4096])
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -81,6 +81,10 @@ int oz_movegen_batch_device(const uint64_t *player, const uint64_t *opponent, ui
  * frontier position depth-first. */
 int oz_perft(const oz_position *root, int depth, int mode, uint64_t *nodes, double *device_ms);
 
+/* Measurement hook: issue rate of the integer pipe the move generator runs on (LOP3 + SHF, eight independent chains
+ * per thread, nothing else in the loop), in thread-operations per second -- the roofline denominator of perft. */
+int oz_debug_int_peak(double *ops_per_second, double *device_ms);
+
 /* ------------------------------------------------------- encoding (transformation.h) */
 
 /* features[i] = positions_to_features(history of item i, history_size, transformation[i])

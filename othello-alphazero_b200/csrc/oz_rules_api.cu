@@ -161,6 +161,30 @@ __device__ __forceinline__ void walk(uint64_t me, uint64_t opp, unsigned long lo
     }
 }
 
+// Issue-rate micro-benchmark of the integer pipe the move generator lives on: eight independent chains of LOP3 (three-input
+// logic) and SHF (funnel shift), the two instructions a 64-bit Kogge-Stone fill compiles to, with nothing else in the
+// loop.  thread-operations per second of this kernel = the roofline denominator of perft.
+constexpr int kIntPeakOpsPerIter = 32;
+#define OZ_LOP3(d, a, b, c) asm volatile("lop3.b32 %0, %1, %2, %3, 0x96;" : "=r"(d) : "r"(a), "r"(b), "r"(c))
+#define OZ_SHF(d, a, b) asm volatile("shf.l.wrap.b32 %0, %1, %2, 7;" : "=r"(d) : "r"(a), "r"(b))
+__global__ void __launch_bounds__(256) int_peak_kernel(uint32_t *out, int iters) {
+    uint32_t a0 = threadIdx.x, a1 = blockIdx.x, a2 = 0x9E3779B9u, a3 = 0x7F4A7C15u, a4 = a0 * 3u, a5 = a1 * 5u, a6 = ~a0, a7 = ~a1;
+    const uint32_t k = 0xBF58476Du ^ (uint32_t)iters;
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {            // 2 x (8 LOP3 + 8 SHF) = 32 operations, eight independent chains
+            OZ_LOP3(a0, a0, a4, k); OZ_LOP3(a1, a1, a5, k); OZ_LOP3(a2, a2, a6, k); OZ_LOP3(a3, a3, a7, k);
+            OZ_LOP3(a4, a4, a0, k); OZ_LOP3(a5, a5, a1, k); OZ_LOP3(a6, a6, a2, k); OZ_LOP3(a7, a7, a3, k);
+            OZ_SHF(a0, a0, a1); OZ_SHF(a1, a1, a2); OZ_SHF(a2, a2, a3); OZ_SHF(a3, a3, a0);
+            OZ_SHF(a4, a4, a5); OZ_SHF(a5, a5, a6); OZ_SHF(a6, a6, a7); OZ_SHF(a7, a7, a4);
+        }
+    }
+    const uint32_t r = a0 ^ a1 ^ a2 ^ a3 ^ a4 ^ a5 ^ a6 ^ a7;
+    if (r == 0x1234567u) *out = r;               // keeps the chains alive; practically never true
+}
+#undef OZ_LOP3
+#undef OZ_SHF
+
 template <int R>
 __global__ void __launch_bounds__(128) dfs_kernel(const FNode *__restrict__ in, size_t n, unsigned long long *counters) {
     const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
@@ -381,6 +405,34 @@ int oz_features_batch(const oz_position *history, const int32_t *n_hist, const i
     } while (0);
     cudaFree(d);
     return st;
+}
+
+// ------------------------------------------------------------------ integer-pipe issue peak (roofline denominator of perft)
+
+int oz_debug_int_peak(double *ops_per_second, double *device_ms) {
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    uint32_t *d_out = nullptr;
+    OZ_CUDA(cudaMalloc(&d_out, sizeof(uint32_t)));
+    const int iters = 4096, blocks = sms * 8, threads = 256;
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    float best = 1e30f;
+    for (int rep = 0; rep < 4; ++rep) {            // first launch warms up; best of the rest
+        cudaEventRecord(e0);
+        int_peak_kernel<<<blocks, threads>>>(d_out, iters); count_launch();
+        cudaEventRecord(e1);
+        cudaError_t err = cudaEventSynchronize(e1);
+        if (err != cudaSuccess) { cudaFree(d_out); return fail(OZ_ERR_CUDA, std::string("int_peak: ") + cudaGetErrorString(err)); }
+        float ms = 0.f; cudaEventElapsedTime(&ms, e0, e1);
+        if (rep > 0 && ms < best) best = ms;
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(d_out);
+    const double ops = (double)blocks * threads * iters * kIntPeakOpsPerIter;
+    if (ops_per_second) *ops_per_second = ops / (best * 1e-3);
+    if (device_ms) *device_ms = best;
+    return OZ_OK;
 }
 
 // ------------------------------------------------------------------ perft

@@ -72,6 +72,7 @@ SIGNATURES = {
     "oz_apply_action_batch": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]),
     "oz_movegen_batch_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     "oz_perft": (C.c_int, [P(OzPosition), C.c_int, C.c_int, P(u64), P(C.c_double)]),
+    "oz_debug_int_peak": (C.c_int, [P(C.c_double), P(C.c_double)]),
     "oz_features_batch": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_size_t]),
     "oz_config_default": (None, [P(OzConfig)]),
     "oz_engine_create": (C.c_int, [P(OzConfig), P(C.c_void_p)]),

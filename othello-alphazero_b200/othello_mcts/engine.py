@@ -87,7 +87,7 @@ class _Engine:
         """Fold and upload an AlphaZeroNet if its weights changed since the last upload."""
         fp = weights.weights_fingerprint(net)
         if fp != self._net_fingerprint:
-            shape, blob = weights.fold_alphazero_net(net)
+            shape, blob = weights.fold_cached(net, fp)
             check(self._lib.oz_engine_load_resnet(self._h, C.byref(shape), blob, len(blob)))
             self._net_fingerprint = fp
 

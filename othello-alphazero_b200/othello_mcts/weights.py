@@ -103,3 +103,17 @@ def weights_fingerprint(net) -> tuple:
     net = unwrap(net)
     items = list(net.parameters()) + list(net.buffers())
     return tuple((t.data_ptr(), t._version) for t in items)
+
+
+_fold_cache: tuple | None = None
+
+
+def fold_cached(net, fingerprint=None) -> tuple[OzResnetShape, bytes]:
+    """fold_alphazero_net, remembering the last result: several engines that load the same unchanged network (match
+    play, one engine per leaf-batch size in a sweep) fold it once."""
+    global _fold_cache
+    fp = fingerprint if fingerprint is not None else weights_fingerprint(net)
+    if _fold_cache is None or _fold_cache[0] != fp:
+        shape, blob = fold_alphazero_net(net)
+        _fold_cache = (fp, shape, blob)
+    return _fold_cache[1], _fold_cache[2]

@@ -315,6 +315,43 @@ def test_pipelined_search_equals_single_stream(evaluator, groups):
         assert cb["eval_ms"] > 0 and cb["select_ms"] > 0
 
 
+def test_match_engine_vs_oracle_players(oracle):
+    """Lockstep match play against the ORACLE: every game is replayed by play_game's loop (player.py:33-96) with two
+    AlphaZeroPlayer-shaped players (player.py:177-259) built on the oracle's MCTS restatement -- own tree each,
+    dirichlet_epsilon = 0, most visited action, BOTH players apply every action -- where the two "networks" are the
+    built-in evaluators 'hash' (player A) and 'synth' (player B).  Final discs, results and every action must agree."""
+    from othello_mcts import MatchEngine
+    po = oracle
+    P = 4
+    kw = dict(history_size=4, num_simulations=64, num_threads=2, batch_size=8, c_puct_base=20000.0, c_puct_init=2.5)
+    match = MatchEngine(P, seed=33, **kw)
+    out = match.play("hash", "synth")
+    assert out["plies"] >= 50 and set(out["result"]) <= {0, 1, 2}
+    final = match.engines()[0].positions_array()
+    ev = {"a": po.EVAL_HASH, "b": po.EVAL_SYNTH}
+    for g in range(2 * P):
+        black, white = ("a", "b") if g < P else ("b", "a")                       # evaluation.py:63-83: both colours
+        players = [po.OracleMCTS(evaluator=ev[black], seed=33, game_id=g, dirichlet_epsilon=0.0, dirichlet_alpha=0.5, **kw),
+                   po.OracleMCTS(evaluator=ev[white], seed=33, game_id=g, dirichlet_epsilon=0.0, dirichlet_alpha=0.5, **kw)]
+        ply = 0
+        while True:                                                                # play_game (player.py:44-76)
+            pos = players[0].position()
+            if pos.player == 0:
+                break
+            mover = players[pos.player - 1]
+            mover.search()                                                         # get_action: search, most visited (player.py:248-259)
+            a = mover.choose_action(ply, 0)
+            players[0].apply_action(a)
+            players[1].apply_action(a)
+            ply += 1
+        assert (pos.p1, pos.p2) == (int(final["p1"][g]), int(final["p2"][g])), g
+        nb, nw = bin(pos.p1).count("1"), bin(pos.p2).count("1")
+        assert out["result"][g] == (1 if nb > nw else 2 if nw > nb else 0)
+        assert (out["black_discs"][g], out["white_discs"][g]) == (nb, nw)
+    rows = MatchEngine.game_results(out, "a", "b")
+    assert len(rows) == 2 * P and rows[0]["player1"] == "a" and rows[1]["player1"] == "b"
+
+
 def test_match_engine_equals_game_by_game_play():
     """Lockstep match play (two engines, each searching the games where its network is to move) must give exactly the
     games the reference's loop gives when it plays them one at a time: play_game (player.py:33-96) with two
