@@ -56,9 +56,10 @@ def flops_per_eval(cin=17, c=128, blocks=9, hv=128):
 # The kernel legitimately skips the tile-taps that only see the zero rows -1 / 8 (6 of 72 per board); the dense FLOP
 # convention of SURVEY.md 8(d) still counts them, so the issued tensor work is this fraction of the dense figure.
 ISSUED_MMA_FRACTION = 66.0 / 72.0
-# thread-instructions per perft node of dfs_kernel<3> at depth 11: smsp__inst_executed.sum x 32 / nodes from the ncu
-# capture profiles/r01_perft_dfs_kernel.json (8 140 593 608 warp instructions for 212 258 800 leaves, 95.7 % on the ALU pipe)
-PERFT_THREAD_INST_PER_NODE = 8140593608 * 32 / 212258800
+# ALU-pipe warp instructions per perft leaf of dfs_kernel<3> at depth 11, from the ncu capture profiles/r02_perft_dfs_ncu.csv:
+# smsp__inst_executed_pipe_alu.sum = 7 129 723 840 for 212 258 800 leaves (8 146 791 858 warp instructions in all; the walk
+# diverges, 38 % of the lane slots carry a thread, so the pipe is counted in warp instructions, as ncu does).
+PERFT_ALU_WARP_INST_PER_NODE = 7129723840 / 212258800
 
 
 def peaks():
@@ -466,14 +467,15 @@ def run_ours(args):
                                            "leaf batch), not measured in this run; algorithmic: 32 KB / 48 KB per board",
                          "peak_source": pk["source"] + ", sustained bf16 (kernel timed inside a long step)"},
             "perft": {"depth": 11, "nodes": int(perft_nodes), "nodes_per_s": perft_rate, "device_ms": perft_ms,
-                      "roofline": {"bound": "integer ALU issue (LOP3 / SHF)", "unit": "G thread-inst/s",
-                                   "achieved": perft_rate * PERFT_THREAD_INST_PER_NODE / 1e9 if perft_rate else None,
-                                   "peak": int_ops.value / 1e9,
-                                   "frac": perft_rate * PERFT_THREAD_INST_PER_NODE / int_ops.value if perft_rate and int_ops.value else None,
-                                   "inst_per_node": PERFT_THREAD_INST_PER_NODE,
-                                   "peak_source": "measured in this run: oz_debug_int_peak (8 independent LOP3 + SHF chains per thread, "
-                                                  f"{int_ms.value:.3f} ms); inst_per_node from profiles/r01_perft_dfs_kernel.json; the event window "
-                                                  "of oz_perft includes the breadth-first frontier levels in front of dfs_kernel"},
+                      "roofline": {"bound": "integer ALU pipe issue (LOP3 / SHF)", "unit": "G warp-inst/s",
+                                   "achieved": perft_rate * PERFT_ALU_WARP_INST_PER_NODE / 1e9 if perft_rate else None,
+                                   "peak": int_ops.value / 32 / 1e9,
+                                   "frac": perft_rate * PERFT_ALU_WARP_INST_PER_NODE / (int_ops.value / 32) if perft_rate and int_ops.value else None,
+                                   "alu_warp_inst_per_node": PERFT_ALU_WARP_INST_PER_NODE,
+                                   "peak_source": "measured in this run: oz_debug_int_peak (8 independent LOP3 + SHF chains per thread, all lanes "
+                                                  f"active, {int_ms.value:.3f} ms) = 16 lanes per clock and SM sub-partition; instructions per node from the "
+                                                  "ncu capture profiles/r02_perft_dfs_ncu.csv (ncu itself: ALU pipe 95.8 % of peak inside dfs_kernel); the "
+                                                  "event window of oz_perft also holds the breadth-first frontier levels in front of dfs_kernel"},
                       "cpu_baseline": None if (world > 1 or args.no_cpu_baseline) else perft_cpu_baseline(cores)},
             "phases_ms_per_step": phases,
             "tree": {"bound": "latency (HBM pointer chasing, sequential within a game)", "bytes_per_sim": tree_bytes / d_sims,

@@ -2,7 +2,8 @@
 PyTorch fp32 reference of the same network.  Floating point, so a stated tolerance instead of bit
 equality:
   * one conv layer (bf16 operands, fp32 accumulate, bf16 output): |d| <= 2^-7 * |ref| + 2e-2
-  * whole 128x10b network vs fp32 torch: policy max |dp| <= 2e-2, value max |dv| <= 5e-2
+  * whole network vs fp32 torch: policy max |dp| <= 5e-3, value max |dv| <= 2e-2 (measured
+    errors at full depth are in profiles/r02_resnet_error.json: 3.2e-5 / 3.8e-4 at 128x10b, 1.1e-4 / 2.2e-3 at 256x20b)
   * the search built on it: same argmax action as the fp32 network in the large majority of roots
 """
 import ctypes as C
@@ -105,7 +106,7 @@ def test_resnet_forward_vs_torch_fp32(blocks, channels, planes, hidden, n):
     dp = np.abs(pol - ref["policy"].numpy()).max()
     dv = np.abs(val - ref["value"].numpy()).max()
     assert np.allclose(pol.sum(axis=1), 1.0, atol=1e-4)
-    assert dp <= 2e-2 and dv <= 5e-2, f"policy max abs diff {dp:.4f}, value max abs diff {dv:.4f}"
+    assert dp <= 5e-3 and dv <= 2e-2, f"policy max abs diff {dp:.4f}, value max abs diff {dv:.4f}"
 
 
 def test_search_with_native_network():

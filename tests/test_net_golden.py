@@ -25,8 +25,8 @@ GOLD = json.loads((ROOT / "tests" / "golden" / "golden_net.json").read_text())
 
 # Tolerances of the native evaluator (bf16 operands, fp32 accumulation, bf16 activations between layers) against the
 # reference's fp32 outputs; the measured errors are recorded in profiles/r02_resnet_error.json (tools/resnet_error.py).
-POLICY_TOL = 2e-2
-VALUE_TOL = {"128x10b": 2e-2, "256x20b": 3e-2}
+POLICY_TOL = 2e-3
+VALUE_TOL = {"128x10b": 5e-3, "256x20b": 1e-2}
 
 
 def _from_bits(bits):
@@ -106,8 +106,9 @@ def test_live_reference_class_equals_mirror(name):
 @pytest.mark.parametrize("name", ["128x10b", "256x20b"])
 def test_native_evaluator_vs_reference_fp32_full_depth(name):
     """oz_resnet_forward (tcgen05 convolutions + fused heads) at the FULL depth of both BASELINE networks against the
-    reference class's own fp32 outputs (golden).  Tolerance: policy max |dp| <= 2e-2; value max |dv| <= 2e-2 (10b) /
-    3e-2 (20b: 39 bf16 activation roundings in sequence)."""
+    reference class's own fp32 outputs (golden).  Tolerance: policy max |dp| <= 2e-3; value max |dv| <= 5e-3 (10b) /
+    1e-2 (20b: 39 bf16 activation roundings in sequence).  Measured on B200 (profiles/r02_resnet_error.json): policy
+    2.5e-5 / 7.8e-5, value 1.9e-4 / 1.6e-3 on these inputs; 3.2e-5 / 1.1e-4 and 3.8e-4 / 2.2e-3 over 256 boards."""
     from othello_mcts import _lib, weights
     lib = _lib.load()
     net, e = _mirror(name)
