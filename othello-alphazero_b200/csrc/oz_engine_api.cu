@@ -59,6 +59,14 @@ struct oz_engine {
     long tree_bound = 1;                  // upper bound on the nodes of the largest live tree
     long rootn_bound = 0;                 // upper bound on any node's visit count (index into the exploration-rate table)
     oz_counters ctr{};
+    // Pinned host mirrors of the small per-ply read-backs (error bits, unfinished games, largest tree, games assigned by
+    // the harvest, chosen actions, root visit counts): the copies into them are truly asynchronous, so a ply blocks the
+    // host exactly once, at its end (a cudaMemcpyAsync into pageable memory is a host-blocking call of its own).
+    bool defer_error_check = false;       // inside oz_engine_play_ply
+    size_t prof_events = 0;               // profiling events of the last search still to be read (after a synchronisation)
+    bool prof_pipelined = false, prof_net = false;
+    int32_t *h_pin = nullptr;             // [8]: 0 error bits, 1 unfinished, 2 largest tree, 3 assigned
+    int32_t *h_actions = nullptr, *h_counts = nullptr;   // [G], [G * kStride]
     bool profiling = false;
     std::vector<cudaEvent_t> ev;          // phase boundaries of one search
 };
@@ -183,17 +191,26 @@ void sync_params(oz_engine *e) {
     t.inv_temperature = 1.0f / e->cfg.self_play_temperature;
 }
 
-int check_device_errors(oz_engine *e) {
-    int32_t err = 0;
-    OZ_CUDA(cudaMemcpyAsync(&err, e->t.error, sizeof(err), cudaMemcpyDeviceToHost, e->stream));
-    OZ_CUDA(cudaStreamSynchronize(e->stream));
+// The error bits travel to the pinned mirror with the stream; device_error_status() reads them after a synchronisation.
+int fetch_device_errors(oz_engine *e) {
+    OZ_CUDA(cudaMemcpyAsync(e->h_pin, e->t.error, sizeof(int32_t), cudaMemcpyDeviceToHost, e->stream));
+    return OZ_OK;
+}
+int device_error_status(oz_engine *e) {
+    const int32_t err = e->h_pin[0];
     if (err == 0) return OZ_OK;
     cudaMemsetAsync(e->t.error, 0, sizeof(int32_t), e->stream);
     std::string msg = "device engine:";
     if (err & kErrArenaFull) msg += " node arena full (raise max_nodes_per_game);";
     if (err & kErrRateTable) msg += " visit count beyond the exploration-rate table;";
     if (err & kErrDepth) msg += " search path deeper than " + std::to_string(kMaxDepth) + ";";
+    e->h_pin[0] = 0;
     return fail(OZ_ERR_CAPACITY, msg);
+}
+int check_device_errors(oz_engine *e) {
+    OZ_TRY(fetch_device_errors(e));
+    OZ_CUDA(cudaStreamSynchronize(e->stream));
+    return device_error_status(e);
 }
 
 int set_device(const oz_engine *e) { OZ_CUDA(cudaSetDevice(e->cfg.device)); return OZ_OK; }
@@ -216,6 +233,7 @@ int grow_pools(oz_engine *e, int new_cap) {
 }
 
 cudaEvent_t next_event(oz_engine *e, size_t i);
+void read_profile(oz_engine *e);
 
 // The reference's trees are heap-allocated and unbounded (search_node.h:29); ours live in fixed arenas, so before
 // a search every game must have room for the worst case.  tree_bound is exact after a re-root (apply_kernel reports
@@ -319,6 +337,7 @@ int end_search(oz_engine *e, const Tree &searched, int active) {
     e->in_search = false;
     e->ctr.searches += 1;
     e->ctr.simulations += (uint64_t)rounds_of(e->cfg) * e->t.inflight * (uint64_t)active;
+    if (e->defer_error_check) return fetch_device_errors(e);     // play_ply: read after the ply's single synchronisation
     return check_device_errors(e);
 }
 int end_search(oz_engine *e) { return end_search(e, e->t, e->active); }
@@ -359,12 +378,47 @@ double union_ms(std::vector<std::pair<float, float>> iv) {
     return total;
 }
 
+// Phase times of the last search from its CUDA events (which must have completed: called after a synchronisation).
+void read_profile(oz_engine *e) {
+    const size_t n_ev = e->prof_events;
+    e->prof_events = 0;
+    if (n_ev == 0) return;
+    const bool net_prof = e->prof_net;
+    if (e->prof_pipelined) {
+        // Phases of different groups overlap: the network and the convolutions are charged the time at least one group
+        // spent in them (union of intervals on the fork event's clock); select / expand are the per-group sums.
+        std::vector<std::pair<float, float>> net_iv, conv_iv;
+        auto at = [&](size_t i) { float ms = 0.f; cudaEventElapsedTime(&ms, e->ev_fork, e->ev[i]); return ms; };
+        for (size_t i = 0; i + 5 < n_ev; i += 6) {
+            const float t0 = at(i), t1 = at(i + 1), t4 = at(i + 4), t5 = at(i + 5);
+            e->ctr.select_ms += std::max(0.f, t1 - t0); e->ctr.expand_ms += std::max(0.f, t5 - t4);
+            net_iv.emplace_back(t1, t4);
+            if (net_prof) { conv_iv.emplace_back(at(i + 2), at(i + 3)); e->ctr.conv_launches += (uint64_t)(1 + 2 * e->net.shape().blocks); }
+        }
+        e->ctr.eval_ms += union_ms(net_iv);
+        e->ctr.conv_ms += union_ms(conv_iv);
+        return;
+    }
+    for (size_t i = 0; i + 5 < n_ev; i += 6) {
+        float a = 0, b = 0, c = 0, d = 0;
+        cudaEventElapsedTime(&a, e->ev[i], e->ev[i + 1]); cudaEventElapsedTime(&b, e->ev[i + 1], e->ev[i + 4]); cudaEventElapsedTime(&c, e->ev[i + 4], e->ev[i + 5]);
+        e->ctr.select_ms += a; e->ctr.eval_ms += b; e->ctr.expand_ms += c;
+        if (net_prof) { cudaEventElapsedTime(&d, e->ev[i + 2], e->ev[i + 3]); e->ctr.conv_ms += d; e->ctr.conv_launches += (uint64_t)(1 + 2 * e->net.shape().blocks); }
+    }
+}
+
 int search_pipelined(oz_engine *e, int groups) {
     const int rounds = rounds_of(e->cfg), G = e->t.G, B = e->t.inflight;
     // Tree kernels go to low-priority streams, the network to one high-priority stream: a pending convolution CTA is
     // always placed before pending tree blocks, which then take the registers the convolution leaves free.
     int prio_lo = 0, prio_hi = 0;
     cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+    {   // experiment switch: OZ_PIPE_PRIO=1 equal priorities, =2 tree streams high / network stream low
+        const char *pe = getenv("OZ_PIPE_PRIO");
+        const int mode = pe ? atoi(pe) : 0;
+        if (mode == 1) prio_hi = prio_lo;
+        else if (mode == 2) std::swap(prio_lo, prio_hi);
+    }
     for (int k = 0; k < groups; ++k) {
         if (!e->gstream[k] && cudaStreamCreateWithPriority(&e->gstream[k], cudaStreamNonBlocking, prio_lo) != cudaSuccess) { e->in_search = false; return fail(OZ_ERR_CUDA, "stream creation failed"); }
         if (!e->ev_join[k]) { cudaEventCreateWithFlags(&e->ev_join[k], cudaEventDisableTiming); cudaEventCreateWithFlags(&e->ev_sel[k], cudaEventDisableTiming); cudaEventCreateWithFlags(&e->ev_net[k], cudaEventDisableTiming); }
@@ -408,20 +462,7 @@ int search_pipelined(oz_engine *e, int groups) {
     e->round = rounds;
     e->warmed = true;
     st = end_search(e);
-    if (!st && e->profiling) {
-        // Phases of different groups overlap: the network and the convolutions are charged the time at least one group
-        // spent in them (union of intervals on the fork event's clock); select / expand are the per-group sums.
-        std::vector<std::pair<float, float>> net_iv, conv_iv;
-        auto at = [&](size_t i) { float ms = 0.f; cudaEventElapsedTime(&ms, e->ev_fork, e->ev[i]); return ms; };
-        for (size_t i = 0; i + 5 < n_ev; i += 6) {
-            const float t0 = at(i), t1 = at(i + 1), t4 = at(i + 4), t5 = at(i + 5);
-            e->ctr.select_ms += std::max(0.f, t1 - t0); e->ctr.expand_ms += std::max(0.f, t5 - t4);
-            net_iv.emplace_back(t1, t4);
-            if (net_prof) { conv_iv.emplace_back(at(i + 2), at(i + 3)); e->ctr.conv_launches += (uint64_t)(1 + 2 * e->net.shape().blocks); }
-        }
-        e->ctr.eval_ms += union_ms(net_iv);
-        e->ctr.conv_ms += union_ms(conv_iv);
-    }
+    if (!st && e->profiling) { e->prof_events = n_ev; e->prof_pipelined = true; e->prof_net = net_prof; if (!e->defer_error_check) read_profile(e); }
     return st;
 }
 
@@ -466,6 +507,12 @@ int oz_engine_create(const oz_config *cfg, oz_engine **out) {
         cudaMemset(t.error, 0, sizeof(int32_t)); cudaMemset(t.stats, 0, 4 * sizeof(unsigned long long));
         e->max_plies = 128;
         if ((st = dalloc(&e->d_records, (size_t)G * e->max_plies))) break;
+        if (cudaHostAlloc((void **)&e->h_pin, 8 * sizeof(int32_t), cudaHostAllocDefault) != cudaSuccess ||
+            cudaHostAlloc((void **)&e->h_actions, (size_t)G * sizeof(int32_t), cudaHostAllocDefault) != cudaSuccess ||
+            cudaHostAlloc((void **)&e->h_counts, (size_t)G * kStride * sizeof(int32_t), cudaHostAllocDefault) != cudaSuccess) {
+            st = fail(OZ_ERR_CUDA, "pinned host allocation failed"); break;
+        }
+        std::memset(e->h_pin, 0, 8 * sizeof(int32_t));
         if ((st = alloc_slots(e))) break;
         if ((st = build_rate_table(e))) break;
         sync_params(e);
@@ -491,6 +538,7 @@ void oz_engine_destroy(oz_engine *e) {
                     e->d_gamma, e->d_actions, e->d_unfinished, e->d_stat_n, e->d_stat_counts, e->d_stat_q, e->d_stat_rootn, e->d_records,
                     e->d_spd_f, e->d_spd_p};
     for (void *p : ptrs) cudaFree(p);
+    cudaFreeHost(e->h_pin); cudaFreeHost(e->h_actions); cudaFreeHost(e->h_counts);
     for (cudaEvent_t x : e->ev) cudaEventDestroy(x);
     for (int k = 0; k < kMaxGroups; ++k) {
         if (e->gstream[k]) cudaStreamDestroy(e->gstream[k]);
@@ -702,11 +750,12 @@ int oz_debug_conv3x3(const uint16_t *in, int cin, const uint16_t *w, const float
     const size_t pad = (boards + kBoardPad - 1) / kBoardPad * kBoardPad;
     uint16_t *d_in = nullptr, *d_w = nullptr, *d_skip = nullptr, *d_out = nullptr;
     float *d_b = nullptr;
+    int *d_work = nullptr;
     int st = OZ_OK;
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     do {
         if ((st = dalloc(&d_in, pad * 64 * cin)) || (st = dalloc(&d_w, (size_t)9 * cout * cin)) || (st = dalloc(&d_b, (size_t)cout)) ||
-            (st = dalloc(&d_out, pad * 64 * cout)) || (skip && (st = dalloc(&d_skip, pad * 64 * cout)))) break;
+            (st = dalloc(&d_out, pad * 64 * cout)) || (skip && (st = dalloc(&d_skip, pad * 64 * cout))) || (st = dalloc(&d_work, 1))) break;
         cudaMemset(d_in, 0, pad * 64 * cin * 2); cudaMemset(d_out, 0, pad * 64 * cout * 2);
         if (skip) { cudaMemset(d_skip, 0, pad * 64 * cout * 2); cudaMemcpy(d_skip, skip, boards * 64 * cout * 2, cudaMemcpyHostToDevice); }
         cudaMemcpy(d_in, in, boards * 64 * cin * 2, cudaMemcpyHostToDevice);
@@ -714,7 +763,7 @@ int oz_debug_conv3x3(const uint16_t *in, int cin, const uint16_t *w, const float
         cudaMemcpy(d_b, bias, cout * sizeof(float), cudaMemcpyHostToDevice);
         cudaEventCreate(&e0); cudaEventCreate(&e1);
         cudaEventRecord(e0);
-        if ((st = ResNet::conv3x3(d_in, cin, d_w, d_b, d_skip, relu, d_out, cout, pad, nullptr))) break;
+        if ((st = ResNet::conv3x3(d_in, cin, d_w, d_b, d_skip, relu, d_out, cout, pad, nullptr, d_work))) break;
         cudaEventRecord(e1);
         cudaError_t err = cudaDeviceSynchronize();
         if (err != cudaSuccess) { st = fail(OZ_ERR_CUDA, std::string("conv3x3: ") + cudaGetErrorString(err)); break; }
@@ -724,7 +773,7 @@ int oz_debug_conv3x3(const uint16_t *in, int cin, const uint16_t *w, const float
     } while (0);
     if (e0) cudaEventDestroy(e0);
     if (e1) cudaEventDestroy(e1);
-    cudaFree(d_in); cudaFree(d_w); cudaFree(d_skip); cudaFree(d_out); cudaFree(d_b);
+    cudaFree(d_in); cudaFree(d_w); cudaFree(d_skip); cudaFree(d_out); cudaFree(d_b); cudaFree(d_work);
     return st;
 }
 
@@ -849,14 +898,7 @@ static int search_games(oz_engine *e, int g0, int g1) {
     if (st) { e->in_search = false; return st; }
     if (whole) e->warmed = true;
     st = end_search(e, v, active);
-    if (!st && e->profiling) {
-        for (size_t i = 0; i + 5 < k; i += 6) {
-            float a = 0, b = 0, c = 0, d = 0;
-            cudaEventElapsedTime(&a, e->ev[i], e->ev[i + 1]); cudaEventElapsedTime(&b, e->ev[i + 1], e->ev[i + 4]); cudaEventElapsedTime(&c, e->ev[i + 4], e->ev[i + 5]);
-            e->ctr.select_ms += a; e->ctr.eval_ms += b; e->ctr.expand_ms += c;
-            if (net_prof) { cudaEventElapsedTime(&d, e->ev[i + 2], e->ev[i + 3]); e->ctr.conv_ms += d; e->ctr.conv_launches += (uint64_t)(1 + 2 * e->net.shape().blocks); }
-        }
-    }
+    if (!st && e->profiling) { e->prof_events = k; e->prof_pipelined = false; e->prof_net = net_prof; if (!e->defer_error_check) read_profile(e); }
     return st;
 }
 
@@ -905,14 +947,15 @@ int oz_engine_self_play_data(oz_engine *e, int game, float *features, float *pol
 static int apply_device_actions(oz_engine *e) {
     OZ_CUDA(cudaMemsetAsync(e->d_unfinished, 0, 2 * sizeof(int32_t), e->stream));
     launch_apply(e->t, e->d_actions, e->d_unfinished, e->stream);
-    int32_t unf2[2] = {0, 0}, assigned = 0;
-    OZ_CUDA(cudaMemcpyAsync(unf2, e->d_unfinished, sizeof(unf2), cudaMemcpyDeviceToHost, e->stream));
+    int32_t *unf2 = e->h_pin + 1;
+    e->h_pin[3] = 0;
+    OZ_CUDA(cudaMemcpyAsync(unf2, e->d_unfinished, 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, e->stream));
     if (e->done.capacity > 0) {            // rolling pool: completed games leave, their slots restart with unplayed games
         launch_harvest(e->t, e->d_records, e->max_plies, e->done, e->pool_total, e->stream);
-        OZ_CUDA(cudaMemcpyAsync(&assigned, e->done.counters + 2, sizeof(assigned), cudaMemcpyDeviceToHost, e->stream));
+        OZ_CUDA(cudaMemcpyAsync(e->h_pin + 3, e->done.counters + 2, sizeof(int32_t), cudaMemcpyDeviceToHost, e->stream));
     }
-    OZ_CUDA(cudaStreamSynchronize(e->stream));
-    const int32_t unf = unf2[0];
+    OZ_CUDA(cudaStreamSynchronize(e->stream));         // the ply's one host synchronisation
+    const int32_t unf = unf2[0], assigned = e->h_pin[3];
     e->tree_bound = std::max<long>(1, unf2[1]);       // exact: the largest live tree after the re-root
     e->ctr.games_finished += (uint64_t)std::max(0, e->active - unf);
     e->active = unf + assigned;
@@ -952,15 +995,23 @@ int oz_engine_choose_actions(oz_engine *e, int32_t *actions) {
 }
 
 int oz_engine_play_ply(oz_engine *e, int32_t *actions, int32_t *visit_counts, int32_t *unfinished) {
-    OZ_TRY(oz_engine_search(e));
+    e->defer_error_check = true;           // one host synchronisation per ply: at the end of apply_device_actions
+    const int st = oz_engine_search(e);
+    e->defer_error_check = false;
+    OZ_TRY(st);
+    const size_t G = (size_t)e->t.G;
     if (visit_counts) {
         launch_root_stats(e->t, e->d_stat_n, e->d_stat_counts, nullptr, nullptr, e->stream);
-        OZ_CUDA(cudaMemcpyAsync(visit_counts, e->d_stat_counts, (size_t)e->t.G * kStride * 4, cudaMemcpyDeviceToHost, e->stream));
+        OZ_CUDA(cudaMemcpyAsync(e->h_counts, e->d_stat_counts, G * kStride * 4, cudaMemcpyDeviceToHost, e->stream));
     }
     launch_choose(e->t, e->d_actions, e->stream);
     launch_record(e->t, e->d_actions, e->d_records, e->max_plies, e->stream);
-    if (actions) OZ_CUDA(cudaMemcpyAsync(actions, e->d_actions, e->t.G * sizeof(int32_t), cudaMemcpyDeviceToHost, e->stream));
+    if (actions) OZ_CUDA(cudaMemcpyAsync(e->h_actions, e->d_actions, G * sizeof(int32_t), cudaMemcpyDeviceToHost, e->stream));
     OZ_TRY(apply_device_actions(e));
+    read_profile(e);                       // the search's phase events have completed now
+    OZ_TRY(device_error_status(e));        // the search's error bits arrived with the same synchronisation
+    if (visit_counts) std::memcpy(visit_counts, e->h_counts, G * kStride * 4);
+    if (actions) std::memcpy(actions, e->h_actions, G * sizeof(int32_t));
     e->ctr.plies += 1;
     if (unfinished) *unfinished = e->active;
     return OZ_OK;

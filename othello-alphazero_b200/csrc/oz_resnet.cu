@@ -67,6 +67,7 @@ struct ConvParams {
     int relu;
     const float *head_w;         // pair kernel, last layer of a 128-channel tower: [3][128] 1x1 head-conv weights (policy 0, policy 1, value)
     float *head_out;             // ... and their pre-activations [boards][64][4] (zeroed by the caller; two column halves add up)
+    int *work;                   // dynamic pass scheduler: this launch's pass counter (zeroed by the caller), or null = static round-robin
 };
 
 // ------------------------------------------------------------------ CTA-pair kernel (cta_group::2)
@@ -85,15 +86,26 @@ namespace pair {
 constexpr int kYPerPass = 2;
 constexpr int kBoxYp = kYPerPass + 2;
 constexpr int kActBoxBytesP = kBoxX * kBoxYp * kSlotBytes;          // 36864
-constexpr int kActStageBytesP = kSlotBytes + kActBoxBytesP;         // guard slot in front
+// Stage layout: [guard slot][box 0][box 1].  The guard slot (zeros) is what tap (-1, -1) reads in front of box 0; in front
+// of box 1 sits the last slot of box 0 = (last row, x = 8), the out-of-bounds column TMA always fills with zeros.
 constexpr int kActStagesP = 2;
 constexpr int kWTileBytes = 64 * kRowBytes;                         // 64 couts x 32 cin = 4096
 constexpr int kWSlots = 36;
 constexpr int kEpiWarps = 8;
 constexpr int kThreadsP = (3 + kEpiWarps) * 32;
-constexpr int kMiscBytes = 4096;
-constexpr int kSmemBytesP = 1024 + kActStagesP * kActStageBytesP + kWSlots * kWTileBytes + kMiscBytes;
-static_assert(kSmemBytesP <= 232448, "shared memory budget");
+constexpr int kMiscBytes = 3072;                                    // barriers + scheduler ring (1 KB), bias / head-conv weights (2 KB)
+// Ring of published pass indices (dynamic scheduler).  Only the epilogue warps -- the last role to read an entry -- report
+// back: when one of them has read entry i, every other role has read entry i - 1 (the accumulator of pass i - 1 it just
+// drained was issued by the MMA thread, fed by both producers, after they had read that entry).  The scheduler overwrites
+// the slot of entry i - 8 once entry i - 4 has been reported, so four entries of slack cover that one-entry lag, and the
+// MMA thread and the producers never execute an arrive on this path.
+constexpr int kSchedSlots = 8;
+constexpr int kSchedLag = 4;
+constexpr int kSchedConsumers = 2 * kEpiWarps;
+constexpr int kSmemBytesP = 1024 + kSlotBytes + kActStagesP * kActBoxBytesP + kWSlots * kWTileBytes + kMiscBytes;
+// 233 472 B per SM, 1 KB of it reserved per resident CTA: what this kernel leaves free (6 144 B) must hold one block of the
+// narrow select kernel (4 352 B static + its 1 KB), or the pipelined search cannot run tree kernels under the convolutions.
+static_assert(kSmemBytesP + 1024 + 4352 + 1024 <= 233472, "shared memory budget (co-residency with select_kernel<1>)");
 // kind::f16 instruction descriptor: bf16 x bf16 -> f32, K-major operands, M = 256 (pair), N = 128.
 constexpr uint32_t kIdescP = (1u << 4) | (1u << 7) | (1u << 10) | ((128u >> 3) << 17) | ((256u >> 4) << 24);
 }  // namespace pair
@@ -130,6 +142,27 @@ __device__ __forceinline__ void mbar_wait_b(uint32_t bar, uint32_t parity) {
             else if (now - t0 > 8000000000ll) { printf("conv3x3_pair_kernel: barrier timeout (block %d thread %d bar %u)\n", (int)blockIdx.x, (int)threadIdx.x, bar); __trap(); }
         }
     }
+}
+// The same wait with cluster-scope acquire: the data the barrier guards was written by the peer CTA (st.shared::cluster).
+__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
+    uint32_t done;
+    long long t0 = 0;
+    for (uint32_t spins = 0;; ++spins) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+        if (done) return;
+        if ((spins & 1023u) == 1023u) {
+            const long long now = clock64();
+            if (t0 == 0) t0 = now;
+            else if (now - t0 > 8000000000ll) { printf("conv3x3_pair_kernel: scheduler barrier timeout (block %d thread %d bar %u)\n", (int)blockIdx.x, (int)threadIdx.x, bar); __trap(); }
+        }
+    }
+}
+__device__ __forceinline__ void st_cluster_b32(uint32_t cluster_addr, int a) {
+    asm volatile("st.shared::cluster.b32 [%0], %1;" ::"r"(cluster_addr), "r"(a) : "memory");
 }
 __device__ __forceinline__ void tma_load_4d_pair(uint32_t dst, const CUtensorMap *map, uint32_t bar_cluster, int c0, int c1, int c2, int c3) {
     asm volatile(
@@ -172,19 +205,21 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap map_act, const __grid_co
     using namespace pair;
     constexpr int kYPerPass = YPP, kRowPasses = 8 / YPP;                      // passes per board column of rows
     constexpr int kActBoxBytesP = kBoxX * (YPP + 2) * kSlotBytes;            // the box carries one halo row above and below
-    constexpr int kActStageBytesP = kSlotBytes + kActBoxBytesP;
+    static_assert(kActBoxBytesP <= pair::kActBoxBytesP && kActBoxBytesP % 1024 == 0, "box size");
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t *gen = smem_raw + (base - smem_u32(smem_raw));
     const uint32_t act0 = base;
-    const uint32_t w0 = act0 + kActStagesP * kActStageBytesP;
+    const uint32_t w0 = act0 + kSlotBytes + kActStagesP * pair::kActBoxBytesP;
     const uint32_t misc = w0 + kWSlots * kWTileBytes;
     const uint32_t bar_act_full = misc, bar_act_empty = misc + 16;          // [2] each
     const uint32_t bar_tmem_full = misc + 32, bar_tmem_empty = misc + 48;    // [2] each
     const uint32_t bar_w_full = misc + 64, bar_w_empty = misc + 64 + 8 * kWSlots;
     uint32_t *tmem_ptr = (uint32_t *)(gen + (misc - base) + 704);
+    const uint32_t bar_sched_full = misc + 720, bar_sched_empty = misc + 784;   // [kSchedSlots] each (dynamic pass scheduler)
+    const uint32_t sched_ring = misc + 848;                                     // [kSchedSlots] pass indices, 8 bytes apart
     float *s_bias = (float *)(gen + (misc - base) + 1024);                   // up to 384 floats
-    float *s_head = (float *)(gen + (misc - base) + 2560);                   // [3][128] head-conv weights (fused heads)
+    float *s_head = s_bias + 128;                                            // [3][128] head-conv weights (fused heads: cout_total = 128)
 
     const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
     const uint32_t rank = cluster_ctarank();
@@ -199,6 +234,7 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap map_act, const __grid_co
         for (int i = 0; i < kActStagesP; ++i) { mbar_init(bar_act_full + 8 * i, 1); mbar_init(bar_act_empty + 8 * i, 1); }
         for (int i = 0; i < 2; ++i) { mbar_init(bar_tmem_full + 8 * i, 1); mbar_init(bar_tmem_empty + 8 * i, 2 * kEpiWarps); }
         for (int i = 0; i < kWSlots; ++i) { mbar_init(bar_w_full + 8 * i, 1); mbar_init(bar_w_empty + 8 * i, 1); }
+        for (int i = 0; i < kSchedSlots; ++i) { mbar_init(bar_sched_full + 8 * i, 1); mbar_init(bar_sched_empty + 8 * i, kSchedConsumers); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_act) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w) : "memory");
@@ -207,10 +243,8 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap map_act, const __grid_co
         asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr)), "r"(kTmemCols) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
     }
-    for (int i = threadIdx.x; i < kActStagesP * (kSlotBytes / 16); i += kThreadsP) {   // zero guard slots
-        const int s = i / (kSlotBytes / 16), o = i % (kSlotBytes / 16);
-        *(uint4 *)(gen + s * kActStageBytesP + o * 16) = make_uint4(0, 0, 0, 0);
-    }
+    for (int i = threadIdx.x; i < kSlotBytes / 16; i += kThreadsP)                    // zero the guard slot
+        *(uint4 *)(gen + i * 16) = make_uint4(0, 0, 0, 0);
     for (int i = threadIdx.x; i < p.cout_total; i += kThreadsP) s_bias[i] = p.bias[i];
     if (p.head_out) for (int i = threadIdx.x; i < 3 * 128; i += kThreadsP) s_head[i] = p.head_w[i];
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -222,6 +256,43 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap map_act, const __grid_co
     // set-up (barriers, TMEM, weight tiles) under our tail; they touch activations only after griddep_wait().
     griddep_launch_dependents();
 
+    // Pass scheduler.  Static (p.work == nullptr): cluster c takes passes c, c + clusters, ...  Dynamic: the passes of a
+    // launch are handed out in arrival order from one global counter, so a cluster that is slowed down -- a tree kernel
+    // of another game group co-resident on its SMs (pipelined search), a late start behind the previous layer's tail --
+    // simply takes fewer passes instead of holding the whole launch back.  One thread per cluster (the leader CTA's
+    // activation producer, the role that runs furthest ahead) draws the indices and publishes them through a small ring
+    // in BOTH CTAs' shared memory; every other role of the pair reads the same sequence from the ring (full / empty
+    // mbarriers, cluster-scope release / acquire).  An index >= num_pp is the end marker.  The atomic for pass i + 1 is
+    // issued at the start of pass i and its result is first touched after the loads of pass i are on their way: the
+    // activation pipeline is two stages deep and latency-critical, a round trip to the counter in front of every pass
+    // cost 10 % of the launch when it sat on that path.
+    const bool dynamic = p.work != nullptr;
+    const uint32_t sched_empty_leader = mapa_rank(bar_sched_empty, 0);
+    auto next_pass = [&](uint32_t si, int &pp, bool report = false) {
+        if (!dynamic) { pp = cluster_id + (int)si * num_clusters; return; }
+        const uint32_t slot = si % kSchedSlots;
+        mbar_wait_cluster(bar_sched_full + 8 * slot, (si / kSchedSlots) & 1);
+        asm volatile("ld.shared.b32 %0, [%1];" : "=r"(pp) : "r"(sched_ring + 8 * slot) : "memory");
+        if (report) {                                                           // epilogue warps only (see kSchedSlots)
+            __syncwarp();
+            if (lane == 0) asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(sched_empty_leader + 8 * slot) : "memory");
+        }
+    };
+    // The pass after entry si, if it is known already (the scheduler runs ahead of the epilogue); num_pp otherwise.
+    auto peek_pass = [&](uint32_t si, int pp) -> int {
+        if (!dynamic) return pp + num_clusters;
+        const uint32_t slot = (si + 1) % kSchedSlots;
+        uint32_t done;
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.test_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done) : "r"(bar_sched_full + 8 * slot), "r"(((si + 1) / kSchedSlots) & 1) : "memory");
+        int v = num_pp;
+        if (done) asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(sched_ring + 8 * slot) : "memory");
+        return v;
+    };
+
     // Roles run with warp-uniform control flow and elect one lane only around the asynchronous
     // instruction itself, so descriptors and coordinates stay in uniform registers (a divergent
     // `if (lane == 0)` loop makes the compiler re-broadcast every operand before every MMA).
@@ -229,15 +300,38 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap map_act, const __grid_co
         // ===== activation TMA producer (one per CTA; bytes complete on the LEADER's barrier) =====
         uint32_t it = 0;
         const uint32_t full0 = mapa_rank(bar_act_full, 0);
+        const bool scheduler = dynamic && leader;
+        int drawn = 0;                                    // lane 0: the index drawn for the next pass (possibly still in flight)
+        if (scheduler && lane == 0) drawn = atomicAdd(p.work, 1);   // the counter does not depend on the previous layer: before the wait
         griddep_wait();                                   // the previous layer's output is complete and visible
-        for (int pp = cluster_id; pp < num_pp; pp += num_clusters) {
+        for (uint32_t si = 0;; ++si) {
+            int pp;
+            if (scheduler) {
+                pp = __shfl_sync(0xffffffffu, drawn, 0);
+                const uint32_t slot = si % kSchedSlots;
+                if (si >= kSchedSlots) {                  // entry si - kSchedLag has been read by every epilogue warp of the pair
+                    const uint32_t sj = si - kSchedLag;
+                    mbar_wait_b(bar_sched_empty + 8 * (sj % kSchedSlots), (sj / kSchedSlots) & 1);
+                }
+                if (elect_one()) {
+                    st_cluster_b32(mapa_rank(sched_ring + 8 * slot, 0), pp);
+                    st_cluster_b32(mapa_rank(sched_ring + 8 * slot, 1), pp);
+                    mbar_arrive_cluster(mapa_rank(bar_sched_full + 8 * slot, 0));
+                    mbar_arrive_cluster(mapa_rank(bar_sched_full + 8 * slot, 1));
+                }
+                __syncwarp();
+                if (pp < num_pp && lane == 0) drawn = atomicAdd(p.work, 1);   // next pass's index: in flight under this pass's loads
+            } else {
+                next_pass(si, pp);
+            }
+            if (pp >= num_pp) break;
             const int up = pp / ntiles, unit = 2 * (up / kRowPasses) + (int)rank, yp = up % kRowPasses;
             for (int kb = 0; kb < p.kblocks; ++kb, ++it) {
                 const uint32_t s = it % kActStagesP, ph = (it / kActStagesP) & 1;
                 mbar_wait_b(bar_act_empty + 8 * s, ph ^ 1);
                 if (elect_one()) {
                     if (leader) mbar_expect_tx(bar_act_full + 8 * s, 2 * kActBoxBytesP);
-                    tma_load_4d_pair(act0 + s * kActStageBytesP + kSlotBytes, &map_act, full0 + 8 * s,
+                    tma_load_4d_pair(act0 + kSlotBytes + s * kActBoxBytesP, &map_act, full0 + 8 * s,
                                      kb * kKBlock, unit * kBoardsPerUnit, 0, yp * kYPerPass - 1);
                 }
                 __syncwarp();
@@ -247,8 +341,11 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap map_act, const __grid_co
         // ===== weight TMA producer: this CTA's 64-cout half of every (K block, tap) tile =====
         uint32_t wit = 0;
         const uint32_t full0 = mapa_rank(bar_w_full, 0);
-        for (int pp = cluster_id; pp < num_pp; pp += num_clusters) {
-            if (resident && wit >= (uint32_t)wtiles) break;
+        for (uint32_t si = 0;; ++si) {
+            int pp;
+            next_pass(si, pp);
+            if (pp >= num_pp) break;
+            if (resident && wit >= (uint32_t)wtiles) { if (!dynamic) break; continue; }   // loaded once; keep reading the schedule
             const int nt = pp % ntiles;
             for (int kb = 0; kb < p.kblocks; ++kb)
                 for (int tap = 0; tap < 9; ++tap, ++wit) {
@@ -265,8 +362,11 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap map_act, const __grid_co
     } else if (warp == 1) {
         // ===== MMA issuer: one elected thread of the leader CTA drives both tensor cores =====
         if (leader) {
-            uint32_t ait = 0, wit = 0, np = 0;
-            for (int pp = cluster_id; pp < num_pp; pp += num_clusters, ++np) {
+            uint32_t ait = 0, wit = 0;
+            for (uint32_t np = 0;; ++np) {
+                int pp;
+                next_pass(np, pp);
+                if (pp >= num_pp) break;
                 const uint32_t acc = np & 1;
                 mbar_wait_b(bar_tmem_empty + 8 * acc, ((np >> 1) & 1) ^ 1);      // both CTAs drained this accumulator
                 tc_fence_after();
@@ -279,7 +379,7 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap map_act, const __grid_co
                     const uint32_t as = ait % kActStagesP;
                     mbar_wait_b(bar_act_full + 8 * as, (ait / kActStagesP) & 1);
                     tc_fence_after();
-                    const uint32_t abox = act0 + as * kActStageBytesP + kSlotBytes;
+                    const uint32_t abox = act0 + kSlotBytes + as * kActBoxBytesP;
                     if (resident && np != 0) {
                         // weights already in place: the whole K block is one uninterrupted issue burst
                         if (elect_one()) {
@@ -337,9 +437,11 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap map_act, const __grid_co
         const int quad = warp & 3, half = (warp - 3) >> 2;
         const int row = quad * 32 + lane, x = row >> 4, bl = row & 15;     // row in tile = x * 16 + board
         const uint32_t empty_remote = mapa_rank(bar_tmem_empty, 0);
-        uint32_t np = 0;
         griddep_wait();
-        for (int pp = cluster_id; pp < num_pp; pp += num_clusters, ++np) {
+        for (uint32_t np = 0;; ++np) {
+            int pp;
+            next_pass(np, pp, true);
+            if (pp >= num_pp) break;
             const int nt = pp % ntiles, up = pp / ntiles, unit = 2 * (up / kRowPasses) + (int)rank, yp = up % kRowPasses;
             const uint32_t acc = np & 1;
             const size_t board = (size_t)unit * kBoardsPerUnit + bl;
@@ -352,8 +454,9 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap map_act, const __grid_co
 #pragma unroll
                     for (int i = 0; i < 4; ++i) ldg256(p.skip + off0 + r * ystride + i * 16, &sk[r][i * 8]);
                 }
-                if (pp + num_clusters < num_pp) {               // next pass's residual rows: HBM -> L2 ahead of use
-                    const int ppn = pp + num_clusters, ntn = ppn % ntiles, un = ppn / ntiles;
+                const int ppn = peek_pass(np, pp);
+                if (ppn < num_pp) {                             // next pass's residual rows: HBM -> L2 ahead of use
+                    const int ntn = ppn % ntiles, un = ppn / ntiles;
                     const size_t board_n = (size_t)(2 * (un / kRowPasses) + (int)rank) * kBoardsPerUnit + bl;
                     const size_t offn = ((board_n * 8 + (un % kRowPasses) * kYPerPass) * 8 + x) * (size_t)p.cout_total + ntn * 128 + half * 64;
 #pragma unroll
@@ -716,8 +819,15 @@ static int launch_conv(const CUtensorMap &ma, const CUtensorMap *ma1, const CUte
     return OZ_OK;
 }
 
+// OZ_CONV_STATIC=1 in the environment switches the convolution back to the static pass-to-cluster assignment (A/B runs).
+bool conv_static_schedule() {
+    static int v = -1;
+    if (v < 0) { const char *e = getenv("OZ_CONV_STATIC"); v = (e && e[0] == '1') ? 1 : 0; }
+    return v == 1;
+}
+
 void ResNet::free_workspaces() {
-    for (Workspace &w : ws_) { cudaFree(w.x0); cudaFree(w.a); cudaFree(w.t); cudaFree(w.head_pre); }
+    for (Workspace &w : ws_) { cudaFree(w.x0); cudaFree(w.a); cudaFree(w.t); cudaFree(w.head_pre); cudaFree(w.work); }
     ws_.clear();
 }
 
@@ -764,13 +874,14 @@ int ResNet::reserve(size_t boards, int ws) {
     Workspace &w = ws_[(size_t)ws];
     const size_t pad = (boards + kBoardPad - 1) / kBoardPad * kBoardPad;
     if (pad <= w.cap) return OZ_OK;
-    cudaFree(w.x0); cudaFree(w.a); cudaFree(w.t); cudaFree(w.head_pre);
+    cudaFree(w.x0); cudaFree(w.a); cudaFree(w.t); cudaFree(w.head_pre); cudaFree(w.work);
     w = Workspace{};
     const size_t C = shape_.channels;
     OZ_CUDA(cudaMalloc(&w.x0, pad * 64 * 32 * 2));
     OZ_CUDA(cudaMalloc(&w.a, pad * 64 * C * 2));
     OZ_CUDA(cudaMalloc(&w.t, pad * 64 * C * 2));
     OZ_CUDA(cudaMalloc(&w.head_pre, pad * 64 * 4 * sizeof(float)));
+    OZ_CUDA(cudaMalloc(&w.work, kMaxConvLayers * sizeof(int)));
     OZ_CUDA(cudaMemset(w.x0, 0, pad * 64 * 32 * 2));
     OZ_CUDA(cudaMemset(w.a, 0, pad * 64 * C * 2));
     OZ_CUDA(cudaMemset(w.t, 0, pad * 64 * C * 2));
@@ -797,6 +908,7 @@ int ResNet::forward(const float *d_features, size_t n, float *d_policy, float *d
     if (n == 0) return OZ_OK;
     OZ_TRY(reserve(n, ws));
     const Workspace &w = ws_[(size_t)ws];
+    dynamic_ = !conv_static_schedule();
     void *const d_x0_ = w.x0, *const d_a_ = w.a, *const d_t_ = w.t;
     float *const d_head_pre_ = w.head_pre;
     const CUtensorMap &map_x0_ = w.map_x0, &map_a_ = w.map_a, &map_t_ = w.map_t;
@@ -812,17 +924,24 @@ int ResNet::forward(const float *d_features, size_t n, float *d_policy, float *d
     // fp32 values, so the final activation tensor is never written and the head kernel reads 1 KB instead of 16 KB per board.
     const bool fuse_heads = C == 128 && shape_.blocks > 0 && d_head_pre_ != nullptr;
     if (fuse_heads) OZ_CUDA(cudaMemsetAsync(d_head_pre_, 0, pad * 64 * 4 * sizeof(float), stream));   // up front: nothing sits between the conv launches
+    // One pass counter per convolution launch of this forward (dynamic pass scheduler), zeroed up front for the same reason.
+    const int nconv = 1 + 2 * shape_.blocks;
+    int *work = (dynamic_ && nconv <= kMaxConvLayers) ? w.work : nullptr;
+    if (work) OZ_CUDA(cudaMemsetAsync(work, 0, (size_t)nconv * sizeof(int), stream));
     if (conv_begin) cudaEventRecord(conv_begin, stream);
     ConvParams cp{};
     cp.units = (int)(pad / kBoardsPerUnit); cp.cout_total = C; cp.relu = 1;
     // conv block (neural_net.py:9-29)
     cp.kblocks = 1; cp.skip = nullptr; cp.out = (__nv_bfloat16 *)d_a_; cp.bias = (const float *)(d_blob_ + layout_.conv_b[0]);
+    cp.work = work;
     OZ_TRY(launch_conv(map_x0_, map_x0_1, map_w_[0], cp, stream, pdl_));
     cp.kblocks = C / kKBlock;
     for (int b = 0; b < shape_.blocks; ++b) {   // residual tower (neural_net.py:32-65)
         cp.skip = nullptr; cp.out = (__nv_bfloat16 *)d_t_; cp.bias = (const float *)(d_blob_ + layout_.conv_b[1 + 2 * b]);
+        cp.work = work ? work + 1 + 2 * b : nullptr;
         OZ_TRY(launch_conv(map_a_, map_a_1, map_w_[1 + 2 * b], cp, stream, pdl_));
         cp.skip = (const __nv_bfloat16 *)d_a_; cp.out = (__nv_bfloat16 *)d_a_; cp.bias = (const float *)(d_blob_ + layout_.conv_b[2 + 2 * b]);
+        cp.work = work ? work + 2 + 2 * b : nullptr;
         if (fuse_heads && b == shape_.blocks - 1) { cp.out = nullptr; cp.head_w = (const float *)(d_blob_ + layout_.head_w); cp.head_out = d_head_pre_; }
         OZ_TRY(launch_conv(map_t_, map_t_1, map_w_[2 + 2 * b], cp, stream, pdl_));
         cp.head_w = nullptr; cp.head_out = nullptr;
@@ -851,7 +970,7 @@ int ResNet::forward(const float *d_features, size_t n, float *d_policy, float *d
 }
 
 int ResNet::conv3x3(const void *d_in, int cin, const void *d_w, const float *d_bias, const void *d_skip, int relu,
-                    void *d_out, int cout, size_t boards_padded, cudaStream_t stream) {
+                    void *d_out, int cout, size_t boards_padded, cudaStream_t stream, int *d_work) {
     if (cin % kKBlock || cout % 128 || boards_padded % kBoardPad)
         return fail(OZ_ERR_INVALID_ARGUMENT, "conv3x3: cin % 32, cout % 128, boards % 32 must be 0");
     CUtensorMap ma, ma1, mw;
@@ -861,6 +980,10 @@ int ResNet::conv3x3(const void *d_in, int cin, const void *d_w, const float *d_b
     ConvParams cp{};
     cp.skip = (const __nv_bfloat16 *)d_skip; cp.out = (__nv_bfloat16 *)d_out; cp.bias = d_bias;
     cp.units = (int)(boards_padded / kBoardsPerUnit); cp.kblocks = cin / kKBlock; cp.cout_total = cout; cp.relu = relu;
+    if (d_work && !conv_static_schedule()) {          // dynamic pass scheduler: the caller's counter, zeroed in stream order
+        OZ_CUDA(cudaMemsetAsync(d_work, 0, sizeof(int), stream));
+        cp.work = d_work;
+    }
     return launch_conv(ma, &ma1, mw, cp, stream);
 }
 

@@ -33,6 +33,9 @@ ResNetLayout resnet_layout(const oz_resnet_shape &s);
 
 // Board counts are padded to this inside the evaluator: a CTA pair convolves two 16-board units at a time.
 constexpr int kBoardPad = 32;
+// Pass counters of the dynamic scheduler: one per convolution launch of a forward (1 + 2 * blocks <= this).
+constexpr int kMaxConvLayers = 128;
+bool conv_static_schedule();
 
 class ResNet {
   public:
@@ -57,8 +60,9 @@ class ResNet {
     // Kernel launches one forward() issues.
     int launches_per_forward() const { return 2 + (1 + 2 * shape_.blocks); }
     // Debug hook: one 3x3 convolution layer on device NHWC bf16 buffers already padded to 32 boards.
+    // d_work: one device int for the dynamic pass scheduler (zeroed here, in stream order), or null = static schedule.
     static int conv3x3(const void *d_in, int cin, const void *d_w, const float *d_bias, const void *d_skip,
-                       int relu, void *d_out, int cout, size_t boards_padded, cudaStream_t stream);
+                       int relu, void *d_out, int cout, size_t boards_padded, cudaStream_t stream, int *d_work = nullptr);
 
   private:
     oz_resnet_shape shape_{};
@@ -68,12 +72,14 @@ class ResNet {
         size_t cap = 0;
         void *x0 = nullptr, *a = nullptr, *t = nullptr;       // bf16 NHWC activations
         float *head_pre = nullptr;                            // [boards][64][4] fused head-conv pre-activations
+        int *work = nullptr;                                  // [kMaxConvLayers] pass counters (dynamic pass scheduler)
         CUtensorMap map_x0, map_a, map_t;                     // 4-row boxes: two board rows per pass
         CUtensorMap map_x0_1, map_a_1, map_t_1;               // 3-row boxes: one board row per pass (small batches)
     };
     void free_workspaces();
     std::vector<Workspace> ws_;
     bool pdl_ = true;
+    bool dynamic_ = true;                                     // dynamic pass scheduler in the convolutions (OZ_CONV_STATIC=1: off)
     std::vector<CUtensorMap> map_w_;
 };
 
