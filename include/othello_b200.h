@@ -233,6 +233,14 @@ int oz_engine_records(oz_engine *e, int32_t *plies, oz_ply_record *records, int 
 int oz_engine_training_samples(oz_engine *e, float *features, float *policy, float *value,
                                size_t capacity, size_t *n_samples);
 
+/* The same expansion for compact records that travelled (a multi-GPU run gathers 176-byte oz_ply_record rows and expands
+ * them on the destination rank instead of shipping 4 612-byte samples): records [n_games][max_plies] + plies [n_games]
+ * as oz_engine_records / oz_engine_finished_records return them; every game counts as finished (its outcome follows from
+ * the last record and action).  Host buffers; the kernel runs on `device`.  Buffers may be NULL to query *n_samples. */
+int oz_training_samples_from_records(int device, const oz_ply_record *records, const int32_t *plies, int n_games, int max_plies,
+                                     int history_size, float *features, float *policy, float *value, size_t capacity,
+                                     size_t *n_samples);
+
 /* Rolling game pool (new capability; the reference replays one MCTS object game after game, train.py:394-410):
  * the engine's num_games slots play `total_games` games with ids first_game_id .. first_game_id + total_games - 1.
  * After every oz_engine_play_ply, finished games move to a store of completed games (completion order) and their

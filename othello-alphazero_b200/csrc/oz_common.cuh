@@ -5,6 +5,8 @@
 
 #include <string>
 
+#include <nvtx3/nvToolsExt.h>
+
 #include "../../include/othello_b200.h"
 
 namespace oz {
@@ -28,6 +30,15 @@ inline bool first_use_on_device(unsigned long long &mask) {
     mask |= bit;
     return true;
 }
+
+// NVTX phase ranges (tracing).  Header-only NVTX v3: free unless a profiler is attached, in which case
+// the host-side ranges bracket the launches of a phase ("search", "round: select+encode", "round: network", ...).
+struct NvtxRange {
+    explicit NvtxRange(const char *name) { nvtxRangePushA(name); }
+    ~NvtxRange() { nvtxRangePop(); }
+    NvtxRange(const NvtxRange &) = delete;
+    NvtxRange &operator=(const NvtxRange &) = delete;
+};
 
 }  // namespace oz
 

@@ -432,6 +432,7 @@ int search_pipelined(oz_engine *e, int groups) {
     e->net.set_pdl(e->pipeline_pdl);
     size_t n_ev = 0;
     int st = OZ_OK;
+    NvtxRange nvtx_pipe("oz: pipelined rounds");
     for (int r = 0; r < rounds && !st; ++r) {
         e->round = r;
         for (int k = 0; k < groups && !st; ++k) {
@@ -827,6 +828,7 @@ static int count_unfinished(oz_engine *e, int g0, int g1, int *out) {
 }
 
 static int search_games(oz_engine *e, int g0, int g1) {
+    NvtxRange nvtx_search("oz: search");
     OZ_TRY(set_device(e));
     const bool whole = g0 == 0 && g1 == e->t.G;
     int active = e->active;
@@ -887,12 +889,11 @@ static int search_games(oz_engine *e, int g0, int g1) {
         e->round = r;
         cudaEvent_t cb = nullptr, ce = nullptr;
         if (e->profiling) { cudaEventRecord(next_event(e, k), e->stream); cb = next_event(e, k + 2); ce = next_event(e, k + 3); }
-        launch_select(v, e->stream);
-        launch_encode(v, feat, e->stream, false, x0);
+        { NvtxRange r("oz: round select+encode"); launch_select(v, e->stream); launch_encode(v, feat, e->stream, false, x0); }
         if (e->profiling) cudaEventRecord(next_event(e, k + 1), e->stream);
-        st = eval_slots(e, first, n, e->stream, 0, net_prof ? cb : nullptr, net_prof ? ce : nullptr, x0 != nullptr);
+        { NvtxRange r("oz: round network"); st = eval_slots(e, first, n, e->stream, 0, net_prof ? cb : nullptr, net_prof ? ce : nullptr, x0 != nullptr); }
         if (e->profiling) cudaEventRecord(next_event(e, k + 4), e->stream);
-        if (!st) launch_expand(v, e->d_policy + first * 65, e->d_value + first, e->stream);
+        if (!st) { NvtxRange r("oz: round expand+backup"); launch_expand(v, e->d_policy + first * 65, e->d_value + first, e->stream); }
         if (e->profiling) { cudaEventRecord(next_event(e, k + 5), e->stream); k += 6; }
     }
     if (st) { e->in_search = false; return st; }
@@ -945,6 +946,7 @@ int oz_engine_self_play_data(oz_engine *e, int game, float *features, float *pol
 }
 
 static int apply_device_actions(oz_engine *e) {
+    NvtxRange nvtx_apply("oz: re-root (apply actions, harvest)");
     OZ_CUDA(cudaMemsetAsync(e->d_unfinished, 0, 2 * sizeof(int32_t), e->stream));
     launch_apply(e->t, e->d_actions, e->d_unfinished, e->stream);
     int32_t *unf2 = e->h_pin + 1;
@@ -995,6 +997,7 @@ int oz_engine_choose_actions(oz_engine *e, int32_t *actions) {
 }
 
 int oz_engine_play_ply(oz_engine *e, int32_t *actions, int32_t *visit_counts, int32_t *unfinished) {
+    NvtxRange nvtx_ply("oz: ply");
     e->defer_error_check = true;           // one host synchronisation per ply: at the end of apply_device_actions
     const int st = oz_engine_search(e);
     e->defer_error_check = false;
@@ -1004,8 +1007,7 @@ int oz_engine_play_ply(oz_engine *e, int32_t *actions, int32_t *visit_counts, in
         launch_root_stats(e->t, e->d_stat_n, e->d_stat_counts, nullptr, nullptr, e->stream);
         OZ_CUDA(cudaMemcpyAsync(e->h_counts, e->d_stat_counts, G * kStride * 4, cudaMemcpyDeviceToHost, e->stream));
     }
-    launch_choose(e->t, e->d_actions, e->stream);
-    launch_record(e->t, e->d_actions, e->d_records, e->max_plies, e->stream);
+    { NvtxRange r("oz: choose+record"); launch_choose(e->t, e->d_actions, e->stream); launch_record(e->t, e->d_actions, e->d_records, e->max_plies, e->stream); }
     if (actions) OZ_CUDA(cudaMemcpyAsync(e->h_actions, e->d_actions, G * sizeof(int32_t), cudaMemcpyDeviceToHost, e->stream));
     OZ_TRY(apply_device_actions(e));
     read_profile(e);                       // the search's phase events have completed now
@@ -1093,6 +1095,63 @@ int oz_engine_training_samples(oz_engine *e, float *features, float *policy, flo
         cudaMemcpy(value, d_v, total * sizeof(float), cudaMemcpyDeviceToHost);
     } while (0);
     cudaFree(d_f); cudaFree(d_p); cudaFree(d_v); cudaFree(d_base); cudaFree(d_plies);
+    return st;
+}
+
+// The same expansion for records that travelled (e.g. gathered from other ranks as 176-byte rows instead of 4 612-byte
+// samples): the final discs of a game follow from its last record and action, so the rows are self-contained.
+int oz_training_samples_from_records(int device, const oz_ply_record *records, const int32_t *plies, int n_games, int max_plies,
+                                     int history_size, float *features, float *policy, float *value, size_t capacity, size_t *n_samples) {
+    if (n_games < 0 || max_plies < 1) return fail(OZ_ERR_INVALID_ARGUMENT, "Expected n_games >= 0 and max_plies >= 1.");
+    if (history_size < 1 || history_size > kMaxHist) return fail(OZ_ERR_INVALID_ARGUMENT, "Expected 1 <= history_size <= " + std::to_string(kMaxHist) + ".");
+    std::vector<int64_t> base((size_t)std::max(n_games, 1));
+    std::vector<int32_t> pl((size_t)std::max(n_games, 1));
+    std::vector<uint64_t> f1((size_t)std::max(n_games, 1)), f2((size_t)std::max(n_games, 1));
+    size_t total = 0;
+    for (int g = 0; g < n_games; ++g) {
+        pl[g] = std::max(0, std::min(plies[g], max_plies));
+        base[g] = (int64_t)total;
+        total += (size_t)pl[g] * 8;
+        f1[g] = kInitialP1; f2[g] = kInitialP2;
+        if (pl[g] > 0) {                                   // final position = last recorded position + its action (train.py:438-439)
+            const oz_ply_record &r = records[(size_t)g * max_plies + pl[g] - 1];
+            Position p{r.player, r.p1, r.p2, 0, 0};
+            const uint64_t me = r.player == 1 ? r.p1 : r.p2, opp = r.player == 1 ? r.p2 : r.p1;
+            p.legal = legal_moves(me, opp);
+            if (p.legal == 0) p.next_legal = legal_moves(opp, me);
+            const Position q = apply_action(p, r.action);
+            f1[g] = q.p1; f2[g] = q.p2;
+        }
+    }
+    *n_samples = total;
+    if (!features || !policy || !value || total == 0) return OZ_OK;
+    if (capacity < total) return fail(OZ_ERR_INVALID_ARGUMENT, "sample buffers too small");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) return fail(OZ_ERR_CUDA, "no CUDA device: the engine has no CPU path");
+    OZ_CUDA(cudaSetDevice(device));
+    const size_t nf = (size_t)(1 + 2 * history_size) * 64, nrec = (size_t)n_games * max_plies;
+    float *d_f = nullptr, *d_p = nullptr, *d_v = nullptr;
+    int64_t *d_base = nullptr;
+    int32_t *d_pl = nullptr;
+    uint64_t *d_f1 = nullptr, *d_f2 = nullptr;
+    PlyRecordDev *d_rec = nullptr;
+    int st = OZ_OK;
+    do {
+        if ((st = dalloc(&d_f, total * nf)) || (st = dalloc(&d_p, total * 65)) || (st = dalloc(&d_v, total)) || (st = dalloc(&d_base, n_games)) ||
+            (st = dalloc(&d_pl, n_games)) || (st = dalloc(&d_f1, n_games)) || (st = dalloc(&d_f2, n_games)) || (st = dalloc(&d_rec, nrec))) break;
+        cudaMemcpy(d_rec, records, nrec * sizeof(PlyRecordDev), cudaMemcpyHostToDevice);
+        cudaMemcpy(d_base, base.data(), (size_t)n_games * 8, cudaMemcpyHostToDevice);
+        cudaMemcpy(d_pl, pl.data(), (size_t)n_games * 4, cudaMemcpyHostToDevice);
+        cudaMemcpy(d_f1, f1.data(), (size_t)n_games * 8, cudaMemcpyHostToDevice);
+        cudaMemcpy(d_f2, f2.data(), (size_t)n_games * 8, cudaMemcpyHostToDevice);
+        launch_training_samples_rows(n_games, history_size, d_rec, d_pl, d_base, d_f1, d_f2, max_plies, d_f, d_p, d_v, nullptr);
+        cudaError_t err = cudaDeviceSynchronize();
+        if (err != cudaSuccess) { st = fail(OZ_ERR_CUDA, std::string("training_samples_from_records: ") + cudaGetErrorString(err)); break; }
+        cudaMemcpy(features, d_f, total * nf * sizeof(float), cudaMemcpyDeviceToHost);
+        cudaMemcpy(policy, d_p, total * 65 * sizeof(float), cudaMemcpyDeviceToHost);
+        cudaMemcpy(value, d_v, total * sizeof(float), cudaMemcpyDeviceToHost);
+    } while (0);
+    cudaFree(d_f); cudaFree(d_p); cudaFree(d_v); cudaFree(d_base); cudaFree(d_pl); cudaFree(d_f1); cudaFree(d_f2); cudaFree(d_rec);
     return st;
 }
 

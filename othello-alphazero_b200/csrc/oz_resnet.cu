@@ -94,14 +94,8 @@ constexpr int kWSlots = 36;
 constexpr int kEpiWarps = 8;
 constexpr int kThreadsP = (3 + kEpiWarps) * 32;
 constexpr int kMiscBytes = 3072;                                    // barriers + scheduler ring (1 KB), bias / head-conv weights (2 KB)
-// Ring of published pass indices (dynamic scheduler).  Only the epilogue warps -- the last role to read an entry -- report
-// back: when one of them has read entry i, every other role has read entry i - 1 (the accumulator of pass i - 1 it just
-// drained was issued by the MMA thread, fed by both producers, after they had read that entry).  The scheduler overwrites
-// the slot of entry i - 8 once entry i - 4 has been reported, so four entries of slack cover that one-entry lag, and the
-// MMA thread and the producers never execute an arrive on this path.
+// Ring of published pass indices (dynamic scheduler; see the kernel).
 constexpr int kSchedSlots = 8;
-constexpr int kSchedLag = 4;
-constexpr int kSchedConsumers = 2 * kEpiWarps;
 constexpr int kSmemBytesP = 1024 + kSlotBytes + kActStagesP * kActBoxBytesP + kWSlots * kWTileBytes + kMiscBytes;
 // 233 472 B per SM, 1 KB of it reserved per resident CTA: what this kernel leaves free (6 144 B) must hold one block of the
 // narrow select kernel (4 352 B static + its 1 KB), or the pipelined search cannot run tree kernels under the convolutions.
@@ -234,7 +228,7 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap map_act, const __grid_co
         for (int i = 0; i < kActStagesP; ++i) { mbar_init(bar_act_full + 8 * i, 1); mbar_init(bar_act_empty + 8 * i, 1); }
         for (int i = 0; i < 2; ++i) { mbar_init(bar_tmem_full + 8 * i, 1); mbar_init(bar_tmem_empty + 8 * i, 2 * kEpiWarps); }
         for (int i = 0; i < kWSlots; ++i) { mbar_init(bar_w_full + 8 * i, 1); mbar_init(bar_w_empty + 8 * i, 1); }
-        for (int i = 0; i < kSchedSlots; ++i) { mbar_init(bar_sched_full + 8 * i, 1); mbar_init(bar_sched_empty + 8 * i, kSchedConsumers); }
+        for (int i = 0; i < kSchedSlots; ++i) { mbar_init(bar_sched_full + 8 * i, 1); mbar_init(bar_sched_empty + 8 * i, 1); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_act) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w) : "memory");
@@ -259,24 +253,23 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap map_act, const __grid_co
     // Pass scheduler.  Static (p.work == nullptr): cluster c takes passes c, c + clusters, ...  Dynamic: the passes of a
     // launch are handed out in arrival order from one global counter, so a cluster that is slowed down -- a tree kernel
     // of another game group co-resident on its SMs (pipelined search), a late start behind the previous layer's tail --
-    // simply takes fewer passes instead of holding the whole launch back.  One thread per cluster (the leader CTA's
-    // activation producer, the role that runs furthest ahead) draws the indices and publishes them through a small ring
-    // in BOTH CTAs' shared memory; every other role of the pair reads the same sequence from the ring (full / empty
-    // mbarriers, cluster-scope release / acquire).  An index >= num_pp is the end marker.  The atomic for pass i + 1 is
-    // issued at the start of pass i and its result is first touched after the loads of pass i are on their way: the
-    // activation pipeline is two stages deep and latency-critical, a round trip to the counter in front of every pass
-    // cost 10 % of the launch when it sat on that path.
+    // simply takes fewer passes instead of holding the whole launch back.  The scheduler is the one warp of the pair
+    // that has no other job (warp 1 of the non-leader CTA; only the leader issues MMAs): it draws an index with an
+    // atomic, publishes it into a small ring in BOTH CTAs' shared memory (cluster-scope release / acquire on the ring's
+    // full barriers) and stays at most two entries ahead of what the leader's activation producer reports to have read,
+    // so a pair never holds more than two passes it has not started.  Every role reads the same sequence from the ring; an
+    // index >= num_pp is the end marker.  None of the working roles executes an atomic, a remote store or a release on
+    // this path -- the activation pipeline is two stages deep and latency-critical: with the draw and the publication
+    // in the producer's loop the launch was 10 % slower, with release-arrives in the MMA thread 5 % more.
+    // Ring safety (8 slots): when the producer reads entry i the MMA thread has read entry i - 3 or later (two stages
+    // of run-ahead) and the epilogue entry i - 5 or later (two accumulator stages), so entry i + 2 never overwrites an
+    // entry (i - 6) somebody still needs.
     const bool dynamic = p.work != nullptr;
-    const uint32_t sched_empty_leader = mapa_rank(bar_sched_empty, 0);
-    auto next_pass = [&](uint32_t si, int &pp, bool report = false) {
+    auto next_pass = [&](uint32_t si, int &pp) {
         if (!dynamic) { pp = cluster_id + (int)si * num_clusters; return; }
         const uint32_t slot = si % kSchedSlots;
         mbar_wait_cluster(bar_sched_full + 8 * slot, (si / kSchedSlots) & 1);
         asm volatile("ld.shared.b32 %0, [%1];" : "=r"(pp) : "r"(sched_ring + 8 * slot) : "memory");
-        if (report) {                                                           // epilogue warps only (see kSchedSlots)
-            __syncwarp();
-            if (lane == 0) asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(sched_empty_leader + 8 * slot) : "memory");
-        }
     };
     // The pass after entry si, if it is known already (the scheduler runs ahead of the epilogue); num_pp otherwise.
     auto peek_pass = [&](uint32_t si, int pp) -> int {
@@ -300,30 +293,13 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap map_act, const __grid_co
         // ===== activation TMA producer (one per CTA; bytes complete on the LEADER's barrier) =====
         uint32_t it = 0;
         const uint32_t full0 = mapa_rank(bar_act_full, 0);
-        const bool scheduler = dynamic && leader;
-        int drawn = 0;                                    // lane 0: the index drawn for the next pass (possibly still in flight)
-        if (scheduler && lane == 0) drawn = atomicAdd(p.work, 1);   // the counter does not depend on the previous layer: before the wait
+        const uint32_t sched_go = mapa_rank(bar_sched_empty, 1);   // the scheduler's "entry read" barriers live in the peer CTA
         griddep_wait();                                   // the previous layer's output is complete and visible
         for (uint32_t si = 0;; ++si) {
             int pp;
-            if (scheduler) {
-                pp = __shfl_sync(0xffffffffu, drawn, 0);
-                const uint32_t slot = si % kSchedSlots;
-                if (si >= kSchedSlots) {                  // entry si - kSchedLag has been read by every epilogue warp of the pair
-                    const uint32_t sj = si - kSchedLag;
-                    mbar_wait_b(bar_sched_empty + 8 * (sj % kSchedSlots), (sj / kSchedSlots) & 1);
-                }
-                if (elect_one()) {
-                    st_cluster_b32(mapa_rank(sched_ring + 8 * slot, 0), pp);
-                    st_cluster_b32(mapa_rank(sched_ring + 8 * slot, 1), pp);
-                    mbar_arrive_cluster(mapa_rank(bar_sched_full + 8 * slot, 0));
-                    mbar_arrive_cluster(mapa_rank(bar_sched_full + 8 * slot, 1));
-                }
-                __syncwarp();
-                if (pp < num_pp && lane == 0) drawn = atomicAdd(p.work, 1);   // next pass's index: in flight under this pass's loads
-            } else {
-                next_pass(si, pp);
-            }
+            next_pass(si, pp);
+            if (dynamic && leader && lane == 0)           // entry si is in use: the scheduler may draw the next one
+                asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(sched_go + 8 * (si % kSchedSlots)) : "memory");
             if (pp >= num_pp) break;
             const int up = pp / ntiles, unit = 2 * (up / kRowPasses) + (int)rank, yp = up % kRowPasses;
             for (int kb = 0; kb < p.kblocks; ++kb, ++it) {
@@ -431,6 +407,25 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap map_act, const __grid_co
                 if (elect_one()) tc_commit_pair(bar_tmem_full + 8 * acc);
                 __syncwarp();
             }
+        } else if (dynamic) {
+            // ===== pass scheduler (the non-leader CTA's otherwise idle warp) =====
+            for (uint32_t si = 0;; ++si) {
+                // Entry si is drawn once the producer has read entry si - 2: the pair holds at most two undrawn passes, and the
+                // round trip (report, atomic, publication: about 2 us) stays hidden even for the 1-K-block first layer.
+                if (si > 1) mbar_wait_b(bar_sched_empty + 8 * ((si - 2) % kSchedSlots), ((si - 2) / kSchedSlots) & 1);
+                int pp = 0;
+                if (lane == 0) pp = atomicAdd(p.work, 1);
+                pp = __shfl_sync(0xffffffffu, pp, 0);
+                const uint32_t slot = si % kSchedSlots;
+                if (elect_one()) {
+                    st_cluster_b32(mapa_rank(sched_ring + 8 * slot, 0), pp);
+                    st_cluster_b32(mapa_rank(sched_ring + 8 * slot, 1), pp);
+                    mbar_arrive_cluster(mapa_rank(bar_sched_full + 8 * slot, 0));
+                    mbar_arrive_cluster(mapa_rank(bar_sched_full + 8 * slot, 1));
+                }
+                __syncwarp();
+                if (pp >= num_pp) break;
+            }
         }
     } else {
         // ===== epilogue warps 3..10: TMEM lane quarter (warp % 4) x column half =====
@@ -440,7 +435,7 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap map_act, const __grid_co
         griddep_wait();
         for (uint32_t np = 0;; ++np) {
             int pp;
-            next_pass(np, pp, true);
+            next_pass(np, pp);
             if (pp >= num_pp) break;
             const int nt = pp % ntiles, up = pp / ntiles, unit = 2 * (up / kRowPasses) + (int)rank, yp = up % kRowPasses;
             const uint32_t acc = np & 1;

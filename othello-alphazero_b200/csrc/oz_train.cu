@@ -866,6 +866,7 @@ int oz_trainer_step(oz_trainer *t, const float *features, const float *policy, c
 
 int oz_trainer_step_device(oz_trainer *t, const float *features, const float *policy, const float *value, int n, const oz_train_config *cfg,
                            int apply_update, float *losses) {
+    NvtxRange nvtx_step("oz: training step");
     OZ_CUDA(cudaSetDevice(t->device));
     if (n < 1 || n > t->max_batch) return fail(OZ_ERR_INVALID_ARGUMENT, "Expected 1 <= batch <= max_batch, but got " + std::to_string(n) + ".");
     // staged into the trainer's own buffers so that the captured step always reads the same addresses

@@ -114,6 +114,8 @@ SIGNATURES = {
     "oz_engine_play_ply": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, P(i32)]),
     "oz_engine_records": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]),
     "oz_engine_training_samples": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, P(C.c_size_t)]),
+    "oz_training_samples_from_records": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
+                                                   C.c_void_p, C.c_size_t, P(C.c_size_t)]),
     "oz_engine_counters": (C.c_int, [C.c_void_p, P(OzCounters)]),
     "oz_engine_set_graphs": (C.c_int, [C.c_void_p, C.c_int]),
     "oz_engine_set_pipeline": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),

@@ -91,6 +91,13 @@ class _Engine:
             check(self._lib.oz_engine_load_resnet(self._h, C.byref(shape), blob, len(blob)))
             self._net_fingerprint = fp
 
+    def load_folded(self, shape, blob: bytes) -> None:
+        """Upload an already folded weight blob (weights.fold_alphazero_net, parallel.broadcast_weights) and select the
+        native evaluator; a later load_network(net) folds again only if `net` differs from what it last uploaded."""
+        check(self._lib.oz_engine_load_resnet(self._h, C.byref(shape), blob, len(blob)))
+        self._net_fingerprint = ("folded", hash(blob))
+        self._set_evaluator(EVAL_RESNET)
+
     # -- search -------------------------------------------------------------------------
     def _search(self, neural_net) -> None:
         if isinstance(neural_net, str):

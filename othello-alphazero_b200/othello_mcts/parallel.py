@@ -76,6 +76,67 @@ def gather_records(records: dict, dst: int = 0, group=None) -> dict | None:
     return {"plies": plies.numpy(), "records": rec.numpy().view(raw.dtype).reshape(-1, raw.shape[1])}
 
 
+def samples_from_records(records: dict, history_size: int, cuda_device: int = 0, max_plies: int | None = None) -> dict:
+    """Expand compact game records (SelfPlayEngine.records() / gather_records(): 176 bytes per ply) into the training
+    tensors `_self_play` returns (train.py:432-450: 8 symmetries per ply, outcome from the final discs) on THIS rank's
+    GPU.  A multi-GPU run gathers the records and calls this on the destination instead of shipping the expanded
+    samples (4 612 bytes each, about 2.2 GB per 1 000 games)."""
+    import ctypes as C
+    from . import _lib
+    lib = _lib.load()
+    plies = np.ascontiguousarray(records["plies"], dtype=np.int32)
+    rec = np.ascontiguousarray(records["records"])
+    n_games = int(plies.shape[0])
+    mp = int(rec.shape[1]) if max_plies is None else int(max_plies)
+    n = C.c_size_t()
+    _lib.check(lib.oz_training_samples_from_records(cuda_device, rec.ctypes.data_as(C.c_void_p), plies.ctypes.data_as(C.c_void_p), n_games, mp,
+                                                    history_size, None, None, None, 0, C.byref(n)))
+    planes = 1 + 2 * history_size
+    f = np.zeros((n.value, planes, 8, 8), np.float32)
+    p = np.zeros((n.value, 65), np.float32)
+    v = np.zeros((n.value,), np.float32)
+    if n.value:
+        _lib.check(lib.oz_training_samples_from_records(cuda_device, rec.ctypes.data_as(C.c_void_p), plies.ctypes.data_as(C.c_void_p), n_games, mp,
+                                                        history_size, f.ctypes.data_as(C.c_void_p), p.ctypes.data_as(C.c_void_p),
+                                                        v.ctypes.data_as(C.c_void_p), n.value, C.byref(n)))
+    return {"features": torch.from_numpy(f), "policies": torch.from_numpy(p), "values": torch.from_numpy(v)}
+
+
+def broadcast_weights(net, engines, src: int = 0, group=None) -> None:
+    """New weights to every rank's engine(s) between training iterations: rank `src` folds `net`
+    (BatchNorm into bf16 convolution weights, weights.fold_alphazero_net) and ONE broadcast moves the folded blob
+    (5.4 MB for 128x10b, half of the fp32 state_dict); every rank uploads it into `engines` (a SelfPlayEngine / MCTS or
+    a list of them).  On other ranks `net` may be None.  Without a process group: a plain local upload."""
+    import ctypes as C
+    import torch.distributed as dist
+    from . import weights
+    from ._lib import OzResnetShape, check
+    engines = engines if isinstance(engines, (list, tuple)) else [engines]
+    active = dist.is_available() and dist.is_initialized()
+    rank = dist.get_rank(group) if active else src
+    shape_t = torch.zeros(5, dtype=torch.int64)
+    blob_t = None
+    if rank == src:
+        shape, blob = weights.fold_cached(net)
+        shape_t = torch.tensor([shape.in_planes, shape.channels, shape.blocks, shape.value_hidden, len(blob)], dtype=torch.int64)
+        blob_t = torch.frombuffer(bytearray(blob), dtype=torch.uint8)
+    if active:
+        on_gpu = dist.get_backend(group) == "nccl"
+        if on_gpu:
+            shape_t = shape_t.cuda()
+        dist.broadcast(shape_t, src=src, group=group)
+        if blob_t is None:
+            blob_t = torch.empty(int(shape_t[4].item()), dtype=torch.uint8)
+        if on_gpu:
+            blob_t = blob_t.cuda()
+        dist.broadcast(blob_t, src=src, group=group)
+        shape_t, blob_t = shape_t.cpu(), blob_t.cpu()
+    shape = OzResnetShape(*[int(x) for x in shape_t[:4].tolist()])
+    blob = blob_t.numpy().tobytes()
+    for eng in engines:
+        eng.load_folded(shape, blob)
+
+
 def reduce_counters(counters: dict, group=None) -> dict:
     """Sum the additive engine counters over ranks (every rank gets the totals)."""
     import torch.distributed as dist

@@ -315,6 +315,20 @@ def test_pipelined_search_equals_single_stream(evaluator, groups):
         assert cb["eval_ms"] > 0 and cb["select_ms"] > 0
 
 
+def test_samples_from_travelled_records_equal_engine_samples():
+    """parallel.samples_from_records (oz_training_samples_from_records): compact records expanded away from the engine
+    that played them -- what a multi-GPU run does on the destination rank -- equal the engine's own training tensors."""
+    import torch
+    from othello_mcts import SelfPlayEngine, parallel
+    eng = SelfPlayEngine(6, history_size=3, num_simulations=32, num_threads=1, batch_size=8, seed=17, temperature_plies=6)
+    rec = eng.run("hash")
+    want = eng.training_samples()
+    got = parallel.samples_from_records(rec, history_size=3)
+    assert want["values"].shape[0] == int(rec["plies"].sum()) * 8 > 0
+    for k in want:
+        assert torch.equal(got[k], want[k]), k
+
+
 def test_match_engine_vs_oracle_players(oracle):
     """Lockstep match play against the ORACLE: every game is replayed by play_game's loop (player.py:33-96) with two
     AlphaZeroPlayer-shaped players (player.py:177-259) built on the oracle's MCTS restatement -- own tree each,

@@ -78,3 +78,50 @@ def test_gather_is_invariant_to_world_size(total):
         p.join(120)
         assert p.exitcode == 0
     assert q.get(timeout=10) is True
+
+
+class _FakeEngine:
+    def __init__(self):
+        self.loaded = None
+
+    def load_folded(self, shape, blob):
+        self.loaded = ((shape.in_planes, shape.channels, shape.blocks, shape.value_hidden), bytes(blob))
+
+
+def _bcast_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from othello_mcts import weights
+        from othello_mcts.neural_net import AlphaZeroNet, randomize_batchnorm
+        net = None
+        if rank == 0:                                      # only the training rank owns the new weights
+            torch.manual_seed(3)
+            net = AlphaZeroNet(9, conv_channels=128, num_residual_blocks=1, value_head_hidden_channels=32).eval()
+            randomize_batchnorm(net, 4)
+        eng = _FakeEngine()
+        parallel.broadcast_weights(net, eng, src=0)
+        if rank == 0:
+            shape, blob = weights.fold_alphazero_net(net)
+            q.put(("want", (shape.in_planes, shape.channels, shape.blocks, shape.value_hidden), blob))
+        q.put(("got", rank) + eng.loaded)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_broadcast_weights_delivers_the_folded_blob_to_every_rank():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_bcast_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    items = [q.get(timeout=120) for _ in range(3)]
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    want = [x for x in items if x[0] == "want"][0]
+    got = [x for x in items if x[0] == "got"]
+    assert len(got) == 2 and all(g[2] == want[1] and g[3] == want[2] for g in got)

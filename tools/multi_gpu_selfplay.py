@@ -45,17 +45,20 @@ def main():
     torch.cuda.synchronize()
     dt = time.perf_counter() - t0
     samples = eng.training_samples()
-    all_rec = parallel.gather_records(rec)
-    all_samples = parallel.gather_samples(samples)
+    all_rec = parallel.gather_records(rec)              # compact: 176 bytes per ply
+    all_samples = parallel.gather_samples(samples)      # expanded: 4 612 bytes per sample (kept for comparison)
     ctr = parallel.reduce_counters(eng.counters())
+    parallel.broadcast_weights(net if rank == 0 else None, eng, src=0)      # next iteration's weights: one NCCL broadcast of the folded blob
     if rank == 0:
+        expanded = parallel.samples_from_records(all_rec, history_size=4, cuda_device=local)   # records expanded on the destination
         solo = om.SelfPlayEngine(a.games, first_game_id=0, **kw)
         want = solo.run(net)
         want_s = solo.training_samples()
         ok_rec = bool(np.array_equal(all_rec["plies"], want["plies"]) and all_rec["records"].tobytes() == want["records"].tobytes())
-        ok_samples = all(torch.equal(all_samples[k], want_s[k]) for k in want_s)
+        ok_samples = all(torch.equal(all_samples[k], want_s[k]) and torch.equal(expanded[k], want_s[k]) for k in want_s)
         ok_ctr = ctr["simulations"] == solo.counters()["simulations"] and ctr["nodes_expanded"] == solo.counters()["nodes_expanded"]
         print(json.dumps({"world_size": world, "games": a.games, "games_per_rank": n, "rank0_play_s": dt, "samples": int(want_s["values"].shape[0]),
+                          "gathered_record_bytes": int(all_rec["records"].nbytes), "gathered_sample_bytes": int(sum(t.numel() * 4 for t in all_samples.values())),
                           "records_identical": ok_rec, "samples_identical": bool(ok_samples), "counters_identical": bool(ok_ctr)}))
         assert ok_rec and ok_samples and ok_ctr
     if world > 1:
