@@ -12,6 +12,7 @@
 #include <string>
 
 #include "oz_resnet.cuh"
+#include "oz_tc.cuh"
 
 namespace oz {
 
@@ -22,30 +23,6 @@ constexpr int kBoxX = 9;                             // halo: x = 8 is the zero 
 constexpr int kRowBytes = kKBlock * 2;               // 64
 constexpr int kSlotBytes = kBoardsPerUnit * kRowBytes;            // 1024: one (y, x) slot
 constexpr int kTmemCols = 512;
-
-// ------------------------------------------------------------------ PTX wrappers
-__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&v)[32]) {
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
-          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
-          "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
-          "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-        : "r"(taddr) : "memory");
-}
-__device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // K-major, SWIZZLE_64B shared-memory matrix descriptor (rows of 64 B, 8-row atoms of 512 B).
 __device__ __forceinline__ uint64_t umma_desc_sw64(uint32_t saddr) {
@@ -104,39 +81,6 @@ static_assert(kSmemBytesP + 1024 + 4352 + 1024 <= 233472, "shared memory budget 
 constexpr uint32_t kIdescP = (1u << 4) | (1u << 7) | (1u << 10) | ((128u >> 3) << 17) | ((256u >> 4) << 24);
 }  // namespace pair
 
-__device__ __forceinline__ bool elect_one() {
-    uint32_t pred;
-    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
-    return pred != 0;
-}
-__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
-__device__ __forceinline__ uint32_t mapa_rank(uint32_t addr, uint32_t rank) {
-    uint32_t r; asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank)); return r;
-}
-__device__ __forceinline__ void cluster_sync_all() {
-    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
-}
-// Bounded wait: a lost arrival traps (and fails the launch) instead of hanging the GPU.
-__device__ __forceinline__ void mbar_wait_b(uint32_t bar, uint32_t parity) {
-    uint32_t done;
-    long long t0 = 0;
-    for (uint32_t spins = 0;; ++spins) {
-        asm volatile(
-            "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-            "selp.u32 %0, 1, 0, p;\n\t}"
-            : "=r"(done) : "r"(bar), "r"(parity) : "memory");
-        if (done) return;
-        if ((spins & 1023u) == 1023u) {
-            const long long now = clock64();
-            if (t0 == 0) t0 = now;
-            else if (now - t0 > 8000000000ll) { printf("conv3x3_pair_kernel: barrier timeout (block %d thread %d bar %u)\n", (int)blockIdx.x, (int)threadIdx.x, bar); __trap(); }
-        }
-    }
-}
 // The same wait with cluster-scope acquire: the data the barrier guards was written by the peer CTA (st.shared::cluster).
 __device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
     uint32_t done;
@@ -172,8 +116,6 @@ __device__ __forceinline__ void stg256(void *ptr, const uint32_t *v) {
     asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
                  ::"l"(ptr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]) : "memory");
 }
-__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
-__device__ __forceinline__ void griddep_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap *map, uint32_t bar_cluster, int c0, int c1) {
     asm volatile(
         "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
@@ -756,12 +698,12 @@ static int get_encode(EncodeTiledFn *fn) {
 }
 
 // NHWC [boards][8][8][C] bf16 viewed as (channel, board, x, y); box = (32, 16, 9, 6).
-static int make_act_map(CUtensorMap *m, void *ptr, size_t boards, int C, int box_y) {
+int make_act_map(CUtensorMap *m, void *ptr, size_t boards, int C, int box_y, int box_x) {
     EncodeTiledFn enc;
     OZ_TRY(get_encode(&enc));
     cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)boards, 8, 8};
     cuuint64_t strides[3] = {(cuuint64_t)64 * C * 2, (cuuint64_t)C * 2, (cuuint64_t)8 * C * 2};
-    cuuint32_t box[4] = {kKBlock, kBoardsPerUnit, kBoxX, (cuuint32_t)box_y};
+    cuuint32_t box[4] = {kKBlock, kBoardsPerUnit, (cuuint32_t)box_x, (cuuint32_t)box_y};
     cuuint32_t estr[4] = {1, 1, 1, 1};
     CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, ptr, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                      CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);

@@ -83,6 +83,16 @@ class ResNet {
     std::vector<CUtensorMap> map_w_;
 };
 
+// TMA map of an NHWC bf16 tensor [boards][8][8][C] viewed as (channel, board, x, y) with a box of (32 channels, 16 boards,
+// box_x, box_y), SWIZZLE_64B, out-of-bounds coordinates (the halo) filled with zeros.  In shared memory a box is rows of
+// 64 bytes, row = ((y * box_x + x) * 16 + board).
+int make_act_map(CUtensorMap *m, void *ptr, size_t boards, int C, int box_y, int box_x = 9);
+
+// Weight gradient of a 3x3 "same" convolution on tcgen05 (oz_wgrad.cu): G[co][tap][ci] (fp32, row stride cinp) =
+// sum over positions p of dZ[p][co] * X[p + tap][ci]; X NHWC bf16 [boards][8][8][cinp] (cinp = 32 or a multiple of 128),
+// dZ NHWC bf16 [boards][8][8][cout] (cout a multiple of 128), boards a multiple of 16.  G is zeroed here (in stream order).
+int launch_wgrad3x3(const void *d_x, int cinp, const void *d_dz, int cout, size_t boards, float *d_G, cudaStream_t stream);
+
 // float planes [n][planes][64] -> bf16 NHWC [n_pad][64][32] (channels >= planes and boards >= n are zero).
 void launch_planes_to_nhwc32(const float *d_features, int planes, size_t n, size_t n_pad, void *d_out, cudaStream_t stream);
 

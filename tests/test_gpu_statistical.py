@@ -144,3 +144,57 @@ def test_self_play_loop_as_train_py_drives_it():
     assert len(features) == 8 * plies
     with pytest.raises(ValueError):
         mcts.self_play_data()                          # mcts.cpp:64-68: terminal position
+
+
+def _golden_stats():
+    import json
+    from pathlib import Path
+    return json.loads((Path(__file__).resolve().parent / "golden" / "golden_stats.json").read_text())
+
+
+def test_root_visit_distribution_2048_searches_vs_reference_golden():
+    """SURVEY.md section 4 (>= 1 k searches): 2 048 engine searches of one position with the engine's own on-device
+    noise (Philox + Marsaglia-Tsang gamma) and symmetry draws against 2 048 searches of the unmodified reference
+    (tests/golden/golden_stats.json, generate_golden_stats.py): two-sample KS on every root child's visit count."""
+    from scipy.stats import ks_2samp
+    from othello_mcts import SelfPlayEngine
+    ref = _golden_stats()["root"]
+    theirs = np.array(ref["visit_counts"])
+    n, k = theirs.shape
+    eng = SelfPlayEngine(n, seed=77, **ref["kwargs"])
+    for a in ref["opening"]:
+        eng.apply_actions(np.full(n, a, np.int32))
+    eng.search("synth")
+    nch, counts, _, _ = eng.root_stats()
+    assert (nch == k).all()
+    ours = counts[:, :k]
+    assert ours.sum(axis=1).tolist() == theirs.sum(axis=1).tolist()
+    for c in range(k):
+        p = ks_2samp(ours[:, c], theirs[:, c]).pvalue
+        assert p > 1e-4, f"child {c}: KS p = {p:.2e}; means {ours[:, c].mean():.2f} vs {theirs[:, c].mean():.2f}"
+        assert abs(ours[:, c].mean() - theirs[:, c].mean()) < 4.0 * theirs[:, c].std() / np.sqrt(n) * np.sqrt(2) + 0.5
+
+
+def test_self_play_histograms_vs_reference_golden():
+    """1 024 whole self-play games of the lockstep engine (device-side action choice: proportional to the visit counts
+    for 12 plies, then a random argmax; on-device noise and symmetries) against 1 024 games the unmodified reference
+    played through train.py's `_self_play` loop (golden_stats.json): first-move histogram (chi-square test of
+    homogeneity), game length in plies and final disc difference (two-sample KS)."""
+    from scipy.stats import chi2_contingency, ks_2samp
+    from othello_mcts import SelfPlayEngine
+    ref = _golden_stats()["games"]
+    n = len(ref["plies"])
+    eng = SelfPlayEngine(n, seed=4242, temperature_plies=ref["temperature_plies"], **ref["kwargs"])
+    rec = eng.run("synth")
+    assert (rec["plies"] > 0).all()
+    first = rec["records"]["action"][:, 0]
+    pos = eng.positions_array()
+    assert (pos["player"] == 0).all()
+    diff = np.bitwise_count(pos["p1"]).astype(np.int64) - np.bitwise_count(pos["p2"]).astype(np.int64)
+    moves = sorted(set(ref["first_move"]) | set(first.tolist()))
+    assert moves == [19, 26, 37, 44]                                   # the four legal opening moves
+    table = np.array([[int((first == m).sum()) for m in moves], [ref["first_move"].count(m) for m in moves]])
+    assert chi2_contingency(table).pvalue > 1e-4, table
+    p_len = ks_2samp(rec["plies"], np.array(ref["plies"])).pvalue
+    p_diff = ks_2samp(diff, np.array(ref["disc_diff"])).pvalue
+    assert p_len > 1e-4 and p_diff > 1e-4, (p_len, p_diff, rec["plies"].mean(), np.mean(ref["plies"]), diff.mean(), np.mean(ref["disc_diff"]))
