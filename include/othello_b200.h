@@ -179,6 +179,12 @@ int oz_resnet_forward_device(oz_resnet *net, const float *features, size_t n, fl
 int oz_debug_conv3x3(const uint16_t *in, int cin, const uint16_t *w, const float *bias, const uint16_t *skip,
                      int relu, uint16_t *out, int cout, size_t boards, double *device_ms);
 
+/* Test hook: weight gradient of one 3x3 "same" convolution layer (the training step's tcgen05 kernel, csrc/oz_wgrad.cu).
+ * Host buffers: x NHWC bf16 [boards][8][8][cinp] (cinp = 32 or a multiple of 128), dz NHWC bf16 [boards][8][8][cout]
+ * (cout a multiple of 128), boards a multiple of 16; G fp32 [cout][9][cinp] (tap = ky*3+kx) = sum over positions of
+ * dz[p][co] * x[p + tap][ci]. */
+int oz_debug_wgrad3x3(const uint16_t *x, int cinp, const uint16_t *dz, int cout, size_t boards, float *G, double *device_ms);
+
 /* MCTS::search (mcts.h:220-256) for every game, with a built-in evaluator
  * (synth / hash / resnet).  Blocking. */
 int oz_engine_search(oz_engine *e);

@@ -29,6 +29,7 @@ SOURCES = {
     "oz_resnet.cu": [],
     "oz_engine_api.cu": ["-fmad=false"],
     "oz_train.cu": [],
+    "oz_wgrad.cu": [],
 }
 
 
@@ -95,7 +96,7 @@ def build_library(force: bool = False, verbose: bool = False) -> Path:
     OBJ.mkdir(exist_ok=True)
     with ThreadPoolExecutor(max_workers=4) as pool:
         objs = list(pool.map(lambda kv: _compile(kv[0], kv[1], verbose), srcs.items()))
-    cmd = [NVCC, *ARCH, "-shared", "-o", str(OUT), *map(str, objs), "-lcudart", "-ldl"]
+    cmd = [NVCC, *ARCH, "-shared", "-o", str(OUT), *map(str, objs), "-lcudart"]
     proc = subprocess.run(cmd, capture_output=True, text=True)
     if proc.returncode != 0:
         raise RuntimeError(f"link failed:\n{proc.stdout}\n{proc.stderr}")

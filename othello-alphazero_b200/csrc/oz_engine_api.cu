@@ -778,6 +778,31 @@ int oz_debug_conv3x3(const uint16_t *in, int cin, const uint16_t *w, const float
     return st;
 }
 
+int oz_debug_wgrad3x3(const uint16_t *x, int cinp, const uint16_t *dz, int cout, size_t boards, float *G, double *device_ms) {
+    uint16_t *d_x = nullptr, *d_dz = nullptr;
+    float *d_G = nullptr;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    int st = OZ_OK;
+    do {
+        if ((st = dalloc(&d_x, boards * 64 * cinp)) || (st = dalloc(&d_dz, boards * 64 * cout)) || (st = dalloc(&d_G, (size_t)cout * 9 * cinp))) break;
+        cudaMemcpy(d_x, x, boards * 64 * cinp * 2, cudaMemcpyHostToDevice);
+        cudaMemcpy(d_dz, dz, boards * 64 * cout * 2, cudaMemcpyHostToDevice);
+        cudaEventCreate(&e0); cudaEventCreate(&e1);
+        cudaEventRecord(e0);
+        if ((st = launch_wgrad3x3(d_x, cinp, d_dz, cout, boards, d_G, nullptr))) break;
+        cudaEventRecord(e1);
+        cudaError_t err = cudaDeviceSynchronize();
+        if (err != cudaSuccess) { st = fail(OZ_ERR_CUDA, std::string("wgrad3x3: ") + cudaGetErrorString(err)); break; }
+        float ms = 0.f; cudaEventElapsedTime(&ms, e0, e1);
+        if (device_ms) *device_ms = ms;
+        cudaMemcpy(G, d_G, (size_t)cout * 9 * cinp * sizeof(float), cudaMemcpyDeviceToHost);
+    } while (0);
+    if (e0) cudaEventDestroy(e0);
+    if (e1) cudaEventDestroy(e1);
+    cudaFree(d_x); cudaFree(d_dz); cudaFree(d_G);
+    return st;
+}
+
 // ---- search ----
 int oz_engine_rounds(const oz_engine *e) { return rounds_of(e->cfg); }
 

@@ -5,13 +5,11 @@
 //
 // The 3x3 convolutions -- forward and input gradients -- run on the tcgen05 implicit-GEMM kernel of oz_resnet.cu in
 // bf16 with fp32 accumulation (the input gradient of a convolution is the same convolution with the taps rotated by 180
-// degrees and the channel roles swapped, so only the weight packing differs).  Weight gradients are a plain GEMM over an
-// im2col view, [C x positions] x [positions x 9 cin], handed to cuBLAS (loaded with dlopen: the library does not link
-// it).  BatchNorm uses batch statistics (train mode) in fp32; the heads, the losses and the optimizer are fp32.  Master
+// degrees and the channel roles swapped, so only the weight packing differs).  Weight gradients run on the tcgen05 kernel
+// of oz_wgrad.cu (MN-major operands staged from the same NHWC tensors, nine taps as slot offsets, split K over the boards):
+// no im2col buffer and no library GEMM -- every kernel of the step is this project's.  BatchNorm uses batch statistics (train mode) in fp32; the heads, the losses and the optimizer are fp32.  Master
 // weights, gradients and momentum are fp32 vectors in the order of AlphaZeroNet.parameters().
-#include <cublas_v2.h>
 #include <cuda_bf16.h>
-#include <dlfcn.h>
 
 #include <algorithm>
 #include <cmath>
@@ -42,35 +40,6 @@ inline void launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t s
     cfg.attrs = attr; cfg.numAttrs = 1;
     cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
     count_launch();
-}
-
-// ------------------------------------------------------------------ cuBLAS through dlopen
-struct Cublas {
-    void *lib = nullptr;
-    cublasStatus_t (*create)(cublasHandle_t *) = nullptr;
-    cublasStatus_t (*destroy)(cublasHandle_t) = nullptr;
-    cublasStatus_t (*set_stream)(cublasHandle_t, cudaStream_t) = nullptr;
-    cublasStatus_t (*set_workspace)(cublasHandle_t, void *, size_t) = nullptr;
-    cublasStatus_t (*gemm_ex)(cublasHandle_t, cublasOperation_t, cublasOperation_t, int, int, int, const void *, const void *, cudaDataType,
-                              int, const void *, cudaDataType, int, const void *, void *, cudaDataType, int, cublasComputeType_t,
-                              cublasGemmAlgo_t) = nullptr;
-};
-
-int load_cublas(Cublas **out) {
-    static Cublas cb;
-    if (!cb.lib) {
-        const char *names[] = {"libcublas.so.12", "/usr/local/cuda/lib64/libcublas.so.12", "libcublas.so"};
-        for (const char *n : names) { cb.lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL); if (cb.lib) break; }
-        if (!cb.lib) return fail(OZ_ERR_CUDA, std::string("the trainer needs cuBLAS for the weight-gradient GEMMs: ") + dlerror());
-        cb.create = (decltype(cb.create))dlsym(cb.lib, "cublasCreate_v2");
-        cb.destroy = (decltype(cb.destroy))dlsym(cb.lib, "cublasDestroy_v2");
-        cb.set_stream = (decltype(cb.set_stream))dlsym(cb.lib, "cublasSetStream_v2");
-        cb.gemm_ex = (decltype(cb.gemm_ex))dlsym(cb.lib, "cublasGemmEx");
-        cb.set_workspace = (decltype(cb.set_workspace))dlsym(cb.lib, "cublasSetWorkspace_v2");
-        if (!cb.create || !cb.destroy || !cb.set_stream || !cb.gemm_ex) { cb.lib = nullptr; return fail(OZ_ERR_CUDA, "cuBLAS symbols missing"); }
-    }
-    *out = &cb;
-    return OZ_OK;
 }
 
 // ------------------------------------------------------------------ small helpers
@@ -250,22 +219,8 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const bf16 *__restric
     if (dy_out) ((uint4 *)dy_out)[i] = pack8(d);
 }
 
-// ------------------------------------------------------------------ weight gradient: im2col + (cuBLAS) + scatter
-// x bf16 [N][8][8][cinp] -> cols bf16 [P][9][cinp], zero outside the board; one thread per 16-byte channel group.
-__global__ void im2col_kernel(const bf16 *__restrict__ x, size_t P, int cinp, bf16 *__restrict__ cols) {
-    OZ_PDL_PROLOGUE();
-    const int gpt = cinp / 8;
-    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= P * 9 * gpt) return;
-    const int g = (int)(i % gpt), tap = (int)((i / gpt) % 9);
-    const size_t p = i / ((size_t)gpt * 9);
-    const int y = (int)((p >> 3) & 7) + tap / 3 - 1, xx = (int)(p & 7) + tap % 3 - 1;
-    uint4 v = make_uint4(0, 0, 0, 0);
-    if (y >= 0 && y < 8 && xx >= 0 && xx < 8) v = *(const uint4 *)(x + ((p & ~(size_t)63) + y * 8 + xx) * cinp + g * 8);
-    *(uint4 *)(cols + (p * 9 + tap) * cinp + g * 8) = v;
-}
-
-// G fp32 [C][9][cinp] (GEMM output) -> dW fp32 [C][cin][9] (OIHW)
+// ------------------------------------------------------------------ weight gradient: wgrad3x3_kernel (oz_wgrad.cu) + scatter
+// G fp32 [C][9][cinp] (output of wgrad3x3_kernel) -> dW fp32 [C][cin][9] (OIHW)
 __global__ void wgrad_scatter_kernel(const float *__restrict__ G, int C, int cin, int cinp, float *__restrict__ dw) {
     OZ_PDL_PROLOGUE();
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
@@ -562,13 +517,10 @@ struct oz_trainer {
     float *d_sums = nullptr;      // [2C] scratch
     float *d_zero_bias = nullptr;
     PackDesc *d_pack = nullptr;
-    bf16 *d_dA = nullptr, *d_dA2 = nullptr, *d_dY = nullptr, *d_dZ = nullptr, *d_cols = nullptr;
+    bf16 *d_dA = nullptr, *d_dA2 = nullptr, *d_dY = nullptr, *d_dZ = nullptr;
     float *d_G = nullptr;
     float *d_h = nullptr, *d_hn = nullptr, *d_dhn = nullptr, *d_dh = nullptr, *d_stat = nullptr, *d_hp = nullptr, *d_hv = nullptr;
     float *d_policy = nullptr, *d_value = nullptr, *d_dlogits = nullptr, *d_u = nullptr, *d_dvpre = nullptr, *d_loss = nullptr;
-    cublasHandle_t blas = nullptr;
-    Cublas *cb = nullptr;
-    void *d_blas_ws = nullptr;
     // CUDA-graph replay of the whole step: at batch 256 the step is some 250 launches of a few microseconds each, so the
     // host, not the GPU, sets the pace when every kernel is launched eagerly.  One graph per (batch, hyper-parameters).
     struct StepKey { int n, apply; oz_train_config cfg; };
@@ -672,7 +624,6 @@ int run_step(oz_trainer *t, int n, const oz_train_config *cfg, int apply) {
     launch_pdl(head_conv_bwd_kernel, dim3(grid_for(P, 64)), dim3(128), 0, s, a_last, t->d_dh, P, C, par + t->pcw, par + t->vcw, dA, grd + t->pcw, grd + t->pcb, grd + t->vcw,
                                                          grd + t->vcb);
     // ---- tower backward
-    const float one = 1.f, zero = 0.f;
     for (int l = L - 1; l >= 0; --l) {
         ConvLayerT &c = t->conv[l];
         const float *mean = t->d_mean + (size_t)l * C, *inv = t->d_invstd + (size_t)l * C;
@@ -683,11 +634,7 @@ int run_step(oz_trainer *t, int n, const oz_train_config *cfg, int apply) {
                                                                 block_out ? t->d_dY : nullptr, grd + c.gamma, grd + c.beta);
         // weight gradient: dW[co][tap][ci] = sum_p dZ[p][co] * cols[p][tap][ci]
         const bf16 *in = l == 0 ? t->d_x0 : t->A[l - 1];
-        const int K9 = 9 * c.cinp;
-        launch_pdl(im2col_kernel, dim3(grid_for(P * 9 * (c.cinp / 8), 256)), dim3(256), 0, s, in, P, c.cinp, t->d_cols);
-        cublasStatus_t bs = t->cb->gemm_ex(t->blas, CUBLAS_OP_N, CUBLAS_OP_T, K9, C, (int)P, &one, t->d_cols, CUDA_R_16BF, K9, t->d_dZ, CUDA_R_16BF, C,
-                                           &zero, t->d_G, CUDA_R_32F, K9, CUBLAS_COMPUTE_32F, CUBLAS_GEMM_DEFAULT);
-        if (bs != CUBLAS_STATUS_SUCCESS) return fail(OZ_ERR_CUDA, "cublasGemmEx (weight gradient) failed: " + std::to_string((int)bs));
+        OZ_TRY(launch_wgrad3x3(in, c.cinp, t->d_dZ, C, (size_t)n, t->d_G, s));
         launch_pdl(wgrad_scatter_kernel, dim3(grid_for((size_t)C * c.cin * 9, 256)), dim3(256), 0, s, t->d_G, C, c.cin, c.cinp, grd + c.w);
         // (the conv bias has no gradient besides the L2 term: BatchNorm removes it)
         if (l == 0) break;
@@ -779,14 +726,7 @@ int oz_trainer_create(int device, const oz_resnet_shape *shape, int max_batch, o
     layout_params(t);
     int st = OZ_OK;
     do {
-        if ((st = load_cublas(&t->cb))) break;
         if (cudaStreamCreateWithFlags(&t->stream, cudaStreamNonBlocking) != cudaSuccess) { st = fail(OZ_ERR_CUDA, "stream creation failed"); break; }
-        if (t->cb->create(&t->blas) != CUBLAS_STATUS_SUCCESS) { st = fail(OZ_ERR_CUDA, "cublasCreate failed"); break; }
-        t->cb->set_stream(t->blas, t->stream);
-        if (t->cb->set_workspace) {                           // a fixed workspace keeps the GEMMs capturable into the step graph
-            if ((st = talloc(t, (char **)&t->d_blas_ws, (size_t)64 << 20))) break;
-            t->cb->set_workspace(t->blas, t->d_blas_ws, (size_t)64 << 20);
-        }
         const size_t C = shape->channels, Hv = shape->value_hidden, N = max_batch, P = N * 64;
         const int L = (int)t->conv.size();
         if ((st = talloc(t, &t->d_params, t->n_params)) || (st = talloc(t, &t->d_grads, t->n_params)) || (st = talloc(t, &t->d_mom, t->n_params)) ||
@@ -794,7 +734,7 @@ int oz_trainer_create(int device, const oz_resnet_shape *shape, int max_batch, o
             (st = talloc(t, &t->d_tpolicy, N * 65)) || (st = talloc(t, &t->d_tvalue, N)) || (st = talloc(t, &t->d_x0, P * 32)) ||
             (st = talloc(t, &t->d_mean, L * C)) || (st = talloc(t, &t->d_invstd, L * C)) || (st = talloc(t, &t->d_sums, (size_t)2 * L * 2 * C)) ||
             (st = talloc(t, &t->d_zero_bias, C)) || (st = talloc(t, &t->d_dA, P * C)) || (st = talloc(t, &t->d_dA2, P * C)) ||
-            (st = talloc(t, &t->d_dY, P * C)) || (st = talloc(t, &t->d_dZ, P * C)) || (st = talloc(t, &t->d_cols, P * 9 * C)) ||
+            (st = talloc(t, &t->d_dY, P * C)) || (st = talloc(t, &t->d_dZ, P * C)) ||
             (st = talloc(t, &t->d_G, C * 9 * C)) || (st = talloc(t, &t->d_h, 3 * P)) || (st = talloc(t, &t->d_hn, 3 * P)) ||
             (st = talloc(t, &t->d_dhn, 3 * P)) || (st = talloc(t, &t->d_dh, 3 * P)) || (st = talloc(t, &t->d_stat, 8)) ||
             (st = talloc(t, &t->d_hp, N * 128)) || (st = talloc(t, &t->d_hv, N * 64)) || (st = talloc(t, &t->d_policy, N * 65)) ||
@@ -826,7 +766,6 @@ void oz_trainer_destroy(oz_trainer *t) {
     cudaSetDevice(t->device);
     if (t->stream) cudaStreamSynchronize(t->stream);
     if (t->graph) cudaGraphExecDestroy(t->graph);
-    if (t->blas && t->cb) t->cb->destroy(t->blas);
     for (void *p : t->allocs) cudaFree(p);
     if (t->stream) cudaStreamDestroy(t->stream);
     delete t;

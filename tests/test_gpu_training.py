@@ -151,3 +151,35 @@ def test_trainer_rejects_bad_batches():
     f, p, v = _batch(96, 9, 1)
     with pytest.raises(ValueError):
         trainer.step(f, p, v)                                # above max_batch
+
+
+@pytest.mark.parametrize("cinp,cout,boards", [
+    (128, 128, 16),        # one unit: every CTA has one unit's eight board rows
+    (128, 128, 16 * 7),    # split K over 7 units
+    (32, 128, 32),         # first layer: planes padded to 32 (N = 32 per MMA)
+    (256, 256, 16 * 3),    # 256 channels: 2 x 2 tiles of (co, ci)
+    (128, 128, 16 * 64),   # 1 024 boards: several passes per CTA, stage ring wraps
+])
+def test_wgrad3x3_vs_torch(cinp, cout, boards):
+    import torch
+    """The tcgen05 weight-gradient kernel (csrc/oz_wgrad.cu) against torch.nn.grad.conv2d_weight in fp32 on the same
+    bf16-rounded operands: fp32 accumulation over up to 65 536 positions, so |d| <= 1e-3 * |ref| + 2e-3 * scale."""
+    import ctypes as C
+    from othello_mcts import _lib
+    lib = _lib.load()
+    g = torch.Generator().manual_seed(cinp + cout + boards)
+    x = torch.randn(boards, 8, 8, cinp, generator=g).to(torch.bfloat16)
+    dz = (torch.randn(boards, 8, 8, cout, generator=g) * 0.25).to(torch.bfloat16)
+    ref = torch.nn.grad.conv2d_weight(x.float().permute(0, 3, 1, 2), (cout, cinp, 3, 3), dz.float().permute(0, 3, 1, 2), padding=1)
+    xb = x.contiguous().view(torch.int16).numpy().view(np.uint16)
+    db = dz.contiguous().view(torch.int16).numpy().view(np.uint16)
+    G = np.zeros((cout, 9, cinp), np.float32)
+    ms = C.c_double()
+    _lib.check(lib.oz_debug_wgrad3x3(xb.ctypes.data_as(C.c_void_p), cinp, db.ctypes.data_as(C.c_void_p), cout, boards,
+                                     G.ctypes.data_as(C.c_void_p), C.byref(ms)))
+    got = torch.from_numpy(G).reshape(cout, 3, 3, cinp).permute(0, 3, 1, 2)
+    err = (got - ref).abs()
+    scale = float(ref.abs().mean())
+    tol = ref.abs() * 1e-3 + 2e-3 * scale
+    bad = int((err > tol).sum())
+    assert bad == 0, f"{bad} of {err.numel()} outside tolerance, max err {err.max():.4f} (mean |ref| {scale:.3f}), kernel {ms.value:.3f} ms"
