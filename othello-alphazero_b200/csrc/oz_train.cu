@@ -98,7 +98,10 @@ __device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
 }
 
 // Shared tail of the two reductions: 16 per-thread partial sums (8 channels x 2 statistics) -> one atomic per channel,
-// statistic and block.  out[c] += first statistic, out[C + c] += second.
+// statistic and block.  out[copy][c] += first statistic, out[copy][C + c] += second, copy = block % kBnCopies: a few hundred
+// blocks adding to the same 2C addresses serialise in L2 (about 50 ns each), which at one copy was the whole run time of the
+// reductions; consumers add the copies up (bn_total).
+constexpr int kBnCopies = 8;
 __device__ __forceinline__ void bn_block_reduce(float (&a)[8], float (&b)[8], int C, int tpr, int rows, int cg, int r0, float *out) {
     __shared__ float red[16][256];
 #pragma unroll
@@ -108,10 +111,25 @@ __device__ __forceinline__ void bn_block_reduce(float (&a)[8], float (&b)[8], in
         for (int r = 1; r < rows; ++r)
 #pragma unroll
             for (int i = 0; i < 8; ++i) { a[i] += red[i][r * tpr + cg]; b[i] += red[8 + i][r * tpr + cg]; }
+        out += (size_t)(blockIdx.x % kBnCopies) * 2 * C;     // one of kBnCopies accumulators: same-address atomics serialise in L2
 #pragma unroll
         for (int i = 0; i < 8; ++i) { atomicAdd(&out[8 * cg + i], a[i]); atomicAdd(&out[C + 8 * cg + i], b[i]); }
     }
 }
+// Total of the kBnCopies partial accumulators of statistic slot `idx` (0 .. 2C-1).
+__device__ __forceinline__ float bn_total(const float *sums, int C, int idx) {
+    float t = 0.f;
+#pragma unroll
+    for (int k = 0; k < kBnCopies; ++k) t += sums[(size_t)k * 2 * C + idx];
+    return t;
+}
+
+// The four BatchNorm passes are pure HBM streams (16 bytes per thread and load).  A thread owns one group of 8 channels
+// (cg) and walks board squares p = first, first + stride, ...: its per-channel constants (scale / shift, mean / invstd, the
+// reduction terms) live in registers for the whole kernel, and kBnUnroll independent 16-byte loads per tensor are in flight
+// before the first is used -- with one load in flight per thread and the constants re-derived per element (two divisions
+// and an rsqrt per channel) the passes ran at 40 % of the HBM bandwidth and were instruction-bound.
+constexpr int kBnUnroll = 4;
 
 // sums[c] += sum z, sums[C + c] += sum z^2.
 __global__ void __launch_bounds__(256) bn_stats_kernel(const bf16 *__restrict__ z, size_t P, int C, float *__restrict__ sums) {
@@ -121,20 +139,28 @@ __global__ void __launch_bounds__(256) bn_stats_kernel(const bf16 *__restrict__ 
     float s[8], q[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) { s[i] = 0.f; q[i] = 0.f; }
-    if (r0 < rows)
-        for (size_t p = (size_t)blockIdx.x * rows + r0; p < P; p += (size_t)gridDim.x * rows) {
-            float v[8];
-            unpack8(*(const uint4 *)(z + p * C + 8 * cg), v);
+    if (r0 < rows) {
+        const size_t stride = (size_t)gridDim.x * rows;
+        for (size_t p = (size_t)blockIdx.x * rows + r0; p < P; p += kBnUnroll * stride) {
+            uint4 zq[kBnUnroll];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) { s[i] += v[i]; q[i] += v[i] * v[i]; }
+            for (int u = 0; u < kBnUnroll; ++u) { const size_t pu = p + u * stride; zq[u] = pu < P ? *(const uint4 *)(z + pu * C + 8 * cg) : make_uint4(0, 0, 0, 0); }
+#pragma unroll
+            for (int u = 0; u < kBnUnroll; ++u) {
+                float v[8];
+                unpack8(zq[u], v);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) { s[i] += v[i]; q[i] += v[i] * v[i]; }
+            }
         }
+    }
     bn_block_reduce(s, q, C, tpr, rows, cg, r0 < rows ? r0 : 1 << 30, sums);
 }
 
 // mean / invstd of channel c from the sums (every consumer recomputes them: two flops instead of a kernel launch).
 __device__ __forceinline__ void bn_moments(const float *sums, int C, int c, float count, float eps, float &mean, float &invstd, float &var) {
-    mean = sums[c] / count;
-    var = fmaxf(sums[C + c] / count - mean * mean, 0.f);
+    mean = bn_total(sums, C, c) / count;
+    var = fmaxf(bn_total(sums, C, C + c) / count - mean * mean, 0.f);
     invstd = rsqrtf(var + eps);
 }
 
@@ -156,21 +182,40 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(const bf16 *__restrict__ 
             run_mean[c] = (1.f - momentum) * run_mean[c] + momentum * (m + conv_bias[c]);
             run_var[c] = (1.f - momentum) * run_var[c] + momentum * var * (count / fmaxf(count - 1.f, 1.f));
         }
-    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;     // one group of 8 channels
-    if (i >= P * (size_t)(C / 8)) return;
-    const int c0 = 8 * (int)(i % (C / 8));
-    float v[8], sk[8];
-    unpack8(((const uint4 *)z)[i], v);
-    if (skip) unpack8(((const uint4 *)skip)[i], sk);
+    const int tpr = C / 8, rows = blockDim.x / tpr;
+    const int cg = threadIdx.x % tpr, r0 = threadIdx.x / tpr;
+    if (r0 >= rows) return;
+    float g[8], m[8], iv[8], bt[8];                       // y = g * (z - m) * iv + bt, evaluated in this order (as before)
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
-        float m, inv, var;
-        bn_moments(sums, C, c0 + k, count, eps, m, inv, var);
-        float y = gamma[c0 + k] * (v[k] - m) * inv + beta[c0 + k];
-        if (skip) y += sk[k];
-        v[k] = fmaxf(y, 0.f);
+        float var;
+        bn_moments(sums, C, 8 * cg + k, count, eps, m[k], iv[k], var);
+        g[k] = gamma[8 * cg + k]; bt[k] = beta[8 * cg + k];
     }
-    ((uint4 *)a)[i] = pack8(v);
+    const size_t stride = (size_t)gridDim.x * rows;
+    for (size_t p = (size_t)blockIdx.x * rows + r0; p < P; p += kBnUnroll * stride) {
+        uint4 zq[kBnUnroll], sq[kBnUnroll];
+#pragma unroll
+        for (int u = 0; u < kBnUnroll; ++u) {
+            const size_t pu = p + u * stride;
+            if (pu < P) { zq[u] = *(const uint4 *)(z + pu * C + 8 * cg); if (skip) sq[u] = *(const uint4 *)(skip + pu * C + 8 * cg); }
+        }
+#pragma unroll
+        for (int u = 0; u < kBnUnroll; ++u) {
+            const size_t pu = p + u * stride;
+            if (pu >= P) break;
+            float v[8], sk[8];
+            unpack8(zq[u], v);
+            if (skip) unpack8(sq[u], sk);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                float y = g[k] * (v[k] - m[k]) * iv[k] + bt[k];
+                if (skip) y += sk[k];
+                v[k] = fmaxf(y, 0.f);
+            }
+            *(uint4 *)(a + pu * C + 8 * cg) = pack8(v);
+        }
+    }
 }
 
 // Backward through ReLU and BatchNorm.  dy = da * [a > 0]; s[c] += sum dy, s[C + c] += sum dy * zhat.
@@ -183,14 +228,25 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const bf16 *__restri
     float m[8], iv[8], s1[8], s2[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) { m[i] = mean[8 * cg + i]; iv[i] = invstd[8 * cg + i]; s1[i] = 0.f; s2[i] = 0.f; }
-    if (r0 < rows)
-        for (size_t p = (size_t)blockIdx.x * rows + r0; p < P; p += (size_t)gridDim.x * rows) {
-            const size_t o = p * C + 8 * cg;
-            float g[8], av[8], zv[8];
-            unpack8(*(const uint4 *)(da + o), g); unpack8(*(const uint4 *)(a + o), av); unpack8(*(const uint4 *)(z + o), zv);
+    if (r0 < rows) {
+        const size_t stride = (size_t)gridDim.x * rows;
+        for (size_t p = (size_t)blockIdx.x * rows + r0; p < P; p += kBnUnroll * stride) {
+            uint4 gq[kBnUnroll], aq[kBnUnroll], zq[kBnUnroll];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) { const float d = av[i] > 0.f ? g[i] : 0.f; s1[i] += d; s2[i] += d * (zv[i] - m[i]) * iv[i]; }
+            for (int u = 0; u < kBnUnroll; ++u) {
+                const size_t pu = p + u * stride, o = pu * C + 8 * cg;
+                if (pu < P) { gq[u] = *(const uint4 *)(da + o); aq[u] = *(const uint4 *)(a + o); zq[u] = *(const uint4 *)(z + o); }
+            }
+#pragma unroll
+            for (int u = 0; u < kBnUnroll; ++u) {
+                if (p + u * stride >= P) break;
+                float g[8], av[8], zv[8];
+                unpack8(gq[u], g); unpack8(aq[u], av); unpack8(zq[u], zv);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) { const float d = av[i] > 0.f ? g[i] : 0.f; s1[i] += d; s2[i] += d * (zv[i] - m[i]) * iv[i]; }
+            }
         }
+    }
     bn_block_reduce(s1, s2, C, tpr, rows, cg, r0 < rows ? r0 : 1 << 30, s);
 }
 
@@ -201,22 +257,41 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const bf16 *__restric
                                                            const float *__restrict__ gamma, const float *__restrict__ s, bf16 *__restrict__ dz,
                                                            bf16 *__restrict__ dy_out, float *__restrict__ dgamma, float *__restrict__ dbeta) {
     OZ_PDL_PROLOGUE();
-    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (blockIdx.x == 0) for (int c = threadIdx.x; c < C; c += blockDim.x) { dgamma[c] = s[C + c]; dbeta[c] = s[c]; }
-    if (i >= P * (size_t)(C / 8)) return;
-    const int c0 = 8 * (int)(i % (C / 8));
+    if (blockIdx.x == 0) for (int c = threadIdx.x; c < C; c += blockDim.x) { dgamma[c] = bn_total(s, C, C + c); dbeta[c] = bn_total(s, C, c); }
+    const int tpr = C / 8, rows = blockDim.x / tpr;
+    const int cg = threadIdx.x % tpr, r0 = threadIdx.x / tpr;
+    if (r0 >= rows) return;
     const float invM = 1.f / (float)P;
-    float g[8], av[8], zv[8], d[8];
-    unpack8(((const uint4 *)da)[i], g); unpack8(((const uint4 *)a)[i], av); unpack8(((const uint4 *)z)[i], zv);
+    float m[8], iv[8], gi[8], t1[8], t2[8];               // dz = gi * (d - t1 - zh * t2)
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
-        const int c = c0 + k;
-        d[k] = av[k] > 0.f ? g[k] : 0.f;
-        const float zh = (zv[k] - mean[c]) * invstd[c];
-        g[k] = gamma[c] * invstd[c] * (d[k] - s[c] * invM - zh * s[C + c] * invM);
+        const int c = 8 * cg + k;
+        m[k] = mean[c]; iv[k] = invstd[c]; gi[k] = gamma[c] * invstd[c]; t1[k] = bn_total(s, C, c) * invM; t2[k] = bn_total(s, C, C + c) * invM;
     }
-    ((uint4 *)dz)[i] = pack8(g);
-    if (dy_out) ((uint4 *)dy_out)[i] = pack8(d);
+    const size_t stride = (size_t)gridDim.x * rows;
+    for (size_t p = (size_t)blockIdx.x * rows + r0; p < P; p += kBnUnroll * stride) {
+        uint4 gq[kBnUnroll], aq[kBnUnroll], zq[kBnUnroll];
+#pragma unroll
+        for (int u = 0; u < kBnUnroll; ++u) {
+            const size_t pu = p + u * stride, o = pu * C + 8 * cg;
+            if (pu < P) { gq[u] = *(const uint4 *)(da + o); aq[u] = *(const uint4 *)(a + o); zq[u] = *(const uint4 *)(z + o); }
+        }
+#pragma unroll
+        for (int u = 0; u < kBnUnroll; ++u) {
+            const size_t pu = p + u * stride, o = pu * C + 8 * cg;
+            if (pu >= P) break;
+            float g[8], av[8], zv[8], d[8];
+            unpack8(gq[u], g); unpack8(aq[u], av); unpack8(zq[u], zv);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                d[k] = av[k] > 0.f ? g[k] : 0.f;
+                const float zh = (zv[k] - m[k]) * iv[k];
+                g[k] = gi[k] * (d[k] - t1[k] - zh * t2[k]);
+            }
+            *(uint4 *)(dz + o) = pack8(g);
+            if (dy_out) *(uint4 *)(dy_out + o) = pack8(d);
+        }
+    }
 }
 
 // ------------------------------------------------------------------ weight gradient: wgrad3x3_kernel (oz_wgrad.cu) + scatter
@@ -353,46 +428,49 @@ __global__ void head_fc_bwd_params_kernel(const float *__restrict__ hp, const fl
                                           float *__restrict__ dlw, float *__restrict__ dlb, float *__restrict__ dw1, float *__restrict__ db1,
                                           float *__restrict__ dw2, float *__restrict__ db2) {
     OZ_PDL_PROLOGUE();
+    // blockIdx.y = slice of the batch: every thread sums its parameter's products over one slice and adds the partial sum
+    // into the (zeroed) gradient -- one thread walking all N samples serially cost 0.85 ms at batch 4 096.
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    const int n0 = (int)((long)N * blockIdx.y / gridDim.y), n1 = (int)((long)N * (blockIdx.y + 1) / gridDim.y);
     const int n_lw = 65 * 128, n_w1 = Hv * 64;
     if (idx < n_lw) {
         const int j = idx / 128, i = idx % 128;
         float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-        int n = 0;
-        for (; n + 3 < N; n += 4) {
+        int n = n0;
+        for (; n + 3 < n1; n += 4) {
             a0 += dlogits[(size_t)n * 65 + j] * hp[(size_t)n * 128 + i];
             a1 += dlogits[(size_t)(n + 1) * 65 + j] * hp[(size_t)(n + 1) * 128 + i];
             a2 += dlogits[(size_t)(n + 2) * 65 + j] * hp[(size_t)(n + 2) * 128 + i];
             a3 += dlogits[(size_t)(n + 3) * 65 + j] * hp[(size_t)(n + 3) * 128 + i];
         }
-        for (; n < N; ++n) a0 += dlogits[(size_t)n * 65 + j] * hp[(size_t)n * 128 + i];
-        dlw[idx] = (a0 + a1) + (a2 + a3);
+        for (; n < n1; ++n) a0 += dlogits[(size_t)n * 65 + j] * hp[(size_t)n * 128 + i];
+        atomicAdd(&dlw[idx], (a0 + a1) + (a2 + a3));
     } else if (idx < n_lw + 65) {
         const int j = idx - n_lw;
         float acc = 0.f;
-        for (int n = 0; n < N; ++n) acc += dlogits[(size_t)n * 65 + j];
-        dlb[j] = acc;
+        for (int n = n0; n < n1; ++n) acc += dlogits[(size_t)n * 65 + j];
+        atomicAdd(&dlb[j], acc);
     } else if (idx < n_lw + 65 + n_w1) {
         const int r = idx - n_lw - 65, k = r / 64, i = r % 64;
         const float wk = w2[k];
         float a0 = 0.f, a1 = 0.f;
-        int n = 0;
-        for (; n + 1 < N; n += 2) {
+        int n = n0;
+        for (; n + 1 < n1; n += 2) {
             a0 += (u[(size_t)n * Hv + k] > 0.f ? dvpre[n] * wk : 0.f) * hv[(size_t)n * 64 + i];
             a1 += (u[(size_t)(n + 1) * Hv + k] > 0.f ? dvpre[n + 1] * wk : 0.f) * hv[(size_t)(n + 1) * 64 + i];
         }
-        for (; n < N; ++n) a0 += (u[(size_t)n * Hv + k] > 0.f ? dvpre[n] * wk : 0.f) * hv[(size_t)n * 64 + i];
-        dw1[r] = a0 + a1;
+        for (; n < n1; ++n) a0 += (u[(size_t)n * Hv + k] > 0.f ? dvpre[n] * wk : 0.f) * hv[(size_t)n * 64 + i];
+        atomicAdd(&dw1[r], a0 + a1);
     } else if (idx < n_lw + 65 + n_w1 + Hv) {
         const int k = idx - n_lw - 65 - n_w1;
         const float wk = w2[k];
         float a1 = 0.f, a2 = 0.f;
-        for (int n = 0; n < N; ++n) { const float uu = u[(size_t)n * Hv + k]; a1 += uu > 0.f ? dvpre[n] * wk : 0.f; a2 += dvpre[n] * uu; }
-        db1[k] = a1; dw2[k] = a2;
+        for (int n = n0; n < n1; ++n) { const float uu = u[(size_t)n * Hv + k]; a1 += uu > 0.f ? dvpre[n] * wk : 0.f; a2 += dvpre[n] * uu; }
+        atomicAdd(&db1[k], a1); atomicAdd(&dw2[k], a2);
     } else if (idx == n_lw + 65 + n_w1 + Hv) {
         float acc = 0.f;
-        for (int n = 0; n < N; ++n) acc += dvpre[n];
-        db2[0] = acc;
+        for (int n = n0; n < n1; ++n) acc += dvpre[n];
+        atomicAdd(&db2[0], acc);
     }
 }
 
@@ -580,25 +658,28 @@ int pack_all_weights(oz_trainer *t) {
 int run_step(oz_trainer *t, int n, const oz_train_config *cfg, int apply) {
     const float *d_features = t->d_features, *d_tp = t->d_tpolicy, *d_tv = t->d_tvalue;
     const int C = t->shape.channels, Hv = t->shape.value_hidden, L = (int)t->conv.size();
-    const size_t P = (size_t)n * 64, vec8 = P * (size_t)(C / 8);
+    const size_t P = (size_t)n * 64;
     cudaStream_t s = t->stream;
     float *par = t->d_params, *grd = t->d_grads, *buf = t->d_buffers;
     OZ_CUDA(cudaMemsetAsync(grd, 0, t->n_params * sizeof(float), s));
     OZ_CUDA(cudaMemsetAsync(t->d_loss, 0, 4 * sizeof(float), s));
-    OZ_CUDA(cudaMemsetAsync(t->d_sums, 0, (size_t)2 * L * 2 * C * sizeof(float), s));     // reduction slots of every layer, forward and backward
+    OZ_CUDA(cudaMemsetAsync(t->d_sums, 0, (size_t)2 * L * 2 * C * kBnCopies * sizeof(float), s));     // reduction slots of every layer, forward and backward
     OZ_TRY(pack_all_weights(t));
     launch_planes_to_nhwc32(d_features, t->shape.in_planes, (size_t)n, (size_t)n, t->d_x0, s);
-    const int bn_block = 256, bn_grid = (int)std::min<size_t>(592, (P + 127) / 128);
+    const int bn_block = 256, bn_rows = 256 / (C / 8);
+    const size_t bn_chunks = (P + (size_t)bn_rows * kBnUnroll - 1) / ((size_t)bn_rows * kBnUnroll);   // every thread gets kBnUnroll rows or more
+    const int bn_grid = (int)std::min<size_t>(1184, bn_chunks);       // streaming passes: up to 8 blocks per SM
+    const int bn_rgrid = (int)std::min<size_t>(296, bn_chunks);       // reductions: fewer blocks, fewer atomics
 
     // ---- forward through the tower (neural_net.py:9-65, train mode)
     for (int l = 0; l < L; ++l) {
         ConvLayerT &c = t->conv[l];
         const bf16 *in = l == 0 ? t->d_x0 : t->A[l - 1];
         OZ_TRY(ResNet::conv3x3(in, c.cinp, c.wf, t->d_zero_bias, nullptr, 0, t->Z[l], C, (size_t)n, s));
-        float *fsum = t->d_sums + (size_t)l * 2 * C;
-        launch_pdl(bn_stats_kernel, dim3(bn_grid), dim3(bn_block), 0, s, t->Z[l], P, C, fsum);
+        float *fsum = t->d_sums + (size_t)l * 2 * C * kBnCopies;
+        launch_pdl(bn_stats_kernel, dim3(bn_rgrid), dim3(bn_block), 0, s, t->Z[l], P, C, fsum);
         const bf16 *skip = (l >= 2 && l % 2 == 0) ? t->A[l - 2] : nullptr;     // second conv of a residual block
-        launch_pdl(bn_apply_kernel, dim3(grid_for(vec8, 256)), dim3(256), 0, s, t->Z[l], skip, P, C, fsum, par + c.gamma, par + c.beta, par + c.b, cfg->bn_eps,
+        launch_pdl(bn_apply_kernel, dim3(bn_grid), dim3(bn_block), 0, s, t->Z[l], skip, P, C, fsum, par + c.gamma, par + c.beta, par + c.b, cfg->bn_eps,
                                                             cfg->bn_momentum, t->d_mean + (size_t)l * C, t->d_invstd + (size_t)l * C, buf + c.rm,
                                                             buf + c.rv, t->A[l]);
     }
@@ -613,7 +694,7 @@ int run_step(oz_trainer *t, int n, const oz_train_config *cfg, int apply) {
                                                                      t->d_u, t->d_dvpre, t->d_loss);
     // ---- heads backward
     const int n_head_params = 65 * 128 + 65 + Hv * 64 + Hv + 1;
-    launch_pdl(head_fc_bwd_params_kernel, dim3(grid_for(n_head_params, 128)), dim3(128), 0, s, t->d_hp, t->d_hv, t->d_dlogits, t->d_u, t->d_dvpre, par + t->v2w, n, Hv,
+    launch_pdl(head_fc_bwd_params_kernel, dim3(grid_for(n_head_params, 128), (unsigned)std::max(1, std::min(32, n / 64))), dim3(128), 0, s, t->d_hp, t->d_hv, t->d_dlogits, t->d_u, t->d_dvpre, par + t->v2w, n, Hv,
                                                                            grd + t->plw, grd + t->plb, grd + t->v1w, grd + t->v1b, grd + t->v2w,
                                                                            grd + t->v2b);
     launch_pdl(head_fc_bwd_input_kernel, dim3(grid_for(3 * P, 256)), dim3(256), 0, s, t->d_dlogits, par + t->plw, t->d_u, t->d_dvpre, par + t->v1w, par + t->v2w, t->d_hn, P,
@@ -628,9 +709,9 @@ int run_step(oz_trainer *t, int n, const oz_train_config *cfg, int apply) {
         ConvLayerT &c = t->conv[l];
         const float *mean = t->d_mean + (size_t)l * C, *inv = t->d_invstd + (size_t)l * C;
         const bool block_out = l >= 2 && l % 2 == 0;            // output of a residual block: dy also flows into the skip connection
-        float *bsum = t->d_sums + (size_t)(L + l) * 2 * C;
-        launch_pdl(bn_bwd_reduce_kernel, dim3(bn_grid), dim3(bn_block), 0, s, dA, t->A[l], t->Z[l], P, C, mean, inv, bsum);
-        launch_pdl(bn_bwd_apply_kernel, dim3(grid_for(vec8, 256)), dim3(256), 0, s, dA, t->A[l], t->Z[l], P, C, mean, inv, par + c.gamma, bsum, t->d_dZ,
+        float *bsum = t->d_sums + (size_t)(L + l) * 2 * C * kBnCopies;
+        launch_pdl(bn_bwd_reduce_kernel, dim3(bn_rgrid), dim3(bn_block), 0, s, dA, t->A[l], t->Z[l], P, C, mean, inv, bsum);
+        launch_pdl(bn_bwd_apply_kernel, dim3(bn_grid), dim3(bn_block), 0, s, dA, t->A[l], t->Z[l], P, C, mean, inv, par + c.gamma, bsum, t->d_dZ,
                                                                 block_out ? t->d_dY : nullptr, grd + c.gamma, grd + c.beta);
         // weight gradient: dW[co][tap][ci] = sum_p dZ[p][co] * cols[p][tap][ci]
         const bf16 *in = l == 0 ? t->d_x0 : t->A[l - 1];
@@ -732,7 +813,7 @@ int oz_trainer_create(int device, const oz_resnet_shape *shape, int max_batch, o
         if ((st = talloc(t, &t->d_params, t->n_params)) || (st = talloc(t, &t->d_grads, t->n_params)) || (st = talloc(t, &t->d_mom, t->n_params)) ||
             (st = talloc(t, &t->d_buffers, t->n_buffers)) || (st = talloc(t, &t->d_features, N * shape->in_planes * 64)) ||
             (st = talloc(t, &t->d_tpolicy, N * 65)) || (st = talloc(t, &t->d_tvalue, N)) || (st = talloc(t, &t->d_x0, P * 32)) ||
-            (st = talloc(t, &t->d_mean, L * C)) || (st = talloc(t, &t->d_invstd, L * C)) || (st = talloc(t, &t->d_sums, (size_t)2 * L * 2 * C)) ||
+            (st = talloc(t, &t->d_mean, L * C)) || (st = talloc(t, &t->d_invstd, L * C)) || (st = talloc(t, &t->d_sums, (size_t)2 * L * 2 * C * kBnCopies)) ||
             (st = talloc(t, &t->d_zero_bias, C)) || (st = talloc(t, &t->d_dA, P * C)) || (st = talloc(t, &t->d_dA2, P * C)) ||
             (st = talloc(t, &t->d_dY, P * C)) || (st = talloc(t, &t->d_dZ, P * C)) ||
             (st = talloc(t, &t->d_G, C * 9 * C)) || (st = talloc(t, &t->d_h, 3 * P)) || (st = talloc(t, &t->d_hn, 3 * P)) ||
