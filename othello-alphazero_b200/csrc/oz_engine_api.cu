@@ -432,6 +432,11 @@ int search_pipelined(oz_engine *e, int groups) {
     e->net.set_pdl(e->pipeline_pdl);
     size_t n_ev = 0;
     int st = OZ_OK;
+    // OZ_PIPE_WIDE=1 (experiment switch): the wide tree kernels, which do not fit beside a convolution CTA and therefore run
+    // only on SMs the convolution leaves free (OZ_CONV_CLUSTERS), instead of the narrow co-resident ones.
+    static int wide = -1;
+    if (wide < 0) { const char *we = getenv("OZ_PIPE_WIDE"); wide = (we && we[0] == '1') ? 1 : 0; }
+    const bool narrow = wide == 0;
     NvtxRange nvtx_pipe("oz: pipelined rounds");
     for (int r = 0; r < rounds && !st; ++r) {
         e->round = r;
@@ -444,8 +449,8 @@ int search_pipelined(oz_engine *e, int groups) {
             if (e->profiling) { cudaEventRecord(next_event(e, n_ev), ts); cb = next_event(e, n_ev + 2); ce = next_event(e, n_ev + 3); }
             void *x0 = nullptr;
             if ((st = encode_target(e, n, k, &x0))) break;
-            launch_select(v, ts, true);
-            launch_encode(v, e->d_features + first * (1 + 2 * e->t.H) * 64, ts, true, x0);
+            launch_select(v, ts, narrow);
+            launch_encode(v, e->d_features + first * (1 + 2 * e->t.H) * 64, ts, narrow, x0);
             cudaEventRecord(e->ev_sel[k], ts);
             cudaStreamWaitEvent(ns, e->ev_sel[k], 0);
             if (e->profiling) cudaEventRecord(next_event(e, n_ev + 1), ns);
@@ -453,7 +458,7 @@ int search_pipelined(oz_engine *e, int groups) {
             if (e->profiling) cudaEventRecord(next_event(e, n_ev + 4), ns);
             cudaEventRecord(e->ev_net[k], ns);
             cudaStreamWaitEvent(ts, e->ev_net[k], 0);
-            if (!st) launch_expand(v, e->d_policy + first * 65, e->d_value + first, ts, true);
+            if (!st) launch_expand(v, e->d_policy + first * 65, e->d_value + first, ts, narrow);
             if (e->profiling) { cudaEventRecord(next_event(e, n_ev + 5), ts); n_ev += 6; }
         }
     }

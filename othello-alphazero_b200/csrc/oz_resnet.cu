@@ -742,15 +742,25 @@ static int launch_conv(const CUtensorMap &ma, const CUtensorMap *ma1, const CUte
     const int pp2 = cp.units * 2 * (cp.cout_total >> 7);
     const bool one_row = ma1 != nullptr && 2 * pp2 <= sms / 2;   // every pair still gets at most one pass, half as long
     const int num_pp = one_row ? 2 * pp2 : pp2;
-    const int clusters = num_pp < sms / 2 ? num_pp : sms / 2;
+    // OZ_CONV_CLUSTERS (experiment switch): cap the persistent grid, e.g. 73 leaves one TPC free for the wide tree kernels of
+    // the pipelined search; with the dynamic pass scheduler the convolution is indifferent to its grid size.
+    static int cap = -1;
+    if (cap < 0) { const char *e = getenv("OZ_CONV_CLUSTERS"); cap = e ? atoi(e) : 0; }
+    const int max_clusters = (cap > 0 && cap < sms / 2) ? cap : sms / 2;
+    const int clusters = num_pp < max_clusters ? num_pp : max_clusters;
+    // The dynamic pass scheduler pays off when clusters run many passes (balance; robustness against co-running kernels); its
+    // first index costs a counter round trip plus a cluster-wide publication (about 1.5 us) before any role can start, which
+    // a launch with a pass or two per cluster -- the launch-bound small leaf batches -- never earns back: static there.
+    ConvParams cpl = cp;
+    if (num_pp < 8 * clusters) cpl.work = nullptr;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(2 * clusters); cfg.blockDim = dim3(pair::kThreadsP); cfg.dynamicSmemBytes = pair::kSmemBytesP; cfg.stream = stream;
     cudaLaunchAttribute attr[1];                       // programmatic dependent launch: see griddep_wait() in the kernel
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr; cfg.numAttrs = pdl ? 1 : 0;
-    if (one_row) OZ_CUDA(cudaLaunchKernelEx(&cfg, conv3x3_pair_kernel<1>, *ma1, mw, cp));
-    else OZ_CUDA(cudaLaunchKernelEx(&cfg, conv3x3_pair_kernel<2>, ma, mw, cp));
+    if (one_row) OZ_CUDA(cudaLaunchKernelEx(&cfg, conv3x3_pair_kernel<1>, *ma1, mw, cpl));
+    else OZ_CUDA(cudaLaunchKernelEx(&cfg, conv3x3_pair_kernel<2>, ma, mw, cpl));
     count_launch();
     OZ_CUDA(cudaGetLastError());
     return OZ_OK;

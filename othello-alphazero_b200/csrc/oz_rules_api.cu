@@ -451,6 +451,7 @@ int oz_perft(const oz_position *root, int depth, int mode, uint64_t *nodes, doub
     FNode h_root = (root->player == 1) ? FNode{root->p1, root->p2} : FNode{root->p2, root->p1};
     unsigned long long *d_cnt = nullptr;   // [0] children, [1] terminals, [2] nodes, [3] mob, [4] cursor
     FNode *cur = nullptr, *next = nullptr;
+    size_t cap_cur = 0, cap_next = 0;      // the two frontier buffers are kept across levels and only grow (no malloc / free per level)
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     int st = OZ_OK;
     unsigned long long early_leaves = 0;   // terminal positions above the walk depth
@@ -458,7 +459,9 @@ int oz_perft(const oz_position *root, int depth, int mode, uint64_t *nodes, doub
 #define PF_CUDA(x) { cudaError_t _e = (x); if (_e != cudaSuccess) { st = fail(OZ_ERR_CUDA, std::string(#x) + ": " + cudaGetErrorString(_e)); break; } }
     do {
         PF_CUDA(cudaMalloc(&d_cnt, 8 * sizeof(unsigned long long)));
-        PF_CUDA(cudaMalloc(&cur, sizeof(FNode)));
+        cap_cur = cap_next = (size_t)1 << 16;
+        PF_CUDA(cudaMalloc(&cur, cap_cur * sizeof(FNode)));
+        PF_CUDA(cudaMalloc(&next, cap_next * sizeof(FNode)));
         PF_CUDA(cudaMemcpy(cur, &h_root, sizeof(FNode), cudaMemcpyHostToDevice));
         PF_CUDA(cudaEventCreate(&ev0)); PF_CUDA(cudaEventCreate(&ev1));
         PF_CUDA(cudaEventRecord(ev0));
@@ -469,11 +472,14 @@ int oz_perft(const oz_position *root, int depth, int mode, uint64_t *nodes, doub
             bfs_count_kernel<<<grid, 256>>>(cur, n, d_cnt); count_launch();
             PF_CUDA(cudaMemcpy(h, d_cnt, sizeof(h), cudaMemcpyDeviceToHost));
             early_leaves += h[1];
-            PF_CUDA(cudaMalloc(&next, std::max<size_t>(1, h[0]) * sizeof(FNode)));
+            if (h[0] > cap_next) {
+                cudaFree(next); next = nullptr;
+                cap_next = std::max<size_t>(h[0], 4 * cap_next);
+                PF_CUDA(cudaMalloc(&next, cap_next * sizeof(FNode)));
+            }
             bfs_expand_kernel<<<grid, 256>>>(cur, n, next, d_cnt + 4); count_launch();
             PF_CUDA(cudaGetLastError());
-            PF_CUDA(cudaDeviceSynchronize());
-            cudaFree(cur); cur = next; next = nullptr; n = h[0];
+            std::swap(cur, next); std::swap(cap_cur, cap_next); n = h[0];      // stream order keeps the levels apart: no synchronisation
         }
         if (st) break;
         unsigned long long h[4] = {0, 0, 0, 0};

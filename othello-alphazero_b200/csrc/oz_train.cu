@@ -101,7 +101,7 @@ __device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
 // statistic and block.  out[copy][c] += first statistic, out[copy][C + c] += second, copy = block % kBnCopies: a few hundred
 // blocks adding to the same 2C addresses serialise in L2 (about 50 ns each), which at one copy was the whole run time of the
 // reductions; consumers add the copies up (bn_total).
-constexpr int kBnCopies = 8;
+constexpr int kBnCopies = 16;
 __device__ __forceinline__ void bn_block_reduce(float (&a)[8], float (&b)[8], int C, int tpr, int rows, int cg, int r0, float *out) {
     __shared__ float red[16][256];
 #pragma unroll
@@ -130,6 +130,7 @@ __device__ __forceinline__ float bn_total(const float *sums, int C, int idx) {
 // before the first is used -- with one load in flight per thread and the constants re-derived per element (two divisions
 // and an rsqrt per channel) the passes ran at 40 % of the HBM bandwidth and were instruction-bound.
 constexpr int kBnUnroll = 4;
+constexpr int kBnStatsUnroll = 8;      // bn_stats reads one tensor only: twice the loads in flight
 
 // sums[c] += sum z, sums[C + c] += sum z^2.
 __global__ void __launch_bounds__(256) bn_stats_kernel(const bf16 *__restrict__ z, size_t P, int C, float *__restrict__ sums) {
@@ -141,12 +142,12 @@ __global__ void __launch_bounds__(256) bn_stats_kernel(const bf16 *__restrict__ 
     for (int i = 0; i < 8; ++i) { s[i] = 0.f; q[i] = 0.f; }
     if (r0 < rows) {
         const size_t stride = (size_t)gridDim.x * rows;
-        for (size_t p = (size_t)blockIdx.x * rows + r0; p < P; p += kBnUnroll * stride) {
-            uint4 zq[kBnUnroll];
+        for (size_t p = (size_t)blockIdx.x * rows + r0; p < P; p += kBnStatsUnroll * stride) {
+            uint4 zq[kBnStatsUnroll];
 #pragma unroll
-            for (int u = 0; u < kBnUnroll; ++u) { const size_t pu = p + u * stride; zq[u] = pu < P ? *(const uint4 *)(z + pu * C + 8 * cg) : make_uint4(0, 0, 0, 0); }
+            for (int u = 0; u < kBnStatsUnroll; ++u) { const size_t pu = p + u * stride; zq[u] = pu < P ? *(const uint4 *)(z + pu * C + 8 * cg) : make_uint4(0, 0, 0, 0); }
 #pragma unroll
-            for (int u = 0; u < kBnUnroll; ++u) {
+            for (int u = 0; u < kBnStatsUnroll; ++u) {
                 float v[8];
                 unpack8(zq[u], v);
 #pragma unroll
@@ -157,10 +158,17 @@ __global__ void __launch_bounds__(256) bn_stats_kernel(const bf16 *__restrict__ 
     bn_block_reduce(s, q, C, tpr, rows, cg, r0 < rows ? r0 : 1 << 30, sums);
 }
 
+// Block-cooperative version for the streaming consumers: thread i adds up the copies of statistic slots i, i + blockDim, ...
+// into shared memory once per block (tot[2C]); 2 * kBnCopies loads per thread instead of 16 * kBnCopies.
+__device__ __forceinline__ void bn_totals_to_smem(const float *sums, int C, float *tot) {
+    for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) tot[i] = bn_total(sums, C, i);
+    __syncthreads();
+}
+
 // mean / invstd of channel c from the sums (every consumer recomputes them: two flops instead of a kernel launch).
-__device__ __forceinline__ void bn_moments(const float *sums, int C, int c, float count, float eps, float &mean, float &invstd, float &var) {
-    mean = bn_total(sums, C, c) / count;
-    var = fmaxf(bn_total(sums, C, C + c) / count - mean * mean, 0.f);
+__device__ __forceinline__ void bn_moments_tot(const float *tot, int C, int c, float count, float eps, float &mean, float &invstd, float &var) {
+    mean = tot[c] / count;
+    var = fmaxf(tot[C + c] / count - mean * mean, 0.f);
     invstd = rsqrtf(var + eps);
 }
 
@@ -173,11 +181,13 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(const bf16 *__restrict__ 
                                                        float *__restrict__ invstd_out, float *__restrict__ run_mean, float *__restrict__ run_var,
                                                        bf16 *__restrict__ a) {
     OZ_PDL_PROLOGUE();
+    __shared__ float tot[2 * 384];
+    bn_totals_to_smem(sums, C, tot);
     const float count = (float)P;
     if (blockIdx.x == 0)
         for (int c = threadIdx.x; c < C; c += blockDim.x) {
             float m, inv, var;
-            bn_moments(sums, C, c, count, eps, m, inv, var);
+            bn_moments_tot(tot, C, c, count, eps, m, inv, var);
             mean_out[c] = m; invstd_out[c] = inv;
             run_mean[c] = (1.f - momentum) * run_mean[c] + momentum * (m + conv_bias[c]);
             run_var[c] = (1.f - momentum) * run_var[c] + momentum * var * (count / fmaxf(count - 1.f, 1.f));
@@ -189,7 +199,7 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(const bf16 *__restrict__ 
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
         float var;
-        bn_moments(sums, C, 8 * cg + k, count, eps, m[k], iv[k], var);
+        bn_moments_tot(tot, C, 8 * cg + k, count, eps, m[k], iv[k], var);
         g[k] = gamma[8 * cg + k]; bt[k] = beta[8 * cg + k];
     }
     const size_t stride = (size_t)gridDim.x * rows;
@@ -257,7 +267,9 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const bf16 *__restric
                                                            const float *__restrict__ gamma, const float *__restrict__ s, bf16 *__restrict__ dz,
                                                            bf16 *__restrict__ dy_out, float *__restrict__ dgamma, float *__restrict__ dbeta) {
     OZ_PDL_PROLOGUE();
-    if (blockIdx.x == 0) for (int c = threadIdx.x; c < C; c += blockDim.x) { dgamma[c] = bn_total(s, C, C + c); dbeta[c] = bn_total(s, C, c); }
+    __shared__ float tot[2 * 384];
+    bn_totals_to_smem(s, C, tot);
+    if (blockIdx.x == 0) for (int c = threadIdx.x; c < C; c += blockDim.x) { dgamma[c] = tot[C + c]; dbeta[c] = tot[c]; }
     const int tpr = C / 8, rows = blockDim.x / tpr;
     const int cg = threadIdx.x % tpr, r0 = threadIdx.x / tpr;
     if (r0 >= rows) return;
@@ -266,7 +278,7 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const bf16 *__restric
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
         const int c = 8 * cg + k;
-        m[k] = mean[c]; iv[k] = invstd[c]; gi[k] = gamma[c] * invstd[c]; t1[k] = bn_total(s, C, c) * invM; t2[k] = bn_total(s, C, C + c) * invM;
+        m[k] = mean[c]; iv[k] = invstd[c]; gi[k] = gamma[c] * invstd[c]; t1[k] = tot[c] * invM; t2[k] = tot[C + c] * invM;
     }
     const size_t stride = (size_t)gridDim.x * rows;
     for (size_t p = (size_t)blockIdx.x * rows + r0; p < P; p += kBnUnroll * stride) {
@@ -321,32 +333,39 @@ __global__ void head_conv_fwd_kernel(const bf16 *__restrict__ a, size_t P, int C
     if (lane == 0) { h[p] = d0 + pb[0]; h[P + p] = d1 + pb[1]; h[2 * P + p] = d2 + vb[0]; }
 }
 
-// BatchNorm + ReLU of the three head channels (block k = channel k): hn[k][p] = relu(bn(h[k][p])); also scattered into the
-// flattened FC inputs hp [N][128] (index k*64 + pos) and hv [N][64].  stat[k] = mean, stat[3 + k] = invstd.
-__global__ void head_bn_fwd_kernel(const float *__restrict__ h, size_t P, const float *__restrict__ gamma_p, const float *__restrict__ beta_p,
+// BatchNorm + ReLU of the three head channels (blockIdx.y = channel k): hn[k][p] = relu(bn(h[k][p])); also scattered into
+// the flattened FC inputs hp [N][128] (index k*64 + pos) and hv [N][64].  stat[k] = mean, stat[3 + k] = invstd.  Two kernels,
+// many blocks each (one block per channel took 0.2 ms at batch 4 096): acc[2k] += sum h, acc[2k + 1] += sum h^2 (zeroed
+// per step), then every block derives the moments from acc.
+__global__ void __launch_bounds__(256) head_bn_stats_kernel(const float *__restrict__ h, size_t P, float *__restrict__ acc) {
+    OZ_PDL_PROLOGUE();
+    __shared__ float scratch[32];
+    const int k = blockIdx.y;
+    const float *hk = h + (size_t)k * P;
+    float s = 0.f, q = 0.f;
+    for (size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x; p < P; p += (size_t)gridDim.x * blockDim.x) { const float v = hk[p]; s += v; q += v * v; }
+    s = block_sum(s, scratch); q = block_sum(q, scratch);
+    if (threadIdx.x == 0) { atomicAdd(&acc[2 * k], s); atomicAdd(&acc[2 * k + 1], q); }
+}
+
+__global__ void __launch_bounds__(256) head_bn_fwd_kernel(const float *__restrict__ h, size_t P, const float *__restrict__ acc,
+                                   const float *__restrict__ gamma_p, const float *__restrict__ beta_p,
                                    const float *__restrict__ gamma_v, const float *__restrict__ beta_v, float eps, float momentum,
                                    float *__restrict__ run_p /* mean[2], var[2] */, float *__restrict__ run_v /* mean[1], var[1] */,
                                    float *__restrict__ stat, float *__restrict__ hn, float *__restrict__ hp, float *__restrict__ hv) {
     OZ_PDL_PROLOGUE();
-    __shared__ float scratch[32];
-    __shared__ float sh_mean, sh_inv;
-    const int k = blockIdx.x;
+    const int k = blockIdx.y;
     const float *hk = h + (size_t)k * P;
-    float s = 0.f, q = 0.f;
-    for (size_t p = threadIdx.x; p < P; p += blockDim.x) { const float v = hk[p]; s += v; q += v * v; }
-    s = block_sum(s, scratch); q = block_sum(q, scratch);
-    if (threadIdx.x == 0) {
-        const float cnt = (float)P, m = s / cnt, var = fmaxf(q / cnt - m * m, 0.f);
-        sh_mean = m; sh_inv = rsqrtf(var + eps);
-        stat[k] = m; stat[3 + k] = sh_inv;
+    const float cnt = (float)P, mean = acc[2 * k] / cnt, var = fmaxf(acc[2 * k + 1] / cnt - mean * mean, 0.f), inv = rsqrtf(var + eps);
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        stat[k] = mean; stat[3 + k] = inv;
         float *rm = k < 2 ? run_p + k : run_v, *rv = k < 2 ? run_p + 2 + k : run_v + 1;
-        *rm = (1.f - momentum) * *rm + momentum * m;
+        *rm = (1.f - momentum) * *rm + momentum * mean;
         *rv = (1.f - momentum) * *rv + momentum * var * (cnt / fmaxf(cnt - 1.f, 1.f));
     }
-    __syncthreads();
     const float g = k < 2 ? gamma_p[k] : gamma_v[0], b = k < 2 ? beta_p[k] : beta_v[0];
-    for (size_t p = threadIdx.x; p < P; p += blockDim.x) {
-        const float y = fmaxf(g * (hk[p] - sh_mean) * sh_inv + b, 0.f);
+    for (size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x; p < P; p += (size_t)gridDim.x * blockDim.x) {
+        const float y = fmaxf(g * (hk[p] - mean) * inv + b, 0.f);
         hn[(size_t)k * P + p] = y;
         const size_t n = p >> 6; const int pos = (int)(p & 63);
         if (k < 2) hp[n * 128 + k * 64 + pos] = y; else hv[n * 64 + pos] = y;
@@ -496,26 +515,32 @@ __global__ void head_fc_bwd_input_kernel(const float *__restrict__ dlogits, cons
 }
 
 // BatchNorm backward of the three head channels (block k): dh[k][p] (gradient wrt the 1x1 conv output), dgamma, dbeta.
-__global__ void head_bn_bwd_kernel(const float *__restrict__ h, const float *__restrict__ dhn, size_t P, const float *__restrict__ stat,
-                                   const float *__restrict__ gamma_p, const float *__restrict__ gamma_v, float *__restrict__ dh,
-                                   float *__restrict__ dgamma_p, float *__restrict__ dbeta_p, float *__restrict__ dgamma_v, float *__restrict__ dbeta_v) {
+__global__ void __launch_bounds__(256) head_bn_bwd_stats_kernel(const float *__restrict__ h, const float *__restrict__ dhn, size_t P,
+                                                                const float *__restrict__ stat, float *__restrict__ acc) {
     OZ_PDL_PROLOGUE();
     __shared__ float scratch[32];
-    __shared__ float sh1, sh2;
-    const int k = blockIdx.x;
+    const int k = blockIdx.y;
     const float mean = stat[k], inv = stat[3 + k];
     const float *hk = h + (size_t)k * P, *dk = dhn + (size_t)k * P;
     float s1 = 0.f, s2 = 0.f;
-    for (size_t p = threadIdx.x; p < P; p += blockDim.x) { const float d = dk[p]; s1 += d; s2 += d * (hk[p] - mean) * inv; }
+    for (size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x; p < P; p += (size_t)gridDim.x * blockDim.x) { const float d = dk[p]; s1 += d; s2 += d * (hk[p] - mean) * inv; }
     s1 = block_sum(s1, scratch); s2 = block_sum(s2, scratch);
-    if (threadIdx.x == 0) {
-        sh1 = s1; sh2 = s2;
+    if (threadIdx.x == 0) { atomicAdd(&acc[2 * k], s1); atomicAdd(&acc[2 * k + 1], s2); }
+}
+
+__global__ void __launch_bounds__(256) head_bn_bwd_kernel(const float *__restrict__ h, const float *__restrict__ dhn, size_t P, const float *__restrict__ stat,
+                                   const float *__restrict__ acc, const float *__restrict__ gamma_p, const float *__restrict__ gamma_v, float *__restrict__ dh,
+                                   float *__restrict__ dgamma_p, float *__restrict__ dbeta_p, float *__restrict__ dgamma_v, float *__restrict__ dbeta_v) {
+    OZ_PDL_PROLOGUE();
+    const int k = blockIdx.y;
+    const float mean = stat[k], inv = stat[3 + k], s1 = acc[2 * k], s2 = acc[2 * k + 1];
+    const float *hk = h + (size_t)k * P, *dk = dhn + (size_t)k * P;
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
         if (k < 2) { dgamma_p[k] = s2; dbeta_p[k] = s1; } else { dgamma_v[0] = s2; dbeta_v[0] = s1; }
     }
-    __syncthreads();
     const float g = k < 2 ? gamma_p[k] : gamma_v[0], invM = 1.f / (float)P;
-    for (size_t p = threadIdx.x; p < P; p += blockDim.x)
-        dh[(size_t)k * P + p] = g * inv * (dk[p] - sh1 * invM - (hk[p] - mean) * inv * sh2 * invM);
+    for (size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x; p < P; p += (size_t)gridDim.x * blockDim.x)
+        dh[(size_t)k * P + p] = g * inv * (dk[p] - s1 * invM - (hk[p] - mean) * inv * s2 * invM);
 }
 
 // 1x1 head convolutions backward.  da[p][c] = sum_k dh[k][p] * w[k][c] (bf16, the gradient entering the tower);
@@ -662,14 +687,14 @@ int run_step(oz_trainer *t, int n, const oz_train_config *cfg, int apply) {
     cudaStream_t s = t->stream;
     float *par = t->d_params, *grd = t->d_grads, *buf = t->d_buffers;
     OZ_CUDA(cudaMemsetAsync(grd, 0, t->n_params * sizeof(float), s));
-    OZ_CUDA(cudaMemsetAsync(t->d_loss, 0, 4 * sizeof(float), s));
+    OZ_CUDA(cudaMemsetAsync(t->d_loss, 0, 16 * sizeof(float), s));      // 4 losses + the head BatchNorm accumulators
     OZ_CUDA(cudaMemsetAsync(t->d_sums, 0, (size_t)2 * L * 2 * C * kBnCopies * sizeof(float), s));     // reduction slots of every layer, forward and backward
     OZ_TRY(pack_all_weights(t));
     launch_planes_to_nhwc32(d_features, t->shape.in_planes, (size_t)n, (size_t)n, t->d_x0, s);
     const int bn_block = 256, bn_rows = 256 / (C / 8);
     const size_t bn_chunks = (P + (size_t)bn_rows * kBnUnroll - 1) / ((size_t)bn_rows * kBnUnroll);   // every thread gets kBnUnroll rows or more
     const int bn_grid = (int)std::min<size_t>(1184, bn_chunks);       // streaming passes: up to 8 blocks per SM
-    const int bn_rgrid = (int)std::min<size_t>(296, bn_chunks);       // reductions: fewer blocks, fewer atomics
+    const int bn_rgrid = (int)std::min<size_t>(592, bn_chunks);       // reductions: fewer blocks, fewer atomics (37 per address and copy)
 
     // ---- forward through the tower (neural_net.py:9-65, train mode)
     for (int l = 0; l < L; ++l) {
@@ -686,7 +711,10 @@ int run_step(oz_trainer *t, int n, const oz_train_config *cfg, int apply) {
     // ---- heads forward + losses (neural_net.py:68-128, train.py:494-495)
     const bf16 *a_last = t->A[L - 1];
     launch_pdl(head_conv_fwd_kernel, dim3(grid_for(P * 32, 256)), dim3(256), 0, s, a_last, P, C, par + t->pcw, par + t->pcb, par + t->vcw, par + t->vcb, t->d_h);
-    launch_pdl(head_bn_fwd_kernel, dim3(3), dim3(1024), 0, s, t->d_h, P, par + t->pg, par + t->pb, par + t->vg, par + t->vb, cfg->bn_eps, cfg->bn_momentum, buf + t->prm,
+    const dim3 hbn_grid((unsigned)std::max<size_t>(1, std::min<size_t>(64, P / 2048)), 3);
+    float *hacc_f = t->d_loss + 4, *hacc_b = t->d_loss + 10;       // [3][2] accumulators, zeroed with the losses
+    launch_pdl(head_bn_stats_kernel, hbn_grid, dim3(256), 0, s, t->d_h, P, hacc_f);
+    launch_pdl(head_bn_fwd_kernel, hbn_grid, dim3(256), 0, s, t->d_h, P, hacc_f, par + t->pg, par + t->pb, par + t->vg, par + t->vb, cfg->bn_eps, cfg->bn_momentum, buf + t->prm,
                                           buf + t->vrm, t->d_stat, t->d_hn, t->d_hp, t->d_hv);
     const size_t fc_smem = (size_t)(65 * 128 + Hv * 64) * sizeof(float);
     launch_pdl(head_fc_fwd_kernel, dim3((unsigned)std::min<size_t>(148, (n + 7) / 8)), dim3(256), fc_smem, s, t->d_hp, t->d_hv, n, Hv, par + t->plw, par + t->plb, par + t->v1w, par + t->v1b,
@@ -699,7 +727,8 @@ int run_step(oz_trainer *t, int n, const oz_train_config *cfg, int apply) {
                                                                            grd + t->v2b);
     launch_pdl(head_fc_bwd_input_kernel, dim3(grid_for(3 * P, 256)), dim3(256), 0, s, t->d_dlogits, par + t->plw, t->d_u, t->d_dvpre, par + t->v1w, par + t->v2w, t->d_hn, P,
                                                                   Hv, t->d_dhn);
-    launch_pdl(head_bn_bwd_kernel, dim3(3), dim3(1024), 0, s, t->d_h, t->d_dhn, P, t->d_stat, par + t->pg, par + t->vg, t->d_dh, grd + t->pg, grd + t->pb, grd + t->vg,
+    launch_pdl(head_bn_bwd_stats_kernel, hbn_grid, dim3(256), 0, s, t->d_h, t->d_dhn, P, t->d_stat, hacc_b);
+    launch_pdl(head_bn_bwd_kernel, hbn_grid, dim3(256), 0, s, t->d_h, t->d_dhn, P, t->d_stat, hacc_b, par + t->pg, par + t->vg, t->d_dh, grd + t->pg, grd + t->pb, grd + t->vg,
                                           grd + t->vb);
     bf16 *dA = t->d_dA, *dA_other = t->d_dA2;
     launch_pdl(head_conv_bwd_kernel, dim3(grid_for(P, 64)), dim3(128), 0, s, a_last, t->d_dh, P, C, par + t->pcw, par + t->vcw, dA, grd + t->pcw, grd + t->pcb, grd + t->vcw,
@@ -820,7 +849,7 @@ int oz_trainer_create(int device, const oz_resnet_shape *shape, int max_batch, o
             (st = talloc(t, &t->d_dhn, 3 * P)) || (st = talloc(t, &t->d_dh, 3 * P)) || (st = talloc(t, &t->d_stat, 8)) ||
             (st = talloc(t, &t->d_hp, N * 128)) || (st = talloc(t, &t->d_hv, N * 64)) || (st = talloc(t, &t->d_policy, N * 65)) ||
             (st = talloc(t, &t->d_value, N)) || (st = talloc(t, &t->d_dlogits, N * 65)) || (st = talloc(t, &t->d_u, N * Hv)) ||
-            (st = talloc(t, &t->d_dvpre, N)) || (st = talloc(t, &t->d_loss, 4)))
+            (st = talloc(t, &t->d_dvpre, N)) || (st = talloc(t, &t->d_loss, 16)))
             break;
         if (cudaFuncSetAttribute(head_fc_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((65 * 128 + Hv * 64) * sizeof(float))) != cudaSuccess) {
             st = fail(OZ_ERR_CUDA, "value_head_hidden_channels too large for the trainer's head kernel"); break;

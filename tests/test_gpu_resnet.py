@@ -33,6 +33,8 @@ def _from_bits(a: np.ndarray) -> torch.Tensor:
     (128, 128, 16 * 20, True, True),      # 40 pair-passes: just above the switch, the two-rows-per-pass kernel
     (256, 256, 16 * 8, True, True),       # 256 channels, 32 pair-passes at two rows per pass: one-row kernel with streamed weights
     (256, 256, 16 * 12, False, True),     # ... and 48: two-row kernel
+    (128, 128, 16 * 320, True, True),     # 640 pair-passes on 74 pairs: the dynamic pass scheduler (>= 8 passes per pair), ring wraps
+    (256, 256, 16 * 160, False, True),    # 640 pair-passes with two cout tiles and streamed weights under the dynamic scheduler
 ])
 def test_conv3x3_vs_torch(cin, cout, boards, skip, relu):
     from othello_mcts import _lib

@@ -443,3 +443,42 @@ def test_full_size_search_invariants():
     assert (root_n_c >= 800).all() and (counts_c.sum(axis=1) >= counts_b.sum(axis=1) + 800 - 32 - 1).all()
     pos = eng.positions_array()
     assert (pos["player"] == 2).all() and (np.bitwise_count(pos["p1"]) + np.bitwise_count(pos["p2"]) == 5).all()
+
+
+def test_exploration_rate_table_grows_with_repeated_searches(oracle):
+    """The reference evaluates logf((1 + N + c_base) / c_base) for any visit count and allows any number of searches from
+    the same root (search_thread.cpp:198-203); the engine's table indexed by N is extended on demand.  300 searches of 16
+    simulations push the root past the initial 4 096 entries; visit counts and Q stay bit-identical to the oracle."""
+    from othello_mcts import MCTS
+    po = oracle
+    kw = dict(history_size=2, num_simulations=16, num_threads=1, batch_size=16, dirichlet_epsilon=0.0)
+    m = MCTS(torch_device="cuda", seed=1, game_id=0, **kw)
+    o = po.OracleMCTS(evaluator=po.EVAL_HASH, seed=1, game_id=0, **kw)
+    for i in range(300):
+        m.search("hash")
+        o.search()
+        if i % 50 == 49 or i == 299:
+            assert m.visit_counts() == o.visit_counts(), i
+            assert [f32_bits(v) for v in m.mean_action_values()] == [f32_bits(v) for v in o.mean_action_values()], i
+    assert sum(m.visit_counts()) == 300 * 16 - 16 and sum(m.visit_counts()) > 4096
+
+
+def test_self_play_temperature_changes_the_sampling_weights():
+    """train.py:423: visit_counts ** (1 / temperature).  A low temperature concentrates the sampled first moves on the most
+    visited child; temperature 1 spreads them in proportion to the counts; a high temperature flattens them."""
+    from othello_mcts import SelfPlayEngine
+    kw = dict(history_size=2, num_simulations=64, num_threads=1, batch_size=8, dirichlet_epsilon=0.25, seed=9)
+    share_of_best, spread = {}, {}
+    for temp in (0.02, 1.0, 20.0):
+        eng = SelfPlayEngine(512, self_play_temperature=temp, **kw)
+        eng.search("hash")
+        n, counts, _, _ = eng.root_stats()
+        acts = eng.choose_actions()
+        legal = [19, 26, 37, 44]
+        idx = np.array([legal.index(a) for a in acts])
+        share_of_best[temp] = float((counts[np.arange(len(idx)), idx] == counts[:, :4].max(axis=1)).mean())   # a most visited child (ties count)
+        spread[temp] = np.bincount(idx, minlength=4) / len(idx)
+    assert share_of_best[0.02] > 0.95 > share_of_best[1.0] > share_of_best[20.0]     # (14 / 15) ** 50 = 0.03: near-argmax
+    assert spread[20.0].min() > 0.15                               # nearly uniform over the four opening moves
+    with pytest.raises(ValueError, match=r"Expected self_play_temperature > 0.0"):
+        SelfPlayEngine(2, self_play_temperature=0.0, **kw)
