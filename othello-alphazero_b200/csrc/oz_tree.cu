@@ -490,15 +490,20 @@ __global__ void choose_kernel(Tree t, int32_t *actions) {
     int pick_j = 0;
     if (nch != 0) {
         if (t.g_ply[g] < t.temperature_plies && t.inv_temperature != 1.0f) {
-            // visit_counts ** (1 / tau), normalised, then one draw (train.py:423-425; np.random.choice walks the cumulative sum)
+            // visit_counts ** (1 / tau), normalised, then one draw (train.py:423-425; np.random.choice walks the cumulative
+            // sum).  The counts are divided by the largest one first: the same distribution, and no float overflow for small
+            // tau (the reference's float32 power overflows to inf there and np.random.choice raises).
+            int nmax = 0;
+            for (int j = 0; j < n; ++j) nmax = max(nmax, t.n_N[base + fc + j]);
+            const float inv_max = nmax > 0 ? 1.0f / (float)nmax : 0.f;
             float wsum = 0.f;
-            for (int j = 0; j < n; ++j) wsum += powf((float)t.n_N[base + fc + j], t.inv_temperature);
+            for (int j = 0; j < n; ++j) wsum += powf((float)t.n_N[base + fc + j] * inv_max, t.inv_temperature);
             if (!(wsum > 0.f)) pick_j = (int)(((uint64_t)r[0] * (uint32_t)n) >> 32);
             else {
                 const float pick = ((float)(r[0] >> 8) * (1.0f / 16777216.0f)) * wsum;
                 float acc = 0.f;
                 pick_j = n - 1;
-                for (int j = 0; j < n; ++j) { acc += powf((float)t.n_N[base + fc + j], t.inv_temperature); if (pick < acc) { pick_j = j; break; } }
+                for (int j = 0; j < n; ++j) { acc += powf((float)t.n_N[base + fc + j] * inv_max, t.inv_temperature); if (pick < acc) { pick_j = j; break; } }
             }
         } else if (t.g_ply[g] < t.temperature_plies) {      // tau = 1: proportional to visit counts, in integers
             uint32_t sum = 0;
