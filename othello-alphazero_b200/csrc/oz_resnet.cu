@@ -456,255 +456,6 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap map_act, const __grid_co
     }
 }
 
-// ------------------------------------------------------------------ whole tower in one launch (launch-bound batches)
-// conv_tower_kernel: every 3x3 layer of a forward in ONE persistent launch, for batches so small that a layer is a pass or
-// two per CTA pair (the single-game MCTS of the reference's CLIs: 32 boards; leaf batches up to a few hundred boards).
-// There a layer's MMAs take 2-5 us and the rest of its 10 us is what a kernel boundary costs even with programmatic
-// dependent launch: barrier / TMEM set-up, the first weight tiles, the tail-to-head hand-over.  Here the set-up happens once,
-// the weight producer streams the NEXT layer's tiles through the 36-slot ring while the current layer is still computing
-// (weights do not depend on activations), and layers are separated by a grid-wide counter instead of a launch:
-//     epilogue stores of layer l -> __threadfence -> atomicAdd(layer_done[l]);   consumers of layer l + 1 spin on it
-//     (ld.acquire.gpu), then fence.proxy.async before the first TMA read of what the generic proxy wrote.
-// All CTAs must be co-resident (grid <= one CTA per SM, cooperative launch).  Same tiles, same MMA order, same epilogue as
-// conv3x3_pair_kernel<1>: one board row per pass, static pass assignment (pass = pair, pair + pairs), streamed weights.
-struct alignas(64) TowerLayer {
-    CUtensorMap map_act, map_w;
-    ConvParams p;
-};
-
-__device__ __forceinline__ void tower_wait_layer(const unsigned *counter, unsigned target) {
-    long long t0 = 0;
-    for (uint32_t spins = 0;; ++spins) {
-        unsigned v;
-        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(counter) : "memory");
-        if (v >= target) break;
-        if ((spins & 255u) == 255u) {
-            const long long now = clock64();
-            if (t0 == 0) t0 = now;
-            else if (now - t0 > 8000000000ll) { printf("conv_tower_kernel: layer barrier timeout (block %d, %u of %u)\n", (int)blockIdx.x, v, target); __trap(); }
-        }
-    }
-}
-
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(pair::kThreadsP, 1)
-conv_tower_kernel(const TowerLayer *__restrict__ layers, int nlayers, unsigned *__restrict__ layer_done) {
-    using namespace pair;
-    constexpr int kRowPasses = 8;                                             // one board row per pass
-    constexpr int kActBoxBytesP = kBoxX * 3 * kSlotBytes;                     // 3-row box: halo row above and below
-    extern __shared__ uint8_t smem_raw[];
-    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-    uint8_t *gen = smem_raw + (base - smem_u32(smem_raw));
-    const uint32_t act0 = base;
-    const uint32_t w0 = act0 + kSlotBytes + kActStagesP * pair::kActBoxBytesP;
-    const uint32_t misc = w0 + kWSlots * kWTileBytes;
-    const uint32_t bar_act_full = misc, bar_act_empty = misc + 16;
-    const uint32_t bar_tmem_full = misc + 32, bar_tmem_empty = misc + 48;
-    const uint32_t bar_w_full = misc + 64, bar_w_empty = misc + 64 + 8 * kWSlots;
-    uint32_t *tmem_ptr = (uint32_t *)(gen + (misc - base) + 704);
-    float *s_bias = (float *)(gen + (misc - base) + 1024);
-    float *s_head = s_bias + 128;
-
-    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
-    const uint32_t rank = cluster_ctarank();
-    const bool leader = rank == 0;
-    const int cluster_id = blockIdx.x >> 1, num_clusters = gridDim.x >> 1;
-    const unsigned num_ctas = gridDim.x;
-
-    if (threadIdx.x == 0) {
-        for (int i = 0; i < kActStagesP; ++i) { mbar_init(bar_act_full + 8 * i, 1); mbar_init(bar_act_empty + 8 * i, 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(bar_tmem_full + 8 * i, 1); mbar_init(bar_tmem_empty + 8 * i, 2 * kEpiWarps); }
-        for (int i = 0; i < kWSlots; ++i) { mbar_init(bar_w_full + 8 * i, 1); mbar_init(bar_w_empty + 8 * i, 1); }
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr)), "r"(kTmemCols) : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
-    }
-    for (int i = threadIdx.x; i < kSlotBytes / 16; i += kThreadsP) *(uint4 *)(gen + i * 16) = make_uint4(0, 0, 0, 0);   // guard slot
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    tc_fence_before();
-    cluster_sync_all();
-    tc_fence_after();
-    const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_ptr, 0);
-    griddep_launch_dependents();
-
-    if (warp == 0) {
-        // ===== activation TMA producer =====
-        uint32_t it = 0;
-        const uint32_t full0 = mapa_rank(bar_act_full, 0);
-        griddep_wait();
-        for (int l = 0; l < nlayers; ++l) {
-            const ConvParams &p = layers[l].p;
-            const int ntiles = p.cout_total >> 7, num_pp = (p.units / 2) * kRowPasses * ntiles;
-            if (l > 0) {                                  // the previous layer's output is complete, visible, and ordered before our TMA reads
-                tower_wait_layer(layer_done + (l - 1), num_ctas);
-                asm volatile("fence.proxy.async;" ::: "memory");
-            }
-            for (int pp = cluster_id; pp < num_pp; pp += num_clusters) {
-                const int up = pp / ntiles, unit = 2 * (up / kRowPasses) + (int)rank, yp = up % kRowPasses;
-                for (int kb = 0; kb < p.kblocks; ++kb, ++it) {
-                    const uint32_t s = it % kActStagesP, ph = (it / kActStagesP) & 1;
-                    mbar_wait_b(bar_act_empty + 8 * s, ph ^ 1);
-                    if (elect_one()) {
-                        if (leader) mbar_expect_tx(bar_act_full + 8 * s, 2 * kActBoxBytesP);
-                        tma_load_4d_pair(act0 + kSlotBytes + s * kActBoxBytesP, &layers[l].map_act, full0 + 8 * s,
-                                         kb * kKBlock, unit * kBoardsPerUnit, 0, yp - 1);
-                    }
-                    __syncwarp();
-                }
-            }
-        }
-    } else if (warp == 2) {
-        // ===== weight TMA producer: runs ahead across layer boundaries (weights do not depend on activations) =====
-        uint32_t wit = 0;
-        const uint32_t full0 = mapa_rank(bar_w_full, 0);
-        for (int l = 0; l < nlayers; ++l) {
-            const ConvParams &p = layers[l].p;
-            const int ntiles = p.cout_total >> 7, num_pp = (p.units / 2) * kRowPasses * ntiles;
-            for (int pp = cluster_id; pp < num_pp; pp += num_clusters) {
-                const int nt = pp % ntiles;
-                for (int kb = 0; kb < p.kblocks; ++kb)
-                    for (int tap = 0; tap < 9; ++tap, ++wit) {
-                        const uint32_t s = wit % kWSlots, ph = (wit / kWSlots) & 1;
-                        mbar_wait_b(bar_w_empty + 8 * s, ph ^ 1);
-                        if (elect_one()) {
-                            if (leader) mbar_expect_tx(bar_w_full + 8 * s, 2 * kWTileBytes);
-                            tma_load_2d_pair(w0 + s * kWTileBytes, &layers[l].map_w, full0 + 8 * s,
-                                             kb * kKBlock, tap * p.cout_total + nt * 128 + (int)rank * 64);
-                        }
-                        __syncwarp();
-                    }
-            }
-        }
-    } else if (warp == 1) {
-        // ===== MMA issuer =====
-        if (leader) {
-            uint32_t ait = 0, wit = 0, np = 0;
-            for (int l = 0; l < nlayers; ++l) {
-                const ConvParams &p = layers[l].p;
-                const int ntiles = p.cout_total >> 7, num_pp = (p.units / 2) * kRowPasses * ntiles;
-                for (int pp = cluster_id; pp < num_pp; pp += num_clusters, ++np) {
-                    const uint32_t acc = np & 1;
-                    mbar_wait_b(bar_tmem_empty + 8 * acc, ((np >> 1) & 1) ^ 1);
-                    tc_fence_after();
-                    const uint32_t dcol = tmem_base + acc * 256;
-                    const int yp = (pp / ntiles) % kRowPasses;
-                    const bool skip_top = yp == 0, skip_bot = yp == kRowPasses - 1;
-                    const int first_tap = skip_top ? 3 : 0;
-                    for (int kb = 0; kb < p.kblocks; ++kb, ++ait) {
-                        const uint32_t as = ait % kActStagesP;
-                        mbar_wait_b(bar_act_full + 8 * as, (ait / kActStagesP) & 1);
-                        tc_fence_after();
-                        const uint32_t abox = act0 + kSlotBytes + as * kActBoxBytesP;
-                        for (int tap = 0; tap < 9; ++tap, ++wit) {
-                            const uint32_t ws = wit % kWSlots;
-                            mbar_wait_b(bar_w_full + 8 * ws, (wit / kWSlots) & 1);
-                            tc_fence_after();
-                            const int dy = tap / 3 - 1, dx = tap % 3 - 1;
-                            const uint32_t wbase = w0 + ws * kWTileBytes;
-                            if (elect_one()) {
-                                if (!((tap < 3 && skip_top) || (tap >= 6 && skip_bot))) {      // taps that only see the zero rows -1 / 8
-                                    const uint32_t arow = abox + (uint32_t)(((1 + dy) * kBoxX + dx) * kSlotBytes);
-#pragma unroll
-                                    for (int j = 0; j < kKBlock / 16; ++j)
-                                        tc_mma_pair(dcol, umma_desc_sw64(arow + j * 32), umma_desc_sw64(wbase + j * 32), kIdescP, (kb | j) != 0 || tap != first_tap);
-                                }
-                                tc_commit_pair(bar_w_empty + 8 * ws);
-                            }
-                            __syncwarp();
-                        }
-                        if (elect_one()) tc_commit_pair(bar_act_empty + 8 * as);
-                        __syncwarp();
-                    }
-                    if (elect_one()) tc_commit_pair(bar_tmem_full + 8 * acc);
-                    __syncwarp();
-                }
-            }
-        }
-    } else {
-        // ===== epilogue warps 3..10 =====
-        const int quad = warp & 3, half = (warp - 3) >> 2;
-        const int row = quad * 32 + lane, x = row >> 4, bl = row & 15;
-        const int et = (int)threadIdx.x - 96;                                  // 0 .. 255 among the epilogue threads
-        const uint32_t empty_remote = mapa_rank(bar_tmem_empty, 0);
-        uint32_t np = 0;
-        griddep_wait();
-        for (int l = 0; l < nlayers; ++l) {
-            const ConvParams &p = layers[l].p;
-            const int ntiles = p.cout_total >> 7, num_pp = (p.units / 2) * kRowPasses * ntiles;
-            // this layer's bias (and fused head weights) into shared memory; the previous layer's readers are these same warps
-            asm volatile("bar.sync 1, 256;" ::: "memory");
-            for (int i = et; i < p.cout_total; i += 256) s_bias[i] = p.bias[i];
-            if (p.head_out) for (int i = et; i < 3 * 128; i += 256) s_head[i] = p.head_w[i];
-            asm volatile("bar.sync 1, 256;" ::: "memory");
-            // (the residual input of a pass was written two layers earlier by this very thread: same pass, same tile mapping)
-            for (int pp = cluster_id; pp < num_pp; pp += num_clusters, ++np) {
-                const int nt = pp % ntiles, up = pp / ntiles, unit = 2 * (up / kRowPasses) + (int)rank, yp = up % kRowPasses;
-                const uint32_t acc = np & 1;
-                const size_t board = (size_t)unit * kBoardsPerUnit + bl;
-                const size_t off0 = ((board * 8 + yp) * 8 + x) * (size_t)p.cout_total + nt * 128 + half * 64;
-                uint32_t sk[32];
-                if (p.skip) {
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) ldg256(p.skip + off0 + i * 16, &sk[i * 8]);
-                }
-                mbar_wait_b(bar_tmem_full + 8 * acc, (np >> 1) & 1);
-                tc_fence_after();
-                float h0 = 0.f, h1 = 0.f, h2 = 0.f;
-#pragma unroll
-                for (int ch = 0; ch < 2; ++ch) {
-                    uint32_t v[32];
-                    tc_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + acc * 256 + half * 64 + ch * 32, v);
-                    tc_wait_ld();
-                    const float *bs = s_bias + nt * 128 + half * 64 + ch * 32;
-                    uint32_t ow[16];
-                    const uint32_t *skw = &sk[ch * 16];
-#pragma unroll
-                    for (int i = 0; i < 16; ++i) {
-                        float a = __uint_as_float(v[2 * i]) + bs[2 * i];
-                        float b = __uint_as_float(v[2 * i + 1]) + bs[2 * i + 1];
-                        if (p.skip) {
-                            const __nv_bfloat162 s2 = *(const __nv_bfloat162 *)&skw[i];
-                            a += __bfloat162float(s2.x);
-                            b += __bfloat162float(s2.y);
-                        }
-                        if (p.relu) { a = fmaxf(a, 0.f); b = fmaxf(b, 0.f); }
-                        if (p.head_out) {
-                            const int c = half * 64 + ch * 32 + 2 * i;
-                            const float2 w0v = *(const float2 *)(s_head + c), w1v = *(const float2 *)(s_head + 128 + c), w2v = *(const float2 *)(s_head + 256 + c);
-                            h0 += a * w0v.x + b * w0v.y; h1 += a * w1v.x + b * w1v.y; h2 += a * w2v.x + b * w2v.y;
-                        }
-                        const __nv_bfloat162 o2 = __floats2bfloat162_rn(a, b);
-                        ow[i] = *(const uint32_t *)&o2;
-                    }
-                    if (p.out) {
-                        __nv_bfloat16 *op = p.out + off0 + ch * 32;
-                        stg256(op, &ow[0]);
-                        stg256(op + 16, &ow[8]);
-                    }
-                }
-                if (p.head_out) {
-                    float *hp = p.head_out + ((board * 8 + yp) * 8 + x) * 4;
-                    atomicAdd(hp, h0); atomicAdd(hp + 1, h1); atomicAdd(hp + 2, h2);
-                }
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive_cluster(empty_remote + 8 * acc);
-            }
-            // layer barrier: this CTA's stores of layer l are done and visible device-wide, then one arrival per CTA
-            __threadfence();
-            asm volatile("bar.sync 1, 256;" ::: "memory");
-            if (et == 0) atomicAdd(layer_done + l, 1u);
-        }
-    }
-    tc_fence_before();
-    cluster_sync_all();
-    if (warp == 1) {
-        tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
-    }
-}
-
 // ------------------------------------------------------------------ input conversion
 // float planes [n][planes][64] -> bf16 NHWC [n_pad][64][32] (channels >= planes are zero).
 __global__ void planes_to_nhwc32_kernel(const float *__restrict__ f, int planes, size_t n, size_t n_pad, __nv_bfloat16 *__restrict__ out) {
@@ -1015,13 +766,6 @@ static int launch_conv(const CUtensorMap &ma, const CUtensorMap *ma1, const CUte
     return OZ_OK;
 }
 
-// OZ_TOWER=0 in the environment keeps the per-layer launches for every batch size (A/B runs).
-static bool tower_enabled() {
-    static int v = -1;
-    if (v < 0) { const char *e = getenv("OZ_TOWER"); v = (e && e[0] == '0') ? 0 : 1; }
-    return v == 1;
-}
-
 // OZ_CONV_STATIC=1 in the environment switches the convolution back to the static pass-to-cluster assignment (A/B runs).
 bool conv_static_schedule() {
     static int v = -1;
@@ -1030,7 +774,7 @@ bool conv_static_schedule() {
 }
 
 void ResNet::free_workspaces() {
-    for (Workspace &w : ws_) { cudaFree(w.x0); cudaFree(w.a); cudaFree(w.t); cudaFree(w.head_pre); cudaFree(w.work); cudaFree(w.tower); }
+    for (Workspace &w : ws_) { cudaFree(w.x0); cudaFree(w.a); cudaFree(w.t); cudaFree(w.head_pre); cudaFree(w.work); }
     ws_.clear();
 }
 
@@ -1077,7 +821,7 @@ int ResNet::reserve(size_t boards, int ws) {
     Workspace &w = ws_[(size_t)ws];
     const size_t pad = (boards + kBoardPad - 1) / kBoardPad * kBoardPad;
     if (pad <= w.cap) return OZ_OK;
-    cudaFree(w.x0); cudaFree(w.a); cudaFree(w.t); cudaFree(w.head_pre); cudaFree(w.work); cudaFree(w.tower);
+    cudaFree(w.x0); cudaFree(w.a); cudaFree(w.t); cudaFree(w.head_pre); cudaFree(w.work);
     w = Workspace{};
     const size_t C = shape_.channels;
     OZ_CUDA(cudaMalloc(&w.x0, pad * 64 * 32 * 2));
@@ -1132,22 +876,6 @@ int ResNet::forward(const float *d_features, size_t n, float *d_policy, float *d
     int *work = (dynamic_ && nconv <= kMaxConvLayers) ? w.work : nullptr;
     if (work) OZ_CUDA(cudaMemsetAsync(work, 0, (size_t)nconv * sizeof(int), stream));
     if (conv_begin) cudaEventRecord(conv_begin, stream);
-    // Launch-bound batches: the whole tower in one persistent launch (conv_tower_kernel).
-    if (tower_enabled() && tower_ok_ && nconv <= kMaxConvLayers) {
-        const int units = (int)(pad / kBoardsPerUnit), passes = (units / 2) * 8 * (C >> 7);
-        int dev = 0, sms = 148;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        if (passes <= 2 * (sms / 2)) {
-            const int rc = launch_tower(ws, pad, fuse_heads, stream);
-            if (rc == OZ_OK) {
-                if (conv_end) cudaEventRecord(conv_end, stream);
-                return launch_heads(w, n, fuse_heads, d_policy, d_value, stream);
-            }
-            if (rc != OZ_ERR_STATE) return rc;            // OZ_ERR_STATE: the cooperative launch was refused; per-layer launches from now on
-            tower_ok_ = false;
-        }
-    }
     ConvParams cp{};
     cp.units = (int)(pad / kBoardsPerUnit); cp.cout_total = C; cp.relu = 1;
     // conv block (neural_net.py:9-29)
@@ -1190,53 +918,6 @@ int ResNet::launch_heads(const Workspace &w, size_t n, bool fuse_heads, float *d
     heads_kernel<<<grid, kHeadWarps * 32, hsm, stream>>>(hp);
     count_launch();
     OZ_CUDA(cudaGetLastError());
-    return OZ_OK;
-}
-
-// The per-layer descriptors of conv_tower_kernel for workspace `ws` (device array, rebuilt when the workspace or the
-// weights moved) and the launch: one cooperative launch of at most one CTA per SM.
-int ResNet::launch_tower(int ws, size_t pad, bool fuse_heads, cudaStream_t stream) {
-    Workspace &w = ws_[(size_t)ws];
-    const int C = shape_.channels, nconv = 1 + 2 * shape_.blocks;
-    if (!w.tower || w.tower_pad != pad || w.tower_blob != d_blob_ || w.tower_fused != fuse_heads) {
-        std::vector<TowerLayer> host((size_t)nconv);
-        for (int i = 0; i < nconv; ++i) {
-            TowerLayer &t = host[(size_t)i];
-            ConvParams &cp = t.p;
-            cp = ConvParams{};
-            cp.units = (int)(pad / kBoardsPerUnit); cp.cout_total = C; cp.relu = 1; cp.kblocks = i == 0 ? 1 : C / kKBlock;
-            cp.bias = (const float *)(d_blob_ + layout_.conv_b[(size_t)i]);
-            t.map_w = map_w_[(size_t)i];
-            if (i == 0) { t.map_act = w.map_x0_1; cp.out = (__nv_bfloat16 *)w.a; }
-            else if (i % 2 == 1) { t.map_act = w.map_a_1; cp.out = (__nv_bfloat16 *)w.t; }          // first conv of a block: a -> t
-            else { t.map_act = w.map_t_1; cp.skip = (const __nv_bfloat16 *)w.a; cp.out = (__nv_bfloat16 *)w.a; }   // second: t (+ a) -> a
-            if (fuse_heads && i == nconv - 1) { cp.out = nullptr; cp.head_w = (const float *)(d_blob_ + layout_.head_w); cp.head_out = w.head_pre; }
-        }
-        if (!w.tower) OZ_CUDA(cudaMalloc(&w.tower, (size_t)kMaxConvLayers * sizeof(TowerLayer)));
-        OZ_CUDA(cudaMemcpy(w.tower, host.data(), host.size() * sizeof(TowerLayer), cudaMemcpyHostToDevice));
-        w.tower_pad = pad; w.tower_blob = d_blob_; w.tower_fused = fuse_heads;
-    }
-    static unsigned long long attr_devices = 0;
-    if (first_use_on_device(attr_devices))
-        OZ_CUDA(cudaFuncSetAttribute(conv_tower_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, pair::kSmemBytesP));
-    int dev = 0, sms = 148;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    const int passes = (int)(pad / kBoardsPerUnit / 2) * 8 * (C >> 7);
-    const int clusters = passes < sms / 2 ? passes : sms / 2;
-    OZ_CUDA(cudaMemsetAsync(w.work, 0, (size_t)nconv * sizeof(int), stream));      // the layer counters
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(2 * clusters); cfg.blockDim = dim3(pair::kThreadsP); cfg.dynamicSmemBytes = pair::kSmemBytesP; cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeCooperative;       // every CTA resident at once: the layers are separated by a grid-wide counter
-    attr[0].val.cooperative = 1;
-    cfg.attrs = attr; cfg.numAttrs = 1;
-    const cudaError_t err = cudaLaunchKernelEx(&cfg, conv_tower_kernel, (const TowerLayer *)w.tower, nconv, (unsigned *)w.work);
-    if (err != cudaSuccess) {
-        cudaGetLastError();
-        return fail(OZ_ERR_STATE, std::string("conv_tower_kernel: cooperative launch refused: ") + cudaGetErrorString(err));
-    }
-    count_launch();
     return OZ_OK;
 }
 

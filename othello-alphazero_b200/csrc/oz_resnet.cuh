@@ -72,16 +72,12 @@ class ResNet {
         size_t cap = 0;
         void *x0 = nullptr, *a = nullptr, *t = nullptr;       // bf16 NHWC activations
         float *head_pre = nullptr;                            // [boards][64][4] fused head-conv pre-activations
-        int *work = nullptr;                                  // [kMaxConvLayers] pass counters (dynamic pass scheduler) / layer counters (tower)
-        void *tower = nullptr;                                // per-layer descriptors of conv_tower_kernel (device), valid for:
-        size_t tower_pad = 0; const char *tower_blob = nullptr; bool tower_fused = false;
+        int *work = nullptr;                                  // [kMaxConvLayers] pass counters (dynamic pass scheduler)
         CUtensorMap map_x0, map_a, map_t;                     // 4-row boxes: two board rows per pass
         CUtensorMap map_x0_1, map_a_1, map_t_1;               // 3-row boxes: one board row per pass (small batches)
     };
     void free_workspaces();
-    int launch_tower(int ws, size_t pad, bool fuse_heads, cudaStream_t stream);
     int launch_heads(const Workspace &w, size_t n, bool fuse_heads, float *d_policy, float *d_value, cudaStream_t stream);
-    bool tower_ok_ = true;                                    // false once a cooperative launch was refused
     std::vector<Workspace> ws_;
     bool pdl_ = true;
     bool dynamic_ = true;                                     // dynamic pass scheduler in the convolutions (OZ_CONV_STATIC=1: off)
