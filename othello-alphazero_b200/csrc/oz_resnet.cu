@@ -45,6 +45,8 @@ struct ConvParams {
     const float *head_w;         // pair kernel, last layer of a 128-channel tower: [3][128] 1x1 head-conv weights (policy 0, policy 1, value)
     float *head_out;             // ... and their pre-activations [boards][64][4] (zeroed by the caller; two column halves add up)
     int *work;                   // dynamic pass scheduler: this launch's pass counter (zeroed by the caller), or null = static round-robin
+    float *stats;                // STATS instantiation (training forward): [copies][2 * cout_total] sum / sum of squares of the fp32 outputs
+    int stats_copies;            // ... accumulated into copy blockIdx.x % stats_copies
 };
 
 // ------------------------------------------------------------------ CTA-pair kernel (cta_group::2)
@@ -135,7 +137,13 @@ __device__ __forceinline__ void tc_mma_pair(uint32_t d_tmem, uint64_t adesc, uin
 // YPP = board rows per pass (and accumulator tiles per pass).  2 is the throughput configuration described above; 1 halves
 // the serial MMA chain of a pass and doubles the number of passes, for batches that cannot give every CTA pair a pass
 // otherwise (the single-game MCTS of the reference's CLIs: 32 boards are 4 pair-passes at YPP = 2).
-template <int YPP>
+// STATS (training forward pass): the epilogue also accumulates, per output channel, the sum and the sum of squares of the
+// fp32 results (BatchNorm batch statistics, nn.BatchNorm2d in train mode) -- a 32 x 32 transpose-reduce across the lanes of a
+// warp (31 shuffles per 32 channels: at step s a lane keeps half of its values and receives its partner's copies of them;
+// after five steps lane j holds channel j's total over the 32 rows), kept in registers over all passes of the CTA and added
+// to the global accumulators once at the end.  Replaces a separate pass over the bf16 tensor (bn_stats_kernel).  The
+// residual input is compiled out of this instantiation (a training forward convolution has none).
+template <int YPP, bool STATS = false>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(pair::kThreadsP, 1)
 conv3x3_pair_kernel(const __grid_constant__ CUtensorMap map_act, const __grid_constant__ CUtensorMap map_w, const ConvParams p) {
     using namespace pair;
@@ -374,6 +382,9 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap map_act, const __grid_co
         const int quad = warp & 3, half = (warp - 3) >> 2;
         const int row = quad * 32 + lane, x = row >> 4, bl = row & 15;     // row in tile = x * 16 + board
         const uint32_t empty_remote = mapa_rank(bar_tmem_empty, 0);
+        float st_sum[3][2], st_sq[3][2];                      // STATS: [cout tile][32-channel chunk] totals of channel (... + lane)
+#pragma unroll
+        for (int a = 0; a < 3; ++a) { st_sum[a][0] = st_sum[a][1] = 0.f; st_sq[a][0] = st_sq[a][1] = 0.f; }
         griddep_wait();
         for (uint32_t np = 0;; ++np) {
             int pp;
@@ -384,8 +395,8 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap map_act, const __grid_co
             const size_t board = (size_t)unit * kBoardsPerUnit + bl;
             const size_t off0 = ((board * 8 + yp * kYPerPass) * 8 + x) * (size_t)p.cout_total + nt * 128 + half * 64;
             const size_t ystride = (size_t)8 * p.cout_total;
-            uint32_t sk[kYPerPass][32];                        // 64 channels of residual input per tile row
-            if (p.skip) {
+            uint32_t sk[STATS ? 1 : kYPerPass][32];            // 64 channels of residual input per tile row
+            if (!STATS && p.skip) {
 #pragma unroll
                 for (int r = 0; r < kYPerPass; ++r) {
 #pragma unroll
@@ -413,12 +424,14 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap map_act, const __grid_co
                     tc_wait_ld();
                     const float *bs = s_bias + nt * 128 + half * 64 + ch * 32;
                     uint32_t ow[16];
-                    const uint32_t *skw = &sk[r][ch * 16];
+                    const uint32_t *skw = &sk[STATS ? 0 : r][ch * 16];
+                    float fx[STATS ? 32 : 1], fq[STATS ? 32 : 1];
 #pragma unroll
                     for (int i = 0; i < 16; ++i) {
                         float a = __uint_as_float(v[2 * i]) + bs[2 * i];
                         float b = __uint_as_float(v[2 * i + 1]) + bs[2 * i + 1];
-                        if (p.skip) {
+                        if (STATS) { fx[2 * i] = a; fx[2 * i + 1] = b; fq[2 * i] = a * a; fq[2 * i + 1] = b * b; }
+                        if (!STATS && p.skip) {
                             const __nv_bfloat162 s2 = *(const __nv_bfloat162 *)&skw[i];
                             a += __bfloat162float(s2.x);
                             b += __bfloat162float(s2.y);
@@ -437,6 +450,22 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap map_act, const __grid_co
                         stg256(op, &ow[0]);
                         stg256(op + 16, &ow[8]);
                     }
+                    if (STATS) {                             // 32 rows (lanes) x 32 channels -> lane j: channel j's sums
+#pragma unroll
+                        for (int sft = 16; sft >= 1; sft >>= 1) {
+                            const bool upper = (lane & sft) != 0;
+#pragma unroll
+                            for (int i = 0; i < sft; ++i) {
+                                const float sx = upper ? fx[i] : fx[i + sft], kx = upper ? fx[i + sft] : fx[i];
+                                const float sq = upper ? fq[i] : fq[i + sft], kq = upper ? fq[i + sft] : fq[i];
+                                fx[i] = kx + __shfl_xor_sync(0xffffffffu, sx, sft);
+                                fq[i] = kq + __shfl_xor_sync(0xffffffffu, sq, sft);
+                            }
+                        }
+#pragma unroll
+                        for (int a = 0; a < 3; ++a)
+                            if (a == nt) { st_sum[a][ch] += fx[0]; st_sq[a][ch] += fq[0]; }
+                    }
                 }
                 if (p.head_out) {                            // the two column halves of a row add into zeroed memory: order-free
                     float *hp = p.head_out + ((board * 8 + yp * kYPerPass + r) * 8 + x) * 4;
@@ -446,6 +475,19 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap map_act, const __grid_co
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive_cluster(empty_remote + 8 * acc);   // accumulator stage back to the leader's MMA thread
+        }
+        if (STATS && p.stats) {                               // this warp's 4 lane quarters x 32 rows each, all passes of the CTA
+            float *dst = p.stats + (size_t)(blockIdx.x % p.stats_copies) * 2 * p.cout_total;
+#pragma unroll
+            for (int a = 0; a < 3; ++a)
+                if (a < ntiles) {
+#pragma unroll
+                    for (int ch = 0; ch < 2; ++ch) {
+                        const int c = a * 128 + half * 64 + ch * 32 + lane;
+                        atomicAdd(dst + c, st_sum[a][ch]);
+                        atomicAdd(dst + p.cout_total + c, st_sq[a][ch]);
+                    }
+                }
         }
     }
     tc_fence_before();
@@ -735,6 +777,8 @@ static int launch_conv(const CUtensorMap &ma, const CUtensorMap *ma1, const CUte
     if (first_use_on_device(attr_devices)) {
         OZ_CUDA(cudaFuncSetAttribute(conv3x3_pair_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, pair::kSmemBytesP));
         OZ_CUDA(cudaFuncSetAttribute(conv3x3_pair_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, pair::kSmemBytesP));
+        OZ_CUDA(cudaFuncSetAttribute(conv3x3_pair_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, pair::kSmemBytesP));
+        OZ_CUDA(cudaFuncSetAttribute(conv3x3_pair_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, pair::kSmemBytesP));
     }
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
@@ -759,7 +803,11 @@ static int launch_conv(const CUtensorMap &ma, const CUtensorMap *ma1, const CUte
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr; cfg.numAttrs = pdl ? 1 : 0;
-    if (one_row) OZ_CUDA(cudaLaunchKernelEx(&cfg, conv3x3_pair_kernel<1>, *ma1, mw, cpl));
+    if (cpl.stats) {
+        if (cpl.skip || cpl.cout_total > 384) return fail(OZ_ERR_INVALID_ARGUMENT, "conv3x3 with statistics: no residual input, at most 384 channels");
+        if (one_row) OZ_CUDA(cudaLaunchKernelEx(&cfg, conv3x3_pair_kernel<1, true>, *ma1, mw, cpl));
+        else OZ_CUDA(cudaLaunchKernelEx(&cfg, conv3x3_pair_kernel<2, true>, ma, mw, cpl));
+    } else if (one_row) OZ_CUDA(cudaLaunchKernelEx(&cfg, conv3x3_pair_kernel<1>, *ma1, mw, cpl));
     else OZ_CUDA(cudaLaunchKernelEx(&cfg, conv3x3_pair_kernel<2>, ma, mw, cpl));
     count_launch();
     OZ_CUDA(cudaGetLastError());
@@ -922,7 +970,7 @@ int ResNet::launch_heads(const Workspace &w, size_t n, bool fuse_heads, float *d
 }
 
 int ResNet::conv3x3(const void *d_in, int cin, const void *d_w, const float *d_bias, const void *d_skip, int relu,
-                    void *d_out, int cout, size_t boards_padded, cudaStream_t stream, int *d_work) {
+                    void *d_out, int cout, size_t boards_padded, cudaStream_t stream, int *d_work, float *d_stats, int stats_copies) {
     if (cin % kKBlock || cout % 128 || boards_padded % kBoardPad)
         return fail(OZ_ERR_INVALID_ARGUMENT, "conv3x3: cin % 32, cout % 128, boards % 32 must be 0");
     CUtensorMap ma, ma1, mw;
@@ -932,6 +980,7 @@ int ResNet::conv3x3(const void *d_in, int cin, const void *d_w, const float *d_b
     ConvParams cp{};
     cp.skip = (const __nv_bfloat16 *)d_skip; cp.out = (__nv_bfloat16 *)d_out; cp.bias = d_bias;
     cp.units = (int)(boards_padded / kBoardsPerUnit); cp.kblocks = cin / kKBlock; cp.cout_total = cout; cp.relu = relu;
+    cp.stats = d_stats; cp.stats_copies = stats_copies > 0 ? stats_copies : 1;
     if (d_work && !conv_static_schedule()) {          // dynamic pass scheduler: the caller's counter, zeroed in stream order
         OZ_CUDA(cudaMemsetAsync(d_work, 0, sizeof(int), stream));
         cp.work = d_work;

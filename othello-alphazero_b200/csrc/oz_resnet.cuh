@@ -62,7 +62,10 @@ class ResNet {
     // Debug hook: one 3x3 convolution layer on device NHWC bf16 buffers already padded to 32 boards.
     // d_work: one device int for the dynamic pass scheduler (zeroed here, in stream order), or null = static schedule.
     static int conv3x3(const void *d_in, int cin, const void *d_w, const float *d_bias, const void *d_skip,
-                       int relu, void *d_out, int cout, size_t boards_padded, cudaStream_t stream, int *d_work = nullptr);
+                       int relu, void *d_out, int cout, size_t boards_padded, cudaStream_t stream, int *d_work = nullptr,
+                       float *d_stats = nullptr, int stats_copies = 1);
+    // d_stats (training forward): [stats_copies][2 * cout] accumulators (zeroed by the caller) that receive the per-channel
+    // sum and sum of squares of the fp32 convolution results (BatchNorm batch statistics); requires d_skip == nullptr.
 
   private:
     oz_resnet_shape shape_{};

@@ -130,33 +130,6 @@ __device__ __forceinline__ float bn_total(const float *sums, int C, int idx) {
 // before the first is used -- with one load in flight per thread and the constants re-derived per element (two divisions
 // and an rsqrt per channel) the passes ran at 40 % of the HBM bandwidth and were instruction-bound.
 constexpr int kBnUnroll = 4;
-constexpr int kBnStatsUnroll = 8;      // bn_stats reads one tensor only: twice the loads in flight
-
-// sums[c] += sum z, sums[C + c] += sum z^2.
-__global__ void __launch_bounds__(256) bn_stats_kernel(const bf16 *__restrict__ z, size_t P, int C, float *__restrict__ sums) {
-    OZ_PDL_PROLOGUE();
-    const int tpr = C / 8, rows = blockDim.x / tpr;
-    const int cg = threadIdx.x % tpr, r0 = threadIdx.x / tpr;
-    float s[8], q[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) { s[i] = 0.f; q[i] = 0.f; }
-    if (r0 < rows) {
-        const size_t stride = (size_t)gridDim.x * rows;
-        for (size_t p = (size_t)blockIdx.x * rows + r0; p < P; p += kBnStatsUnroll * stride) {
-            uint4 zq[kBnStatsUnroll];
-#pragma unroll
-            for (int u = 0; u < kBnStatsUnroll; ++u) { const size_t pu = p + u * stride; zq[u] = pu < P ? *(const uint4 *)(z + pu * C + 8 * cg) : make_uint4(0, 0, 0, 0); }
-#pragma unroll
-            for (int u = 0; u < kBnStatsUnroll; ++u) {
-                float v[8];
-                unpack8(zq[u], v);
-#pragma unroll
-                for (int i = 0; i < 8; ++i) { s[i] += v[i]; q[i] += v[i] * v[i]; }
-            }
-        }
-    }
-    bn_block_reduce(s, q, C, tpr, rows, cg, r0 < rows ? r0 : 1 << 30, sums);
-}
 
 // Block-cooperative version for the streaming consumers: thread i adds up the copies of statistic slots i, i + blockDim, ...
 // into shared memory once per block (tot[2C]); 2 * kBnCopies loads per thread instead of 16 * kBnCopies.
@@ -700,9 +673,9 @@ int run_step(oz_trainer *t, int n, const oz_train_config *cfg, int apply) {
     for (int l = 0; l < L; ++l) {
         ConvLayerT &c = t->conv[l];
         const bf16 *in = l == 0 ? t->d_x0 : t->A[l - 1];
-        OZ_TRY(ResNet::conv3x3(in, c.cinp, c.wf, t->d_zero_bias, nullptr, 0, t->Z[l], C, (size_t)n, s));
+        // the convolution's epilogue also accumulates the BatchNorm batch statistics of its fp32 results (STATS instantiation)
         float *fsum = t->d_sums + (size_t)l * 2 * C * kBnCopies;
-        launch_pdl(bn_stats_kernel, dim3(bn_rgrid), dim3(bn_block), 0, s, t->Z[l], P, C, fsum);
+        OZ_TRY(ResNet::conv3x3(in, c.cinp, c.wf, t->d_zero_bias, nullptr, 0, t->Z[l], C, (size_t)n, s, nullptr, fsum, kBnCopies));
         const bf16 *skip = (l >= 2 && l % 2 == 0) ? t->A[l - 2] : nullptr;     // second conv of a residual block
         launch_pdl(bn_apply_kernel, dim3(bn_grid), dim3(bn_block), 0, s, t->Z[l], skip, P, C, fsum, par + c.gamma, par + c.beta, par + c.b, cfg->bn_eps,
                                                             cfg->bn_momentum, t->d_mean + (size_t)l * C, t->d_invstd + (size_t)l * C, buf + c.rm,
