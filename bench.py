@@ -16,7 +16,8 @@ synchronize on both sides, max over ranks.  Rank 0 prints one JSON line.
 Beside the headline (BASELINE.json configs[2], 1 000 lockstep games per GPU = weak scaling) the same line carries two
 sub-records so that the driver's own runs hold BASELINE configs 4 and 5 (skip them with --no-extra-configs):
   "config4": 8 192 lockstep games partitioned over the N GPUs (8192/N per GPU; N = 1 is the strong-scaling denominator),
-  "config5": 256x20b, 1 600 sims/move, leaf batch 64 ... 4096 per network call and GPU, on the N GPUs.
+  "config5": 256x20b, 1 600 sims/move, leaf batch 64 ... 4096 per network call and GPU, on the N GPUs,
+  "config3_leaf_batch_256": the headline network with 8 games per GPU, i.e. configs[2]'s "leaf batch 256" read literally.
 """
 from __future__ import annotations
 
@@ -425,6 +426,7 @@ def run_ours(args):
     if not args.no_extra_configs:
         extra["config4"] = run_config4(args, om, net, kw, rank, world, local, timed, allsum)
         extra["config5"] = run_config5(args, om, rank, world, local, timed, allsum)
+        extra["config3_leaf_batch_256"] = run_config3_leaf256(args, om, net, kw, rank, world, local, timed, allsum)
 
     if rank == 0:
         f_all, f_conv = flops_per_eval(c=args.channels, blocks=args.blocks, hv=args.hidden)
@@ -520,6 +522,35 @@ def run_config4(args, om, net, kw, rank, world, local, timed, allsum) -> dict:
                 "metric": "mcts_simulations_per_second", "value": sims / (ms * 1e-3), "unit": "sims/s", "n_gpus": world,
                 "games_total": G * world, "games_per_gpu": G, "steps": steps, "warmup": warmup, "ms_per_step": ms / steps,
                 "scaling": "strong", "collectives_on_hot_path": 0}
+    except Exception as exc:
+        return {"error": repr(exc)}
+
+
+def run_config3_leaf256(args, om, net, kw, rank, world, local, timed, allsum) -> dict:
+    """BASELINE.json configs[2] read literally -- "leaf batch 256" per network call: 8 lockstep games per GPU x (T x B = 32)
+    leaves.  The headline runs the same search with 1 000 games per GPU (32 000 boards per call) because a B200 needs about
+    10^4 boards per launch to fill its SMs; this is the measured point at a 256-board call."""
+    try:
+        inflight = kw["num_threads"] * kw["batch_size"]
+        G = max(1, 256 // inflight)
+        eng = om.SelfPlayEngine(G, seed=args.seed, first_game_id=rank * G, cuda_device=local, **kw)
+        eng.prepare(net)
+        step = lambda: eng.play_ply(want_counts=False)
+        steps, warmup = 10, 3
+        for _ in range(warmup):
+            step()
+        c0 = eng.counters()
+        ms = timed(eng, step, steps)
+        c1 = eng.counters()
+        sims, evals = allsum(c1["simulations"] - c0["simulations"], c1["evaluations"] - c0["evaluations"])
+        del eng
+        f_all, _ = flops_per_eval(c=args.channels, blocks=args.blocks, hv=args.hidden)
+        tf = evals / world * f_all / (ms * 1e-3) / 1e12
+        return {"workload": f"{args.channels}x{args.blocks + 1}b self-play, {G} lockstep games per GPU = leaf batch {G * inflight} per network call, "
+                            f"{kw['num_simulations']} sims/move, {world} GPU(s)",
+                "metric": "mcts_simulations_per_second", "value": sims / (ms * 1e-3), "unit": "sims/s", "n_gpus": world, "games_per_gpu": G,
+                "leaf_batch_per_gpu": G * inflight, "steps": steps, "warmup": warmup, "ms_per_step": ms / steps, "tflops_per_gpu": tf,
+                "frac_of_sustained_peak": tf / peaks()["bf16_sustained"]}
     except Exception as exc:
         return {"error": repr(exc)}
 
