@@ -114,3 +114,49 @@ def test_unmodified_alphazero_player_and_play_game(ref_pkg, tmp_path):
     assert result == (1 if b > w else 2 if w > b else 0)
     assert p1.mcts.counters()["evaluations"] > 0 and p2.mcts.counters()["evaluations"] > 0
     assert p1.mcts._evaluator == 3 and p2.mcts._evaluator == 3            # both ran on the native evaluator
+
+
+@pytest.mark.parametrize("binding", ["ctypes", "pybind11"])
+def test_unmodified_cli_entry_points_train_resume_play(ref_pkg, tmp_path, binding):
+    """The north-star sentence "so `othello-train` and the play CLI drive it unchanged", executed: the reference's
+    `othello_alphazero.train.main()` (one tiny iteration from scratch: self-play through `othello_mcts.MCTS`, training,
+    checkpoint), again with `--from-checkpoint` (train.py:316-350: `MCTS(**config["mcts"])` from the saved config), then
+    `othello_alphazero.play.main()` with an AlphaZero player loaded from that checkpoint against the greedy player -- in
+    fresh interpreters with `othello_mcts` resolved to the drop-in (ctypes package / compiled pybind11 module)."""
+    import os
+    import subprocess
+    pkg_root = ROOT / "othello-alphazero_b200"
+    if binding == "pybind11":
+        if not list((pkg_root / "cpp_binding" / "othello_mcts").glob("_othello_mcts_impl*.so")):
+            pytest.skip("pybind11 binding not built")
+        pkg_root = pkg_root / "cpp_binding"
+    env = dict(os.environ, PYTHONPATH=f"{pkg_root}:{REF_PY}")
+    out = tmp_path / "ckpt"
+    common = ["--device", "cuda", "--iterations", "1", "--self-play-games-per-iteration", "2", "--history-size", "4",
+              "--neural-net-conv-channels", "128", "--neural-net-residual-blocks", "2", "--neural-net-value-head-hidden-channels", "32",
+              "--mcts-simulations", "32", "--mcts-threads", "1", "--mcts-batch-size", "8", "--training-batch-size", "64",
+              "--training-dataloader-workers", "0", "--output-dir", str(out)]
+
+    def run(module, argv):
+        code = (f"import sys, othello_mcts; assert r'{pkg_root}' in othello_mcts.__file__, othello_mcts.__file__; "
+                f"from othello_alphazero import {module}; sys.argv = ['othello-{module}'] + {argv!r}; {module}.main()")
+        return subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=900)
+
+    r = run("train", common)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    for name in ("config.json", "neural_net.pth", "optimizer.pth", "lr_scheduler.pth", "stats.json", "iteration.txt"):
+        assert (out / "001" / name).exists(), name
+    stats = json.loads((out / "001" / "stats.json").read_text())
+    assert all(np.isfinite(stats[k]) for k in ("total_loss", "policy_loss", "value_loss", "l2_loss"))
+    cfg = json.loads((out / "001" / "config.json").read_text())
+    assert cfg["mcts"]["num_simulations"] == 32 and cfg["neural_net"]["in_channels"] == 9
+
+    r = run("train", common + ["--from-checkpoint", str(out / "001")])
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert (out / "002" / "neural_net.pth").exists()
+
+    r = run("play", ["--player1", "alphazero", "--player2", "greedy", "--alphazero-device", "cuda", "--alphazero-checkpoint", str(out / "002"),
+                     "--alphazero-simulations", "32", "--alphazero-threads", "1", "--alphazero-batch-size", "8"])
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "Game over" in r.stdout and ("Black wins" in r.stdout or "White wins" in r.stdout or "Draw" in r.stdout)
+    assert "  a b c d e f g h" in r.stdout and "Action-value:" in r.stdout          # Position.__str__ and mean_action_values() in use

@@ -149,3 +149,21 @@ def test_search_with_native_network():
     finally:
         lib.oz_resnet_destroy(h)
     assert native.counters()["evaluations"] > 0
+
+
+def test_second_device_in_one_process():
+    """cudaFuncSetAttribute is per device: an engine on cuda:1 after one on cuda:0 in the same process must get the
+    convolution's dynamic shared-memory limit too (and identical results).  Needs two GPUs; skipped otherwise."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    from othello_mcts import MCTS
+    net = _net(2, 128, 9, 64)
+    kw = dict(history_size=4, num_simulations=64, num_threads=1, batch_size=16, dirichlet_epsilon=0.25, seed=3)
+    a, b = MCTS(torch_device="cuda:0", **kw), MCTS(torch_device="cuda:1", **kw)
+    for _ in range(3):
+        a.search(net)
+        b.search(net)
+        assert a.visit_counts() == b.visit_counts() and a.mean_action_values() == b.mean_action_values()
+        act = a.position().legal_actions()[int(np.argmax(a.visit_counts()))]
+        a.apply_action(act)
+        b.apply_action(act)
