@@ -409,13 +409,15 @@ void read_profile(oz_engine *e) {
 
 int search_pipelined(oz_engine *e, int groups) {
     const int rounds = rounds_of(e->cfg), G = e->t.G, B = e->t.inflight;
-    // Tree kernels go to low-priority streams, the network to one high-priority stream: a pending convolution CTA is
-    // always placed before pending tree blocks, which then take the registers the convolution leaves free.
+    // Tree streams and the network stream get the SAME priority.  Round 1 put the network on a high-priority stream; with
+    // programmatic dependent launch there is then always a pending, not yet placeable high-priority convolution grid, and the
+    // block scheduler does not place lower-priority blocks while it waits: nothing overlapped (profiles/r02_dynamic_scheduler.md).
+    // OZ_PIPE_PRIO=0 restores that setting, =2 inverts it (experiment switches).
     int prio_lo = 0, prio_hi = 0;
     cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
-    {   // experiment switch: OZ_PIPE_PRIO=1 equal priorities, =2 tree streams high / network stream low
+    {
         const char *pe = getenv("OZ_PIPE_PRIO");
-        const int mode = pe ? atoi(pe) : 0;
+        const int mode = pe ? atoi(pe) : 1;
         if (mode == 1) prio_hi = prio_lo;
         else if (mode == 2) std::swap(prio_lo, prio_hi);
     }
