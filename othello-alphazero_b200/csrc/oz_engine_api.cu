@@ -508,11 +508,11 @@ int oz_engine_create(const oz_config *cfg, oz_engine **out) {
             (st = dalloc(&t.g_ply, G)) || (st = dalloc(&t.g_search, G)) || (st = dalloc(&t.g_gameid, G)) || (st = dalloc(&t.h_p1, (size_t)G * kMaxHist)) ||
             (st = dalloc(&t.h_p2, (size_t)G * kMaxHist)) || (st = dalloc(&t.h_player, (size_t)G * kMaxHist)) || (st = dalloc(&t.h_n, G)) ||
             (st = dalloc(&t.r_p1, G)) || (st = dalloc(&t.r_p2, G)) || (st = dalloc(&t.r_player, G)) || (st = dalloc(&t.error, 1)) ||
-            (st = dalloc(&t.stats, 4)) || (st = dalloc(&t.round, 1 + kMaxGroups)) || (st = dalloc(&e->d_actions, G)) || (st = dalloc(&e->d_unfinished, 2)) ||
+            (st = dalloc(&t.stats, 4 * kStatCopies)) || (st = dalloc(&t.round, 1 + kMaxGroups)) || (st = dalloc(&e->d_actions, G)) || (st = dalloc(&e->d_unfinished, 2)) ||
             (st = dalloc(&e->d_stat_n, G)) || (st = dalloc(&e->d_stat_counts, (size_t)G * kStride)) || (st = dalloc(&e->d_stat_q, (size_t)G * kStride)) ||
             (st = dalloc(&e->d_stat_rootn, G)) || (st = dalloc(&e->d_spd_p, 8 * 65)))
             break;
-        cudaMemset(t.error, 0, sizeof(int32_t)); cudaMemset(t.stats, 0, 4 * sizeof(unsigned long long));
+        cudaMemset(t.error, 0, sizeof(int32_t)); cudaMemset(t.stats, 0, 4 * kStatCopies * sizeof(unsigned long long));
         e->max_plies = 128;
         if ((st = dalloc(&e->d_records, (size_t)G * e->max_plies))) break;
         if (cudaHostAlloc((void **)&e->h_pin, 8 * sizeof(int32_t), cudaHostAllocDefault) != cudaSuccess ||
@@ -1189,8 +1189,9 @@ int oz_training_samples_from_records(int device, const oz_ply_record *records, c
 
 int oz_engine_counters(oz_engine *e, oz_counters *out) {
     OZ_TRY(set_device(e));
-    unsigned long long s[4] = {0, 0, 0, 0};
-    OZ_CUDA(cudaMemcpy(s, e->t.stats, sizeof(s), cudaMemcpyDeviceToHost));
+    unsigned long long sc[4 * kStatCopies], s[4] = {0, 0, 0, 0};
+    OZ_CUDA(cudaMemcpy(sc, e->t.stats, sizeof(sc), cudaMemcpyDeviceToHost));
+    for (int k = 0; k < kStatCopies; ++k) for (int i = 0; i < 4; ++i) s[i] += sc[4 * k + i];
     e->ctr.nodes_expanded = s[0]; e->ctr.path_nodes = s[1]; e->ctr.children_read = s[2];
     e->ctr.kernel_launches = g_kernel_launches;
     *out = e->ctr;

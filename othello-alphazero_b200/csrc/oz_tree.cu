@@ -235,7 +235,7 @@ __global__ void __launch_bounds__(WARPS * 32) select_kernel(Tree t) {
     }
     if (lane == 0) t.n_N[base + root] = root_n;
     }
-    if (lane == 0 && path_nodes) { atomicAdd(&t.stats[1], path_nodes); atomicAdd(&t.stats[2], children_read); }
+    if (lane == 0 && path_nodes) { unsigned long long *st = t.stats + 4 * ((blockIdx.x * WARPS + wib) % kStatCopies); atomicAdd(&st[1], path_nodes); atomicAdd(&st[2], children_read); }
 }
 
 // ------------------------------------------------------------------ encode (search_thread.cpp:87-100, transformation.h:83-116)
@@ -450,7 +450,7 @@ __global__ void __launch_bounds__(WARPS * 32) expand_kernel(Tree t, const float 
     }
     if (lane == 0) t.g_count[g] = count;
     }
-    if (lane == 0 && expanded) atomicAdd(&t.stats[0], expanded);
+    if (lane == 0 && expanded) atomicAdd(&t.stats[4 * ((blockIdx.x * WARPS + wib) % kStatCopies)], expanded);
 }
 
 __global__ void end_search_kernel(Tree t) {

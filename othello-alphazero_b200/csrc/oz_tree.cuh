@@ -23,6 +23,7 @@ namespace oz {
 constexpr int kMaxDepth = 128;   // longest root-to-leaf path kept per slot
 constexpr int kMaxHist = 16;     // retired ancestors kept per game (history_size <= 16)
 constexpr int kStride = 36;      // OZ_MAX_CHILDREN
+constexpr int kStatCopies = 32;  // copies of the engine counters (Tree::stats)
 
 enum TreeError { kErrArenaFull = 1, kErrRateTable = 2, kErrDepth = 4 };
 
@@ -46,7 +47,10 @@ struct Tree {
     const float *gamma_table; int gamma_len;    // injected Dirichlet draws (tests)
     int32_t *round;                      // round of the current search (device-side, so one CUDA graph serves every round)
     int32_t *error;                      // TreeError bits
-    unsigned long long *stats;           // [0] nodes expanded, [1] path nodes walked by select, [2] child statistics read by select
+    // [kStatCopies][4]: [0] nodes expanded, [1] path nodes walked by select, [2] child statistics read by select.  A warp adds
+    // to copy (its game % kStatCopies): a thousand games adding to one address serialise in L2 at the end of every select /
+    // expand launch; the host sums the copies.
+    unsigned long long *stats;
     // configuration
     int G, cap, H, inflight;
     float eps, alpha;
