@@ -179,6 +179,13 @@ int oz_resnet_forward_device(oz_resnet *net, const float *features, size_t n, fl
 int oz_debug_conv3x3(const uint16_t *in, int cin, const uint16_t *w, const float *bias, const uint16_t *skip,
                      int relu, uint16_t *out, int cout, size_t boards, double *device_ms);
 
+/* Test / measurement hook: the native evaluator runs launch-bound batches of a 128-channel network (<= 32 boards per
+ * 16-CTA cluster: the single-game MCTS.search of train.py:415-416 / player.py:251) as ONE cluster launch with the
+ * activations in distributed shared memory (tower_cluster_kernel).  mode 0 forces the per-layer launches, 1 the tower
+ * where it is eligible, -1 returns to the default (on; OZ_TOWER=0 in the environment turns it off).  Both paths issue the
+ * same MMAs in the same order: results are bit-identical.  Applies to forwards launched (or graphs captured) afterwards. */
+int oz_debug_set_tower(int mode);
+
 /* Test hook: weight gradient of one 3x3 "same" convolution layer (the training step's tcgen05 kernel, csrc/oz_wgrad.cu).
  * Host buffers: x NHWC bf16 [boards][8][8][cinp] (cinp = 32 or a multiple of 128), dz NHWC bf16 [boards][8][8][cout]
  * (cout a multiple of 128), boards a multiple of 16; G fp32 [cout][9][cinp] (tap = ky*3+kx) = sum over positions of

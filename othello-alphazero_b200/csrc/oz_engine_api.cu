@@ -753,6 +753,17 @@ int oz_resnet_forward(oz_resnet *n, const float *f, size_t cnt, float *p, float 
     return OZ_OK;
 }
 
+int oz_debug_set_tower(int mode) {
+    oz::set_tower_mode(mode);
+    return OZ_OK;
+}
+extern "C" int oz_debug_tower_timeline(long long *out) {   // temporary: [64][8] clock stamps of the last tower launch
+    if (!oz::tower_dbg_ptr()) return OZ_ERR_STATE;
+    cudaDeviceSynchronize();
+    cudaMemcpy(out, oz::tower_dbg_ptr(), 64 * 8 * sizeof(long long), cudaMemcpyDeviceToHost);
+    return OZ_OK;
+}
+
 int oz_debug_conv3x3(const uint16_t *in, int cin, const uint16_t *w, const float *bias, const uint16_t *skip, int relu,
                      uint16_t *out, int cout, size_t boards, double *device_ms) {
     const size_t pad = (boards + kBoardPad - 1) / kBoardPad * kBoardPad;

@@ -498,6 +498,323 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap map_act, const __grid_co
     }
 }
 
+// ------------------------------------------------------------------ cluster tower (launch-bound batches)
+// tower_cluster_kernel: EVERY convolution layer of a 128-channel forward over 32 boards in one launch of one 16-CTA
+// cluster -- the batch the reference's own callers produce (`MCTS.search` of one game, T x B = 32 leaves per network
+// call: train.py:415-416, player.py:251).  The per-layer path pays a kernel boundary per layer (about 10 us, of which
+// 2.4 us are MMAs); a software grid barrier through global memory is no cheaper (profiles/r02_tower_experiment.md).
+// Here the activations never leave the cluster's shared memory:
+//   * CTA (y, u) = cluster rank 2 y + u owns board row y of unit u (16 boards): its 128-row M tile is the pass of
+//     conv3x3_pair_kernel<1>, the pair (y, 0) / (y, 1) issues the same cta_group::2 MMAs in the same order (so the
+//     result equals the per-layer path bit for bit).
+//   * One activation buffer per CTA, 4 K blocks x (3 board rows x 9 x-slots) KB in the layout TMA would have written
+//     (SWIZZLE_64B, row = (y * 9 + x) * 16 + board): row 1 is the CTA's own board row, rows 0 / 2 the halo.  The epilogue
+//     writes a layer's bf16 output straight into row 1 of that layout; one warp then pushes the row, K block by K block,
+//     into the halo rows of the CTAs above and below with bulk shared-to-shared copies (cp.async.bulk, 8 KB each, async
+//     proxy end to end: no generic remote stores, no release fences).  The zero column x = 8, the guard slot and the rows
+//     outside the board are zeroed once and never written.
+//   * Layer hand-over is per K block and by mbarriers only, no grid or cluster barrier: `rows[kb]` counts the epilogue
+//     warps that wrote K block kb of the own row, `halo[kb]` the bytes the neighbours' copies deliver, `peer[kb]` (leader)
+//     one arrival from the other CTA of the pair once ITS rows[kb] and halo[kb] completed; the next layer's MMAs of K block
+//     kb start as soon as those three completed, while the later K blocks are still in flight.  `nbr_done` receives the
+//     tcgen05.commit of the neighbouring pairs' MMA threads (multicast to four CTAs): a row is only overwritten after the
+//     neighbours' MMAs that read its copies.  The accumulator is double-buffered in TMEM (layer parity).
+//   * The residual input of a block is the value the same epilogue thread produced two layers earlier: it stays in
+//     32 registers (bf16 pairs), no memory at all.
+//   * Weights: each CTA streams its 64-cout half of every (layer, K block) group of 9 tap tiles (36 KB) through a ring of
+//     three groups, running ahead into the next layer; a K block is ONE barrier wait, one burst of 18 MMAs and one commit
+//     (with a wait and a commit per tap the issue thread, not the tensor pipe, set the pace: 417 clocks per tap measured).
+//   * The last layer's epilogue applies the 1x1 head convolutions (as the per-layer path does) -- no activation is ever
+//     written to global memory.
+// Several clusters = several independent 32-board groups (blockIdx.x / 16).
+namespace tower {
+constexpr int kCluster = 16;
+constexpr int kBoxSlots = 3 * kBoxX;                                 // 27 slots: 3 board rows x 9
+constexpr int kBoxBytes = kBoxSlots * kSlotBytes;                    // 27 648 per K block
+constexpr int kRowCopyBytes = 8 * kSlotBytes;                        // x = 0..7 of one board row of one K block
+constexpr int kActBytes = kSlotBytes + 4 * kBoxBytes;                // guard + 4 K blocks = 111 616
+constexpr int kGroups = 3;                                           // weight ring: groups of 9 tap tiles
+constexpr int kGroupBytes = 9 * pair::kWTileBytes;                   // 36 864
+constexpr int kBarBytes = 512;
+constexpr int kHeadBytes = 3 * 128 * 4;
+constexpr int kBiasBytes = pair::kEpiWarps * 64 * 4;                 // one private 64-float slice per epilogue warp
+constexpr int kSmemBytes = 1024 + kActBytes + kGroups * kGroupBytes + kBarBytes + kHeadBytes + kBiasBytes;
+constexpr int kThreads = pair::kThreadsP;
+static_assert(kSmemBytes <= 232448, "tower shared memory");
+}  // namespace tower
+
+struct TowerParams {
+    const float *bias0;          // layer 0 bias [128]
+    const float *bias1;          // layer 1 bias; layer l >= 1 at bias1 + (l - 1) * bias_stride floats
+    size_t bias_stride;
+    const float *head_w;         // [3][128]
+    float *head_out;             // [boards][64][4], zeroed by the caller
+    int nlayers;                 // 1 + 2 * blocks
+    long long *dbg;              // timeline of cluster rank 8 (debug): [layer][8] clock64 stamps, or null
+    int dbg_flags;
+};
+
+__device__ __forceinline__ void tma_load_3d_pair(uint32_t dst, const CUtensorMap *map, uint32_t bar_cluster, int c0, int c1, int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(dst), "l"(map), "r"(bar_cluster), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void tc_commit_mask(uint32_t bar, uint16_t mask) {   // arrives on the same barrier offset in every CTA of `mask`
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(bar), "h"(mask) : "memory");
+}
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, const uint32_t *v) {
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]) : "memory");
+}
+// Shared memory of this CTA -> shared memory of another CTA of the cluster; the bytes complete on a barrier of the destination CTA.
+__device__ __forceinline__ void bulk_copy_to_cta(uint32_t dst_cluster, uint32_t src_cta, uint32_t bytes, uint32_t bar_cluster) {
+    asm volatile("cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst_cluster), "r"(src_cta), "r"(bytes), "r"(bar_cluster) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_local(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+
+__global__ void __launch_bounds__(tower::kThreads, 1)
+tower_cluster_kernel(const __grid_constant__ CUtensorMap map_x0, const __grid_constant__ CUtensorMap map_w0,
+                     const __grid_constant__ CUtensorMap map_wr, const TowerParams p) {
+    using namespace tower;
+    constexpr int kWTileBytes = pair::kWTileBytes;
+    constexpr uint32_t kIdescP = pair::kIdescP;
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t *gen = smem_raw + (base - smem_u32(smem_raw));
+    const uint32_t act0 = base;                                            // guard slot, then the 4 K-block boxes
+    const uint32_t box1 = act0 + kSlotBytes;
+    const uint32_t w0 = act0 + kActBytes;
+    const uint32_t misc = w0 + kGroups * kGroupBytes;
+    const uint32_t bar_in_full = misc, bar_tmem_full = misc + 8, bar_nbr_done = misc + 16;
+    const uint32_t bar_rows = misc + 32, bar_halo = misc + 64, bar_peer = misc + 96;      // [4] each, per K block
+    const uint32_t bar_w_full = misc + 128, bar_w_empty = misc + 160;                     // [kGroups] each
+    uint32_t *tmem_ptr = (uint32_t *)(gen + (misc - base) + 192);
+    float *s_head = (float *)(gen + (misc - base) + kBarBytes);
+    float *s_bias = s_head + 3 * 128;                                      // [8 epilogue warps][64]
+
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const uint32_t lead_rank = rank & ~1u;
+    const bool leader = rank == lead_rank;
+    const int y = (int)(rank >> 1), u = (int)(rank & 1);
+    const int unit = 2 * (int)(blockIdx.x / kCluster) + u;
+    const int n_up = y > 0 ? 1 : 0, n_dn = y < 7 ? 1 : 0;
+    const int L = p.nlayers;
+
+    if (threadIdx.x == 0) {
+        mbar_init(bar_in_full, 1);
+        mbar_init(bar_tmem_full, 1);
+        mbar_init(bar_nbr_done, n_up + n_dn);
+        for (int i = 0; i < 4; ++i) { mbar_init(bar_rows + 8 * i, 4); mbar_init(bar_halo + 8 * i, 1); mbar_init(bar_peer + 8 * i, 1); }
+        for (int i = 0; i < kGroups; ++i) { mbar_init(bar_w_full + 8 * i, 1); mbar_init(bar_w_empty + 8 * i, 1); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_x0) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w0) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_wr) : "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr)), "r"(kTmemCols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+    for (int i = threadIdx.x; i < kActBytes / 16; i += kThreads)           // zeros: guard, x = 8 column, rows outside the board
+        *(uint4 *)(gen + i * 16) = make_uint4(0, 0, 0, 0);
+    for (int i = threadIdx.x; i < 3 * 128; i += kThreads) s_head[i] = p.head_w[i];
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    tc_fence_before();
+    cluster_sync_all();
+    tc_fence_after();
+    const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_ptr, 0);
+    griddep_launch_dependents();
+
+    if (warp == 0) {
+        // ===== weight TMA producer: this CTA's 64-cout half of every (layer, K block) group of 9 tap tiles, in MMA order =====
+        const uint32_t full0 = mapa_rank(bar_w_full, lead_rank);
+        uint32_t git = 0;
+        for (int l = 0; l < L; ++l) {
+            const int kblocks = l == 0 ? 1 : 4;
+            for (int kb = 0; kb < kblocks; ++kb, ++git) {
+                const uint32_t g = git % kGroups, ph = (git / kGroups) & 1;
+                mbar_wait_b(bar_w_empty + 8 * g, ph ^ 1);
+                if (elect_one()) {
+                    if (leader) mbar_expect_tx(bar_w_full + 8 * g, 2 * kGroupBytes);
+#pragma unroll
+                    for (int tap = 0; tap < 9; ++tap) {
+                        const uint32_t dst = w0 + g * kGroupBytes + tap * kWTileBytes;
+                        if (l == 0) tma_load_2d_pair(dst, &map_w0, full0 + 8 * g, 0, tap * 128 + u * 64);
+                        else tma_load_3d_pair(dst, &map_wr, full0 + 8 * g, kb * kKBlock, tap * 128 + u * 64, l - 1);
+                    }
+                }
+                __syncwarp();
+            }
+        }
+    } else if (warp == 2) {
+        // ===== network input, then the halo pushes: own board row -> row 2 of the CTA above, row 0 of the CTA below =====
+        griddep_wait();
+        if (elect_one()) {
+            if (leader) mbar_expect_tx(bar_in_full, 2 * kBoxBytes);
+            tma_load_4d_pair(box1, &map_x0, mapa_rank(bar_in_full, lead_rank), 0, unit * kBoardsPerUnit, 0, y - 1);
+        }
+        __syncwarp();
+        const uint32_t src_row = box1 + kBoxX * kSlotBytes;
+        const uint32_t up_row = n_up ? mapa_rank(box1 + 2 * kBoxX * kSlotBytes, rank - 2) : 0u;
+        const uint32_t dn_row = n_dn ? mapa_rank(box1, rank + 2) : 0u;
+        const uint32_t up_bar = n_up ? mapa_rank(bar_halo, rank - 2) : 0u, dn_bar = n_dn ? mapa_rank(bar_halo, rank + 2) : 0u;
+        for (int l = 0; l + 1 < L; ++l) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int kb = ((k & 1) << 1) | (k >> 1);                    // the order the epilogue finishes them: 0, 2, 1, 3
+                mbar_wait_b(bar_rows + 8 * kb, (uint32_t)l & 1);             // written, proxy-fenced; the neighbours' MMAs of layer l are done
+                if (elect_one()) {
+                    mbar_expect_tx(bar_halo + 8 * kb, (uint32_t)(n_up + n_dn) * kRowCopyBytes);   // what the neighbours send us
+                    const uint32_t off = (uint32_t)kb * kBoxBytes;
+                    if (n_up) bulk_copy_to_cta(up_row + off, src_row + off, kRowCopyBytes, up_bar + 8 * kb);
+                    if (n_dn) bulk_copy_to_cta(dn_row + off, src_row + off, kRowCopyBytes, dn_bar + 8 * kb);
+                }
+                __syncwarp();
+            }
+        }
+    } else if (warp == 1) {
+        if (leader) {
+            // ===== MMA issuer (pair leader) =====
+            const uint16_t pair_mask = (uint16_t)(3u << lead_rank);
+            const uint16_t nbr_mask = (uint16_t)((n_up ? (3u << (lead_rank - 2)) : 0u) | (n_dn ? (3u << (lead_rank + 2)) : 0u));
+            const bool skip_top = y == 0, skip_bot = y == 7;                 // rows -1 / 8 are zero padding: taps not issued
+            const int first_tap = skip_top ? 3 : 0;
+            uint32_t git = 0;
+            for (int l = 0; l < L; ++l) {
+                const uint32_t dcol = tmem_base + (uint32_t)(l & 1) * 128;
+                const int kblocks = l == 0 ? 1 : 4;
+                for (int kb = 0; kb < kblocks; ++kb, ++git) {
+                    if (l == 0) mbar_wait_b(bar_in_full, 0);
+                    else {
+                        const uint32_t ph = (uint32_t)(l - 1) & 1;
+                        mbar_wait_b(bar_rows + 8 * kb, ph);                  // own row, K block kb
+                        mbar_wait_b(bar_halo + 8 * kb, ph);                  // halo rows from above / below
+                        mbar_wait_cluster(bar_peer + 8 * kb, ph);            // the same two in the other CTA of the pair
+                    }
+                    const uint32_t g = git % kGroups;
+                    mbar_wait_b(bar_w_full + 8 * g, (git / kGroups) & 1);
+                    tc_fence_after();
+                    if (p.dbg && rank == 8 && lane == 0 && kb == 0) p.dbg[l * 8 + 0] = clock64();
+                    const uint32_t abox = box1 + (uint32_t)kb * kBoxBytes;
+                    if (elect_one()) {
+#pragma unroll
+                        for (int tap = 0; tap < 9; ++tap) {
+                            if ((tap < 3 && skip_top) || (tap >= 6 && skip_bot)) continue;
+                            const int dy = tap / 3 - 1, dx = tap % 3 - 1;
+                            const uint32_t wbase = w0 + g * kGroupBytes + tap * kWTileBytes;
+                            const uint32_t arow = abox + (uint32_t)(((1 + dy) * kBoxX + dx) * kSlotBytes);
+#pragma unroll
+                            for (int j = 0; j < kKBlock / 16; ++j)
+                                tc_mma_pair(dcol, umma_desc_sw64(arow + j * 32), umma_desc_sw64(wbase + j * 32),
+                                            kIdescP, (kb | j) != 0 || tap != first_tap);
+                        }
+                        tc_commit_mask(bar_w_empty + 8 * g, pair_mask);
+                    }
+                    __syncwarp();
+                }
+                if (elect_one()) {
+                    tc_commit_mask(bar_tmem_full, pair_mask);
+                    if (l + 1 < L && nbr_mask) tc_commit_mask(bar_nbr_done, nbr_mask);   // the neighbours may overwrite our halo rows
+                }
+                __syncwarp();
+                if (p.dbg && rank == 8 && lane == 0) p.dbg[l * 8 + 1] = clock64();
+            }
+        } else {
+            // ===== relay (the pair's other CTA): tell the leader when K block kb of OUR buffer is complete =====
+            const uint32_t peer0 = mapa_rank(bar_peer, lead_rank);
+            for (int l = 0; l + 1 < L; ++l)
+                for (int kb = 0; kb < 4; ++kb) {
+                    mbar_wait_b(bar_rows + 8 * kb, (uint32_t)l & 1);
+                    mbar_wait_b(bar_halo + 8 * kb, (uint32_t)l & 1);
+                    if (lane == 0) mbar_arrive_cluster(peer0 + 8 * kb);
+                    __syncwarp();
+                }
+        }
+    } else if (warp >= 3) {
+        // ===== epilogue warps 3..10: TMEM lane quarter (warp % 4) x column half =====
+        const int quad = warp & 3, half = (warp - 3) >> 2;
+        const int row = quad * 32 + lane, x = row >> 4, bl = row & 15;        // row in tile = x * 16 + board
+        const uint32_t sw = (uint32_t)(bl >> 1) & 3u;                         // SWIZZLE_64B: 16-byte chunk ^= address bits 7..8
+        const uint32_t row_addr = box1 + (uint32_t)((kBoxX + x) * kSlotBytes + bl * kRowBytes);   // own board row = row 1 of a box
+        const size_t board = (size_t)unit * kBoardsPerUnit + bl;
+        float *bias_w = s_bias + (warp - 3) * 64;                             // this warp's 64 bias values of the current layer
+        uint32_t keep[32];                                                    // block input of this thread's 64 channels (bf16 pairs)
+#pragma unroll
+        for (int i = 0; i < 32; ++i) keep[i] = 0u;
+        griddep_wait();
+        for (int l = 0; l < L; ++l) {
+            const bool last = l + 1 == L;
+            const bool residual = l >= 2 && (l & 1) == 0;                     // second convolution of a block (neural_net.py:57-64)
+            if (lane < 16) {
+                const float *bsrc = (l == 0 ? p.bias0 : p.bias1 + (size_t)(l - 1) * p.bias_stride) + half * 64 + lane * 4;
+                *(float4 *)(bias_w + lane * 4) = __ldg((const float4 *)bsrc);
+            }
+            __syncwarp();
+            mbar_wait_b(bar_tmem_full, (uint32_t)l & 1);
+            const bool stamp = p.dbg && rank == 8 && warp == 3 && lane == 0;
+            if (stamp) p.dbg[l * 8 + 2] = clock64();
+            tc_fence_after();
+            float h0 = 0.f, h1 = 0.f, h2 = 0.f;
+#pragma unroll
+            for (int ch = 0; ch < 2; ++ch) {
+                uint32_t v[32];
+                tc_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(l & 1) * 128 + half * 64 + ch * 32, v);
+                tc_wait_ld();
+                const float *bs = bias_w + ch * 32;
+                uint32_t ow[16];
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    float a = __uint_as_float(v[2 * i]) + bs[2 * i];
+                    float b = __uint_as_float(v[2 * i + 1]) + bs[2 * i + 1];
+                    if (residual) {
+                        const __nv_bfloat162 s2 = *(const __nv_bfloat162 *)&keep[ch * 16 + i];
+                        a += __bfloat162float(s2.x);
+                        b += __bfloat162float(s2.y);
+                    }
+                    a = fmaxf(a, 0.f); b = fmaxf(b, 0.f);
+                    if (last) {
+                        const int c = half * 64 + ch * 32 + 2 * i;
+                        const float2 w0h = *(const float2 *)(s_head + c), w1h = *(const float2 *)(s_head + 128 + c), w2h = *(const float2 *)(s_head + 256 + c);
+                        h0 += a * w0h.x + b * w0h.y; h1 += a * w1h.x + b * w1h.y; h2 += a * w2h.x + b * w2h.y;
+                    }
+                    const __nv_bfloat162 o2 = __floats2bfloat162_rn(a, b);
+                    ow[i] = *(const uint32_t *)&o2;
+                    if ((l & 1) == 0) keep[ch * 16 + i] = ow[i];             // a block's output is the next block's residual input
+                }
+                if (!last) {
+                    // The row we overwrite is the source of the previous layer's pushes and what the neighbours' MMAs of THIS
+                    // layer read as halo (through their copies): both are over once the neighbours' layer-l MMAs committed.
+                    if (ch == 0) mbar_wait_b(bar_nbr_done, (uint32_t)l & 1);
+                    if (stamp && ch == 0) p.dbg[l * 8 + 3] = clock64();
+                    const int kb = half * 2 + ch;
+                    const uint32_t dst = row_addr + (uint32_t)kb * kBoxBytes;
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) st_shared_v4(dst + (((uint32_t)q ^ sw) * 16u), &ow[4 * q]);
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic stores -> bulk copy / tensor-core reads
+                    if (ch == 1) tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive_local(bar_rows + 8 * kb);
+                    if (stamp) p.dbg[l * 8 + 4 + ch] = clock64();
+                }
+            }
+            if (last) {
+                float *hp = p.head_out + ((board * 8 + y) * 8 + x) * 4;      // two column halves add into zeroed memory
+                atomicAdd(hp, h0); atomicAdd(hp + 1, h1); atomicAdd(hp + 2, h2);
+            }
+        }
+    }
+    tc_fence_before();
+    cluster_sync_all();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
+    }
+}
+
 // ------------------------------------------------------------------ input conversion
 // float planes [n][planes][64] -> bf16 NHWC [n_pad][64][32] (channels >= planes are zero).
 __global__ void planes_to_nhwc32_kernel(const float *__restrict__ f, int planes, size_t n, size_t n_pad, __nv_bfloat16 *__restrict__ out) {
@@ -767,6 +1084,90 @@ static int make_w_map(CUtensorMap *m, void *ptr, int cin, int cout, int box_rows
     return OZ_OK;
 }
 
+// Residual-layer weights of a 128-channel blob as ONE 3-D map (cin, tap * cout, layer): the layers lie at a constant pitch
+// (weights + bias, both 256-byte aligned), so the cluster tower addresses a tile by (K block, tap row, layer).
+static int make_w_map_layers(CUtensorMap *m, void *ptr, int C, int layers, size_t layer_pitch_bytes) {
+    EncodeTiledFn enc;
+    OZ_TRY(get_encode(&enc));
+    cuuint64_t dims[3] = {(cuuint64_t)C, (cuuint64_t)9 * C, (cuuint64_t)layers};
+    cuuint64_t strides[2] = {(cuuint64_t)C * 2, (cuuint64_t)layer_pitch_bytes};
+    cuuint32_t box[3] = {kKBlock, 64, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, ptr, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(OZ_ERR_CUDA, "cuTensorMapEncodeTiled(weights, layers) failed: " + std::to_string((int)r));
+    return OZ_OK;
+}
+
+// OZ_TOWER=0 in the environment keeps launch-bound batches on the per-layer path (A/B runs).
+long long *g_tower_dbg = nullptr;
+long long *tower_dbg_ptr() { return g_tower_dbg; }
+static int g_tower_mode = -1;                                // -1: environment, 0 / 1: set by oz_debug_set_tower
+void set_tower_mode(int mode) { g_tower_mode = mode < 0 ? -1 : (mode ? 1 : 0); }
+static bool tower_enabled() {
+    if (g_tower_mode >= 0) return g_tower_mode == 1;
+    static int v = -1;
+    if (v < 0) { const char *e = getenv("OZ_TOWER"); v = (e && e[0] == '0') ? 0 : 1; }
+    return v == 1;
+}
+
+// How many 16-CTA clusters of tower_cluster_kernel the current device can hold at once (0: the tower is not used).
+static int tower_max_clusters() {
+    static int cached[64] = {};                              // per device ordinal: -1 unusable, > 0 clusters
+    int dev = 0;
+    cudaGetDevice(&dev);
+    int &c = cached[dev & 63];
+    if (c != 0) return c > 0 ? c : 0;
+    c = -1;
+    const int smem = tower::kSmemBytes;
+    if (cudaFuncSetAttribute(tower_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tower::kSmemBytes) != cudaSuccess ||
+        cudaFuncSetAttribute(tower_cluster_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(tower::kCluster); cfg.blockDim = dim3(tower::kThreads); cfg.dynamicSmemBytes = (size_t)smem;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = tower::kCluster; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    int n = 0;
+    if (cudaOccupancyMaxActiveClusters(&n, tower_cluster_kernel, &cfg) != cudaSuccess) { cudaGetLastError(); return 0; }
+    if (n > 0) c = n;
+    return n;
+}
+
+int ResNet::launch_tower(const Workspace &w, size_t pad, cudaStream_t stream) {
+    const int nconv = 1 + 2 * shape_.blocks;
+    TowerParams tp{};
+    tp.bias0 = (const float *)(d_blob_ + layout_.conv_b[0]);
+    tp.bias1 = (const float *)(d_blob_ + layout_.conv_b[1]);
+    tp.bias_stride = nconv > 2 ? (layout_.conv_b[2] - layout_.conv_b[1]) / sizeof(float) : 0;
+    tp.head_w = (const float *)(d_blob_ + layout_.head_w);
+    tp.head_out = w.head_pre;
+    tp.nlayers = nconv;
+    {
+        static long long *dbg = nullptr;
+        const char *e = getenv("OZ_TOWER_DBG");
+        if (e && !dbg) { cudaMalloc(&dbg, 64 * 8 * sizeof(long long)); cudaMemset(dbg, 0, 64 * 8 * sizeof(long long)); }
+        tp.dbg = dbg; tp.dbg_flags = e ? atoi(e) : 0;
+        g_tower_dbg = dbg;
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(pad / 32) * tower::kCluster); cfg.blockDim = dim3(tower::kThreads);
+    cfg.dynamicSmemBytes = (size_t)tower::kSmemBytes; cfg.stream = stream;
+    cudaLaunchAttribute attr[2];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = tower::kCluster; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = pdl_ ? 2 : 1;
+    OZ_CUDA(cudaLaunchKernelEx(&cfg, tower_cluster_kernel, w.map_x0_1, map_w_[0], map_wr_, tp));
+    count_launch();
+    OZ_CUDA(cudaGetLastError());
+    return OZ_OK;
+}
+
 // ma = activation map with a 4-row box (two board rows per pass), ma1 = the same tensor with a 3-row box (one row per pass)
 // or null.  One row per pass is used when that still leaves every CTA pair with at most one pass: the pass is half as
 // long and twice as many pairs work.  (Beyond that it only costs: a pair would run two half passes instead of one, and
@@ -855,6 +1256,12 @@ int ResNet::load(const oz_resnet_shape &shape, const void *blob, size_t bytes) {
         for (size_t i = 0; i < L.conv_w.size(); ++i)
             OZ_TRY(make_w_map(&map_w_[i], d_blob_ + L.conv_w[i], i == 0 ? 32 : shape.channels, shape.channels, 64));
         if (shape.channels != shape_.channels) free_workspaces();
+        has_wr_ = false;
+        if (shape.channels == 128 && shape.blocks >= 1 && L.conv_w.size() <= 64) {   // cluster tower (launch-bound batches)
+            const size_t pitch = L.conv_w.size() > 2 ? L.conv_w[2] - L.conv_w[1] : 9 * 128 * 128 * 2 + 512;
+            OZ_TRY(make_w_map_layers(&map_wr_, d_blob_ + L.conv_w[1], 128, (int)L.conv_w.size() - 1, pitch));
+            has_wr_ = true;
+        }
     }
     shape_ = shape; layout_ = L;
     OZ_CUDA(cudaMemcpy(d_blob_, blob, L.head_w, cudaMemcpyHostToDevice));
@@ -921,9 +1328,16 @@ int ResNet::forward(const float *d_features, size_t n, float *d_policy, float *d
     if (fuse_heads) OZ_CUDA(cudaMemsetAsync(d_head_pre_, 0, pad * 64 * 4 * sizeof(float), stream));   // up front: nothing sits between the conv launches
     // One pass counter per convolution launch of this forward (dynamic pass scheduler), zeroed up front for the same reason.
     const int nconv = 1 + 2 * shape_.blocks;
-    int *work = (dynamic_ && nconv <= kMaxConvLayers) ? w.work : nullptr;
+    const bool use_tower = fuse_heads && has_wr_ && tower_enabled() && (int)(pad / 32) <= tower_max_clusters();
+    int *work = (dynamic_ && nconv <= kMaxConvLayers && !use_tower) ? w.work : nullptr;
     if (work) OZ_CUDA(cudaMemsetAsync(work, 0, (size_t)nconv * sizeof(int), stream));
     if (conv_begin) cudaEventRecord(conv_begin, stream);
+    // Launch-bound batches of a 128-channel network: the whole tower in one cluster launch (tower_cluster_kernel).
+    if (use_tower) {
+        OZ_TRY(launch_tower(w, pad, stream));
+        if (conv_end) cudaEventRecord(conv_end, stream);
+        return launch_heads(w, n, fuse_heads, d_policy, d_value, stream);
+    }
     ConvParams cp{};
     cp.units = (int)(pad / kBoardsPerUnit); cp.cout_total = C; cp.relu = 1;
     // conv block (neural_net.py:9-29)

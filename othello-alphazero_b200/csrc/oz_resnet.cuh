@@ -36,6 +36,9 @@ constexpr int kBoardPad = 32;
 // Pass counters of the dynamic scheduler: one per convolution launch of a forward (1 + 2 * blocks <= this).
 constexpr int kMaxConvLayers = 128;
 bool conv_static_schedule();
+// Cluster tower for launch-bound batches: 1 on, 0 off (per-layer launches), -1 back to the environment (OZ_TOWER, default on).
+void set_tower_mode(int mode);
+long long *tower_dbg_ptr();   // temporary (timeline instrumentation)
 
 class ResNet {
   public:
@@ -81,10 +84,13 @@ class ResNet {
     };
     void free_workspaces();
     int launch_heads(const Workspace &w, size_t n, bool fuse_heads, float *d_policy, float *d_value, cudaStream_t stream);
+    int launch_tower(const Workspace &w, size_t pad, cudaStream_t stream);   // every conv layer in one cluster launch (<= 32 boards per cluster)
     std::vector<Workspace> ws_;
     bool pdl_ = true;
     bool dynamic_ = true;                                     // dynamic pass scheduler in the convolutions (OZ_CONV_STATIC=1: off)
     std::vector<CUtensorMap> map_w_;
+    CUtensorMap map_wr_{};                                    // residual-layer weights as one 3-D map (cluster tower)
+    bool has_wr_ = false;
 };
 
 // TMA map of an NHWC bf16 tensor [boards][8][8][C] viewed as (channel, board, x, y) with a box of (32 channels, 16 boards,
