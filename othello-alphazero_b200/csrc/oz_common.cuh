@@ -40,6 +40,21 @@ struct NvtxRange {
     NvtxRange &operator=(const NvtxRange &) = delete;
 };
 
+// Kernel launch with (pdl = true) or without the programmatic-dependent-launch attribute.  A kernel launched with it may
+// become resident as soon as every block of its predecessor in the stream has executed griddepcontrol.launch_dependents (or
+// exited); it must execute griddepcontrol.wait before it touches anything the predecessor -- or, transitively, anything
+// earlier -- wrote.  Both instructions are no-ops in a kernel launched without the attribute.
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_kernel(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, bool pdl, Args &&...args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
 }  // namespace oz
 
 #define OZ_CUDA(expr)                                                                     \

@@ -44,7 +44,8 @@ struct oz_engine {
     ResNet net;
     bool in_search = false;
     int round = 0;
-    cudaGraphExec_t round_graph = nullptr;   // one search round (select, encode, network, expand) for launch-bound batches
+    cudaGraphExec_t round_graph = nullptr;   // every round of a search (select, encode, network, expand) for launch-bound batches
+    int graph_rounds = 0;                    // rounds captured in round_graph
     unsigned long long graph_launches = 0;   // kernels inside round_graph
     bool warmed = false;
     int graph_mode = 1;                      // 0 never, 1 when the leaf batch is launch-bound, 2 always                     // an eager search has run with the current allocations
@@ -887,6 +888,7 @@ static int search_games(oz_engine *e, int g0, int g1) {
     const bool want_graph = whole && !e->profiling && e->warmed && (e->graph_mode == 2 || (e->graph_mode == 1 && boards <= 8192));
     const int groups = whole ? pipeline_groups(e) : 1;
     if (groups > 1 && !(want_graph && e->pipeline == 0)) return search_pipelined(e, groups);
+    if (want_graph && e->round_graph && e->graph_rounds != rounds) drop_graph(e);   // num_simulations / batch changed
     if (want_graph && !e->round_graph) {
         cudaGraph_t g = nullptr;
         const unsigned long long before = g_kernel_launches;
@@ -894,10 +896,15 @@ static int search_games(oz_engine *e, int g0, int g1) {
         void *gx0 = nullptr;
         if ((st = encode_target(e, boards, 0, &gx0))) { e->in_search = false; return st; }
         if (cudaStreamBeginCapture(e->stream, cudaStreamCaptureModeThreadLocal) != cudaSuccess) { e->in_search = false; return fail(OZ_ERR_CUDA, "cudaStreamBeginCapture failed"); }
-        launch_select(e->t, e->stream);
-        launch_encode(e->t, e->d_features, e->stream, false, gx0);
-        st = eval_slots(e, 0, boards, e->stream, 0, nullptr, nullptr, gx0 != nullptr);
-        if (!st) launch_expand(e->t, e->d_policy, e->d_value, e->stream);
+        // Every round of the search in ONE graph, the kernels chained by programmatic dependent launch: each becomes resident
+        // while its predecessor runs and waits (griddepcontrol.wait) before it touches the predecessor's results.
+        for (int r = 0; r < rounds && !st; ++r) {
+            launch_select(e->t, e->stream, false, true);
+            launch_encode(e->t, e->d_features, e->stream, false, gx0, true);
+            st = eval_slots(e, 0, boards, e->stream, 0, nullptr, nullptr, gx0 != nullptr);
+            if (!st) launch_expand(e->t, e->d_policy, e->d_value, e->stream, false, true);
+        }
+        e->graph_rounds = rounds;
         cudaError_t ce = cudaStreamEndCapture(e->stream, &g);
         e->graph_launches = g_kernel_launches - before;
         g_kernel_launches = before;                    // capturing launched nothing
@@ -913,12 +920,10 @@ static int search_games(oz_engine *e, int g0, int g1) {
         if (ce != cudaSuccess) { e->round_graph = nullptr; e->in_search = false; return fail(OZ_ERR_CUDA, std::string("cudaGraphInstantiate: ") + cudaGetErrorString(ce)); }
     }
     if (want_graph) {
-        for (int r = 0; r < rounds; ++r) {
-            const cudaError_t ge = cudaGraphLaunch(e->round_graph, e->stream);
-            if (ge != cudaSuccess) { e->in_search = false; return fail(OZ_ERR_CUDA, std::string("cudaGraphLaunch: ") + cudaGetErrorString(ge)); }
-            count_launch((int)e->graph_launches);
-            e->ctr.evaluations += boards;
-        }
+        const cudaError_t ge = cudaGraphLaunch(e->round_graph, e->stream);
+        if (ge != cudaSuccess) { e->in_search = false; return fail(OZ_ERR_CUDA, std::string("cudaGraphLaunch: ") + cudaGetErrorString(ge)); }
+        count_launch((int)e->graph_launches);
+        e->ctr.evaluations += boards * (uint64_t)rounds;
         e->round = rounds;
         return end_search(e);
     }

@@ -548,7 +548,7 @@ struct TowerParams {
     const float *bias1;          // layer 1 bias; layer l >= 1 at bias1 + (l - 1) * bias_stride floats
     size_t bias_stride;
     const float *head_w;         // [3][128]
-    float *head_out;             // [boards][64][4], zeroed by the caller
+    float *head_out;             // [boards][64][4] (every element of the cluster's 32 boards is stored: no zeroing needed)
     int nlayers;                 // 1 + 2 * blocks
     long long *dbg;              // timeline of cluster rank 8 (debug): [layer][8] clock64 stamps, or null
     int dbg_flags;
@@ -692,7 +692,9 @@ tower_cluster_kernel(const __grid_constant__ CUtensorMap map_x0, const __grid_co
                     else {
                         const uint32_t ph = (uint32_t)(l - 1) & 1;
                         mbar_wait_b(bar_rows + 8 * kb, ph);                  // own row, K block kb
+                        if (p.dbg && rank == 8 && lane == 0 && kb == 0) p.dbg[l * 8 + 6] = clock64();
                         mbar_wait_b(bar_halo + 8 * kb, ph);                  // halo rows from above / below
+                        if (p.dbg && rank == 8 && lane == 0 && kb == 0) p.dbg[l * 8 + 7] = clock64();
                         mbar_wait_cluster(bar_peer + 8 * kb, ph);            // the same two in the other CTA of the pair
                     }
                     const uint32_t g = git % kGroups;
@@ -730,7 +732,9 @@ tower_cluster_kernel(const __grid_constant__ CUtensorMap map_x0, const __grid_co
                 for (int kb = 0; kb < 4; ++kb) {
                     mbar_wait_b(bar_rows + 8 * kb, (uint32_t)l & 1);
                     mbar_wait_b(bar_halo + 8 * kb, (uint32_t)l & 1);
-                    if (lane == 0) mbar_arrive_cluster(peer0 + 8 * kb);
+                    // relaxed: what the arrival announces is already in this CTA's shared memory (the bulk copies' bytes completed on
+                    // `halo`, the epilogue's stores were proxy-fenced before `rows`); a release here costs about 600 clocks
+                    if (lane == 0) asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(peer0 + 8 * kb) : "memory");
                     __syncwarp();
                 }
         }
@@ -802,8 +806,16 @@ tower_cluster_kernel(const __grid_constant__ CUtensorMap map_x0, const __grid_co
                 }
             }
             if (last) {
-                float *hp = p.head_out + ((board * 8 + y) * 8 + x) * 4;      // two column halves add into zeroed memory
-                atomicAdd(hp, h0); atomicAdd(hp + 1, h1); atomicAdd(hp + 2, h2);
+                // The per-layer path adds the two column halves of a row into zeroed memory with atomics (a + b in either order:
+                // the same bits).  Here the upper half hands its sums over through shared memory (the activation buffer is free
+                // after the last MMA) and the lower half stores the total: no atomics, and head_out needs no zeroing.
+                float4 *xch = (float4 *)(gen + kSlotBytes) + row;
+                if (half == 1) *xch = make_float4(h0, h1, h2, 0.f);
+                asm volatile("bar.sync 1, 256;" ::: "memory");                // the eight epilogue warps
+                if (half == 0) {
+                    const float4 o = *xch;
+                    *(float4 *)(p.head_out + ((board * 8 + y) * 8 + x) * 4) = make_float4(h0 + o.x, h1 + o.y, h2 + o.z, 0.f);
+                }
             }
         }
     }
@@ -866,12 +878,18 @@ __global__ void __launch_bounds__(kHeadWarps * 32, 2) heads_kernel(const HeadPar
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
     // per warp and board: [128] policy features (channel-major), then [64] value features
     float *s_feat = sm + ((heads_cw_offset(Hv) + 3 * C + 2 * Hv + 3) & ~3) + warp * kHeadBoards * kFeatStride;
-    for (int i = t; i < 65 * 128; i += kHeadWarps * 32) s_pfc[(i >> 7) * kPfcStride + (i & 127)] = p.pfc_w[i];
-    for (int i = t; i < Hv * 64; i += kHeadWarps * 32) s_vfc1[(i >> 6) * kVfcStride + (i & 63)] = p.vfc1_w[i];
+    // Behind the cluster tower this kernel is launched with programmatic dependent launch: the weight staging below (constant
+    // data) runs while the tower still computes; the activations are touched after griddep_wait().
+    griddep_launch_dependents();
+    for (int i = t; i < 65 * 32; i += kHeadWarps * 32)          // 128-bit loads; both row strides are multiples of 4 floats
+        *(float4 *)(s_pfc + (i >> 5) * kPfcStride + (i & 31) * 4) = __ldg((const float4 *)p.pfc_w + i);
+    for (int i = t; i < Hv * 16; i += kHeadWarps * 32)
+        *(float4 *)(s_vfc1 + (i >> 4) * kVfcStride + (i & 15) * 4) = __ldg((const float4 *)p.vfc1_w + i);
     for (int i = t; i < 2 * C; i += kHeadWarps * 32) s_cw[i] = p.pconv_w[i];
     for (int i = t; i < C; i += kHeadWarps * 32) s_cw[2 * C + i] = p.vconv_w[i];
     for (int i = t; i < Hv; i += kHeadWarps * 32) { s_vb1[i] = p.vfc1_b[i]; s_vw2[i] = p.vfc2_w[i]; }
     __syncthreads();
+    griddep_wait();
     const float pb0 = p.pconv_b[0], pb1 = p.pconv_b[1], vb = p.vconv_b[0], v2b = p.vfc2_b[0];
     const float pfb0 = p.pfc_b[lane], pfb1 = p.pfc_b[lane + 32], pfb64 = p.pfc_b[64];
     const float4 *cw0 = (const float4 *)s_cw, *cw1 = (const float4 *)(s_cw + C), *cw2 = (const float4 *)(s_cw + 2 * C);
@@ -1325,10 +1343,10 @@ int ResNet::forward(const float *d_features, size_t n, float *d_policy, float *d
     // Last layer of a 128-channel tower (pair kernel): the epilogue also applies the three 1x1 head convolutions to its
     // fp32 values, so the final activation tensor is never written and the head kernel reads 1 KB instead of 16 KB per board.
     const bool fuse_heads = C == 128 && shape_.blocks > 0 && d_head_pre_ != nullptr;
-    if (fuse_heads) OZ_CUDA(cudaMemsetAsync(d_head_pre_, 0, pad * 64 * 4 * sizeof(float), stream));   // up front: nothing sits between the conv launches
-    // One pass counter per convolution launch of this forward (dynamic pass scheduler), zeroed up front for the same reason.
     const int nconv = 1 + 2 * shape_.blocks;
     const bool use_tower = fuse_heads && has_wr_ && tower_enabled() && (int)(pad / 32) <= tower_max_clusters();
+    if (fuse_heads && !use_tower) OZ_CUDA(cudaMemsetAsync(d_head_pre_, 0, pad * 64 * 4 * sizeof(float), stream));   // up front: nothing sits between the conv launches
+    // One pass counter per convolution launch of this forward (dynamic pass scheduler), zeroed up front for the same reason.
     int *work = (dynamic_ && nconv <= kMaxConvLayers && !use_tower) ? w.work : nullptr;
     if (work) OZ_CUDA(cudaMemsetAsync(work, 0, (size_t)nconv * sizeof(int), stream));
     if (conv_begin) cudaEventRecord(conv_begin, stream);
@@ -1336,7 +1354,7 @@ int ResNet::forward(const float *d_features, size_t n, float *d_policy, float *d
     if (use_tower) {
         OZ_TRY(launch_tower(w, pad, stream));
         if (conv_end) cudaEventRecord(conv_end, stream);
-        return launch_heads(w, n, fuse_heads, d_policy, d_value, stream);
+        return launch_heads(w, n, fuse_heads, d_policy, d_value, stream, pdl_ && conv_end == nullptr);
     }
     ConvParams cp{};
     cp.units = (int)(pad / kBoardsPerUnit); cp.cout_total = C; cp.relu = 1;
@@ -1359,7 +1377,7 @@ int ResNet::forward(const float *d_features, size_t n, float *d_policy, float *d
     return launch_heads(w, n, fuse_heads, d_policy, d_value, stream);
 }
 
-int ResNet::launch_heads(const Workspace &w, size_t n, bool fuse_heads, float *d_policy, float *d_value, cudaStream_t stream) {
+int ResNet::launch_heads(const Workspace &w, size_t n, bool fuse_heads, float *d_policy, float *d_value, cudaStream_t stream, bool pdl) {
     const int C = shape_.channels;
     HeadParams hp{};
     hp.act = (const __nv_bfloat16 *)w.a;
@@ -1377,7 +1395,7 @@ int ResNet::launch_heads(const Workspace &w, size_t n, bool fuse_heads, float *d
     if (hsm > hsm_set[hdev & 63]) { OZ_CUDA(cudaFuncSetAttribute(heads_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hsm)); hsm_set[hdev & 63] = hsm; }
     const size_t want = (n + kHeadWarps * kHeadBoards - 1) / (kHeadWarps * kHeadBoards);
     const unsigned grid = (unsigned)(want < 148 * 2 ? want : 148 * 2);
-    heads_kernel<<<grid, kHeadWarps * 32, hsm, stream>>>(hp);
+    OZ_CUDA(launch_kernel(heads_kernel, dim3(grid), dim3(kHeadWarps * 32), hsm, stream, pdl, hp));
     count_launch();
     OZ_CUDA(cudaGetLastError());
     return OZ_OK;

@@ -83,7 +83,7 @@ class ResNet {
         CUtensorMap map_x0_1, map_a_1, map_t_1;               // 3-row boxes: one board row per pass (small batches)
     };
     void free_workspaces();
-    int launch_heads(const Workspace &w, size_t n, bool fuse_heads, float *d_policy, float *d_value, cudaStream_t stream);
+    int launch_heads(const Workspace &w, size_t n, bool fuse_heads, float *d_policy, float *d_value, cudaStream_t stream, bool pdl = false);
     int launch_tower(const Workspace &w, size_t pad, cudaStream_t stream);   // every conv layer in one cluster launch (<= 32 boards per cluster)
     std::vector<Workspace> ws_;
     bool pdl_ = true;

@@ -11,6 +11,7 @@
 #include "oz_common.cuh"
 #include "oz_rules.cuh"
 #include "oz_tree.cuh"
+#include "oz_tc.cuh"
 
 namespace oz {
 
@@ -107,6 +108,8 @@ template <int WARPS>
 __global__ void __launch_bounds__(WARPS * 32) select_kernel(Tree t) {
     __shared__ float s_gamma[WARPS][32][33];                   // [selection of the chunk][root child]
     __shared__ float s_gsum[WARPS][32];
+    griddep_launch_dependents();                               // launch-bound searches chain their kernels (launch_kernel, oz_common.cuh)
+    griddep_wait();
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int B = t.inflight, round = *t.round;
     unsigned long long path_nodes = 0, children_read = 0;      // traffic counters (oz_counters)
@@ -304,6 +307,8 @@ __device__ __forceinline__ void write_planes_nhwc(uint16_t *x, int nh, const uin
 template <int WARPS>
 __global__ void __launch_bounds__(WARPS * 32) encode_kernel(Tree t, float *features, uint16_t *nhwc) {
     __shared__ uint64_t s1[WARPS][kMaxHist], s2[WARPS][kMaxHist];
+    griddep_launch_dependents();
+    griddep_wait();
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const size_t slots = (size_t)t.G * t.inflight;
     for (size_t slot = (size_t)blockIdx.x * WARPS + wib; slot < slots; slot += (size_t)gridDim.x * WARPS) {
@@ -342,9 +347,11 @@ __global__ void __launch_bounds__(WARPS * 32) encode_kernel(Tree t, float *featu
 template <int WARPS>
 __global__ void __launch_bounds__(WARPS * 32) expand_kernel(Tree t, const float *__restrict__ policy, const float *__restrict__ value) {
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    if (blockIdx.x == 0 && threadIdx.x == 0) *t.round += 1;     // select / encode of this round are done
     const int B = t.inflight;
     unsigned long long expanded = 0;
+    griddep_launch_dependents();
+    griddep_wait();                                             // nothing of the tree or the round counter is touched before this
+    if (blockIdx.x == 0 && threadIdx.x == 0) *t.round += 1;     // select / encode of this round are done
     for (int g = blockIdx.x * WARPS + wib; g < t.G; g += gridDim.x * WARPS) {
     if (t.g_status[g] & 1) continue;
     const size_t base = arena_base(t, g);
@@ -854,20 +861,20 @@ static void narrow_attributes() {
 }
 
 void launch_reset(const Tree &t, cudaStream_t s) { reset_kernel<<<blocks(t.G, 128), 128, 0, s>>>(t); count_launch(); }
-void launch_select(const Tree &t, cudaStream_t s, bool narrow) {
+void launch_select(const Tree &t, cudaStream_t s, bool narrow, bool pdl) {
     if (narrow) narrow_attributes();
     if (narrow) select_kernel<1><<<std::min(blocks(t.G, 1), kNarrowGrid), 32, 0, s>>>(t);
-    else select_kernel<4><<<blocks(t.G, 4), 128, 0, s>>>(t);
+    else launch_kernel(select_kernel<4>, dim3(blocks(t.G, 4)), dim3(128), 0, s, pdl, t);
     count_launch();
 }
-void launch_encode(const Tree &t, float *features, cudaStream_t s, bool narrow, void *nhwc) {
+void launch_encode(const Tree &t, float *features, cudaStream_t s, bool narrow, void *nhwc, bool pdl) {
     if (narrow) encode_kernel<2><<<std::min(blocks((size_t)t.G * t.inflight, 2), kNarrowGrid), 64, 0, s>>>(t, features, (uint16_t *)nhwc);
-    else encode_kernel<4><<<blocks((size_t)t.G * t.inflight, 4), 128, 0, s>>>(t, features, (uint16_t *)nhwc);
+    else launch_kernel(encode_kernel<4>, dim3(blocks((size_t)t.G * t.inflight, 4)), dim3(128), 0, s, pdl, t, features, (uint16_t *)nhwc);
     count_launch();
 }
-void launch_expand(const Tree &t, const float *policy, const float *value, cudaStream_t s, bool narrow) {
+void launch_expand(const Tree &t, const float *policy, const float *value, cudaStream_t s, bool narrow, bool pdl) {
     if (narrow) expand_kernel<1><<<std::min(blocks(t.G, 1), kNarrowGrid), 32, 0, s>>>(t, policy, value);
-    else expand_kernel<4><<<blocks(t.G, 4), 128, 0, s>>>(t, policy, value);
+    else launch_kernel(expand_kernel<4>, dim3(blocks(t.G, 4)), dim3(128), 0, s, pdl, t, policy, value);
     count_launch();
 }
 void launch_end_search(const Tree &t, cudaStream_t s) { end_search_kernel<<<blocks(t.G, 128), 128, 0, s>>>(t); count_launch(); }

@@ -68,10 +68,12 @@ struct PlyRecordDev {     // matches oz_ply_record
 void launch_reset(const Tree &t, cudaStream_t s);
 // select / encode read the round from *t.round; expand increments it.
 // narrow = small blocks (one game per block) that co-reside with a convolution CTA: the pipelined search.
-void launch_select(const Tree &t, cudaStream_t s, bool narrow = false);
+// pdl = launch with programmatic dependent launch (launch_kernel, oz_common.cuh): the launch-bound searches chain the
+// kernels of all their rounds this way, so a kernel's launch latency and set-up overlap its predecessor's execution.
+void launch_select(const Tree &t, cudaStream_t s, bool narrow = false, bool pdl = false);
 // nhwc != nullptr: write bf16 NHWC [slot][64][32] (the native network's input tensor) instead of the float planes.
-void launch_encode(const Tree &t, float *features, cudaStream_t s, bool narrow = false, void *nhwc = nullptr);
-void launch_expand(const Tree &t, const float *policy, const float *value, cudaStream_t s, bool narrow = false);
+void launch_encode(const Tree &t, float *features, cudaStream_t s, bool narrow = false, void *nhwc = nullptr, bool pdl = false);
+void launch_expand(const Tree &t, const float *policy, const float *value, cudaStream_t s, bool narrow = false, bool pdl = false);
 void launch_end_search(const Tree &t, cudaStream_t s);
 void launch_root_stats(const Tree &t, int32_t *n_children, int32_t *counts, float *q, int32_t *root_n, cudaStream_t s);
 void launch_choose(const Tree &t, int32_t *actions, cudaStream_t s);

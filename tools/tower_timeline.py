@@ -30,4 +30,5 @@ for l in range(19):
     r = buf[l] - t0
     nxt = (buf[l + 1, 0] - buf[l, 4]) if l < 18 else None
     print(l, r[:6].tolist(), "| issue", r[1] - r[0], "tmem_full-issue_done", r[2] - r[1], "ld+math+nbr", r[3] - r[2], "ch0 store+fence+arrive", r[4] - r[3],
-          "ch1", r[5] - r[4], "| next layer first MMA after ch0 arrive", nxt, "| layer period", (buf[l + 1, 0] - buf[l, 0]) if l < 18 else None)
+          "ch1", r[5] - r[4], "| next: rows0 seen after ch0 arrive", (buf[l + 1, 6] - buf[l, 4]) if l < 18 else None, "halo0 after rows0", (buf[l + 1, 7] - buf[l + 1, 6]) if l < 18 else None,
+          "peer0+w after halo0", (buf[l + 1, 0] - buf[l + 1, 7]) if l < 18 else None, "| next layer first MMA after ch0 arrive", nxt, "| layer period", (buf[l + 1, 0] - buf[l, 0]) if l < 18 else None)
