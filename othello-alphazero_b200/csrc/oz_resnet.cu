@@ -70,6 +70,7 @@ constexpr int kActBoxBytesP = kBoxX * kBoxYp * kSlotBytes;          // 36864
 constexpr int kActStagesP = 2;
 constexpr int kWTileBytes = 64 * kRowBytes;                         // 64 couts x 32 cin = 4096
 constexpr int kWSlots = 36;
+constexpr int kWGroups = kWSlots / 9;                                 // the weight ring is handed over in groups of nine tap tiles (one K block)
 constexpr int kEpiWarps = 8;
 constexpr int kThreadsP = (3 + kEpiWarps) * 32;
 constexpr int kMiscBytes = 3072;                                    // barriers + scheduler ring (1 KB), bias / head-conv weights (2 KB)
@@ -171,8 +172,7 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap map_act, const __grid_co
     const int ntiles = p.cout_total >> 7;
     const int num_pp = (p.units / 2) * kRowPasses * ntiles;  // pair-passes: (unit pair, row group, cout tile)
     const int cluster_id = blockIdx.x >> 1, num_clusters = gridDim.x >> 1;
-    const int wtiles = p.kblocks * 9;
-    const bool resident = ntiles == 1 && wtiles <= kWSlots;
+    const bool resident = ntiles == 1 && p.kblocks <= kWGroups;
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < kActStagesP; ++i) { mbar_init(bar_act_full + 8 * i, 1); mbar_init(bar_act_empty + 8 * i, 1); }
@@ -265,30 +265,32 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap map_act, const __grid_co
         }
     } else if (warp == 2) {
         // ===== weight TMA producer: this CTA's 64-cout half of every (K block, tap) tile =====
-        uint32_t wit = 0;
+        // The ring is handed over in GROUPS of nine tap tiles (one K block, 36 KB; four groups): one barrier per group.
+        uint32_t wgit = 0;
         const uint32_t full0 = mapa_rank(bar_w_full, 0);
         for (uint32_t si = 0;; ++si) {
             int pp;
             next_pass(si, pp);
             if (pp >= num_pp) break;
-            if (resident && wit >= (uint32_t)wtiles) { if (!dynamic) break; continue; }   // loaded once; keep reading the schedule
+            if (resident && wgit >= (uint32_t)p.kblocks) { if (!dynamic) break; continue; }   // loaded once; keep reading the schedule
             const int nt = pp % ntiles;
-            for (int kb = 0; kb < p.kblocks; ++kb)
-                for (int tap = 0; tap < 9; ++tap, ++wit) {
-                    const uint32_t s = wit % kWSlots, ph = (wit / kWSlots) & 1;
-                    mbar_wait_b(bar_w_empty + 8 * s, ph ^ 1);
-                    if (elect_one()) {
-                        if (leader) mbar_expect_tx(bar_w_full + 8 * s, 2 * kWTileBytes);
-                        tma_load_2d_pair(w0 + s * kWTileBytes, &map_w, full0 + 8 * s,
+            for (int kb = 0; kb < p.kblocks; ++kb, ++wgit) {
+                const uint32_t g = wgit % kWGroups, ph = (wgit / kWGroups) & 1;
+                mbar_wait_b(bar_w_empty + 8 * g, ph ^ 1);
+                if (elect_one()) {
+                    if (leader) mbar_expect_tx(bar_w_full + 8 * g, 2 * 9 * kWTileBytes);
+#pragma unroll
+                    for (int tap = 0; tap < 9; ++tap)
+                        tma_load_2d_pair(w0 + (g * 9 + tap) * kWTileBytes, &map_w, full0 + 8 * g,
                                          kb * kKBlock, tap * p.cout_total + nt * 128 + (int)rank * 64);
-                    }
-                    __syncwarp();
                 }
+                __syncwarp();
+            }
         }
     } else if (warp == 1) {
         // ===== MMA issuer: one elected thread of the leader CTA drives both tensor cores =====
         if (leader) {
-            uint32_t ait = 0, wit = 0;
+            uint32_t ait = 0, wgit = 0;
             for (uint32_t np = 0;; ++np) {
                 int pp;
                 next_pass(np, pp);
@@ -304,39 +306,18 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap map_act, const __grid_co
                 for (int kb = 0; kb < p.kblocks; ++kb, ++ait) {
                     const uint32_t as = ait % kActStagesP;
                     mbar_wait_b(bar_act_full + 8 * as, (ait / kActStagesP) & 1);
+                    // A K block's nine tap tiles are one ring group: ONE wait, one uninterrupted burst of MMAs, one commit.  (With
+                    // a wait and a commit per tap the issue thread set the pace of the streamed-weight towers: 417 clocks per tap
+                    // measured in the cluster tower against 256 clocks of tensor work, tensor pipe 66 % active at 256 channels.)
+                    const uint32_t g = resident ? (uint32_t)kb : wgit % kWGroups;
+                    if (!resident || np == 0) mbar_wait_b(bar_w_full + 8 * g, resident ? 0u : (wgit / kWGroups) & 1);
                     tc_fence_after();
                     const uint32_t abox = act0 + kSlotBytes + as * kActBoxBytesP;
-                    if (resident && np != 0) {
-                        // weights already in place: the whole K block is one uninterrupted issue burst
-                        if (elect_one()) {
+                    if (elect_one()) {
 #pragma unroll
-                            for (int tap = 0; tap < 9; ++tap) {
-                                const int dy = tap / 3 - 1, dx = tap % 3 - 1;
-                                const uint32_t wbase = w0 + (uint32_t)(kb * 9 + tap) * kWTileBytes;
-#pragma unroll
-                                for (int r = 0; r < kYPerPass; ++r) {
-                                    if ((r == 0 && tap < 3 && skip_top) || (r == kYPerPass - 1 && tap >= 6 && skip_bot)) continue;
-                                    const int first_tap = (r == 0 && skip_top) ? 3 : 0;
-                                    const uint32_t arow = abox + (uint32_t)(((r + 1 + dy) * kBoxX + dx) * kSlotBytes);
-#pragma unroll
-                                    for (int j = 0; j < kKBlock / 16; ++j)
-                                        tc_mma_pair(dcol + r * 128, umma_desc_sw64(arow + j * 32), umma_desc_sw64(wbase + j * 32),
-                                                    kIdescP, (kb | j) != 0 || tap != first_tap);
-                                }
-                            }
-                            tc_commit_pair(bar_act_empty + 8 * as);
-                        }
-                        __syncwarp();
-                        wit += 9;
-                        continue;
-                    }
-                    for (int tap = 0; tap < 9; ++tap, ++wit) {
-                        const uint32_t ws = wit % kWSlots;
-                        mbar_wait_b(bar_w_full + 8 * ws, (wit / kWSlots) & 1);
-                        tc_fence_after();
-                        const int dy = tap / 3 - 1, dx = tap % 3 - 1;
-                        const uint32_t wbase = w0 + ws * kWTileBytes;
-                        if (elect_one()) {
+                        for (int tap = 0; tap < 9; ++tap) {
+                            const int dy = tap / 3 - 1, dx = tap % 3 - 1;
+                            const uint32_t wbase = w0 + (g * 9 + (uint32_t)tap) * kWTileBytes;
 #pragma unroll
                             for (int r = 0; r < kYPerPass; ++r) {
                                 if ((r == 0 && tap < 3 && skip_top) || (r == kYPerPass - 1 && tap >= 6 && skip_bot)) continue;
@@ -347,12 +328,12 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap map_act, const __grid_co
                                     tc_mma_pair(dcol + r * 128, umma_desc_sw64(arow + j * 32), umma_desc_sw64(wbase + j * 32),
                                                 kIdescP, (kb | j) != 0 || tap != first_tap);
                             }
-                            if (!resident) tc_commit_pair(bar_w_empty + 8 * ws);
                         }
-                        __syncwarp();
+                        tc_commit_pair(bar_act_empty + 8 * as);
+                        if (!resident) tc_commit_pair(bar_w_empty + 8 * g);
                     }
-                    if (elect_one()) tc_commit_pair(bar_act_empty + 8 * as);
                     __syncwarp();
+                    ++wgit;
                 }
                 if (elect_one()) tc_commit_pair(bar_tmem_full + 8 * acc);
                 __syncwarp();
