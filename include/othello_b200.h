@@ -185,6 +185,12 @@ int oz_debug_conv3x3(const uint16_t *in, int cin, const uint16_t *w, const float
  * where it is eligible, -1 returns to the default (on; OZ_TOWER=0 in the environment turns it off).  Both paths issue the
  * same MMAs in the same order: results are bit-identical.  Applies to forwards launched (or graphs captured) afterwards. */
 int oz_debug_set_tower(int mode);
+/* Measurement hook for the same kernel.  *max_clusters (optional) = how many 16-CTA clusters the current device runs at once
+ * (0: the tower cannot be used here).  out (optional): [64][8] int64 clock64 stamps of cluster rank 8 during the last tower
+ * launch, per layer: first MMA issued, all MMAs issued, accumulator seen by the epilogue, neighbours' MMAs seen, first / second
+ * 32-channel half written, then (next layer's hand-over) own rows seen, halo rows seen.  Recorded only when OZ_TOWER_DBG is set
+ * in the environment; profiles/r02_tower_timeline.txt is such a record. */
+int oz_debug_tower_timeline(long long *out, int *max_clusters);
 
 /* Test hook: weight gradient of one 3x3 "same" convolution layer (the training step's tcgen05 kernel, csrc/oz_wgrad.cu).
  * Host buffers: x NHWC bf16 [boards][8][8][cinp] (cinp = 32 or a multiple of 128), dz NHWC bf16 [boards][8][8][cout]

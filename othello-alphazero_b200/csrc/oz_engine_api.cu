@@ -758,10 +758,12 @@ int oz_debug_set_tower(int mode) {
     oz::set_tower_mode(mode);
     return OZ_OK;
 }
-extern "C" int oz_debug_tower_timeline(long long *out) {   // temporary: [64][8] clock stamps of the last tower launch
-    if (!oz::tower_dbg_ptr()) return OZ_ERR_STATE;
-    cudaDeviceSynchronize();
-    cudaMemcpy(out, oz::tower_dbg_ptr(), 64 * 8 * sizeof(long long), cudaMemcpyDeviceToHost);
+int oz_debug_tower_timeline(long long *out, int *max_clusters) {
+    if (max_clusters) *max_clusters = oz::tower_max_clusters();
+    if (!out) return OZ_OK;
+    if (!oz::tower_dbg_ptr()) return fail(OZ_ERR_STATE, "no tower timeline: set OZ_TOWER_DBG=0 in the environment before the first forward");
+    OZ_CUDA(cudaDeviceSynchronize());
+    OZ_CUDA(cudaMemcpy(out, oz::tower_dbg_ptr(), 64 * 8 * sizeof(long long), cudaMemcpyDeviceToHost));
     return OZ_OK;
 }
 

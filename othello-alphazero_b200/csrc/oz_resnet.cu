@@ -1098,6 +1098,9 @@ static int make_w_map_layers(CUtensorMap *m, void *ptr, int C, int layers, size_
     return OZ_OK;
 }
 
+// Clusters are independent 32-board groups, so a forward may hold more of them than the device can run at once: two waves of
+// the tower (2 x 85 us at 128x10b) still beat the per-layer launches (230 us at 256 boards); beyond that they do not.
+constexpr int kTowerWaves = 2;
 // OZ_TOWER=0 in the environment keeps launch-bound batches on the per-layer path (A/B runs).
 long long *g_tower_dbg = nullptr;
 long long *tower_dbg_ptr() { return g_tower_dbg; }
@@ -1111,7 +1114,7 @@ static bool tower_enabled() {
 }
 
 // How many 16-CTA clusters of tower_cluster_kernel the current device can hold at once (0: the tower is not used).
-static int tower_max_clusters() {
+int tower_max_clusters() {
     static int cached[64] = {};                              // per device ordinal: -1 unusable, > 0 clusters
     int dev = 0;
     cudaGetDevice(&dev);
@@ -1325,7 +1328,7 @@ int ResNet::forward(const float *d_features, size_t n, float *d_policy, float *d
     // fp32 values, so the final activation tensor is never written and the head kernel reads 1 KB instead of 16 KB per board.
     const bool fuse_heads = C == 128 && shape_.blocks > 0 && d_head_pre_ != nullptr;
     const int nconv = 1 + 2 * shape_.blocks;
-    const bool use_tower = fuse_heads && has_wr_ && tower_enabled() && (int)(pad / 32) <= tower_max_clusters();
+    const bool use_tower = fuse_heads && has_wr_ && tower_enabled() && (int)(pad / 32) <= kTowerWaves * tower_max_clusters();
     if (fuse_heads && !use_tower) OZ_CUDA(cudaMemsetAsync(d_head_pre_, 0, pad * 64 * 4 * sizeof(float), stream));   // up front: nothing sits between the conv launches
     // One pass counter per convolution launch of this forward (dynamic pass scheduler), zeroed up front for the same reason.
     int *work = (dynamic_ && nconv <= kMaxConvLayers && !use_tower) ? w.work : nullptr;

@@ -38,7 +38,8 @@ constexpr int kMaxConvLayers = 128;
 bool conv_static_schedule();
 // Cluster tower for launch-bound batches: 1 on, 0 off (per-layer launches), -1 back to the environment (OZ_TOWER, default on).
 void set_tower_mode(int mode);
-long long *tower_dbg_ptr();   // temporary (timeline instrumentation)
+long long *tower_dbg_ptr();   // timeline of the last tower launch (OZ_TOWER_DBG set), or null
+int tower_max_clusters();      // 16-CTA clusters of the tower the current device runs at once (0: tower unusable)
 
 class ResNet {
   public:

@@ -111,6 +111,72 @@ def test_resnet_forward_vs_torch_fp32(blocks, channels, planes, hidden, n):
     assert dp <= 5e-3 and dv <= 2e-2, f"policy max abs diff {dp:.4f}, value max abs diff {dv:.4f}"
 
 
+@pytest.mark.parametrize("blocks,hidden", [(1, 32), (9, 128)])
+def test_cluster_tower_equals_per_layer_launches(blocks, hidden):
+    """Launch-bound batches of a 128-channel network run every convolution layer in ONE launch of 16-CTA clusters with the
+    activations in distributed shared memory (tower_cluster_kernel, csrc/oz_resnet.cu).  It issues the same MMAs in the same
+    order as the per-layer kernels, so policy and value must be BIT-identical -- for ragged board counts, for several
+    clusters, and for more clusters than the device runs at once -- and both stay within the evaluator's tolerance of the
+    fp32 PyTorch network (neural_net.py:138-172)."""
+    from othello_mcts import _lib, weights
+    lib = _lib.load()
+    resident = C.c_int()
+    _lib.check(lib.oz_debug_tower_timeline(None, C.byref(resident)))
+    assert resident.value >= 1, "the cluster tower cannot be launched on this device"
+    net = _net(blocks, 128, 17, hidden, seed=blocks)
+    shape, blob = weights.fold_alphazero_net(net)
+    h = C.c_void_p()
+    _lib.check(lib.oz_resnet_create(0, C.byref(h)))
+    try:
+        _lib.check(lib.oz_resnet_load(h, C.byref(shape), blob, len(blob)))
+        for n in (1, 16, 32, 33, 100, 32 * resident.value, 32 * resident.value + 5, 64 * resident.value):
+            x = _random_feature_planes(n, 17, 100 + n)
+            with torch.no_grad():
+                ref = net(x)
+            xs = x.numpy()
+            out = {}
+            for mode in (0, 1):
+                _lib.check(lib.oz_debug_set_tower(mode))
+                pol = np.zeros((n, 65), np.float32)
+                val = np.zeros(n, np.float32)
+                _lib.check(lib.oz_resnet_forward(h, xs.ctypes.data_as(C.c_void_p), n, pol.ctypes.data_as(C.c_void_p),
+                                                 val.ctypes.data_as(C.c_void_p)))
+                out[mode] = (pol, val)
+            assert np.array_equal(out[0][0], out[1][0]) and np.array_equal(out[0][1], out[1][1]), f"tower != per-layer path at {n} boards"
+            dp = np.abs(out[1][0] - ref["policy"].numpy()).max()
+            dv = np.abs(out[1][1] - ref["value"].numpy()).max()
+            assert dp <= 5e-3 and dv <= 2e-2, f"{n} boards: policy max abs diff {dp:.4f}, value max abs diff {dv:.4f}"
+    finally:
+        _lib.check(lib.oz_debug_set_tower(-1))
+        lib.oz_resnet_destroy(h)
+
+
+def test_single_game_search_same_tree_with_and_without_tower():
+    """The reference-shaped single-game MCTS.search (32 leaves per network call, graph replay of the whole search with the
+    kernels chained by programmatic dependent launch) must build the same tree on the cluster tower and on the per-layer
+    launches, ply after ply."""
+    from othello_mcts import MCTS, _lib
+    lib = _lib.load()
+    net = _net(2, 128, 9, 64).cuda()
+    kw = dict(history_size=4, torch_device="cuda", num_simulations=160, num_threads=2, batch_size=16, dirichlet_epsilon=0.25, seed=11)
+    try:
+        _lib.check(lib.oz_debug_set_tower(1))
+        a = MCTS(**kw)
+        _lib.check(lib.oz_debug_set_tower(0))
+        b = MCTS(**kw)
+        for ply in range(12):
+            _lib.check(lib.oz_debug_set_tower(1))
+            a.search(net)
+            _lib.check(lib.oz_debug_set_tower(0))
+            b.search(net)
+            assert a.visit_counts() == b.visit_counts() and a.mean_action_values() == b.mean_action_values(), ply
+            act = a.position().legal_actions()[int(np.argmax(a.visit_counts()))]
+            a.apply_action(act)
+            b.apply_action(act)
+    finally:
+        _lib.check(lib.oz_debug_set_tower(-1))
+
+
 def test_search_with_native_network():
     """MCTS.search(AlphaZeroNet) takes the fused native path (tree kernels + in-engine evaluator).  Driving
     the same search through the callable contract, with the callable running the SAME folded network via

@@ -26,6 +26,9 @@ def main():
     a = ap.parse_args()
     lib = _lib.load()
     ok = True
+    mc = C.c_int()
+    _lib.check(lib.oz_debug_tower_timeline(None, C.byref(mc)))
+    print(json.dumps({"tower_clusters_resident_at_once": mc.value}), flush=True)
     for blocks, hidden in ((1, 32), (9, 128), (19, 128)):
         torch.manual_seed(blocks)
         net = AlphaZeroNet(17, conv_channels=128, num_residual_blocks=blocks, value_head_hidden_channels=hidden).eval()
@@ -34,7 +37,7 @@ def main():
         h = C.c_void_p()
         _lib.check(lib.oz_resnet_create(0, C.byref(h)))
         _lib.check(lib.oz_resnet_load(h, C.byref(shape), blob, len(blob)))
-        for n in (1, 16, 32, 33, 64, 100, 256):
+        for n in (1, 16, 32, 33, 64, 100, 256, 512, 1024):
             g = torch.Generator().manual_seed(n)
             x = (torch.rand(n, 17, 8, 8, generator=g) < 0.3).to(torch.float32)
             with torch.no_grad():

@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""Temporary: per-layer clock stamps of tower_cluster_kernel (cluster rank 8).  OZ_TOWER_DBG=<flags> must be set."""
+"""Per-layer clock stamps of tower_cluster_kernel (cluster rank 8).  OZ_TOWER_DBG=<flags> must be set."""
 import ctypes as C, sys, os
 from pathlib import Path
 ROOT = Path(__file__).resolve().parents[1]
@@ -8,7 +8,6 @@ import numpy as np, torch
 from othello_mcts import _lib, weights
 from othello_mcts.neural_net import AlphaZeroNet
 lib = _lib.load()
-raw = C.CDLL(str(ROOT / "othello-alphazero_b200/othello_mcts/libothello_b200.so"))
 net = AlphaZeroNet(17, conv_channels=128, num_residual_blocks=9, value_head_hidden_channels=128).eval()
 shape, blob = weights.fold_alphazero_net(net)
 h = C.c_void_p(); _lib.check(lib.oz_resnet_create(0, C.byref(h))); _lib.check(lib.oz_resnet_load(h, C.byref(shape), blob, len(blob)))
@@ -23,7 +22,9 @@ for _ in range(200): lib.oz_resnet_forward_device(*args)
 e1.record(); torch.cuda.synchronize()
 print("flags", os.environ.get("OZ_TOWER_DBG"), "us per forward", 1e3 * e0.elapsed_time(e1) / 200)
 buf = np.zeros((64, 8), np.int64)
-raw.oz_debug_tower_timeline(buf.ctypes.data_as(C.c_void_p))
+mc = C.c_int()
+_lib.check(lib.oz_debug_tower_timeline(buf.ctypes.data_as(C.c_void_p), C.byref(mc)))
+print("clusters the device runs at once:", mc.value)
 t0 = buf[0, 0]
 print("layer: [first_mma, issue_done, tmem_full_seen, nbr_done_seen(after ch0 math), ch0_arrived, ch1_arrived] clocks since layer-0 start")
 for l in range(19):
