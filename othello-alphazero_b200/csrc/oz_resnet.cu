@@ -47,7 +47,16 @@ struct ConvParams {
     int *work;                   // dynamic pass scheduler: this launch's pass counter (zeroed by the caller), or null = static round-robin
     float *stats;                // STATS instantiation (training forward): [copies][2 * cout_total] sum / sum of squares of the fp32 outputs
     int stats_copies;            // ... accumulated into copy blockIdx.x % stats_copies
+#ifdef OZ_CONV_TIMELINE
+    unsigned long long *tl;      // measurement build only: [8] %globaltimer stamps of CTA 0 for this launch
+#endif
 };
+#ifdef OZ_CONV_TIMELINE
+__device__ __forceinline__ unsigned long long gtime() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+#define OZ_TL(k, cond) do { if (p.tl && blockIdx.x == 0 && (cond)) p.tl[k] = gtime(); } while (0)
+#else
+#define OZ_TL(k, cond) do { } while (0)
+#endif
 
 // ------------------------------------------------------------------ CTA-pair kernel (cta_group::2)
 // conv3x3_pair_kernel: the same implicit GEMM issued for a CTA PAIR (cluster of 2, one TPC):
@@ -152,6 +161,7 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap map_act, const __grid_co
     constexpr int kActBoxBytesP = kBoxX * (YPP + 2) * kSlotBytes;            // the box carries one halo row above and below
     static_assert(kActBoxBytesP <= pair::kActBoxBytesP && kActBoxBytesP % 1024 == 0, "box size");
     extern __shared__ uint8_t smem_raw[];
+    OZ_TL(0, threadIdx.x == 0);
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t *gen = smem_raw + (base - smem_u32(smem_raw));
     const uint32_t act0 = base;
@@ -199,6 +209,7 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap map_act, const __grid_co
     // Programmatic dependent launch: the next layer's CTAs may become resident as ours retire and run their own
     // set-up (barriers, TMEM, weight tiles) under our tail; they touch activations only after griddep_wait().
     griddep_launch_dependents();
+    OZ_TL(1, threadIdx.x == 0);
 
     // Pass scheduler.  Static (p.work == nullptr): cluster c takes passes c, c + clusters, ...  Dynamic: the passes of a
     // launch are handed out in arrival order from one global counter, so a cluster that is slowed down -- a tree kernel
@@ -245,6 +256,7 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap map_act, const __grid_co
         const uint32_t full0 = mapa_rank(bar_act_full, 0);
         const uint32_t sched_go = mapa_rank(bar_sched_empty, 1);   // the scheduler's "entry read" barriers live in the peer CTA
         griddep_wait();                                   // the previous layer's output is complete and visible
+        OZ_TL(2, lane == 0);
         for (uint32_t si = 0;; ++si) {
             int pp;
             next_pass(si, pp);
@@ -306,6 +318,7 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap map_act, const __grid_co
                 for (int kb = 0; kb < p.kblocks; ++kb, ++ait) {
                     const uint32_t as = ait % kActStagesP;
                     mbar_wait_b(bar_act_full + 8 * as, (ait / kActStagesP) & 1);
+                    OZ_TL(3, lane == 0 && np == 0 && kb == 0);
                     // A K block's nine tap tiles are one ring group: ONE wait, one uninterrupted burst of MMAs, one commit.  (With
                     // a wait and a commit per tap the issue thread set the pace of the streamed-weight towers: 417 clocks per tap
                     // measured in the cluster tower against 256 clocks of tensor work, tensor pipe 66 % active at 256 channels.)
@@ -337,6 +350,7 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap map_act, const __grid_co
                 }
                 if (elect_one()) tc_commit_pair(bar_tmem_full + 8 * acc);
                 __syncwarp();
+                OZ_TL(4, lane == 0);
             }
         } else if (dynamic) {
             // ===== pass scheduler (the non-leader CTA's otherwise idle warp) =====
@@ -394,6 +408,7 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap map_act, const __grid_co
                 }
             }
             mbar_wait_b(bar_tmem_full + 8 * acc, (np >> 1) & 1);
+            OZ_TL(5, threadIdx.x == 96);
             tc_fence_after();
 #pragma unroll
             for (int r = 0; r < kYPerPass; ++r) {
@@ -455,6 +470,7 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap map_act, const __grid_co
             }
             tc_fence_before();
             __syncwarp();
+            OZ_TL(6, threadIdx.x == 96);
             if (lane == 0) mbar_arrive_cluster(empty_remote + 8 * acc);   // accumulator stage back to the leader's MMA thread
         }
         if (STATS && p.stats) {                               // this warp's 4 lane quarters x 32 rows each, all passes of the CTA
@@ -477,6 +493,7 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap map_act, const __grid_co
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
     }
+    OZ_TL(7, threadIdx.x == 32);
 }
 
 // ------------------------------------------------------------------ cluster tower (launch-bound batches)
@@ -1103,6 +1120,10 @@ static int make_w_map_layers(CUtensorMap *m, void *ptr, int C, int layers, size_
 constexpr int kTowerWaves = 2;
 // OZ_TOWER=0 in the environment keeps launch-bound batches on the per-layer path (A/B runs).
 long long *g_tower_dbg = nullptr;
+#ifdef OZ_CONV_TIMELINE
+unsigned long long *g_conv_tl = nullptr;
+extern "C" int oz_debug_conv_timeline(unsigned long long *out) { cudaDeviceSynchronize(); return g_conv_tl ? (int)cudaMemcpy(out, g_conv_tl, 128 * 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost) : -1; }
+#endif
 long long *tower_dbg_ptr() { return g_tower_dbg; }
 static int g_tower_mode = -1;                                // -1: environment, 0 / 1: set by oz_debug_set_tower
 void set_tower_mode(int mode) { g_tower_mode = mode < 0 ? -1 : (mode ? 1 : 0); }
@@ -1342,18 +1363,30 @@ int ResNet::forward(const float *d_features, size_t n, float *d_policy, float *d
     }
     ConvParams cp{};
     cp.units = (int)(pad / kBoardsPerUnit); cp.cout_total = C; cp.relu = 1;
+#ifdef OZ_CONV_TIMELINE
+    static unsigned long long *tl = nullptr;
+    if (!tl) { cudaMalloc(&tl, 128 * 8 * sizeof(unsigned long long)); cudaMemset(tl, 0, 128 * 8 * sizeof(unsigned long long)); }
+    g_conv_tl = tl;
+    int tl_layer = 0;
+    #define OZ_TL_NEXT() (cp.tl = tl + 8 * (tl_layer++))
+#else
+    #define OZ_TL_NEXT() ((void)0)
+#endif
     // conv block (neural_net.py:9-29)
     cp.kblocks = 1; cp.skip = nullptr; cp.out = (__nv_bfloat16 *)d_a_; cp.bias = (const float *)(d_blob_ + layout_.conv_b[0]);
     cp.work = work;
+    OZ_TL_NEXT();
     OZ_TRY(launch_conv(map_x0_, map_x0_1, map_w_[0], cp, stream, pdl_));
     cp.kblocks = C / kKBlock;
     for (int b = 0; b < shape_.blocks; ++b) {   // residual tower (neural_net.py:32-65)
         cp.skip = nullptr; cp.out = (__nv_bfloat16 *)d_t_; cp.bias = (const float *)(d_blob_ + layout_.conv_b[1 + 2 * b]);
         cp.work = work ? work + 1 + 2 * b : nullptr;
+        OZ_TL_NEXT();
         OZ_TRY(launch_conv(map_a_, map_a_1, map_w_[1 + 2 * b], cp, stream, pdl_));
         cp.skip = (const __nv_bfloat16 *)d_a_; cp.out = (__nv_bfloat16 *)d_a_; cp.bias = (const float *)(d_blob_ + layout_.conv_b[2 + 2 * b]);
         cp.work = work ? work + 2 + 2 * b : nullptr;
         if (fuse_heads && b == shape_.blocks - 1) { cp.out = nullptr; cp.head_w = (const float *)(d_blob_ + layout_.head_w); cp.head_out = d_head_pre_; }
+        OZ_TL_NEXT();
         OZ_TRY(launch_conv(map_t_, map_t_1, map_w_[2 + 2 * b], cp, stream, pdl_));
         cp.head_w = nullptr; cp.head_out = nullptr;
     }
