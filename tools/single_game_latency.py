@@ -41,7 +41,7 @@ def main():
     sims_per_search = -(-a.sims // inflight) * inflight
     for _ in range(3):                                   # warm-up: weights upload, eager search, graph capture
         m.search(net)
-    times = []
+    times, applies = [], []
     for _ in range(a.searches):
         if m.position().is_terminal():
             m.reset_position()
@@ -50,11 +50,17 @@ def main():
         m.search(net)                                    # blocking, as in the reference
         times.append(time.perf_counter() - t0)
         counts = m.visit_counts()
-        m.apply_action(m.position().legal_actions()[int(np.argmax(counts))])
+        act = m.position().legal_actions()[int(np.argmax(counts))]
+        torch.cuda.synchronize()
+        t1 = time.perf_counter()
+        m.apply_action(act)                              # re-root (mcts.cpp:114-165), blocking
+        torch.cuda.synchronize()
+        applies.append(time.perf_counter() - t1)
     ms = 1e3 * float(np.median(times))
     print(json.dumps({"network": f"{a.channels}x{a.blocks + 1}b", "sims_per_search": sims_per_search, "leaves_per_network_call": inflight,
                       "graphs": a.graphs, "ms_per_search_median": ms, "ms_per_search_min": 1e3 * min(times), "ms_per_search_max": 1e3 * max(times),
-                      "sims_per_s": sims_per_search / (ms * 1e-3), "ms_per_round": ms / (sims_per_search / inflight)}))
+                      "sims_per_s": sims_per_search / (ms * 1e-3), "ms_per_round": ms / (sims_per_search / inflight),
+                      "ms_per_apply_action_median": 1e3 * float(np.median(applies))}))
 
 
 if __name__ == "__main__":
