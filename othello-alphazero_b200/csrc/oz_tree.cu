@@ -550,107 +550,17 @@ __global__ void record_kernel(Tree t, const int32_t *actions, PlyRecordDev *reco
 // The chosen child's subtree is copied breadth-first into the game's other arena (children stay
 // contiguous and ordered); everything else is dropped by switching arenas.  The old root joins
 // the retired-ancestor ring that feeds the history planes.
-__global__ void __launch_bounds__(128) apply_kernel(Tree t, const int32_t *__restrict__ actions, int32_t *unfinished) {
-    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    const int g = blockIdx.x * 4 + wib;
-    if (g >= t.G) return;
-    const int action = actions[g];
-    if (action < 0 || (t.g_status[g] & 1)) {
-        if (lane == 0 && !(t.g_status[g] & 1)) { atomicAdd(unfinished, 1); atomicMax(unfinished + 1, t.g_count[g]); }
-        return;
-    }
-    const int which = t.g_which[g];
-    const size_t src = ((size_t)g * 2 + which) * t.cap, dst = ((size_t)g * 2 + (which ^ 1)) * t.cap;
-    const int root = t.g_root[g];
-    const int rm = t.n_meta[src + root];
-    const int player = rm & 3, nch = rm >> 8;
-    const uint64_t rp1 = t.n_p1[src + root], rp2 = t.n_p2[src + root];
-    __syncwarp();
-    if (lane == 0) {                                   // retire the old root into the history ring
-        const size_t h = (size_t)g * kMaxHist;
-        int hn = t.h_n[g];
-        for (int k = (hn < kMaxHist ? hn : kMaxHist - 1); k > 0; --k) { t.h_p1[h + k] = t.h_p1[h + k - 1]; t.h_p2[h + k] = t.h_p2[h + k - 1]; t.h_player[h + k] = t.h_player[h + k - 1]; }
-        t.h_p1[h] = rp1; t.h_p2[h] = rp2; t.h_player[h] = player;
-        t.h_n[g] = hn < kMaxHist ? hn + 1 : kMaxHist;
-    }
-    int new_count = 1;
-    int new_player;
-    uint64_t np1, np2;
-    if (nch == 0) {                                    // unexpanded root: fresh childless node (:140-148)
-        Position s; s.player = player; s.p1 = rp1; s.p2 = rp2;
-        const uint64_t me = player == 1 ? rp1 : rp2, opp = player == 1 ? rp2 : rp1;
-        s.legal = legal_moves(me, opp); s.next_legal = s.legal ? 0 : legal_moves(opp, me);
-        const Position c = apply_action(s, action);
-        np1 = c.p1; np2 = c.p2; new_player = c.player;
-        if (lane == 0) {
-            t.n_p1[dst] = np1; t.n_p2[dst] = np2; t.n_meta[dst] = new_player; t.n_parent[dst] = -1; t.n_child[dst] = -1;
-            t.n_N[dst] = 0; t.n_W[dst] = 0.f; t.n_Q[dst] = 0.f; t.n_P[dst] = 1.f;
-        }
-    } else {
-        int idx = 0;
-        if (action != 0 && nch > 1) {                  // rank of the action among the legal moves (:150-157)
-            const uint64_t me = player == 1 ? rp1 : rp2, opp = player == 1 ? rp2 : rp1;
-            idx = __popcll(legal_moves(me, opp) & (~0ull << (64 - action)));
-        }
-        const size_t c = src + t.n_child[src + root] + idx;
-        np1 = t.n_p1[c]; np2 = t.n_p2[c]; new_player = t.n_meta[c] & 3;
-        if (lane == 0) {
-            t.n_p1[dst] = np1; t.n_p2[dst] = np2; t.n_meta[dst] = t.n_meta[c]; t.n_parent[dst] = -1;
-            t.n_child[dst] = t.n_child[c];             // still an id in the OLD arena until processed below
-            t.n_N[dst] = t.n_N[c]; t.n_W[dst] = t.n_W[c]; t.n_Q[dst] = t.n_Q[c]; t.n_P[dst] = t.n_P[c];
-        }
-        __syncwarp();
-        int head = 0;
-        while (head < new_count) {
-            const int batch = min(32, new_count - head);
-            const bool valid = lane < batch;
-            const int my = head + lane;
-            const int fc_old = valid ? t.n_child[dst + my] : -1;
-            const int nc = (valid && fc_old >= 0) ? (t.n_meta[dst + my] >> 8) : 0;
-            int incl = nc;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
-            const int total = __shfl_sync(0xffffffffu, incl, 31);
-            const int off = incl - nc;
-            if (nc > 0) t.n_child[dst + my] = new_count + off;
-            // All children of the batch as one flat range, 32 at a time with every lane busy: child k of the batch belongs
-            // to the first parent whose inclusive prefix exceeds k (a 5-step search over the lanes' prefixes) and lands at
-            // new_count + k -- the same order as copying parent by parent, a quarter of the dependent round trips.
-            for (int k0 = 0; k0 < total; k0 += 32) {
-                const int k = k0 + lane;
-                int s = 0;
-#pragma unroll
-                for (int step = 16; step; step >>= 1) {
-                    const int cand = s + step;
-                    const int v = __shfl_sync(0xffffffffu, incl, (cand - 1) & 31);
-                    if (cand <= 31 && v <= k) s = cand;
-                }
-                const int f = __shfl_sync(0xffffffffu, fc_old, s), o2 = __shfl_sync(0xffffffffu, off, s);
-                if (k < total) {
-                    const size_t a = src + f + (k - o2), d = dst + new_count + k;
-                    t.n_p1[d] = t.n_p1[a]; t.n_p2[d] = t.n_p2[a]; t.n_meta[d] = t.n_meta[a]; t.n_parent[d] = head + s;
-                    t.n_child[d] = t.n_child[a]; t.n_N[d] = t.n_N[a]; t.n_W[d] = t.n_W[a]; t.n_Q[d] = t.n_Q[a]; t.n_P[d] = t.n_P[a];
-                }
-            }
-            new_count += total;
-            head += batch;
-            __syncwarp();
-        }
-    }
-    if (lane == 0) {
-        t.g_which[g] = which ^ 1; t.g_root[g] = 0; t.g_count[g] = new_count; t.g_ply[g] += 1;
-        t.r_p1[g] = np1; t.r_p2[g] = np2; t.r_player[g] = new_player;
-        if (new_player == 0) t.g_status[g] |= 1; else atomicAdd(unfinished, 1);
-        atomicMax(unfinished + 1, new_count);         // largest tree after the re-root (arena sizing on the host)
-    }
-}
-
-// The same re-root for a handful of games (the reference's one-game-at-a-time callers): one BLOCK of 32 warps per game.
-// A breadth-first batch is up to 1 024 parents; the warps' child totals are scanned through shared memory, so the children
-// land in exactly the order the one-warp version gives them (parent order), 32 times as many copies in flight: the re-root
-// of a single game's 5-20 k node subtree drops from 0.4-0.7 ms to a few tens of microseconds.
+// One BLOCK of WARPS warps per game.  A breadth-first batch is up to 32 * WARPS parents: every thread owns a parent, the
+// warps' child totals are scanned through shared memory, and each warp copies the children of its 32 parents as one flat
+// range with every lane busy (child k belongs to the first parent whose inclusive prefix exceeds k: a 5-step search over
+// the lanes' prefixes) -- so the children land in parent order, contiguous per parent, exactly as a sequential copy would
+// place them, with 32 * WARPS copies in flight.  Round 1 copied with one warp per game (0.4-0.7 ms for a single game's
+// 5-20 k node subtree, 0.5 ms per ply for 1 000 games); 32 warps per game for a handful of games (the reference's
+// one-game-at-a-time callers: apply_action 0.12 ms end to end), 8 warps per game otherwise (1 000 games: the rest of a ply
+// 1.7 -> 0.9 ms).
 constexpr int kWideApplyGames = 64;
-__global__ void __launch_bounds__(1024) apply_wide_kernel(Tree t, const int32_t *__restrict__ actions, int32_t *unfinished) {
+template <int WARPS>
+__global__ void __launch_bounds__(WARPS * 32) apply_kernel(Tree t, const int32_t *__restrict__ actions, int32_t *unfinished) {
     __shared__ int s_wtot[32], s_woff[32], s_total;
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int g = blockIdx.x;
@@ -702,7 +612,7 @@ __global__ void __launch_bounds__(1024) apply_wide_kernel(Tree t, const int32_t 
         __syncthreads();
         int head = 0;
         while (head < new_count) {
-            const int batch = min(1024, new_count - head);
+            const int batch = min(WARPS * 32, new_count - head);
             const bool valid = (int)threadIdx.x < batch;
             const int my = head + (int)threadIdx.x;
             const int fc_old = valid ? t.n_child[dst + my] : -1;
@@ -714,7 +624,7 @@ __global__ void __launch_bounds__(1024) apply_wide_kernel(Tree t, const int32_t 
             if (lane == 31) s_wtot[wib] = wtotal;
             __syncthreads();
             if (wib == 0) {                            // exclusive scan of the 32 warp totals
-                const int v = s_wtot[lane];
+                const int v = lane < WARPS ? s_wtot[lane] : 0;
                 int inc = v;
 #pragma unroll
                 for (int o = 1; o < 32; o <<= 1) { const int u = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += u; }
@@ -725,7 +635,7 @@ __global__ void __launch_bounds__(1024) apply_wide_kernel(Tree t, const int32_t 
             const int wbase = new_count + s_woff[wib], total = s_total;
             const int off = incl - nc;
             if (nc > 0) t.n_child[dst + my] = wbase + off;
-            for (int k0 = 0; k0 < wtotal; k0 += 32) {  // this warp's children as one flat range (see apply_kernel)
+            for (int k0 = 0; k0 < wtotal; k0 += 32) {  // this warp's children as one flat range
                 const int k = k0 + lane;
                 int s = 0;
 #pragma unroll
@@ -1003,8 +913,8 @@ __global__ void max_count_kernel(Tree t, int32_t *out) {
 }
 void launch_max_count(const Tree &t, int32_t *out, cudaStream_t s) { max_count_kernel<<<blocks(t.G, 128), 128, 0, s>>>(t, out); count_launch(); }
 void launch_apply(const Tree &t, const int32_t *actions, int32_t *unfinished, cudaStream_t s) {
-    if (t.G <= kWideApplyGames) apply_wide_kernel<<<t.G, 1024, 0, s>>>(t, actions, unfinished);
-    else apply_kernel<<<blocks(t.G, 4), 128, 0, s>>>(t, actions, unfinished);
+    if (t.G <= kWideApplyGames) apply_kernel<32><<<t.G, 1024, 0, s>>>(t, actions, unfinished);
+    else apply_kernel<8><<<t.G, 256, 0, s>>>(t, actions, unfinished);
     count_launch();
 }
 void launch_self_play_data(const Tree &t, int game, float *features, float *policy, cudaStream_t s) {
