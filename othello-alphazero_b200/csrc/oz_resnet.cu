@@ -548,8 +548,7 @@ struct TowerParams {
     const float *head_w;         // [3][128]
     float *head_out;             // [boards][64][4] (every element of the cluster's 32 boards is stored: no zeroing needed)
     int nlayers;                 // 1 + 2 * blocks
-    long long *dbg;              // timeline of cluster rank 8 (debug): [layer][8] clock64 stamps, or null
-    int dbg_flags;
+    long long *dbg;              // timeline of cluster rank 8 (OZ_TOWER_DBG set): [layer][8] clock64 stamps, or null
 };
 
 __device__ __forceinline__ void tma_load_3d_pair(uint32_t dst, const CUtensorMap *map, uint32_t bar_cluster, int c0, int c1, int c2) {
@@ -1173,7 +1172,7 @@ int ResNet::launch_tower(const Workspace &w, size_t pad, cudaStream_t stream) {
         static long long *dbg = nullptr;
         const char *e = getenv("OZ_TOWER_DBG");
         if (e && !dbg) { cudaMalloc(&dbg, 64 * 8 * sizeof(long long)); cudaMemset(dbg, 0, 64 * 8 * sizeof(long long)); }
-        tp.dbg = dbg; tp.dbg_flags = e ? atoi(e) : 0;
+        tp.dbg = dbg;
         g_tower_dbg = dbg;
     }
     cudaLaunchConfig_t cfg = {};

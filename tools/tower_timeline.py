@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""Per-layer clock stamps of tower_cluster_kernel (cluster rank 8).  OZ_TOWER_DBG=<flags> must be set."""
+"""Per-layer clock stamps of tower_cluster_kernel (cluster rank 8).  OZ_TOWER_DBG must be set in the environment."""
 import ctypes as C, sys, os
 from pathlib import Path
 ROOT = Path(__file__).resolve().parents[1]
