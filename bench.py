@@ -605,7 +605,7 @@ def main():
     ap.add_argument("--blocks", type=int, default=9, help="residual blocks (config 5: 19)")
     ap.add_argument("--hidden", type=int, default=128, help="value head hidden units (config 5: 256)")
     ap.add_argument("--no-profiling", action="store_true", help="no per-phase CUDA events inside the searches (roofline fields stay empty)")
-    ap.add_argument("--pipeline", type=int, default=0, help="game groups of the pipelined search: 0 auto, 1 off, 2..4")
+    ap.add_argument("--pipeline", type=int, default=0, help="game groups of the pipelined search (branches of a graph-replayed search): 0 auto, 1 off, 2..8")
     ap.add_argument("--pipeline-pdl", type=int, default=1, help="keep programmatic dependent launch while pipelined")
     ap.add_argument("--cpu-steps", type=int, default=36, help="searches of the CPU baseline sample (about 10-15 s on 16 host cores)")
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -289,14 +289,18 @@ typedef struct {
 } oz_counters;
 int oz_engine_counters(oz_engine *e, oz_counters *out);
 int oz_engine_set_profiling(oz_engine *e, int on);
-/* CUDA-graph replay of the search rounds: 0 never, 1 (default) when the leaf batch is launch-bound (<= 8192 boards,
- * e.g. the single-game MCTS of the reference's play CLI), 2 always.  Results are identical either way. */
+/* CUDA-graph replay of a search (all its rounds in one graph, kernels chained by programmatic dependent launch): 0 never,
+ * 1 (default) when the leaf batch is launch-bound (<= 8192 boards, e.g. the single-game MCTS of the reference's play CLI),
+ * 2 always.  Results are identical either way. */
 int oz_engine_set_graphs(oz_engine *e, int mode);
 /* Pipelined search (new capability; the reference evaluates one 16-leaf batch at a time on one thread, mcts.h:220-256):
  * the games are split into `groups` contiguous groups that run select -> network -> expand on their own streams, so one
- * group's tree kernels run underneath another group's convolutions.  groups: 0 = automatic (currently off: on B200 the
- * convolutions lose more to the co-running tree kernels than the hidden tree time gives back), 1 = off, 2..4.  pdl != 0 keeps programmatic dependent launch between the conv layers while
- * pipelined.  Results are identical for every setting (every game's search is independent of the others). */
+ * group's tree kernels run underneath another group's convolutions.  groups: 0 = automatic, 1 = off, 2..8.  Automatic is
+ * off for the eager searches of large batches (on B200 the convolutions lose more to the co-running tree kernels than the
+ * hidden tree time gives back) and 8 groups for graph-replayed searches of 8 to 48 games of a 128-channel network, where the
+ * groups are parallel BRANCHES of the search's graph, each with its own cluster-tower launches (8 games of 128x10b: 8.6 ->
+ * 6.7 ms per ply).  pdl != 0 keeps programmatic dependent launch between the conv layers while pipelined eagerly.
+ * Results are identical for every setting (every game's search is independent of the others). */
 int oz_engine_set_pipeline(oz_engine *e, int groups, int pdl);
 /* Stream the engine launches on (a cudaStream_t), for callers that time with CUDA events. */
 void *oz_engine_stream(oz_engine *e);

@@ -24,7 +24,7 @@ struct oz_resnet {
     size_t cap = 0;
 };
 
-constexpr int kMaxGroups = 4;             // game groups of the pipelined search
+constexpr int kMaxGroups = 8;             // game groups of the pipelined search / branches of a graph-replayed search
 
 struct oz_engine {
     oz_config cfg{};
@@ -46,6 +46,7 @@ struct oz_engine {
     int round = 0;
     cudaGraphExec_t round_graph = nullptr;   // every round of a search (select, encode, network, expand) for launch-bound batches
     int graph_rounds = 0;                    // rounds captured in round_graph
+    int graph_branches = 1;                  // game groups captured as parallel branches of round_graph
     unsigned long long graph_launches = 0;   // kernels inside round_graph
     bool warmed = false;
     int graph_mode = 1;                      // 0 never, 1 when the leaf batch is launch-bound, 2 always                     // an eager search has run with the current allocations
@@ -889,24 +890,57 @@ static int search_games(oz_engine *e, int g0, int g1) {
     const size_t boards = (size_t)e->t.G * e->t.inflight;
     const bool want_graph = whole && !e->profiling && e->warmed && (e->graph_mode == 2 || (e->graph_mode == 1 && boards <= 8192));
     const int groups = whole ? pipeline_groups(e) : 1;
-    if (groups > 1 && !(want_graph && e->pipeline == 0)) return search_pipelined(e, groups);
-    if (want_graph && e->round_graph && e->graph_rounds != rounds) drop_graph(e);   // num_simulations / batch changed
+    if (groups > 1 && !want_graph) return search_pipelined(e, groups);
+    // Graph-replayed searches split the games into BRANCHES instead: game groups are independent for a whole search, so each
+    // group's rounds are a chain of their own (own stream while capturing, own network workspace, own round counter) and the
+    // branches run side by side -- one group's tree kernels and kernel boundaries under another group's MMAs.
+    // Automatic (pipeline = 0): on where it was measured to pay -- a network the cluster tower serves, more 32-board clusters
+    // than the device runs at once (7) and at most 48: one tower wave per branch instead of waves of one launch, or instead of
+    // the per-layer path (128x10b, 8 / 16 / 24 / 32 games: 8.6 -> 6.7, 10.4 -> 7.2, 12.1 -> 8.3, 12.9 -> 10.3 ms per ply;
+    // no change below 8 games, slower from 64 games; 256-channel networks: slower at every size).
+    int want_branches = e->pipeline > 1 ? e->pipeline : 1;
+    if (e->pipeline == 0 && e->cfg.evaluator == OZ_EVAL_RESNET && e->net.tower_capable()) {
+        const size_t clusters = (boards + 31) / 32;
+        if (clusters > 7 && clusters <= 48) want_branches = kMaxGroups;
+    }
+    const int branches = want_graph ? std::max(1, std::min({want_branches, kMaxGroups, e->t.G})) : 1;
+    if (want_graph && e->round_graph && (e->graph_rounds != rounds || e->graph_branches != branches)) drop_graph(e);   // num_simulations / batch / pipeline changed
     if (want_graph && !e->round_graph) {
         cudaGraph_t g = nullptr;
         const unsigned long long before = g_kernel_launches;
         const uint64_t evals_before = e->ctr.evaluations;
-        void *gx0 = nullptr;
-        if ((st = encode_target(e, boards, 0, &gx0))) { e->in_search = false; return st; }
+        void *gx0[kMaxGroups] = {};
+        int bg0[kMaxGroups + 1] = {};
+        for (int k = 0; k <= branches; ++k) bg0[k] = (int)((long)e->t.G * k / branches);
+        for (int k = 0; k < branches && !st; ++k) {      // everything that allocates happens before the capture
+            st = encode_target(e, (size_t)(bg0[k + 1] - bg0[k]) * e->t.inflight, k, &gx0[k]);
+            if (!st && branches > 1) {
+                if (!e->gstream[k] && cudaStreamCreateWithFlags(&e->gstream[k], cudaStreamNonBlocking) != cudaSuccess) st = fail(OZ_ERR_CUDA, "stream creation failed");
+                if (!e->ev_join[k]) { cudaEventCreateWithFlags(&e->ev_join[k], cudaEventDisableTiming); cudaEventCreateWithFlags(&e->ev_sel[k], cudaEventDisableTiming); cudaEventCreateWithFlags(&e->ev_net[k], cudaEventDisableTiming); }
+            }
+        }
+        if (!st && branches > 1 && !e->ev_fork) cudaEventCreate(&e->ev_fork);
+        if (st) { e->in_search = false; return st; }
         if (cudaStreamBeginCapture(e->stream, cudaStreamCaptureModeThreadLocal) != cudaSuccess) { e->in_search = false; return fail(OZ_ERR_CUDA, "cudaStreamBeginCapture failed"); }
         // Every round of the search in ONE graph, the kernels chained by programmatic dependent launch: each becomes resident
         // while its predecessor runs and waits (griddepcontrol.wait) before it touches the predecessor's results.
-        for (int r = 0; r < rounds && !st; ++r) {
-            launch_select(e->t, e->stream, false, true);
-            launch_encode(e->t, e->d_features, e->stream, false, gx0, true);
-            st = eval_slots(e, 0, boards, e->stream, 0, nullptr, nullptr, gx0 != nullptr);
-            if (!st) launch_expand(e->t, e->d_policy, e->d_value, e->stream, false, true);
+        if (branches > 1) {
+            cudaEventRecord(e->ev_fork, e->stream);
+            for (int k = 0; k < branches; ++k) cudaStreamWaitEvent(e->gstream[k], e->ev_fork, 0);
         }
-        e->graph_rounds = rounds;
+        for (int r = 0; r < rounds && !st; ++r)
+            for (int k = 0; k < branches && !st; ++k) {
+                const Tree v = branches > 1 ? group_view(e, bg0[k], bg0[k + 1], k) : e->t;
+                cudaStream_t bs = branches > 1 ? e->gstream[k] : e->stream;
+                const size_t first = (size_t)bg0[k] * e->t.inflight, n = (size_t)(bg0[k + 1] - bg0[k]) * e->t.inflight;
+                launch_select(v, bs, false, true);
+                launch_encode(v, e->d_features + first * (1 + 2 * e->t.H) * 64, bs, false, gx0[k], true);
+                st = eval_slots(e, first, n, bs, k, nullptr, nullptr, gx0[k] != nullptr);
+                if (!st) launch_expand(v, e->d_policy + first * 65, e->d_value + first, bs, false, true);
+            }
+        if (branches > 1)
+            for (int k = 0; k < branches; ++k) { cudaEventRecord(e->ev_join[k], e->gstream[k]); cudaStreamWaitEvent(e->stream, e->ev_join[k], 0); }
+        e->graph_rounds = rounds; e->graph_branches = branches;
         cudaError_t ce = cudaStreamEndCapture(e->stream, &g);
         e->graph_launches = g_kernel_launches - before;
         g_kernel_launches = before;                    // capturing launched nothing

@@ -1159,6 +1159,8 @@ int tower_max_clusters() {
     return n;
 }
 
+bool ResNet::tower_capable() const { return has_wr_ && shape_.channels == 128 && shape_.blocks > 0 && tower_enabled() && tower_max_clusters() > 0; }
+
 int ResNet::launch_tower(const Workspace &w, size_t pad, cudaStream_t stream) {
     const int nconv = 1 + 2 * shape_.blocks;
     TowerParams tp{};

@@ -63,6 +63,8 @@ class ResNet {
     void set_pdl(bool on) { pdl_ = on; }
     // Kernel launches one forward() issues.
     int launches_per_forward() const { return 2 + (1 + 2 * shape_.blocks); }
+    // Launch-bound batches of this network run on the cluster tower (128 channels, the device can launch 16-CTA clusters).
+    bool tower_capable() const;
     // Debug hook: one 3x3 convolution layer on device NHWC bf16 buffers already padded to 32 boards.
     // d_work: one device int for the dynamic pass scheduler (zeroed here, in stream order), or null = static schedule.
     static int conv3x3(const void *d_in, int cin, const void *d_w, const float *d_bias, const void *d_skip,

@@ -175,7 +175,8 @@ class _Engine:
 
     def set_pipeline(self, groups: int, pdl: bool = True) -> None:
         """Pipelined search: split the games into `groups` groups on their own streams so one group's tree kernels run
-        underneath another group's convolutions.  0 = automatic, 1 = off, 2..4.  Results do not depend on it."""
+        underneath another group's convolutions (graph-replayed searches: parallel branches of the graph).  0 = automatic,
+        1 = off, 2..8.  Results do not depend on it."""
         check(self._lib.oz_engine_set_pipeline(self._h, int(groups), int(pdl)))
 
 

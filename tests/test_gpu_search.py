@@ -286,7 +286,7 @@ def test_graph_replay_equals_eager_launches(evaluator):
     assert graph.counters()["kernel_launches"] > launches0
 
 
-@pytest.mark.parametrize("evaluator,groups", [("hash", 2), ("hash", 3), ("resnet", 2), ("resnet", 4)])
+@pytest.mark.parametrize("evaluator,groups", [("hash", 2), ("hash", 3), ("resnet", 2), ("resnet", 4), ("resnet", 8)])
 def test_pipelined_search_equals_single_stream(evaluator, groups):
     """The pipelined search splits the games into groups on their own streams (one group's tree kernels run underneath
     another group's convolutions).  Every game's search is independent of the others, so whole games must come out
@@ -313,6 +313,28 @@ def test_pipelined_search_equals_single_stream(evaluator, groups):
         assert ca[name] == cb[name], name
     if groups == 2:
         assert cb["eval_ms"] > 0 and cb["select_ms"] > 0
+
+
+def test_automatic_graph_branches_equal_single_chain():
+    """Graph-replayed searches of 8 to 48 games on a 128-channel network split the games into parallel branches of the
+    search's graph by themselves (each branch its own cluster-tower launches).  Whole games must come out identical to the
+    same engine with the split switched off."""
+    import torch
+    from othello_mcts import SelfPlayEngine
+    from othello_mcts.neural_net import AlphaZeroNet
+    torch.manual_seed(3)
+    net = AlphaZeroNet(9, conv_channels=128, num_residual_blocks=2, value_head_hidden_channels=32).eval().cuda()
+    kw = dict(history_size=4, num_simulations=64, num_threads=2, batch_size=16, dirichlet_epsilon=0.25, seed=5, temperature_plies=8)
+    one, auto = SelfPlayEngine(12, **kw), SelfPlayEngine(12, **kw)      # 12 games x 32 leaves = 12 clusters of 32 boards
+    one.set_pipeline(1)
+    a = one.run(net)
+    b = auto.run(net)
+    assert (a["plies"] == b["plies"]).all() and a["plies"].min() > 8
+    for name in ("p1", "p2", "player", "action", "n_children", "visit_counts"):
+        assert np.array_equal(a["records"][name], b["records"][name]), name
+    ca, cb = one.counters(), auto.counters()
+    for name in ("simulations", "evaluations", "nodes_expanded", "searches", "plies"):
+        assert ca[name] == cb[name], name
 
 
 def test_samples_from_travelled_records_equal_engine_samples():
