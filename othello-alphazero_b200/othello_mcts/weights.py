@@ -98,11 +98,25 @@ def fold_alphazero_net(net) -> tuple[OzResnetShape, bytes]:
     return shape, bytes(blob)
 
 
+def _walk_tensors(module, out: list) -> None:
+    for p in module._parameters.values():
+        if p is not None:
+            out.append((p.data_ptr(), p._version))
+    for b in module._buffers.values():
+        if b is not None:
+            out.append((b.data_ptr(), b._version))
+    for child in module._modules.values():
+        if child is not None:
+            _walk_tensors(child, out)
+
+
 def weights_fingerprint(net) -> tuple:
-    """Changes whenever a parameter or buffer is updated in place or replaced (re-fold trigger)."""
-    net = unwrap(net)
-    items = list(net.parameters()) + list(net.buffers())
-    return tuple((t.data_ptr(), t._version) for t in items)
+    """Changes whenever a parameter or buffer is updated in place or replaced (re-fold trigger).  Runs before EVERY search
+    (a single-game search is 5.9 ms), so it walks the module tree directly: `net.parameters()` / `net.buffers()` build
+    names and de-duplication sets on the way and cost 0.2-0.4 ms for 128x10b, this 0.1 ms."""
+    out: list = []
+    _walk_tensors(unwrap(net), out)
+    return tuple(out)
 
 
 _fold_cache: tuple | None = None
