@@ -343,9 +343,22 @@ __global__ void __launch_bounds__(WARPS * 32) encode_kernel(Tree t, float *featu
 //      sequential order would have given it;
 //   2. all new children of the chunk as one flat range, 32 per step with every lane busy: position after the move
 //      (flips + the mover's next legal moves), prior gathered from the policy row through the symmetry;
-//   3. the 32 backups in slot order.
+//   3. the 32 backups in slot order.  Slot order only matters PER NODE (a node's W is a float sum in the order of the slots
+//      whose paths cross it), and two path entries can be the same node only at the same depth.  So for paths of at most 16
+//      nodes (practically always) the chunk's W values live in shared memory for the duration of the backups: lane = slot
+//      finds, depth by depth, the first slot of the chunk holding the same node (__match_any_sync) and loads W and N of the
+//      nodes it is first for (every load of the chunk in flight at once); then lane = depth k adds the 32 slots' values
+//      into its depth's nodes in slot order -- 16 independent register/shared-memory chains, no memory round trip between
+//      two backups (each backup used to wait for an L2 round trip: 32 x 0.45 us per round for a single game); then the
+//      owners write W and Q = W / N back once.  Same float additions in the same order: the same bits.
+constexpr int kFastBackupDepth = 16;
 template <int WARPS>
 __global__ void __launch_bounds__(WARPS * 32) expand_kernel(Tree t, const float *__restrict__ policy, const float *__restrict__ value) {
+    __shared__ float s_bw[WARPS == 4 ? WARPS : 1][32 * kFastBackupDepth];          // W of the chunk's nodes, at [first slot][depth]
+    __shared__ int s_bn[WARPS == 4 ? WARPS : 1][32 * kFastBackupDepth];            // their visit counts
+    __shared__ __align__(16) uint8_t s_bfirst[WARPS == 4 ? WARPS : 1][32 * kFastBackupDepth];   // [slot][depth] -> first slot with that node
+    __shared__ float s_bv[WARPS == 4 ? WARPS : 1][32];                             // value backed up from slot li
+    __shared__ int s_blen[WARPS == 4 ? WARPS : 1][32];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int B = t.inflight;
     unsigned long long expanded = 0;
@@ -416,7 +429,73 @@ __global__ void __launch_bounds__(WARPS * 32) expand_kernel(Tree t, const float 
         count += total;
         expanded += (unsigned)total;
         __syncwarp();
-        // ---- 3. backups in slot order.  The first eight path entries of every slot are fetched up front, transposed over
+        // ---- 3. backups in slot order.
+        if (WARPS == 4 && __reduce_max_sync(0xffffffffu, c_valid ? c_len : 0) <= kFastBackupDepth) {
+            const int bw = WARPS == 4 ? wib : 0;
+            // value of every slot, lane = slot
+            float my_v = 0.f;
+            if (c_valid) {
+                if (c_player != 0) my_v = -c_val;          // edge value is from the parent's view (:156-157)
+                else {                                     // terminal: disc count from the parent's side (:158-177)
+                    const int par = t.n_parent[base + c_leaf];
+                    const int pp = par >= 0 ? (t.n_meta[base + par] & 3) : t.h_player[(size_t)g * kMaxHist];
+                    const int pc = __popcll(pp == 1 ? c_p1 : c_p2), oc = __popcll(pp == 1 ? c_p2 : c_p1);
+                    my_v = pc > oc ? 1.0f : (pc < oc ? -1.0f : 0.0f);
+                }
+            }
+            int pnode[kFastBackupDepth];
+            {
+                const int4 *row = (const int4 *)(t.s_path + (slot0 + (c_valid ? lane : 0)) * kMaxDepth);
+#pragma unroll
+                for (int q = 0; q < kFastBackupDepth / 4; ++q) {
+                    int4 v4 = make_int4(0, 0, 0, 0);
+                    if (c_valid && 4 * q < c_len) v4 = row[q];
+                    pnode[4 * q] = v4.x; pnode[4 * q + 1] = v4.y; pnode[4 * q + 2] = v4.z; pnode[4 * q + 3] = v4.w;
+                }
+            }
+            uint32_t fpack[kFastBackupDepth / 4];
+            unsigned mine = 0;                             // depths at which this slot is the first holder of its node
+#pragma unroll
+            for (int q = 0; q < kFastBackupDepth / 4; ++q) fpack[q] = 0;
+#pragma unroll
+            for (int k = 0; k < kFastBackupDepth; ++k) {
+                const bool has = c_valid && k < c_len;
+                const unsigned m = __match_any_sync(0xffffffffu, has ? pnode[k] : -1 - lane);
+                const int f = __ffs(m) - 1;
+                fpack[k >> 2] |= (uint32_t)f << (8 * (k & 3));
+                if (has && f == lane) {
+                    mine |= 1u << k;
+                    s_bw[bw][lane * kFastBackupDepth + k] = t.n_W[base + pnode[k]];
+                    s_bn[bw][lane * kFastBackupDepth + k] = t.n_N[base + pnode[k]];
+                }
+            }
+            *(uint4 *)(s_bfirst[bw] + lane * kFastBackupDepth) = make_uint4(fpack[0], fpack[1], fpack[2], fpack[3]);
+            s_bv[bw][lane] = my_v;
+            s_blen[bw][lane] = c_valid ? c_len : 0;
+            __syncwarp();
+            if (lane < kFastBackupDepth) {                 // lane = depth: this depth's nodes, slots in order
+                for (int li = 0; li < chunk; ++li) {
+                    const int len = s_blen[bw][li];
+                    if (lane < len) {
+                        const int idx = (int)s_bfirst[bw][li * kFastBackupDepth + lane] * kFastBackupDepth + lane;
+                        const float v = s_bv[bw][li];
+                        const float vk = ((len - 1 - lane) & 1) ? -v : v;
+                        s_bw[bw][idx] = __fadd_rn(s_bw[bw][idx], __fadd_rn(1.0f, vk));   // W += 1 + v cancels the virtual loss (:184)
+                    }
+                }
+            }
+            __syncwarp();
+#pragma unroll
+            for (int k = 0; k < kFastBackupDepth; ++k)
+                if (mine & (1u << k)) {
+                    const float w = s_bw[bw][lane * kFastBackupDepth + k];
+                    const size_t a = base + pnode[k];
+                    t.n_W[a] = w; t.n_Q[a] = __fdiv_rn(w, (float)s_bn[bw][lane * kFastBackupDepth + k]);
+                }
+            __syncwarp();
+            continue;
+        }
+        // Longer paths: one backup after the other.  The first eight path entries of every slot are fetched up front, transposed over
         // the warp (lane 8 * (s % 4) + k holds entry k of slots s = 4 r + ..., r = 0..7), so the sequential part below
         // starts with the nodes' W and N instead of a dependent read of the path; longer paths read the rest from memory.
         int pa[8];
