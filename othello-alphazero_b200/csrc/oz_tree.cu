@@ -104,6 +104,38 @@ __global__ void reset_kernel(Tree t) {
 //     Gamma draw per lane inside every selection (a few hundred dependent instructions on the critical path, 32 times per
 //     round), lane s draws the noise of simulation s for all root children up front -- 32 selections in parallel, each a
 //     loop over the handful of children -- into shared memory, together with the sequential child-order sum.
+// PUCT over the children a warp holds (lane = child, a 33rd child in the *1 registers): ucb = Q + (mult * P) / (1 + N),
+// first maximum wins (search_thread.cpp:192-228).
+__device__ __forceinline__ int puct_pick(int nch, float mult, int n0, int n1, float q0, float q1, float p0, float p1,
+                                         bool v0, bool v1, int c0, int c1) {
+    float u = -INFINITY;
+    int idx = INT_MAX;
+    if (v0) { u = __fadd_rn(q0, __fdiv_rn(__fmul_rn(mult, p0), __fadd_rn(1.0f, (float)n0))); idx = c0; }
+    if (nch > 32 && v1) {                            // a 33rd child exists in a handful of positions only: warp-uniform branch
+        const float u1 = __fadd_rn(q1, __fdiv_rn(__fmul_rn(mult, p1), __fadd_rn(1.0f, (float)n1)));
+        if (u1 > u) { u = u1; idx = c1; }
+    }
+    // First maximum wins (strict > in the reference): the largest value through an order-preserving integer key
+    // (-0 folded into +0 first, they compare equal as floats), then the smallest index that holds it.
+    uint32_t key = __float_as_uint(__fadd_rn(u, 0.0f));
+    key ^= (uint32_t)((int32_t)key >> 31) | 0x80000000u;
+    const uint32_t kmax = __reduce_max_sync(0xffffffffu, key);
+    return __reduce_min_sync(0xffffffffu, key == kmax ? idx : INT_MAX);
+}
+// Statistics and headers of all children of a node (first child at `a`), lane = child: one round trip.
+__device__ __forceinline__ void load_child_block(const Tree &t, size_t a, int nch, int lane, int &n0, float &w0, float &q0, float &p0, int &cm0, int &cf0,
+                                                 int &n1, float &w1, float &q1, float &p1, int &cm1, int &cf1) {
+    const bool v0 = lane < nch, v1 = lane + 32 < nch;
+    const size_t a0 = a + lane, a1 = a + lane + 32;
+    n0 = v0 ? t.n_N[a0] : 0; w0 = v0 ? t.n_W[a0] : 0.f; q0 = v0 ? t.n_Q[a0] : 0.f; p0 = v0 ? t.n_P[a0] : 0.f;
+    cm0 = v0 ? t.n_meta[a0] : 0; cf0 = v0 ? t.n_child[a0] : -1;
+    n1 = 0; w1 = 0.f; q1 = 0.f; p1 = 0.f; cm1 = 0; cf1 = -1;
+    if (nch > 32) {
+        n1 = v1 ? t.n_N[a1] : 0; w1 = v1 ? t.n_W[a1] : 0.f; q1 = v1 ? t.n_Q[a1] : 0.f; p1 = v1 ? t.n_P[a1] : 0.f;
+        cm1 = v1 ? t.n_meta[a1] : 0; cf1 = v1 ? t.n_child[a1] : -1;
+    }
+}
+
 template <int WARPS>
 __global__ void __launch_bounds__(WARPS * 32) select_kernel(Tree t) {
     __shared__ float s_gamma[WARPS][32][33];                   // [selection of the chunk][root child]
@@ -127,6 +159,7 @@ __global__ void __launch_bounds__(WARPS * 32) select_kernel(Tree t) {
     int root_n = t.n_N[base + root];
     int rn0 = 0, rn1 = 0, rcm0 = 0, rcm1 = 0, rcf0 = -1, rcf1 = -1;
     float rw0 = 0.f, rw1 = 0.f, rq0 = 0.f, rq1 = 0.f, rp0 = 0.f, rp1 = 0.f;
+    bool rdirty0 = false, rdirty1 = false;
     if ((rm & 3) != 0) {
         const int rnch = rm >> 8;
         children_read += (unsigned)rnch;
@@ -135,15 +168,17 @@ __global__ void __launch_bounds__(WARPS * 32) select_kernel(Tree t) {
     }
 
     const bool noisy = t.eps > 0.0f && (rm & 3) != 0 && (rm >> 8) > 1;    // noise is only drawn where PUCT runs at the root
-    for (int i = 0; i < B; ++i) {
-        const uint32_t sim = (uint32_t)(round * B + i);
-        if (noisy && (i & 31) == 0) {                // the next 32 selections' draws, one selection per lane
+    const int rnch_all = rm >> 8;
+    const bool root_open = (rm & 3) != 0 && rnch_all != 0;                // terminal or childless root: every selection ends there (:65)
+    const float pm = __fsub_rn(1.0f, t.eps);
+    for (int i0 = 0; i0 < B; i0 += 32) {
+        const int chunk = min(32, B - i0);
+        if (noisy) {                                 // the chunk's Dirichlet draws, one selection per lane
             __syncwarp();
-            const int rnch = rm >> 8;
-            if (i + lane < B) {
+            if (lane < chunk) {
                 float sum = 0.0f;                    // sequential float sum in child order (:236-241)
-                for (int c = 0; c < rnch; ++c) {
-                    const float gc = gamma_draw(t, game_id, search, sim + (uint32_t)lane, c);
+                for (int c = 0; c < rnch_all; ++c) {
+                    const float gc = gamma_draw(t, game_id, search, (uint32_t)(round * B + i0 + lane), c);
                     s_gamma[wib][lane][c] = gc;
                     sum = __fadd_rn(sum, gc);
                 }
@@ -151,90 +186,152 @@ __global__ void __launch_bounds__(WARPS * 32) select_kernel(Tree t) {
             }
             __syncwarp();
         }
-        int node = root, depth = 0;
-        int pr0 = 0, pr1 = 0, pr2 = 0, pr3 = 0;      // path nodes lane, lane + 32, lane + 64, lane + 96
-        int m = rm, fc = rfc, nn = root_n;           // header of the current node (meta, first child, visit count)
-        while (true) {
-            const int nch = m >> 8;
-            if ((m & 3) == 0 || nch == 0) break;     // terminal or childless (search_thread.cpp:65)
-            const bool at_root = depth == 0;
-            const int c0 = lane, c1 = lane + 32;
-            const bool v0 = c0 < nch, v1 = c1 < nch;
+        // Per-slot state, lane = slot of the chunk: the node the selection stands on, its header (meta, first child) and its
+        // visit count BEFORE this selection's virtual loss (the rate-table index when the selection decides there).
+        // The exploration rate of that count is fetched by the slot's lane as soon as the count is known, a level before it is
+        // used (in the arrival loop it would be a dependent global load in front of every decision).
+        int s_node = root, s_m = rm, s_fc = rfc, s_nn = 0, s_depth = 0;
+        float s_rate = 0.f;
+        int *gpath_mine = t.s_path + ((size_t)g * B + i0 + (lane < chunk ? lane : 0)) * kMaxDepth;
+#ifdef OZ_SELECT_TIMELINE
+        long long tl0 = clock64(), tl_root = 0, tl_arr = 0, tl_wait = 0; int tl_nodes = 0, tl_arrivals = 0, tl_levels = 0;
+#endif
+        // ---- level 0: the root's arrivals in slot order, statistics in registers
+        for (int s = 0; s < chunk; ++s) {
+            int next = root, nm = rm, nfc = rfc, nnn = root_n, dep = 0;
+            if (root_open) {
+                const int nch = rnch_all;
+                const int c0 = lane, c1 = lane + 32;
+                const bool v0 = c0 < nch, v1 = c1 < nch;
+                int idx = 0;                         // a single child is taken without any arithmetic (:194-196)
+                if (nch > 1) {
+                    int nn = root_n;
+                    if (nn >= t.rate_len) { if (lane == 0) atomicOr(t.error, kErrRateTable); nn = t.rate_len - 1; }
+                    const float rate = t.rate[nn];   // logf((1 + N + c_base) / c_base) + c_init, host libm
+                    const int total = __reduce_add_sync(0xffffffffu, rn0 + rn1);
+                    const float mult = __fmul_rn(rate, __fsqrt_rn((float)total));
+                    float p0 = rp0, p1 = rp1;
+                    if (noisy) {                     // Dirichlet noise, re-drawn per selection (:230-249)
+                        const float g0 = v0 ? s_gamma[wib][s][c0] : 0.f;
+                        const float g1 = (nch > 32 && v1) ? s_gamma[wib][s][c1] : 0.f;
+                        const float nm2 = __fdiv_rn(t.eps, s_gsum[wib][s]);
+                        p0 = __fadd_rn(__fmul_rn(p0, pm), __fmul_rn(g0, nm2));
+                        if (nch > 32) p1 = __fadd_rn(__fmul_rn(p1, pm), __fmul_rn(g1, nm2));
+                    }
+                    idx = puct_pick(nch, mult, rn0, rn1, rq0, rq1, p0, p1, v0, v1, c0, c1);
+                }
+                next = rfc + idx;
+                const bool hi = idx >= 32;
+                nm = __shfl_sync(0xffffffffu, hi ? rcm1 : rcm0, idx & 31);
+                nfc = __shfl_sync(0xffffffffu, hi ? rcf1 : rcf0, idx & 31);
+                nnn = __shfl_sync(0xffffffffu, hi ? rn1 : rn0, idx & 31);     // the child's count BEFORE this selection's virtual loss
+                if (lane == (idx & 31)) {            // virtual loss by the lane that holds the chosen child (written back after the chunk's root pass)
+                    if (hi) { rn1 += 1; rw1 = __fsub_rn(rw1, 1.0f); rq1 = __fdiv_rn(rw1, (float)rn1); rdirty1 = true; }
+                    else { rn0 += 1; rw0 = __fsub_rn(rw0, 1.0f); rq0 = __fdiv_rn(rw0, (float)rn0); rdirty0 = true; }
+                }
+                dep = 1;
+            }
+            root_n += 1;                             // root visit count (:78)
+            if (lane == s) { s_node = next; s_m = nm; s_fc = nfc; s_nn = nnn; s_depth = dep; s_rate = t.rate[nnn < t.rate_len ? nnn : t.rate_len - 1]; }
+        }
+        if (lane < chunk && s_depth == 1) gpath_mine[0] = s_node;
+#ifdef OZ_SELECT_TIMELINE
+        tl_root = clock64() - tl0;
+#endif
+        // ---- levels >= 1.  What a node decides for an arriving selection depends on the node's own children and on the
+        // selections that arrived there EARLIER in slot order -- on nothing else in the tree.  So the chunk advances level by
+        // level: the slots standing on the same node are grouped (__match_any_sync), each distinct node's child block is read
+        // ONCE (the next node's block is already in flight while the current node's arrivals are decided), its arrivals are
+        // decided in slot order from registers, and the touched children are written back once.
+        for (int level = 1;; ++level) {
+            const bool active = lane < chunk && s_depth == level && (s_m & 3) != 0 && (s_m >> 8) != 0;
+            if (!__ballot_sync(0xffffffffu, active)) break;
+            const unsigned grp = __match_any_sync(0xffffffffu, active ? s_node : -1 - lane);
+            unsigned leaders = __ballot_sync(0xffffffffu, active && (__ffs(grp) - 1) == lane);
+            // block of the first node
+            int L = __ffs(leaders) - 1;
+            leaders &= leaders - 1;
+            int fcX = __shfl_sync(0xffffffffu, s_fc, L), nchX = __shfl_sync(0xffffffffu, s_m, L) >> 8;
+            unsigned arr = __shfl_sync(0xffffffffu, grp, L);
             int n0, n1, cm0, cm1, cf0, cf1;
             float w0, w1, q0, q1, p0, p1;
-            if (at_root) {
-                n0 = rn0; n1 = rn1; w0 = rw0; w1 = rw1; q0 = rq0; q1 = rq1; p0 = rp0; p1 = rp1; cm0 = rcm0; cm1 = rcm1; cf0 = rcf0; cf1 = rcf1;
-            } else {                                 // one round trip: statistics and headers of all children
-                const size_t a0 = base + fc + c0, a1 = base + fc + c1;
-                n0 = v0 ? t.n_N[a0] : 0; w0 = v0 ? t.n_W[a0] : 0.f; q0 = v0 ? t.n_Q[a0] : 0.f; p0 = v0 ? t.n_P[a0] : 0.f;
-                cm0 = v0 ? t.n_meta[a0] : 0; cf0 = v0 ? t.n_child[a0] : -1;
-                n1 = 0; w1 = 0.f; q1 = 0.f; p1 = 0.f; cm1 = 0; cf1 = -1;
-                if (nch > 32) {                      // a 33rd child exists in a handful of positions only: warp-uniform branch
-                    n1 = v1 ? t.n_N[a1] : 0; w1 = v1 ? t.n_W[a1] : 0.f; q1 = v1 ? t.n_Q[a1] : 0.f; p1 = v1 ? t.n_P[a1] : 0.f;
-                    cm1 = v1 ? t.n_meta[a1] : 0; cf1 = v1 ? t.n_child[a1] : -1;
+            load_child_block(t, base + fcX, nchX, lane, n0, w0, q0, p0, cm0, cf0, n1, w1, q1, p1, cm1, cf1);
+            while (true) {
+                // the next distinct node's block: in flight while this node's arrivals are decided
+                const bool more = leaders != 0;
+                int L2 = 0, fcY = 0, nchY = 0;
+                unsigned arrY = 0;
+                int yn0 = 0, yn1 = 0, ycm0 = 0, ycm1 = 0, ycf0 = -1, ycf1 = -1;
+                float yw0 = 0.f, yw1 = 0.f, yq0 = 0.f, yq1 = 0.f, yp0 = 0.f, yp1 = 0.f;
+                if (more) {
+                    L2 = __ffs(leaders) - 1;
+                    leaders &= leaders - 1;
+                    fcY = __shfl_sync(0xffffffffu, s_fc, L2); nchY = __shfl_sync(0xffffffffu, s_m, L2) >> 8;
+                    arrY = __shfl_sync(0xffffffffu, grp, L2);
+                    load_child_block(t, base + fcY, nchY, lane, yn0, yw0, yq0, yp0, ycm0, ycf0, yn1, yw1, yq1, yp1, ycm1, ycf1);
                 }
+                // this node's arrivals, in slot order
+#ifdef OZ_SELECT_TIMELINE
+                { long long a0 = clock64(); volatile int touch = n0 + cm0 + cf0 + __float_as_int(w0) + __float_as_int(q0) + __float_as_int(p0); (void)touch; tl_wait += clock64() - a0; ++tl_nodes; }
+                long long a1 = clock64();
+#endif
+                const int nch = nchX;
+                const int c0 = lane, c1 = lane + 32;
+                const bool v0 = c0 < nch, v1 = c1 < nch;
+                bool dirty0 = false, dirty1 = false;
+                while (arr) {
+                    const int s = __ffs(arr) - 1;
+                    arr &= arr - 1;
+                    int idx = 0;
+                    if (nch > 1) {
+                        const int nn = __shfl_sync(0xffffffffu, s_nn, s);
+                        if (nn >= t.rate_len && lane == 0) atomicOr(t.error, kErrRateTable);
+                        const float rate = __shfl_sync(0xffffffffu, s_rate, s);   // rate[nn]: logf((1 + N + c_base) / c_base) + c_init, host libm
+                        const int total = __reduce_add_sync(0xffffffffu, n0 + n1);
+                        children_read += (unsigned)nch;
+                        const float mult = __fmul_rn(rate, __fsqrt_rn((float)total));
+                        idx = puct_pick(nch, mult, n0, n1, q0, q1, p0, p1, v0, v1, c0, c1);
+                    }
+                    const int next = fcX + idx;
+                    const bool hi = idx >= 32;
+                    const int nm = __shfl_sync(0xffffffffu, hi ? cm1 : cm0, idx & 31);
+                    const int nfc = __shfl_sync(0xffffffffu, hi ? cf1 : cf0, idx & 31);
+                    const int nnn = __shfl_sync(0xffffffffu, hi ? n1 : n0, idx & 31);
+                    if (lane == (idx & 31)) {        // virtual loss (search_thread.cpp:70-76), in the register copy
+                        if (hi) { n1 += 1; w1 = __fsub_rn(w1, 1.0f); q1 = __fdiv_rn(w1, (float)n1); dirty1 = true; }
+                        else { n0 += 1; w0 = __fsub_rn(w0, 1.0f); q0 = __fdiv_rn(w0, (float)n0); dirty0 = true; }
+                    }
+#ifdef OZ_SELECT_TIMELINE
+                    ++tl_arrivals;
+#endif
+                    if (lane == s) {
+                        if (s_depth < kMaxDepth) gpath_mine[s_depth] = next; else atomicOr(t.error, kErrDepth);
+                        s_node = next; s_m = nm; s_fc = nfc; s_nn = nnn; s_depth += 1;
+                        s_rate = t.rate[nnn < t.rate_len ? nnn : t.rate_len - 1];
+                    }
+                }
+#ifdef OZ_SELECT_TIMELINE
+                tl_arr += clock64() - a1;
+#endif
+                if (dirty0) { const size_t a = base + fcX + c0; t.n_N[a] = n0; t.n_W[a] = w0; t.n_Q[a] = q0; }
+                if (dirty1) { const size_t a = base + fcX + c1; t.n_N[a] = n1; t.n_W[a] = w1; t.n_Q[a] = q1; }
+                if (!more) break;
+                fcX = fcY; nchX = nchY; arr = arrY;
+                n0 = yn0; n1 = yn1; cm0 = ycm0; cm1 = ycm1; cf0 = ycf0; cf1 = ycf1;
+                w0 = yw0; w1 = yw1; q0 = yq0; q1 = yq1; p0 = yp0; p1 = yp1;
             }
-            int idx = 0;                             // a single child is taken without any arithmetic (:194-196)
-            if (nch > 1) {
-                if (nn >= t.rate_len) { if (lane == 0) atomicOr(t.error, kErrRateTable); nn = t.rate_len - 1; }
-                const float rate = t.rate[nn];       // logf((1 + N + c_base) / c_base) + c_init, host libm
-                const int total = __reduce_add_sync(0xffffffffu, n0 + n1);
-                if (!at_root) children_read += (unsigned)nch;   // the root's children were read once for the round
-                const float mult = __fmul_rn(rate, __fsqrt_rn((float)total));
-                if (at_root && noisy) {              // Dirichlet noise, re-drawn per selection (:230-249)
-                    const float g0 = v0 ? s_gamma[wib][i & 31][c0] : 0.f;
-                    const float g1 = (nch > 32 && v1) ? s_gamma[wib][i & 31][c1] : 0.f;
-                    const float sum = s_gsum[wib][i & 31];
-                    const float pm = __fsub_rn(1.0f, t.eps), nm2 = __fdiv_rn(t.eps, sum);
-                    p0 = __fadd_rn(__fmul_rn(p0, pm), __fmul_rn(g0, nm2));
-                    if (nch > 32) p1 = __fadd_rn(__fmul_rn(p1, pm), __fmul_rn(g1, nm2));
-                }
-                // ucb = Q + (mult * P) / (1 + N)
-                float u = -INFINITY; idx = INT_MAX;
-                if (v0) { u = __fadd_rn(q0, __fdiv_rn(__fmul_rn(mult, p0), __fadd_rn(1.0f, (float)n0))); idx = c0; }
-                if (nch > 32 && v1) {
-                    const float u1 = __fadd_rn(q1, __fdiv_rn(__fmul_rn(mult, p1), __fadd_rn(1.0f, (float)n1)));
-                    if (u1 > u) { u = u1; idx = c1; }
-                }
-                // First maximum wins (strict > in the reference): the largest value through an order-preserving integer key
-                // (-0 folded into +0 first, they compare equal as floats), then the smallest index that holds it.
-                uint32_t key = __float_as_uint(__fadd_rn(u, 0.0f));
-                key ^= (uint32_t)((int32_t)key >> 31) | 0x80000000u;
-                const uint32_t kmax = __reduce_max_sync(0xffffffffu, key);
-                idx = __reduce_min_sync(0xffffffffu, key == kmax ? idx : INT_MAX);
-            }
-            const int next = fc + idx;
-            const bool hi = idx >= 32;
-            const int nm = __shfl_sync(0xffffffffu, hi ? cm1 : cm0, idx & 31);
-            const int nfc = __shfl_sync(0xffffffffu, hi ? cf1 : cf0, idx & 31);
-            const int nnn = __shfl_sync(0xffffffffu, hi ? n1 : n0, idx & 31);     // the child's count BEFORE this selection's virtual loss
-            if (lane == (idx & 31)) {                // virtual loss by the lane that holds the chosen child
-                const int nv = (hi ? n1 : n0) + 1;
-                const float wv = __fsub_rn(hi ? w1 : w0, 1.0f), qv = __fdiv_rn(wv, (float)nv);
-                const size_t a = base + next;
-                t.n_N[a] = nv; t.n_W[a] = wv; t.n_Q[a] = qv;
-                if (at_root) { if (hi) { rn1 = nv; rw1 = wv; rq1 = qv; } else { rn0 = nv; rw0 = wv; rq0 = qv; } }
-            }
-            if (depth < kMaxDepth) {
-                if (lane == (depth & 31)) {
-                    const int q = depth >> 5;
-                    if (q == 0) pr0 = next; else if (q == 1) pr1 = next; else if (q == 2) pr2 = next; else pr3 = next;
-                }
-            } else if (lane == 0) atomicOr(t.error, kErrDepth);
-            ++depth;
-            node = next; m = nm; fc = nfc; nn = nnn;
         }
-        if (depth > kMaxDepth) depth = kMaxDepth;
-        path_nodes += (unsigned)depth;
-        int *gpath = t.s_path + ((size_t)g * B + i) * kMaxDepth;     // the path, for the backup of expand_kernel
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            const int k = lane + 32 * q;
-            if (k < depth) gpath[k] = q == 0 ? pr0 : (q == 1 ? pr1 : (q == 2 ? pr2 : pr3));
-        }
-        root_n += 1;                                 // root visit count (:78)
-        if (lane == 0) { leaf_out[i] = node; t.s_len[(size_t)g * B + i] = depth; }
-        __syncwarp();                                // the virtual-loss stores are ordered before the next selection's reads
+#ifdef OZ_SELECT_TIMELINE
+        if (lane == 0 && g == 0) printf("select round %d: total %lld clk, root %lld, waiting for blocks %lld, arrivals %lld (%d arrivals at %d nodes)\n", round, clock64() - tl0, tl_root, tl_wait, tl_arr, tl_arrivals, tl_nodes);
+#endif
+        // the chunk's results
+        const int dclip = s_depth > kMaxDepth ? kMaxDepth : s_depth;
+        path_nodes += (unsigned)__reduce_add_sync(0xffffffffu, lane < chunk ? dclip : 0);
+        if (lane < chunk) { leaf_out[i0 + lane] = s_node; t.s_len[(size_t)g * B + i0 + lane] = dclip; }
+        // the root's children: written back once per chunk (later chunks and kernels read them from memory / these registers)
+        if (rdirty0) { const size_t a = base + rfc + lane; t.n_N[a] = rn0; t.n_W[a] = rw0; t.n_Q[a] = rq0; rdirty0 = false; }
+        if (rdirty1) { const size_t a = base + rfc + lane + 32; t.n_N[a] = rn1; t.n_W[a] = rw1; t.n_Q[a] = rq1; rdirty1 = false; }
+        __syncwarp();                                // this chunk's stores are ordered before the next chunk's reads
     }
     if (lane == 0) t.n_N[base + root] = root_n;
     }
