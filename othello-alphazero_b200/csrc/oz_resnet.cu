@@ -87,8 +87,8 @@ constexpr int kMiscBytes = 3072;                                    // barriers 
 constexpr int kSchedSlots = 8;
 constexpr int kSmemBytesP = 1024 + kSlotBytes + kActStagesP * kActBoxBytesP + kWSlots * kWTileBytes + kMiscBytes;
 // 233 472 B per SM, 1 KB of it reserved per resident CTA: what this kernel leaves free (6 144 B) must hold one block of the
-// narrow select kernel (4 352 B static + its 1 KB), or the pipelined search cannot run tree kernels under the convolutions.
-static_assert(kSmemBytesP + 1024 + 4352 + 1024 <= 233472, "shared memory budget (co-residency with select_kernel<1>)");
+// narrow select kernel (5 120 B static + its 1 KB), or the pipelined search cannot run tree kernels under the convolutions.
+static_assert(kSmemBytesP + 1024 + 5120 + 1024 <= 233472, "shared memory budget (co-residency with select_kernel<1>)");
 // kind::f16 instruction descriptor: bf16 x bf16 -> f32, K-major operands, M = 256 (pair), N = 128.
 constexpr uint32_t kIdescP = (1u << 4) | (1u << 7) | (1u << 10) | ((128u >> 3) << 17) | ((256u >> 4) << 24);
 }  // namespace pair

@@ -136,31 +136,34 @@ __device__ __forceinline__ void load_child_block(const Tree &t, size_t a, int nc
     }
 }
 
-template <int WARPS>
-__global__ void __launch_bounds__(WARPS * 32) select_kernel(Tree t) {
-    __shared__ float s_gamma[WARPS][32][33];                   // [selection of the chunk][root child]
-    __shared__ float s_gsum[WARPS][32];
+template <int GW>
+__global__ void __launch_bounds__(GW * 32) select_kernel(Tree t) {
+    __shared__ float s_gamma[32][33];                          // [selection of the chunk][root child]
+    __shared__ float s_gsum[32];
+    // per-slot state of the chunk, handed from level to level (and between the warps of the game)
+    __shared__ int sh_node[32], sh_m[32], sh_fc[32], sh_nn[32], sh_depth[32];
+    __shared__ float sh_rate[32];
     griddep_launch_dependents();                               // launch-bound searches chain their kernels (launch_kernel, oz_common.cuh)
     griddep_wait();
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int B = t.inflight, round = *t.round;
     unsigned long long path_nodes = 0, children_read = 0;      // traffic counters (oz_counters)
-    for (int g = blockIdx.x * WARPS + wib; g < t.G; g += gridDim.x * WARPS) {
+    for (int g = blockIdx.x; g < t.G; g += gridDim.x) {
     int *leaf_out = t.s_leaf + (size_t)g * B;
     if (t.g_status[g] & 1) {                         // finished game: nothing in flight
-        for (int i = lane; i < B; i += 32) leaf_out[i] = -1;
+        for (int i = threadIdx.x; i < B; i += GW * 32) leaf_out[i] = -1;
         continue;
     }
     const size_t base = arena_base(t, g);
     const int root = t.g_root[g];
     const uint32_t game_id = t.g_gameid[g], search = t.g_search[g];
-    // root header and root children, cached for the round
+    // root header and root children, cached for the round (warp 0 decides at the root)
     const int rm = t.n_meta[base + root], rfc = t.n_child[base + root];
     int root_n = t.n_N[base + root];
     int rn0 = 0, rn1 = 0, rcm0 = 0, rcm1 = 0, rcf0 = -1, rcf1 = -1;
     float rw0 = 0.f, rw1 = 0.f, rq0 = 0.f, rq1 = 0.f, rp0 = 0.f, rp1 = 0.f;
     bool rdirty0 = false, rdirty1 = false;
-    if ((rm & 3) != 0) {
+    if (wib == 0 && (rm & 3) != 0) {
         const int rnch = rm >> 8;
         children_read += (unsigned)rnch;
         if (lane < rnch) { const size_t a = base + rfc + lane; rn0 = t.n_N[a]; rw0 = t.n_W[a]; rq0 = t.n_Q[a]; rp0 = t.n_P[a]; rcm0 = t.n_meta[a]; rcf0 = t.n_child[a]; }
@@ -173,169 +176,175 @@ __global__ void __launch_bounds__(WARPS * 32) select_kernel(Tree t) {
     const float pm = __fsub_rn(1.0f, t.eps);
     for (int i0 = 0; i0 < B; i0 += 32) {
         const int chunk = min(32, B - i0);
-        if (noisy) {                                 // the chunk's Dirichlet draws, one selection per lane
-            __syncwarp();
-            if (lane < chunk) {
-                float sum = 0.0f;                    // sequential float sum in child order (:236-241)
-                for (int c = 0; c < rnch_all; ++c) {
-                    const float gc = gamma_draw(t, game_id, search, (uint32_t)(round * B + i0 + lane), c);
-                    s_gamma[wib][lane][c] = gc;
-                    sum = __fadd_rn(sum, gc);
-                }
-                s_gsum[wib][lane] = sum == 0.0f ? 1.0f : sum;
-            }
-            __syncwarp();
-        }
-        // Per-slot state, lane = slot of the chunk: the node the selection stands on, its header (meta, first child) and its
-        // visit count BEFORE this selection's virtual loss (the rate-table index when the selection decides there).
-        // The exploration rate of that count is fetched by the slot's lane as soon as the count is known, a level before it is
-        // used (in the arrival loop it would be a dependent global load in front of every decision).
-        int s_node = root, s_m = rm, s_fc = rfc, s_nn = 0, s_depth = 0;
-        float s_rate = 0.f;
         int *gpath_mine = t.s_path + ((size_t)g * B + i0 + (lane < chunk ? lane : 0)) * kMaxDepth;
-#ifdef OZ_SELECT_TIMELINE
-        long long tl0 = clock64(), tl_root = 0, tl_arr = 0, tl_wait = 0; int tl_nodes = 0, tl_arrivals = 0, tl_levels = 0;
-#endif
-        // ---- level 0: the root's arrivals in slot order, statistics in registers
-        for (int s = 0; s < chunk; ++s) {
-            int next = root, nm = rm, nfc = rfc, nnn = root_n, dep = 0;
-            if (root_open) {
-                const int nch = rnch_all;
-                const int c0 = lane, c1 = lane + 32;
-                const bool v0 = c0 < nch, v1 = c1 < nch;
-                int idx = 0;                         // a single child is taken without any arithmetic (:194-196)
-                if (nch > 1) {
-                    int nn = root_n;
-                    if (nn >= t.rate_len) { if (lane == 0) atomicOr(t.error, kErrRateTable); nn = t.rate_len - 1; }
-                    const float rate = t.rate[nn];   // logf((1 + N + c_base) / c_base) + c_init, host libm
-                    const int total = __reduce_add_sync(0xffffffffu, rn0 + rn1);
-                    const float mult = __fmul_rn(rate, __fsqrt_rn((float)total));
-                    float p0 = rp0, p1 = rp1;
-                    if (noisy) {                     // Dirichlet noise, re-drawn per selection (:230-249)
-                        const float g0 = v0 ? s_gamma[wib][s][c0] : 0.f;
-                        const float g1 = (nch > 32 && v1) ? s_gamma[wib][s][c1] : 0.f;
-                        const float nm2 = __fdiv_rn(t.eps, s_gsum[wib][s]);
-                        p0 = __fadd_rn(__fmul_rn(p0, pm), __fmul_rn(g0, nm2));
-                        if (nch > 32) p1 = __fadd_rn(__fmul_rn(p1, pm), __fmul_rn(g1, nm2));
+        if (wib == 0) {
+            if (noisy) {                                 // the chunk's Dirichlet draws, one selection per lane
+                if (lane < chunk) {
+                    float sum = 0.0f;                    // sequential float sum in child order (:236-241)
+                    for (int c = 0; c < rnch_all; ++c) {
+                        const float gc = gamma_draw(t, game_id, search, (uint32_t)(round * B + i0 + lane), c);
+                        s_gamma[lane][c] = gc;
+                        sum = __fadd_rn(sum, gc);
                     }
-                    idx = puct_pick(nch, mult, rn0, rn1, rq0, rq1, p0, p1, v0, v1, c0, c1);
+                    s_gsum[lane] = sum == 0.0f ? 1.0f : sum;
                 }
-                next = rfc + idx;
-                const bool hi = idx >= 32;
-                nm = __shfl_sync(0xffffffffu, hi ? rcm1 : rcm0, idx & 31);
-                nfc = __shfl_sync(0xffffffffu, hi ? rcf1 : rcf0, idx & 31);
-                nnn = __shfl_sync(0xffffffffu, hi ? rn1 : rn0, idx & 31);     // the child's count BEFORE this selection's virtual loss
-                if (lane == (idx & 31)) {            // virtual loss by the lane that holds the chosen child (written back after the chunk's root pass)
-                    if (hi) { rn1 += 1; rw1 = __fsub_rn(rw1, 1.0f); rq1 = __fdiv_rn(rw1, (float)rn1); rdirty1 = true; }
-                    else { rn0 += 1; rw0 = __fsub_rn(rw0, 1.0f); rq0 = __fdiv_rn(rw0, (float)rn0); rdirty0 = true; }
-                }
-                dep = 1;
+                __syncwarp();
             }
-            root_n += 1;                             // root visit count (:78)
-            if (lane == s) { s_node = next; s_m = nm; s_fc = nfc; s_nn = nnn; s_depth = dep; s_rate = t.rate[nnn < t.rate_len ? nnn : t.rate_len - 1]; }
+            // Per-slot state, lane = slot of the chunk: the node the selection stands on, its header (meta, first child), its
+            // visit count BEFORE this selection's virtual loss (the rate-table index when the selection decides there) and
+            // the exploration rate of that count, fetched by the slot's lane as soon as the count is known -- a level before
+            // it is used (in the arrival loop it would be a dependent global load in front of every decision).
+            int s_node = root, s_m = rm, s_fc = rfc, s_nn = 0, s_depth = 0;
+            float s_rate = 0.f;
+            // ---- level 0: the root's arrivals in slot order, statistics in registers
+            for (int s = 0; s < chunk; ++s) {
+                int next = root, nm = rm, nfc = rfc, nnn = root_n, dep = 0;
+                if (root_open) {
+                    const int nch = rnch_all;
+                    const int c0 = lane, c1 = lane + 32;
+                    const bool v0 = c0 < nch, v1 = c1 < nch;
+                    int idx = 0;                         // a single child is taken without any arithmetic (:194-196)
+                    if (nch > 1) {
+                        int nn = root_n;
+                        if (nn >= t.rate_len) { if (lane == 0) atomicOr(t.error, kErrRateTable); nn = t.rate_len - 1; }
+                        const float rate = t.rate[nn];   // logf((1 + N + c_base) / c_base) + c_init, host libm
+                        const int total = __reduce_add_sync(0xffffffffu, rn0 + rn1);
+                        const float mult = __fmul_rn(rate, __fsqrt_rn((float)total));
+                        float p0 = rp0, p1 = rp1;
+                        if (noisy) {                     // Dirichlet noise, re-drawn per selection (:230-249)
+                            const float g0 = v0 ? s_gamma[s][c0] : 0.f;
+                            const float g1 = (nch > 32 && v1) ? s_gamma[s][c1] : 0.f;
+                            const float nm2 = __fdiv_rn(t.eps, s_gsum[s]);
+                            p0 = __fadd_rn(__fmul_rn(p0, pm), __fmul_rn(g0, nm2));
+                            if (nch > 32) p1 = __fadd_rn(__fmul_rn(p1, pm), __fmul_rn(g1, nm2));
+                        }
+                        idx = puct_pick(nch, mult, rn0, rn1, rq0, rq1, p0, p1, v0, v1, c0, c1);
+                    }
+                    next = rfc + idx;
+                    const bool hi = idx >= 32;
+                    nm = __shfl_sync(0xffffffffu, hi ? rcm1 : rcm0, idx & 31);
+                    nfc = __shfl_sync(0xffffffffu, hi ? rcf1 : rcf0, idx & 31);
+                    nnn = __shfl_sync(0xffffffffu, hi ? rn1 : rn0, idx & 31);     // the child's count BEFORE this selection's virtual loss
+                    if (lane == (idx & 31)) {            // virtual loss by the lane that holds the chosen child (written back after the chunk)
+                        if (hi) { rn1 += 1; rw1 = __fsub_rn(rw1, 1.0f); rq1 = __fdiv_rn(rw1, (float)rn1); rdirty1 = true; }
+                        else { rn0 += 1; rw0 = __fsub_rn(rw0, 1.0f); rq0 = __fdiv_rn(rw0, (float)rn0); rdirty0 = true; }
+                    }
+                    dep = 1;
+                }
+                root_n += 1;                             // root visit count (:78)
+                if (lane == s) { s_node = next; s_m = nm; s_fc = nfc; s_nn = nnn; s_depth = dep; s_rate = t.rate[nnn < t.rate_len ? nnn : t.rate_len - 1]; }
+            }
+            if (lane < chunk && s_depth == 1) gpath_mine[0] = s_node;
+            sh_node[lane] = s_node; sh_m[lane] = s_m; sh_fc[lane] = s_fc; sh_nn[lane] = s_nn; sh_depth[lane] = s_depth; sh_rate[lane] = s_rate;
         }
-        if (lane < chunk && s_depth == 1) gpath_mine[0] = s_node;
-#ifdef OZ_SELECT_TIMELINE
-        tl_root = clock64() - tl0;
-#endif
         // ---- levels >= 1.  What a node decides for an arriving selection depends on the node's own children and on the
         // selections that arrived there EARLIER in slot order -- on nothing else in the tree.  So the chunk advances level by
         // level: the slots standing on the same node are grouped (__match_any_sync), each distinct node's child block is read
         // ONCE (the next node's block is already in flight while the current node's arrivals are decided), its arrivals are
-        // decided in slot order from registers, and the touched children are written back once.
+        // decided in slot order from registers, and the touched children are written back once.  Distinct nodes of a level
+        // are independent of each other: the GW warps of the block take them in turn (the slot state travels through shared
+        // memory), so a level costs its busiest warp's decisions, not the sum -- a decision is some 200 dependent
+        // instructions (IEEE square root, two IEEE divisions, three warp reductions), about 950 clocks, and there are 120 to
+        // 150 of them below the root in a 32-selection round.
         for (int level = 1;; ++level) {
+            __syncthreads();                             // the previous level's (or the root pass's) slot state is in shared memory
+            int s_node = sh_node[lane], s_m = sh_m[lane], s_fc = sh_fc[lane], s_nn = sh_nn[lane], s_depth = sh_depth[lane];
+            float s_rate = sh_rate[lane];
             const bool active = lane < chunk && s_depth == level && (s_m & 3) != 0 && (s_m >> 8) != 0;
-            if (!__ballot_sync(0xffffffffu, active)) break;
+            if (!__ballot_sync(0xffffffffu, active)) break;       // the same for every warp of the block
             const unsigned grp = __match_any_sync(0xffffffffu, active ? s_node : -1 - lane);
-            unsigned leaders = __ballot_sync(0xffffffffu, active && (__ffs(grp) - 1) == lane);
-            // block of the first node
-            int L = __ffs(leaders) - 1;
-            leaders &= leaders - 1;
-            int fcX = __shfl_sync(0xffffffffu, s_fc, L), nchX = __shfl_sync(0xffffffffu, s_m, L) >> 8;
-            unsigned arr = __shfl_sync(0xffffffffu, grp, L);
-            int n0, n1, cm0, cm1, cf0, cf1;
-            float w0, w1, q0, q1, p0, p1;
-            load_child_block(t, base + fcX, nchX, lane, n0, w0, q0, p0, cm0, cf0, n1, w1, q1, p1, cm1, cf1);
-            while (true) {
-                // the next distinct node's block: in flight while this node's arrivals are decided
-                const bool more = leaders != 0;
-                int L2 = 0, fcY = 0, nchY = 0;
-                unsigned arrY = 0;
-                int yn0 = 0, yn1 = 0, ycm0 = 0, ycm1 = 0, ycf0 = -1, ycf1 = -1;
-                float yw0 = 0.f, yw1 = 0.f, yq0 = 0.f, yq1 = 0.f, yp0 = 0.f, yp1 = 0.f;
-                if (more) {
-                    L2 = __ffs(leaders) - 1;
-                    leaders &= leaders - 1;
-                    fcY = __shfl_sync(0xffffffffu, s_fc, L2); nchY = __shfl_sync(0xffffffffu, s_m, L2) >> 8;
-                    arrY = __shfl_sync(0xffffffffu, grp, L2);
-                    load_child_block(t, base + fcY, nchY, lane, yn0, yw0, yq0, yp0, ycm0, ycf0, yn1, yw1, yq1, yp1, ycm1, ycf1);
+            const unsigned all_leaders = __ballot_sync(0xffffffffu, active && (__ffs(grp) - 1) == lane);
+            // this warp's share: the leaders whose rank among the level's leaders is wib modulo GW
+            unsigned leaders = 0;
+            {
+                unsigned rest = all_leaders;
+                for (int r = 0; rest; ++r) { const unsigned low = rest & (0u - rest); if (r % GW == wib) leaders |= low; rest ^= low; }
+            }
+            __syncthreads();                             // everybody has read the state before anybody writes the next level's
+            unsigned touched = 0;                        // slots whose state this warp advanced
+            if (leaders) {
+                int L = __ffs(leaders) - 1;
+                leaders &= leaders - 1;
+                int fcX = __shfl_sync(0xffffffffu, s_fc, L), nchX = __shfl_sync(0xffffffffu, s_m, L) >> 8;
+                unsigned arr = __shfl_sync(0xffffffffu, grp, L);
+                int n0, n1, cm0, cm1, cf0, cf1;
+                float w0, w1, q0, q1, p0, p1;
+                load_child_block(t, base + fcX, nchX, lane, n0, w0, q0, p0, cm0, cf0, n1, w1, q1, p1, cm1, cf1);
+                while (true) {
+                    // the next distinct node's block: in flight while this node's arrivals are decided
+                    const bool more = leaders != 0;
+                    int fcY = 0, nchY = 0;
+                    unsigned arrY = 0;
+                    int yn0 = 0, yn1 = 0, ycm0 = 0, ycm1 = 0, ycf0 = -1, ycf1 = -1;
+                    float yw0 = 0.f, yw1 = 0.f, yq0 = 0.f, yq1 = 0.f, yp0 = 0.f, yp1 = 0.f;
+                    if (more) {
+                        const int L2 = __ffs(leaders) - 1;
+                        leaders &= leaders - 1;
+                        fcY = __shfl_sync(0xffffffffu, s_fc, L2); nchY = __shfl_sync(0xffffffffu, s_m, L2) >> 8;
+                        arrY = __shfl_sync(0xffffffffu, grp, L2);
+                        load_child_block(t, base + fcY, nchY, lane, yn0, yw0, yq0, yp0, ycm0, ycf0, yn1, yw1, yq1, yp1, ycm1, ycf1);
+                    }
+                    // this node's arrivals, in slot order
+                    const int nch = nchX;
+                    const int c0 = lane, c1 = lane + 32;
+                    const bool v0 = c0 < nch, v1 = c1 < nch;
+                    bool dirty0 = false, dirty1 = false;
+                    touched |= arr;
+                    while (arr) {
+                        const int s = __ffs(arr) - 1;
+                        arr &= arr - 1;
+                        int idx = 0;
+                        if (nch > 1) {
+                            const int nn = __shfl_sync(0xffffffffu, s_nn, s);
+                            if (nn >= t.rate_len && lane == 0) atomicOr(t.error, kErrRateTable);
+                            const float rate = __shfl_sync(0xffffffffu, s_rate, s);   // rate[nn]: logf((1 + N + c_base) / c_base) + c_init, host libm
+                            const int total = __reduce_add_sync(0xffffffffu, n0 + n1);
+                            children_read += (unsigned)nch;
+                            const float mult = __fmul_rn(rate, __fsqrt_rn((float)total));
+                            idx = puct_pick(nch, mult, n0, n1, q0, q1, p0, p1, v0, v1, c0, c1);
+                        }
+                        const int next = fcX + idx;
+                        const bool hi = idx >= 32;
+                        const int nm = __shfl_sync(0xffffffffu, hi ? cm1 : cm0, idx & 31);
+                        const int nfc = __shfl_sync(0xffffffffu, hi ? cf1 : cf0, idx & 31);
+                        const int nnn = __shfl_sync(0xffffffffu, hi ? n1 : n0, idx & 31);
+                        if (lane == (idx & 31)) {        // virtual loss (search_thread.cpp:70-76), in the register copy
+                            if (hi) { n1 += 1; w1 = __fsub_rn(w1, 1.0f); q1 = __fdiv_rn(w1, (float)n1); dirty1 = true; }
+                            else { n0 += 1; w0 = __fsub_rn(w0, 1.0f); q0 = __fdiv_rn(w0, (float)n0); dirty0 = true; }
+                        }
+                        if (lane == s) {
+                            if (s_depth < kMaxDepth) gpath_mine[s_depth] = next; else atomicOr(t.error, kErrDepth);
+                            s_node = next; s_m = nm; s_fc = nfc; s_nn = nnn; s_depth += 1;
+                            s_rate = t.rate[nnn < t.rate_len ? nnn : t.rate_len - 1];
+                        }
+                    }
+                    if (dirty0) { const size_t a = base + fcX + c0; t.n_N[a] = n0; t.n_W[a] = w0; t.n_Q[a] = q0; }
+                    if (dirty1) { const size_t a = base + fcX + c1; t.n_N[a] = n1; t.n_W[a] = w1; t.n_Q[a] = q1; }
+                    if (!more) break;
+                    fcX = fcY; nchX = nchY; arr = arrY;
+                    n0 = yn0; n1 = yn1; cm0 = ycm0; cm1 = ycm1; cf0 = ycf0; cf1 = ycf1;
+                    w0 = yw0; w1 = yw1; q0 = yq0; q1 = yq1; p0 = yp0; p1 = yp1;
                 }
-                // this node's arrivals, in slot order
-#ifdef OZ_SELECT_TIMELINE
-                { long long a0 = clock64(); volatile int touch = n0 + cm0 + cf0 + __float_as_int(w0) + __float_as_int(q0) + __float_as_int(p0); (void)touch; tl_wait += clock64() - a0; ++tl_nodes; }
-                long long a1 = clock64();
-#endif
-                const int nch = nchX;
-                const int c0 = lane, c1 = lane + 32;
-                const bool v0 = c0 < nch, v1 = c1 < nch;
-                bool dirty0 = false, dirty1 = false;
-                while (arr) {
-                    const int s = __ffs(arr) - 1;
-                    arr &= arr - 1;
-                    int idx = 0;
-                    if (nch > 1) {
-                        const int nn = __shfl_sync(0xffffffffu, s_nn, s);
-                        if (nn >= t.rate_len && lane == 0) atomicOr(t.error, kErrRateTable);
-                        const float rate = __shfl_sync(0xffffffffu, s_rate, s);   // rate[nn]: logf((1 + N + c_base) / c_base) + c_init, host libm
-                        const int total = __reduce_add_sync(0xffffffffu, n0 + n1);
-                        children_read += (unsigned)nch;
-                        const float mult = __fmul_rn(rate, __fsqrt_rn((float)total));
-                        idx = puct_pick(nch, mult, n0, n1, q0, q1, p0, p1, v0, v1, c0, c1);
-                    }
-                    const int next = fcX + idx;
-                    const bool hi = idx >= 32;
-                    const int nm = __shfl_sync(0xffffffffu, hi ? cm1 : cm0, idx & 31);
-                    const int nfc = __shfl_sync(0xffffffffu, hi ? cf1 : cf0, idx & 31);
-                    const int nnn = __shfl_sync(0xffffffffu, hi ? n1 : n0, idx & 31);
-                    if (lane == (idx & 31)) {        // virtual loss (search_thread.cpp:70-76), in the register copy
-                        if (hi) { n1 += 1; w1 = __fsub_rn(w1, 1.0f); q1 = __fdiv_rn(w1, (float)n1); dirty1 = true; }
-                        else { n0 += 1; w0 = __fsub_rn(w0, 1.0f); q0 = __fdiv_rn(w0, (float)n0); dirty0 = true; }
-                    }
-#ifdef OZ_SELECT_TIMELINE
-                    ++tl_arrivals;
-#endif
-                    if (lane == s) {
-                        if (s_depth < kMaxDepth) gpath_mine[s_depth] = next; else atomicOr(t.error, kErrDepth);
-                        s_node = next; s_m = nm; s_fc = nfc; s_nn = nnn; s_depth += 1;
-                        s_rate = t.rate[nnn < t.rate_len ? nnn : t.rate_len - 1];
-                    }
-                }
-#ifdef OZ_SELECT_TIMELINE
-                tl_arr += clock64() - a1;
-#endif
-                if (dirty0) { const size_t a = base + fcX + c0; t.n_N[a] = n0; t.n_W[a] = w0; t.n_Q[a] = q0; }
-                if (dirty1) { const size_t a = base + fcX + c1; t.n_N[a] = n1; t.n_W[a] = w1; t.n_Q[a] = q1; }
-                if (!more) break;
-                fcX = fcY; nchX = nchY; arr = arrY;
-                n0 = yn0; n1 = yn1; cm0 = ycm0; cm1 = ycm1; cf0 = ycf0; cf1 = ycf1;
-                w0 = yw0; w1 = yw1; q0 = yq0; q1 = yq1; p0 = yp0; p1 = yp1;
+            }
+            if (touched & (1u << lane)) {                // hand the advanced slots to the next level
+                sh_node[lane] = s_node; sh_m[lane] = s_m; sh_fc[lane] = s_fc; sh_nn[lane] = s_nn; sh_depth[lane] = s_depth; sh_rate[lane] = s_rate;
             }
         }
-#ifdef OZ_SELECT_TIMELINE
-        if (lane == 0 && g == 0) printf("select round %d: total %lld clk, root %lld, waiting for blocks %lld, arrivals %lld (%d arrivals at %d nodes)\n", round, clock64() - tl0, tl_root, tl_wait, tl_arr, tl_arrivals, tl_nodes);
-#endif
-        // the chunk's results
-        const int dclip = s_depth > kMaxDepth ? kMaxDepth : s_depth;
-        path_nodes += (unsigned)__reduce_add_sync(0xffffffffu, lane < chunk ? dclip : 0);
-        if (lane < chunk) { leaf_out[i0 + lane] = s_node; t.s_len[(size_t)g * B + i0 + lane] = dclip; }
-        // the root's children: written back once per chunk (later chunks and kernels read them from memory / these registers)
-        if (rdirty0) { const size_t a = base + rfc + lane; t.n_N[a] = rn0; t.n_W[a] = rw0; t.n_Q[a] = rq0; rdirty0 = false; }
-        if (rdirty1) { const size_t a = base + rfc + lane + 32; t.n_N[a] = rn1; t.n_W[a] = rw1; t.n_Q[a] = rq1; rdirty1 = false; }
-        __syncwarp();                                // this chunk's stores are ordered before the next chunk's reads
+        // the chunk's results (the loop was left behind a barrier: the state in shared memory is final)
+        if (wib == 0) {
+            const int d = sh_depth[lane];
+            const int dclip = d > kMaxDepth ? kMaxDepth : d;
+            path_nodes += (unsigned)__reduce_add_sync(0xffffffffu, lane < chunk ? dclip : 0);
+            if (lane < chunk) { leaf_out[i0 + lane] = sh_node[lane]; t.s_len[(size_t)g * B + i0 + lane] = dclip; }
+            // the root's children: written back once per chunk (later chunks read these registers, later kernels the memory)
+            if (rdirty0) { const size_t a = base + rfc + lane; t.n_N[a] = rn0; t.n_W[a] = rw0; t.n_Q[a] = rq0; rdirty0 = false; }
+            if (rdirty1) { const size_t a = base + rfc + lane + 32; t.n_N[a] = rn1; t.n_W[a] = rw1; t.n_Q[a] = rq1; rdirty1 = false; }
+        }
+        __syncthreads();                                 // this chunk's stores and shared state are done with before the next chunk
     }
-    if (lane == 0) t.n_N[base + root] = root_n;
+    if (wib == 0 && lane == 0) t.n_N[base + root] = root_n;
     }
-    if (lane == 0 && path_nodes) { unsigned long long *st = t.stats + 4 * ((blockIdx.x * WARPS + wib) % kStatCopies); atomicAdd(&st[1], path_nodes); atomicAdd(&st[2], children_read); }
+    if (lane == 0 && (path_nodes | children_read)) { unsigned long long *st = t.stats + 4 * ((blockIdx.x * GW + wib) % kStatCopies); atomicAdd(&st[1], path_nodes); atomicAdd(&st[2], children_read); }
 }
 
 // ------------------------------------------------------------------ encode (search_thread.cpp:87-100, transformation.h:83-116)
@@ -1059,7 +1068,7 @@ void launch_reset(const Tree &t, cudaStream_t s) { reset_kernel<<<blocks(t.G, 12
 void launch_select(const Tree &t, cudaStream_t s, bool narrow, bool pdl) {
     if (narrow) narrow_attributes();
     if (narrow) select_kernel<1><<<std::min(blocks(t.G, 1), kNarrowGrid), 32, 0, s>>>(t);
-    else launch_kernel(select_kernel<4>, dim3(blocks(t.G, 4)), dim3(128), 0, s, pdl, t);
+    else launch_kernel(select_kernel<4>, dim3((unsigned)t.G), dim3(128), 0, s, pdl, t);
     count_launch();
 }
 void launch_encode(const Tree &t, float *features, cudaStream_t s, bool narrow, void *nhwc, bool pdl) {
