@@ -139,7 +139,7 @@ __device__ __forceinline__ void load_child_block(const Tree &t, size_t a, int nc
 template <int GW>
 __global__ void __launch_bounds__(GW * 32) select_kernel(Tree t) {
     __shared__ float s_gamma[32][33];                          // [selection of the chunk][root child]
-    __shared__ float s_gsum[32];
+    __shared__ float s_gsum[32];                               // eps / (sum of the selection's draws)
     // per-slot state of the chunk, handed from level to level (and between the warps of the game)
     __shared__ int sh_node[32], sh_m[32], sh_fc[32], sh_nn[32], sh_depth[32];
     __shared__ float sh_rate[32];
@@ -186,7 +186,7 @@ __global__ void __launch_bounds__(GW * 32) select_kernel(Tree t) {
                         s_gamma[lane][c] = gc;
                         sum = __fadd_rn(sum, gc);
                     }
-                    s_gsum[lane] = sum == 0.0f ? 1.0f : sum;
+                    s_gsum[lane] = __fdiv_rn(t.eps, sum == 0.0f ? 1.0f : sum);   // the selection's noise weight eps / sum (:243-247), off the decision chain
                 }
                 __syncwarp();
             }
@@ -214,7 +214,7 @@ __global__ void __launch_bounds__(GW * 32) select_kernel(Tree t) {
                         if (noisy) {                     // Dirichlet noise, re-drawn per selection (:230-249)
                             const float g0 = v0 ? s_gamma[s][c0] : 0.f;
                             const float g1 = (nch > 32 && v1) ? s_gamma[s][c1] : 0.f;
-                            const float nm2 = __fdiv_rn(t.eps, s_gsum[s]);
+                            const float nm2 = s_gsum[s];
                             p0 = __fadd_rn(__fmul_rn(p0, pm), __fmul_rn(g0, nm2));
                             if (nch > 32) p1 = __fadd_rn(__fmul_rn(p1, pm), __fmul_rn(g1, nm2));
                         }
@@ -1068,7 +1068,13 @@ void launch_reset(const Tree &t, cudaStream_t s) { reset_kernel<<<blocks(t.G, 12
 void launch_select(const Tree &t, cudaStream_t s, bool narrow, bool pdl) {
     if (narrow) narrow_attributes();
     if (narrow) select_kernel<1><<<std::min(blocks(t.G, 1), kNarrowGrid), 32, 0, s>>>(t);
-    else launch_kernel(select_kernel<4>, dim3((unsigned)t.G), dim3(128), 0, s, pdl, t);
+    // Warps per game: a handful of games (the reference's one-game-at-a-time callers) have the SMs to themselves, 16 warps
+    // spread a level's nodes widest (single game: 4.55 / 4.22 / 4.09 / 4.02 ms per search with 2 / 4 / 8 / 16 warps); a
+    // thousand games already fill the machine, two warps per game are best there (select + encode 4.96 / 5.37 / 7.13 ms per
+    // ply with 2 / 4 / 8 warps).
+    else if (t.G <= 64) launch_kernel(select_kernel<16>, dim3((unsigned)t.G), dim3(512), 0, s, pdl, t);
+    else if (t.G <= 512) launch_kernel(select_kernel<4>, dim3((unsigned)t.G), dim3(128), 0, s, pdl, t);
+    else launch_kernel(select_kernel<2>, dim3((unsigned)t.G), dim3(64), 0, s, pdl, t);
     count_launch();
 }
 void launch_encode(const Tree &t, float *features, cudaStream_t s, bool narrow, void *nhwc, bool pdl) {
