@@ -457,21 +457,26 @@ __global__ void __launch_bounds__(WARPS * 32) encode_kernel(Tree t, float *featu
 //      into its depth's nodes in slot order -- 16 independent register/shared-memory chains, no memory round trip between
 //      two backups (each backup used to wait for an L2 round trip: 32 x 0.45 us per round for a single game); then the
 //      owners write W and Q = W / N back once.  Same float additions in the same order: the same bits.
+// GW warps work on one game.  Creating children (2.) and backing up (3.) touch different things -- new nodes and the expanding
+// leaves' headers on one side, W and Q of path nodes on the other -- so with GW > 1 warp 0 runs the backups while the other
+// warps create the chunk's children, 32 * (GW - 1) at a step; every warp derives step 1 for itself (the same loads, the same
+// numbers).  GW = 1 (the narrow kernel of the pipelined search) does 1, 2, 3 in turn.
 constexpr int kFastBackupDepth = 16;
-template <int WARPS>
-__global__ void __launch_bounds__(WARPS * 32) expand_kernel(Tree t, const float *__restrict__ policy, const float *__restrict__ value) {
-    __shared__ float s_bw[WARPS == 4 ? WARPS : 1][32 * kFastBackupDepth];          // W of the chunk's nodes, at [first slot][depth]
-    __shared__ int s_bn[WARPS == 4 ? WARPS : 1][32 * kFastBackupDepth];            // their visit counts
-    __shared__ __align__(16) uint8_t s_bfirst[WARPS == 4 ? WARPS : 1][32 * kFastBackupDepth];   // [slot][depth] -> first slot with that node
-    __shared__ float s_bv[WARPS == 4 ? WARPS : 1][32];                             // value backed up from slot li
-    __shared__ int s_blen[WARPS == 4 ? WARPS : 1][32];
-    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+template <int GW>
+__global__ void __launch_bounds__(GW * 32) expand_kernel(Tree t, const float *__restrict__ policy, const float *__restrict__ value) {
+    __shared__ float s_bw[1][32 * kFastBackupDepth];          // W of the chunk's nodes, at [first slot][depth]
+    __shared__ int s_bn[1][32 * kFastBackupDepth];            // their visit counts
+    __shared__ __align__(16) uint8_t s_bfirst[1][32 * kFastBackupDepth];   // [slot][depth] -> first slot with that node
+    __shared__ float s_bv[1][32];                             // value backed up from slot li
+    __shared__ int s_blen[1][32];
+    constexpr int WARPS = GW > 1 ? 4 : 1;                     // (the backup fast path below is compiled in for GW > 1)
+    const int lane = threadIdx.x & 31, wib = 0, gwarp = threadIdx.x >> 5;
     const int B = t.inflight;
     unsigned long long expanded = 0;
     griddep_launch_dependents();
     griddep_wait();                                             // nothing of the tree or the round counter is touched before this
     if (blockIdx.x == 0 && threadIdx.x == 0) *t.round += 1;     // select / encode of this round are done
-    for (int g = blockIdx.x * WARPS + wib; g < t.G; g += gridDim.x * WARPS) {
+    for (int g = blockIdx.x; g < t.G; g += gridDim.x) {
     if (t.g_status[g] & 1) continue;
     const size_t base = arena_base(t, g);
     int count = t.g_count[g];                            // nodes in the arena; kept in a register, written back once
@@ -489,6 +494,7 @@ __global__ void __launch_bounds__(WARPS * 32) expand_kernel(Tree t, const float 
             c_leaf = t.s_leaf[sl]; c_len = t.s_len[sl]; c_tf = t.s_tf[sl]; c_val = value[sl];
             c_meta = t.n_meta[base + c_leaf]; c_p1 = t.n_p1[base + c_leaf]; c_p2 = t.n_p2[base + c_leaf];
         }
+        if (GW > 1) __syncthreads();                      // every warp has read the leaves' headers before a creator rewrites one
         const int c_player = c_meta & 3;
         const unsigned same = __match_any_sync(0xffffffffu, c_leaf);          // lanes holding the same leaf
         const bool expands = c_valid && c_player != 0 && (c_meta >> 8) == 0 && (__ffs(same) - 1) == lane;
@@ -505,8 +511,8 @@ __global__ void __launch_bounds__(WARPS * 32) expand_kernel(Tree t, const float 
             if (lane == 0) atomicOr(t.error, kErrArenaFull);
             total = 0;
         }
-        // ---- 2. the children of the chunk, flat
-        for (int k0 = 0; k0 < total; k0 += 32) {
+        // ---- 2. the children of the chunk, flat (GW > 1: warps 1 .. GW - 1, warp 0 goes straight to the backups)
+        for (int k0 = GW > 1 ? 32 * (gwarp - 1) : 0; k0 < total && (GW == 1 || gwarp > 0); k0 += GW > 1 ? 32 * (GW - 1) : 32) {
             const int k = k0 + lane;
             int sidx = 0;                                // first lane whose inclusive prefix exceeds k
 #pragma unroll
@@ -531,10 +537,11 @@ __global__ void __launch_bounds__(WARPS * 32) expand_kernel(Tree t, const float 
                 t.n_P[d] = policy[(slot0 + sidx) * 65 + transform_action(a, tf_s)];   // raw softmax output, no renormalisation (:139-149)
             }
         }
-        if (expands && total > 0) { t.n_child[base + c_leaf] = count + c_off; t.n_meta[base + c_leaf] = c_player | (c_n << 8); }
+        if ((GW == 1 || gwarp == 1) && expands && total > 0) { t.n_child[base + c_leaf] = count + c_off; t.n_meta[base + c_leaf] = c_player | (c_n << 8); }
         count += total;
-        expanded += (unsigned)total;
+        if (gwarp == 0) expanded += (unsigned)total;
         __syncwarp();
+        if (GW > 1 && gwarp > 0) { __syncthreads(); continue; }        // the creators are done with this chunk
         // ---- 3. backups in slot order.
         if (WARPS == 4 && __reduce_max_sync(0xffffffffu, c_valid ? c_len : 0) <= kFastBackupDepth) {
             const int bw = WARPS == 4 ? wib : 0;
@@ -599,6 +606,7 @@ __global__ void __launch_bounds__(WARPS * 32) expand_kernel(Tree t, const float 
                     t.n_W[a] = w; t.n_Q[a] = __fdiv_rn(w, (float)s_bn[bw][lane * kFastBackupDepth + k]);
                 }
             __syncwarp();
+            if (GW > 1) __syncthreads();                  // chunk barrier (matches the creators')
             continue;
         }
         // Longer paths: one backup after the other.  The first eight path entries of every slot are fetched up front, transposed over
@@ -639,10 +647,11 @@ __global__ void __launch_bounds__(WARPS * 32) expand_kernel(Tree t, const float 
             }
             __syncwarp();
         }
+        if (GW > 1) __syncthreads();                      // chunk barrier (matches the creators')
     }
-    if (lane == 0) t.g_count[g] = count;
+    if (gwarp == 0 && lane == 0) t.g_count[g] = count;
     }
-    if (lane == 0 && expanded) atomicAdd(&t.stats[4 * ((blockIdx.x * WARPS + wib) % kStatCopies)], expanded);
+    if (gwarp == 0 && lane == 0 && expanded) atomicAdd(&t.stats[4 * (blockIdx.x % kStatCopies)], expanded);
 }
 
 __global__ void end_search_kernel(Tree t) {
@@ -1084,7 +1093,8 @@ void launch_encode(const Tree &t, float *features, cudaStream_t s, bool narrow, 
 }
 void launch_expand(const Tree &t, const float *policy, const float *value, cudaStream_t s, bool narrow, bool pdl) {
     if (narrow) expand_kernel<1><<<std::min(blocks(t.G, 1), kNarrowGrid), 32, 0, s>>>(t, policy, value);
-    else launch_kernel(expand_kernel<4>, dim3(blocks(t.G, 4)), dim3(128), 0, s, pdl, t, policy, value);
+    else if (t.G <= 64) launch_kernel(expand_kernel<4>, dim3((unsigned)t.G), dim3(128), 0, s, pdl, t, policy, value);
+    else launch_kernel(expand_kernel<2>, dim3((unsigned)t.G), dim3(64), 0, s, pdl, t, policy, value);
     count_launch();
 }
 void launch_end_search(const Tree &t, cudaStream_t s) { end_search_kernel<<<blocks(t.G, 128), 128, 0, s>>>(t); count_launch(); }
