@@ -196,6 +196,17 @@ __global__ void __launch_bounds__(GW * 32) select_kernel(Tree t) {
             // it is used (in the arrival loop it would be a dependent global load in front of every decision).
             int s_node = root, s_m = rm, s_fc = rfc, s_nn = 0, s_depth = 0;
             float s_rate = 0.f;
+            // The exploration factor rate(N) * sqrt(sum of the children's counts) of the root's s-th arrival of the chunk is known
+            // up front -- every arrival adds exactly one visit to the root and to one child -- so lane s computes it for its
+            // selection (table load, IEEE square root) and the sequential loop below only fetches it with a shuffle.
+            float mult_mine = 0.f;
+            if (root_open && rnch_all > 1) {
+                const int total0 = __reduce_add_sync(0xffffffffu, rn0 + rn1);
+                int nn = root_n + lane;
+                if (lane < chunk && nn >= t.rate_len) atomicOr(t.error, kErrRateTable);
+                if (nn >= t.rate_len) nn = t.rate_len - 1;
+                mult_mine = __fmul_rn(t.rate[nn], __fsqrt_rn((float)(total0 + lane)));   // rate: logf((1 + N + c_base) / c_base) + c_init, host libm
+            }
             // ---- level 0: the root's arrivals in slot order, statistics in registers
             for (int s = 0; s < chunk; ++s) {
                 int next = root, nm = rm, nfc = rfc, nnn = root_n, dep = 0;
@@ -205,11 +216,7 @@ __global__ void __launch_bounds__(GW * 32) select_kernel(Tree t) {
                     const bool v0 = c0 < nch, v1 = c1 < nch;
                     int idx = 0;                         // a single child is taken without any arithmetic (:194-196)
                     if (nch > 1) {
-                        int nn = root_n;
-                        if (nn >= t.rate_len) { if (lane == 0) atomicOr(t.error, kErrRateTable); nn = t.rate_len - 1; }
-                        const float rate = t.rate[nn];   // logf((1 + N + c_base) / c_base) + c_init, host libm
-                        const int total = __reduce_add_sync(0xffffffffu, rn0 + rn1);
-                        const float mult = __fmul_rn(rate, __fsqrt_rn((float)total));
+                        const float mult = __shfl_sync(0xffffffffu, mult_mine, s);
                         float p0 = rp0, p1 = rp1;
                         if (noisy) {                     // Dirichlet noise, re-drawn per selection (:230-249)
                             const float g0 = v0 ? s_gamma[s][c0] : 0.f;
@@ -290,7 +297,10 @@ __global__ void __launch_bounds__(GW * 32) select_kernel(Tree t) {
                     const bool v0 = c0 < nch, v1 = c1 < nch;
                     bool dirty0 = false, dirty1 = false;
                     touched |= arr;
-                    while (arr) {
+                    // the j-th arrival sees the children's counts sum to (sum on arrival of the first) + j: lane j takes its square root now
+                    float sq_mine = 0.f;
+                    if (nch > 1) sq_mine = __fsqrt_rn((float)(__reduce_add_sync(0xffffffffu, n0 + n1) + lane));
+                    for (int j = 0; arr; ++j) {
                         const int s = __ffs(arr) - 1;
                         arr &= arr - 1;
                         int idx = 0;
@@ -298,9 +308,8 @@ __global__ void __launch_bounds__(GW * 32) select_kernel(Tree t) {
                             const int nn = __shfl_sync(0xffffffffu, s_nn, s);
                             if (nn >= t.rate_len && lane == 0) atomicOr(t.error, kErrRateTable);
                             const float rate = __shfl_sync(0xffffffffu, s_rate, s);   // rate[nn]: logf((1 + N + c_base) / c_base) + c_init, host libm
-                            const int total = __reduce_add_sync(0xffffffffu, n0 + n1);
                             children_read += (unsigned)nch;
-                            const float mult = __fmul_rn(rate, __fsqrt_rn((float)total));
+                            const float mult = __fmul_rn(rate, __shfl_sync(0xffffffffu, sq_mine, j));
                             idx = puct_pick(nch, mult, n0, n1, q0, q1, p0, p1, v0, v1, c0, c1);
                         }
                         const int next = fcX + idx;
