@@ -87,23 +87,24 @@ __global__ void reset_kernel(Tree t) {
 }
 
 // ------------------------------------------------------------------ select (search_thread.cpp:60-79, 192-260)
-// WARPS = warps (games) per block; a warp walks games g, g + stride, ...  The pipelined search launches a bounded grid
-// of single-warp blocks (4.3 KB of static shared memory for the precomputed noise): they fit into the registers a resident convolution CTA leaves free on
-// its SM (6 400 of 65 536), so one game group's tree work runs underneath the other group's network and never keeps a
-// convolution CTA off an SM.  The path of a selection lives in registers (lane k holds nodes k, k + 32, ...).
-//
-// A selection is a chain of dependent memory round trips, one per tree level, and the B selections of a game are
-// sequential by the reference's semantics; the chain is kept as short as it can be:
-//   * the root's header and the statistics of its children stay in registers for all B selections of the round (every
-//     selection starts there), updated in place and written through;
-//   * a level's read brings N, W, Q, P AND the header of every child, so the chosen child's header needs no second read;
-//   * the virtual loss (N += 1, W -= 1, Q = W / N, search_thread.cpp:70-76) is applied on the way down by the lane that
-//     already holds the chosen child's N and W -- the reference applies it after the descent, which gives the same
-//     numbers because a selection visits every node of its path once -- so there is no read-modify-write pass afterwards.
-//   * the Dirichlet draws of a selection depend on (game, search, simulation, child) only, not on the tree: instead of one
-//     Gamma draw per lane inside every selection (a few hundred dependent instructions on the critical path, 32 times per
-//     round), lane s draws the noise of simulation s for all root children up front -- 32 selections in parallel, each a
-//     loop over the handful of children -- into shared memory, together with the sequential child-order sum.
+// GW warps of a block work on one game (the pipelined search launches single-warp blocks: 5 KB of static shared memory,
+// they fit beside a resident convolution CTA).  The reference selects the B leaves of a round one after the other; what
+// makes that order matter is the virtual loss, and the virtual loss only couples selections that meet at the SAME node:
+//   * what a node decides for an arriving selection depends on the node's own children and on the selections that arrived
+//     there earlier in slot order -- the rate-table index is the node's count before the arrival, the children's N / W / Q
+//     change only by the virtual losses of earlier arrivals at this node, Dirichlet noise exists only at the root;
+//   * so a chunk of 32 selections advances LEVEL BY LEVEL: the root's arrivals are decided first, in slot order, from
+//     registers (the root's children stay there for the whole round); below the root the slots standing on the same node
+//     are grouped, each distinct node's child block (N, W, Q, P and the header of every child) is read once, its arrivals
+//     are decided in slot order from registers, the touched children are written back once;
+//   * the virtual loss (N += 1, W -= 1, Q = W / N, search_thread.cpp:70-76) is applied by the lane that holds the chosen
+//     child as the selection passes -- the reference applies it after the descent, which gives the same numbers because a
+//     selection visits every node of its path once;
+//   * everything a decision needs that does not depend on the earlier arrivals is computed beside the chain: the
+//     Dirichlet draws and the noise weight of all 32 selections up front (lane = selection), the exploration factor
+//     rate(N) * sqrt(sum of the children's counts) of every arrival (the sum grows by exactly one per arrival).
+// Round 1 walked one selection at a time, a dependent chain of some 200 instructions and an L2 round trip per level:
+// 105 us per round for a single game, now about 35.
 // PUCT over the children a warp holds (lane = child, a 33rd child in the *1 registers): ucb = Q + (mult * P) / (1 + N),
 // first maximum wins (search_thread.cpp:192-228).
 __device__ __forceinline__ int puct_pick(int nch, float mult, int n0, int n1, float q0, float q1, float p0, float p1,
