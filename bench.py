@@ -308,11 +308,21 @@ def run_ours(args):
         e1.record(stream)
         barrier()
         ms = e0.elapsed_time(e1)
+        timed.local_ms = ms                                       # this rank's own time (per-rank breakdown below)
         if dist is not None:
             t = torch.tensor([ms], device="cuda")
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             ms = float(t.item())
         return ms
+
+    def allgather(*vals):
+        """[rank][i]: every rank's values (one small all_gather outside the timed region)."""
+        t = torch.tensor([float(v) for v in vals], device="cuda", dtype=torch.float64)
+        if dist is None:
+            return [t.tolist()]
+        out = [torch.empty_like(t) for _ in range(world)]
+        dist.all_gather(out, t)
+        return [o.tolist() for o in out]
 
     def allsum(*vals):
         t = torch.tensor([float(v) for v in vals], device="cuda", dtype=torch.float64)
@@ -360,6 +370,7 @@ def run_ours(args):
     if rank == 0:
         sampler.start()
     ms = timed(eng, dev_step, steps)
+    ms_local = timed.local_ms
     clocks = sampler.stop() if rank == 0 else None
     c1 = eng.counters()
     sims = (c1["simulations"] - c0["simulations"])
@@ -369,6 +380,9 @@ def run_ours(args):
     conv_ms = c1["conv_ms"] - c0["conv_ms"]
     conv_launches = c1["conv_launches"] - c0["conv_launches"]
     tot = allsum(sims, evals, launches)                           # the only collective: final counters
+    # every rank's own step time and phases: `ms` is the slowest rank's, the phase counters below are rank 0's, so at
+    # N > 1 the difference between the two (GPUs under the power cap settle at different clocks) must not be read as host time
+    per_rank = allgather(ms_local, eval_ms, conv_ms, c1["select_ms"] - c0["select_ms"], c1["expand_ms"] - c0["expand_ms"])
     value = tot[0] / (ms * 1e-3)
 
     # Same device-resident step measured in the middle game: every game is fast-forwarded to ply `--midgame-ply` with
@@ -409,7 +423,14 @@ def run_ours(args):
     else:
         phases = {"pipeline_groups": 1, "select_encode": sel_ms, "network": eval_ms / steps, "of_which_conv": conv_ms / steps,
                   "expand_backup": exp_ms,
-                  "rest_of_ply (choose, record, re-root, syncs)": (ms - eval_ms) / steps - sel_ms - exp_ms}
+                  "rest_of_ply (choose, record, re-root, syncs)": (ms_local - eval_ms) / steps - sel_ms - exp_ms}
+        if world > 1:
+            phases["note"] = ("rank 0's own phases and own step time; ms_per_step above is the slowest rank's; per_rank lists "
+                              "every rank's step time and phases (CUDA events on that rank's engine stream)")
+    per_rank_rec = {"ms_per_step": [r[0] / steps for r in per_rank], "network": [r[1] / steps for r in per_rank],
+                    "of_which_conv": [r[2] / steps for r in per_rank], "select_encode": [r[3] / steps for r in per_rank],
+                    "expand_backup": [r[4] / steps for r in per_rank],
+                    "rest_of_ply": [(r[0] - r[1] - r[3] - r[4]) / steps for r in per_rank]}
     # Tree traffic: algorithmic bytes of select / encode / expand from the engine's counters, per simulation:
     # select reads a (N, W, Q, P, meta, child) row = 24 B per child per level below the root (the root's children once per
     # round), then writes the virtual loss along the path (N, W, Q and the path entry = 16 B per node); expand reads the leaf (20 B), writes 44 B
@@ -480,6 +501,7 @@ def run_ours(args):
                                                   "event window of oz_perft also holds the breadth-first frontier levels in front of dfs_kernel"},
                       "cpu_baseline": None if (world > 1 or args.no_cpu_baseline) else perft_cpu_baseline(cores)},
             "phases_ms_per_step": phases,
+            "per_rank": per_rank_rec,
             "tree": {"bound": "latency (HBM pointer chasing, sequential within a game)", "bytes_per_sim": tree_bytes / d_sims,
                      "mean_path_nodes": d_path / d_sims, "mean_children_per_level": d_child / max(1, d_path),
                      "nodes_expanded_per_sim": d_nodes / d_sims, "achieved": (tree_bytes / (tree_ms * 1e-3) / 1e9) if tree_ms > 0 else None,
