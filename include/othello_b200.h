@@ -185,6 +185,11 @@ int oz_debug_conv3x3(const uint16_t *in, int cin, const uint16_t *w, const float
  * where it is eligible, -1 returns to the default (on; OZ_TOWER=0 in the environment turns it off).  Both paths issue the
  * same MMAs in the same order: results are bit-identical.  Applies to forwards launched (or graphs captured) afterwards. */
 int oz_debug_set_tower(int mode);
+/* Test / measurement hook: heads_kernel (neural_net.py:68-128) works on one board per warp while the batch is a single
+ * wave of CTAs (<= 2 368 boards) and on four boards per warp beyond.  boards = 1 or 4 forces one of the two, anything else
+ * returns to the choice by batch size (OZ_HEADS_BOARDS in the environment does the same).  Every output is the same sum in
+ * the same order in both: results are bit-identical.  Applies to forwards launched (or graphs captured) afterwards. */
+int oz_debug_set_heads_boards(int boards);
 /* Measurement hook for the same kernel.  *max_clusters (optional) = how many 16-CTA clusters the current device runs at once
  * (0: the tower cannot be used here).  out (optional): [64][8] int64 clock64 stamps of cluster rank 8 during the last tower
  * launch, per layer: first MMA issued, all MMAs issued, accumulator seen by the epilogue, neighbours' MMAs seen, first / second

@@ -759,6 +759,10 @@ int oz_debug_set_tower(int mode) {
     oz::set_tower_mode(mode);
     return OZ_OK;
 }
+int oz_debug_set_heads_boards(int boards) {
+    oz::set_heads_boards(boards);
+    return OZ_OK;
+}
 int oz_debug_tower_timeline(long long *out, int *max_clusters) {
     if (max_clusters) *max_clusters = oz::tower_max_clusters();
     if (!out) return OZ_OK;

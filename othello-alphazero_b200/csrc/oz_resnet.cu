@@ -856,14 +856,19 @@ struct HeadParams {
 // 128-bit loads) and every weight vector read is used for all kHeadBoards boards, so the kernel is no longer bound by
 // shared-memory bandwidth (the one-board-per-warp version did 3 LDS per 2 FMA).  Summation order per output is the plain
 // i = 0, 1, 2, ... order.
+// Small batches (the single-game search: 32 boards; 256x20b at leaf 64 ... 1 024) run the <1> instantiation: one board
+// per warp, four times as many warps in flight, a quarter of the serial work per warp -- the kernel is then a latency
+// chain, not a throughput problem.  Every output is the same sum in the same order in both instantiations (the 1x1
+// convolutions are written as explicit fused multiply-adds for that reason), so which one runs is invisible in the bits.
 constexpr int kHeadWarps = 8;
-constexpr int kHeadBoards = 4;
+constexpr int kHeadBoardsWide = 4;
 constexpr int kPfcStride = 132, kVfcStride = 68, kFeatStride = 192;   // floats
 __host__ __device__ inline int heads_cw_offset(int Hv) { return (65 * kPfcStride + Hv * kVfcStride + 3) & ~3; }       // floats
-__host__ __device__ inline int heads_smem_floats(int C, int Hv) {
-    return ((heads_cw_offset(Hv) + 3 * C + 2 * Hv + 3) & ~3) + kHeadWarps * kHeadBoards * kFeatStride;
+__host__ __device__ inline int heads_smem_floats(int C, int Hv, int boards_per_warp) {
+    return ((heads_cw_offset(Hv) + 3 * C + 2 * Hv + 3) & ~3) + kHeadWarps * boards_per_warp * kFeatStride;
 }
 
+template <int kHeadBoards>
 __global__ void __launch_bounds__(kHeadWarps * 32, 2) heads_kernel(const HeadParams p) {
     extern __shared__ __align__(16) float sm[];
     const int C = p.C, Hv = p.Hv;
@@ -911,7 +916,7 @@ __global__ void __launch_bounds__(kHeadWarps * 32, 2) heads_kernel(const HeadPar
                     const int sq = lane + 32 * h;
                     const __nv_bfloat16 *a = p.act + (b * 64 + sq) * (size_t)C;
                     float d0 = 0.f, d1 = 0.f, d2 = 0.f;
-#pragma unroll 2
+#pragma unroll (kHeadBoards == 1 ? 4 : 2)
                     for (int c16 = 0; c16 < C / 16; ++c16) {        // one full 32-byte sector (16 channels) per load
                         uint32_t q[8];
                         ldg256(a + c16 * 16, q);
@@ -921,12 +926,16 @@ __global__ void __launch_bounds__(kHeadWarps * 32, 2) heads_kernel(const HeadPar
                             const float x0 = __bfloat162float(hh[0].x), x1 = __bfloat162float(hh[0].y), x2 = __bfloat162float(hh[1].x), x3 = __bfloat162float(hh[1].y);
                             const float x4 = __bfloat162float(hh[2].x), x5 = __bfloat162float(hh[2].y), x6 = __bfloat162float(hh[3].x), x7 = __bfloat162float(hh[3].y);
                             const int c8 = 2 * c16 + h2;
-                            float4 wa = cw0[2 * c8], wb = cw0[2 * c8 + 1];
-                            d0 += x0 * wa.x + x1 * wa.y + x2 * wa.z + x3 * wa.w + x4 * wb.x + x5 * wb.y + x6 * wb.z + x7 * wb.w;
-                            wa = cw1[2 * c8]; wb = cw1[2 * c8 + 1];
-                            d1 += x0 * wa.x + x1 * wa.y + x2 * wa.z + x3 * wa.w + x4 * wb.x + x5 * wb.y + x6 * wb.z + x7 * wb.w;
-                            wa = cw2[2 * c8]; wb = cw2[2 * c8 + 1];
-                            d2 += x0 * wa.x + x1 * wa.y + x2 * wa.z + x3 * wa.w + x4 * wb.x + x5 * wb.y + x6 * wb.z + x7 * wb.w;
+                            // eight channels: one product, seven explicit fmas, then one add into the running sum
+                            auto dot8 = [&](const float4 wa, const float4 wb) {
+                                float s8 = __fmul_rn(x0, wa.x);
+                                s8 = __fmaf_rn(x1, wa.y, s8); s8 = __fmaf_rn(x2, wa.z, s8); s8 = __fmaf_rn(x3, wa.w, s8);
+                                s8 = __fmaf_rn(x4, wb.x, s8); s8 = __fmaf_rn(x5, wb.y, s8); s8 = __fmaf_rn(x6, wb.z, s8);
+                                return __fmaf_rn(x7, wb.w, s8);
+                            };
+                            d0 = __fadd_rn(d0, dot8(cw0[2 * c8], cw0[2 * c8 + 1]));
+                            d1 = __fadd_rn(d1, dot8(cw1[2 * c8], cw1[2 * c8 + 1]));
+                            d2 = __fadd_rn(d2, dot8(cw2[2 * c8], cw2[2 * c8 + 1]));
                         }
                     }
                     feat[sq] = fmaxf(d0 + pb0, 0.f);
@@ -1126,6 +1135,14 @@ extern "C" int oz_debug_conv_timeline(unsigned long long *out) { cudaDeviceSynch
 long long *tower_dbg_ptr() { return g_tower_dbg; }
 static int g_tower_mode = -1;                                // -1: environment, 0 / 1: set by oz_debug_set_tower
 void set_tower_mode(int mode) { g_tower_mode = mode < 0 ? -1 : (mode ? 1 : 0); }
+static int g_heads_boards = 0;                               // 0: by batch size, 1 / 4: set by oz_debug_set_heads_boards
+void set_heads_boards(int boards) { g_heads_boards = boards == 1 ? 1 : (boards == kHeadBoardsWide ? kHeadBoardsWide : 0); }
+static int heads_boards_override() {
+    if (g_heads_boards) return g_heads_boards;
+    static int v = -1;
+    if (v < 0) { const char *e = getenv("OZ_HEADS_BOARDS"); v = e ? atoi(e) : 0; if (v != 1 && v != kHeadBoardsWide) v = 0; }
+    return v;
+}
 static bool tower_enabled() {
     if (g_tower_mode >= 0) return g_tower_mode == 1;
     static int v = -1;
@@ -1406,14 +1423,23 @@ int ResNet::launch_heads(const Workspace &w, size_t n, bool fuse_heads, float *d
     hp.vfc2_w = (const float *)(d_blob_ + layout_.vfc2_w); hp.vfc2_b = (const float *)(d_blob_ + layout_.vfc2_b);
     hp.pre = fuse_heads ? w.head_pre : nullptr;
     hp.policy = d_policy; hp.value = d_value; hp.C = C; hp.Hv = shape_.value_hidden; hp.n = n;
-    const size_t hsm = (size_t)heads_smem_floats(C, hp.Hv) * sizeof(float);
-    static size_t hsm_set[64] = {};                      // per device ordinal: the attribute belongs to the current device
+    // one board per warp while that still is a single wave of CTAs (2 per SM), four boards per warp beyond
+    const int forced = heads_boards_override();
+    const bool narrow = forced ? forced == 1 : n <= (size_t)148 * 2 * kHeadWarps;
+    const int bpw = narrow ? 1 : kHeadBoardsWide;
+    const size_t hsm = (size_t)heads_smem_floats(C, hp.Hv, bpw) * sizeof(float);
+    static size_t hsm_set[2][64] = {};                   // per instantiation and device ordinal: the attribute belongs to the current device
     int hdev = 0;
     cudaGetDevice(&hdev);
-    if (hsm > hsm_set[hdev & 63]) { OZ_CUDA(cudaFuncSetAttribute(heads_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hsm)); hsm_set[hdev & 63] = hsm; }
-    const size_t want = (n + kHeadWarps * kHeadBoards - 1) / (kHeadWarps * kHeadBoards);
+    if (hsm > hsm_set[narrow][hdev & 63]) {
+        if (narrow) OZ_CUDA(cudaFuncSetAttribute(heads_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hsm));
+        else OZ_CUDA(cudaFuncSetAttribute(heads_kernel<kHeadBoardsWide>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hsm));
+        hsm_set[narrow][hdev & 63] = hsm;
+    }
+    const size_t want = (n + kHeadWarps * bpw - 1) / (kHeadWarps * bpw);
     const unsigned grid = (unsigned)(want < 148 * 2 ? want : 148 * 2);
-    OZ_CUDA(launch_kernel(heads_kernel, dim3(grid), dim3(kHeadWarps * 32), hsm, stream, pdl, hp));
+    if (narrow) OZ_CUDA(launch_kernel(heads_kernel<1>, dim3(grid), dim3(kHeadWarps * 32), hsm, stream, pdl, hp));
+    else OZ_CUDA(launch_kernel(heads_kernel<kHeadBoardsWide>, dim3(grid), dim3(kHeadWarps * 32), hsm, stream, pdl, hp));
     count_launch();
     OZ_CUDA(cudaGetLastError());
     return OZ_OK;

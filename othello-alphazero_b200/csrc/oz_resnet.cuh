@@ -38,6 +38,7 @@ constexpr int kMaxConvLayers = 128;
 bool conv_static_schedule();
 // Cluster tower for launch-bound batches: 1 on, 0 off (per-layer launches), -1 back to the environment (OZ_TOWER, default on).
 void set_tower_mode(int mode);
+void set_heads_boards(int boards);
 long long *tower_dbg_ptr();   // timeline of the last tower launch (OZ_TOWER_DBG set), or null
 int tower_max_clusters();      // 16-CTA clusters of the tower the current device runs at once (0: tower unusable)
 

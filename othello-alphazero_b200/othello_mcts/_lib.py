@@ -101,6 +101,7 @@ SIGNATURES = {
     "oz_debug_conv3x3": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p,
                                    C.c_int, C.c_size_t, P(C.c_double)]),
     "oz_debug_set_tower": (C.c_int, [C.c_int]),
+    "oz_debug_set_heads_boards": (C.c_int, [C.c_int]),
     "oz_debug_tower_timeline": (C.c_int, [C.c_void_p, P(C.c_int)]),
     "oz_debug_wgrad3x3": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_size_t, C.c_void_p, P(C.c_double)]),
     "oz_engine_search": (C.c_int, [C.c_void_p]),

@@ -151,6 +151,36 @@ def test_cluster_tower_equals_per_layer_launches(blocks, hidden):
         lib.oz_resnet_destroy(h)
 
 
+@pytest.mark.parametrize("blocks,channels,hidden", [(2, 128, 128), (1, 256, 256), (1, 128, 32)])
+def test_heads_one_board_per_warp_equals_four(blocks, channels, hidden):
+    """heads_kernel (neural_net.py:68-128) runs one board per warp for launch-bound batches and four beyond; every output is
+    the same sum in the same order, so policy and value must be BIT-identical whichever instantiation runs -- with the 1x1
+    head convolutions fused into the last conv layer (128 channels) and computed by the kernel itself (256 channels)."""
+    from othello_mcts import _lib, weights
+    lib = _lib.load()
+    net = _net(blocks, channels, 17, hidden, seed=7)
+    shape, blob = weights.fold_alphazero_net(net)
+    h = C.c_void_p()
+    _lib.check(lib.oz_resnet_create(0, C.byref(h)))
+    try:
+        _lib.check(lib.oz_resnet_load(h, C.byref(shape), blob, len(blob)))
+        for n in (1, 31, 32, 257, 2400):
+            xs = _random_feature_planes(n, 17, 300 + n).numpy()
+            out = {}
+            for boards in (1, 4):
+                _lib.check(lib.oz_debug_set_heads_boards(boards))
+                pol = np.zeros((n, 65), np.float32)
+                val = np.zeros(n, np.float32)
+                _lib.check(lib.oz_resnet_forward(h, xs.ctypes.data_as(C.c_void_p), n, pol.ctypes.data_as(C.c_void_p),
+                                                 val.ctypes.data_as(C.c_void_p)))
+                out[boards] = (pol, val)
+            assert np.array_equal(out[1][0], out[4][0]) and np.array_equal(out[1][1], out[4][1]), f"heads<1> != heads<4> at {n} boards"
+            assert np.allclose(out[1][0].sum(axis=1), 1.0, atol=1e-4)
+    finally:
+        _lib.check(lib.oz_debug_set_heads_boards(0))
+        lib.oz_resnet_destroy(h)
+
+
 def test_single_game_search_same_tree_with_and_without_tower():
     """The reference-shaped single-game MCTS.search (32 leaves per network call, graph replay of the whole search with the
     kernels chained by programmatic dependent launch) must build the same tree on the cluster tower and on the per-layer
