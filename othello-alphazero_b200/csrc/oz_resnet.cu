@@ -883,8 +883,22 @@ __global__ void __launch_bounds__(kHeadWarps * 32, 2) heads_kernel(const HeadPar
     // Behind the cluster tower this kernel is launched with programmatic dependent launch: the weight staging below (constant
     // data) runs while the tower still computes; the activations are touched after griddep_wait().
     griddep_launch_dependents();
-    for (int i = t; i < 65 * 32; i += kHeadWarps * 32)          // 128-bit loads; both row strides are multiples of 4 floats
-        *(float4 *)(s_pfc + (i >> 5) * kPfcStride + (i & 31) * 4) = __ldg((const float4 *)p.pfc_w + i);
+    {   // 128-bit loads; both row strides are multiples of 4 floats.  All of a thread's loads are issued before the first
+        // store: one L2 round trip instead of nine (this loop was not unrolled and cost 6 us wherever the kernel cannot
+        // start under its predecessor -- every per-layer forward, whose last convolution fills the SMs' shared memory)
+        constexpr int kPfcIters = (65 * 32 + kHeadWarps * 32 - 1) / (kHeadWarps * 32);
+        float4 stage[kPfcIters];
+#pragma unroll
+        for (int k = 0; k < kPfcIters; ++k) {
+            const int i = t + k * kHeadWarps * 32;
+            if (i < 65 * 32) stage[k] = __ldg((const float4 *)p.pfc_w + i);
+        }
+#pragma unroll
+        for (int k = 0; k < kPfcIters; ++k) {
+            const int i = t + k * kHeadWarps * 32;
+            if (i < 65 * 32) *(float4 *)(s_pfc + (i >> 5) * kPfcStride + (i & 31) * 4) = stage[k];
+        }
+    }
     for (int i = t; i < Hv * 16; i += kHeadWarps * 32)
         *(float4 *)(s_vfc1 + (i >> 4) * kVfcStride + (i & 15) * 4) = __ldg((const float4 *)p.vfc1_w + i);
     for (int i = t; i < 2 * C; i += kHeadWarps * 32) s_cw[i] = p.pconv_w[i];
