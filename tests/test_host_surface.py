@@ -60,6 +60,34 @@ def test_position_matches_golden(golden):
             pos = None
 
 
+def test_position_random_playouts_vs_oracle(oracle):
+    """The host-side Position value type (position.h:39-149, 264-427) against the oracle on 150 seeded random playouts
+    (about 9 000 positions with passes, double passes and early ends): every field, the action list, the flips of the move
+    played and the successor -- bit for bit."""
+    from helpers import playout_positions
+    from othello_mcts import Position, get_flips, get_legal_moves
+    rows = playout_positions(oracle, 150, seed=77)
+    assert len(rows) > 8000 and any(a == 64 for _, _, a, _ in rows)
+    pos = None
+    for p, acts, a, q in rows:
+        if pos is None or (pos.player(), pos.player1_discs(), pos.player2_discs()) != (p.player, p.p1, p.p2):
+            pos = Position.initial_position()                      # a new playout starts
+        assert (pos.player(), pos.player1_discs(), pos.player2_discs(), pos.legal_moves()) == (p.player, p.p1, p.p2, p.legal)
+        assert pos.legal_actions() == acts and not pos.is_terminal()
+        me, opp = (p.p1, p.p2) if p.player == 1 else (p.p2, p.p1)
+        assert get_legal_moves(me, opp) == p.legal
+        if a != 64:
+            flips = get_flips(1 << (63 - a), me, opp)
+            assert flips != 0 and (flips & ~opp) == 0              # a legal move flips opponent discs only
+            assert (q.p1 if p.player == 1 else q.p2) == me | flips | (1 << (63 - a))
+        pos = pos.apply_action(a)
+        assert (pos.player(), pos.player1_discs(), pos.player2_discs(), pos.legal_moves()) == (q.player, q.p1, q.p2, q.legal)
+        assert pos.is_terminal() == (q.player == 0)
+        if pos.is_terminal():
+            assert pos.legal_actions() == []
+            pos = None
+
+
 def test_position_api_and_errors():
     from othello_mcts import Position
     p = Position.initial_position()
